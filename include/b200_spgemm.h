@@ -1,0 +1,129 @@
+/*
+ * b200_spgemm.h -- C ABI of the B200-native SpGEMM engine (libb200spgemm.so / .a).
+ *
+ * Drop-in boundary for the ONE hot path of imlvts/sparse-linear-algebra-tests:
+ * CSR x CSR SpGEMM over saturating unsigned path-count matrices.  The reference has
+ * no FFI of its own (pure Rust); each entry point below names the reference item it
+ * replaces (paths relative to the reference root).  A Rust `graph_b200.rs` shim binds
+ * these with `extern "C"` (see INTEGRATION.md and rust/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every call returns an int status (B200_OK == 0);
+ *     b200_last_error() gives the text of the last failure on the calling thread.
+ *   - the reference panics (assert_eq!) on shape mismatch (src/graph_csr.rs:307,351;
+ *     src/graph_magnus.rs:226,236); the ABI returns B200_ERR_SHAPE and the host shim
+ *     turns that back into a panic / exception.
+ *   - a b200_ctx is bound to one CUDA device and one stream and must be used by one
+ *     host thread at a time.  There is NO CPU fallback: without a usable sm_100 device
+ *     b200_ctx_create fails with B200_ERR_CUDA.
+ *   - matrices are device-resident handles (b200_csr).  Layout = the reference's CSR
+ *     (src/graph_csr.rs:42-53): row_ptr u64[rows+1] (Rust usize), col_idx u32[nnz]
+ *     sorted and unique per row, values u32[nnz] (graph_csr.rs:17 `Val`) or u64[nnz]
+ *     (graph_sprs.rs:16 `Sat64`, linalg/src/csr.rs:75 `Value for u64`).
+ *   - explicit zeros are not representable in the reference's constructors
+ *     (from_coo drops them, graph_csr.rs:108); upload rejects them.
+ */
+#ifndef B200_SPGEMM_H
+#define B200_SPGEMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK          0
+#define B200_ERR_BADARG  1
+#define B200_ERR_SHAPE   2   /* operand shapes / value widths do not agree            */
+#define B200_ERR_ALLOC   3   /* device or pinned-host allocation failed               */
+#define B200_ERR_CUDA    4   /* no device, launch failure, or any other CUDA error    */
+#define B200_ERR_FORMAT  5   /* CSR invariant violated (explicit zero, col >= cols)   */
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_csr b200_csr;
+
+/* Per-multiply measurements; device times are CUDA-event times on the ctx stream. */
+typedef struct b200_stats {
+    uint64_t rows, cols, nnz_a, nnz_b, nnz_c;
+    uint64_t products;          /* intermediate products = sum over (i,k) in A of nnz(B[k,:]) */
+    uint64_t max_row_products;
+    uint64_t max_row_nnz;
+    uint64_t bytes_algorithmic; /* (nnzA+nnzB+nnzC)*(4+sizeof(Val)) + (rowsA+rowsB+rowsC+3)*8 */
+    float    ms_symbolic;       /* product count + binning + exact nnz/row + row_ptr scan       */
+    float    ms_numeric;        /* per-bin numeric kernels                                       */
+    float    ms_total;          /* first kernel to last kernel, incl. the one host read-back     */
+    int32_t  acc_mode;          /* 0: 32-bit accumulators proved safe, 1: 64-bit, 2: saturating  */
+    int32_t  kernel_launches;   /* kernels launched by this multiply                             */
+    uint32_t sym_bin_rows[16];  /* rows per symbolic bin                                         */
+    uint32_t num_bin_rows[16];  /* rows per numeric bin                                          */
+} b200_stats;
+
+const char *b200_last_error(void);
+/* Number of CUDA devices visible (0 when there is none or no driver). */
+int b200_device_count(void);
+
+/* Context lifecycle.  `cuda_stream` may be NULL (the engine creates its own stream) or a
+ * cudaStream_t owned by the caller (e.g. torch's current stream) on `device`. */
+int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out);
+int b200_ctx_destroy(b200_ctx *ctx);
+int b200_ctx_synchronize(b200_ctx *ctx);
+/* Total kernels launched through this context so far (bench.py's gpu_launches). */
+int b200_ctx_kernel_launches(b200_ctx *ctx, uint64_t *out);
+/* Per-phase CUDA-event timing in b200_stats costs a few event records; on by default. */
+int b200_ctx_set_timing(b200_ctx *ctx, int enabled);
+
+/* Host CSR -> device handle.  Replaces constructing a CsrMatrix / MagnusMatrix from its three
+ * arrays (src/graph_csr.rs:42-53; SparseMatrixCSR::new at src/graph_magnus.rs:74).
+ * val_bits is 32 or 64.  rows x cols may be rectangular so that row blocks of a left operand
+ * can be held per GPU; the reference itself only multiplies square matrices. */
+int b200_csr_upload(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint64_t *row_ptr,
+                    const uint32_t *col_idx, const void *values, int val_bits, b200_csr **out);
+/* Same with MAGNUS' usize (u64) column indices (src/graph_magnus.rs:13,52-74). */
+int b200_csr_upload_idx64(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint64_t *row_ptr,
+                          const uint64_t *col_idx, const void *values, int val_bits, b200_csr **out);
+/* Adopt (copy) arrays that already live on this context's device, e.g. an NCCL-broadcast B. */
+int b200_csr_from_device(b200_ctx *ctx, uint64_t rows, uint64_t cols, uint64_t nnz,
+                         const void *d_row_ptr, const void *d_col_idx, const void *d_values,
+                         int val_bits, b200_csr **out);
+int b200_csr_free(b200_ctx *ctx, b200_csr *m);
+
+/* Shape / size queries: CsrMatrix::nnz (src/graph_csr.rs:260), MagnusMatrix::nnz (:220). */
+int b200_csr_info(const b200_csr *m, uint64_t *rows, uint64_t *cols, uint64_t *nnz, int *val_bits);
+/* Raw device pointers (row_ptr u64*, col_idx u32*, values) for zero-copy consumers. */
+int b200_csr_device_ptrs(const b200_csr *m, void **d_row_ptr, void **d_col_idx, void **d_values);
+/* Largest stored value (device-side reduction kept with every handle). */
+int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *out);
+
+/* Device handle -> caller-allocated host arrays (sizes from b200_csr_info). */
+int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values);
+int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values);
+/* Asynchronous variant into pinned host memory on the ctx stream (no synchronize). */
+int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values);
+
+/* C = A x B.  Replaces CsrMatrix::matmul / matmul_par (src/graph_csr.rs:306-346, 350-484),
+ * Csr<I,V>::matmul / matmul_par (linalg/src/csr.rs:308-356, 361-466) and
+ * MagnusMatrix::matmul / matmul_seq (src/graph_magnus.rs:225-242).  Result: ascending unique
+ * columns per row, saturating sums of saturating products, zeros dropped, row_ptr[0] = 0 --
+ * bit-identical to the reference's CSR output.  `stats` may be NULL. */
+int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C, b200_stats *stats);
+
+/* Per-row intermediate-product counts of A x B (host array of A.rows u64); the quantity the
+ * multi-GPU row split is balanced on. */
+int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, uint64_t *host_out);
+/* Contiguous row cut points cuts[0..nparts] (cuts[0]=0, cuts[nparts]=A.rows) so that every part
+ * holds ~1/nparts of the intermediate products of A x B. */
+int b200_shard_rows_by_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int nparts, uint64_t *cuts);
+/* Rows [row_begin,row_end) of A as a new (row_end-row_begin) x cols handle. */
+int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t row_begin, uint64_t row_end, b200_csr **out);
+
+/* C = A + B, element-wise saturating sorted merge: CsrMatrix::add (src/graph_csr.rs:487-542),
+ * MagnusMatrix::add (src/graph_magnus.rs:245-302). */
+int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C);
+/* 1 if A and B have identical row_ptr and col_idx (the stabilisation test of
+ * power_until_stable, src/graph_csr.rs:567-570). */
+int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SPGEMM_H */

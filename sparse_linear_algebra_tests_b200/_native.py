@@ -1,0 +1,235 @@
+"""ctypes binding of libb200spgemm.so (the C ABI in include/b200_spgemm.h).
+
+The shared library is built in-tree by `make -C sparse_linear_algebra_tests_b200/csrc`
+(or `__graft_entry__.build()`).  There is no fallback of any kind: if the library is
+missing, or no sm_100 device is usable, the first call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200spgemm.so")
+
+B200_OK, B200_ERR_BADARG, B200_ERR_SHAPE, B200_ERR_ALLOC, B200_ERR_CUDA, B200_ERR_FORMAT = range(6)
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200 error {code}: {msg}")
+        self.code = code
+
+
+class ShapeMismatch(B200Error, AssertionError):
+    """The reference panics via assert_eq!(self.n, other.n) (src/graph_csr.rs:307,351)."""
+
+
+class Stats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("cols", C.c_uint64), ("nnz_a", C.c_uint64), ("nnz_b", C.c_uint64),
+                ("nnz_c", C.c_uint64), ("products", C.c_uint64), ("max_row_products", C.c_uint64),
+                ("max_row_nnz", C.c_uint64), ("bytes_algorithmic", C.c_uint64), ("ms_symbolic", C.c_float),
+                ("ms_numeric", C.c_float), ("ms_total", C.c_float), ("acc_mode", C.c_int32),
+                ("kernel_launches", C.c_int32), ("sym_bin_rows", C.c_uint32 * 16), ("num_bin_rows", C.c_uint32 * 16)]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.endswith("_rows")}
+        d["sym_bin_rows"] = list(self.sym_bin_rows)
+        d["num_bin_rows"] = list(self.num_bin_rows)
+        return d
+
+
+EXPORTS = [
+    "b200_last_error", "b200_device_count", "b200_ctx_create", "b200_ctx_destroy", "b200_ctx_synchronize",
+    "b200_ctx_kernel_launches", "b200_ctx_set_timing", "b200_csr_upload", "b200_csr_upload_idx64",
+    "b200_csr_from_device", "b200_csr_free", "b200_csr_info", "b200_csr_device_ptrs", "b200_csr_max_value",
+    "b200_csr_download", "b200_csr_download_idx64", "b200_csr_download_async", "b200_spgemm", "b200_row_products",
+    "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
+]
+
+_lib = None
+
+
+def load():
+    """Load the engine; raises if the in-tree shared library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build the CUDA engine first "
+                          f"(make -C {os.path.dirname(LIB_PATH)}); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_device_count.restype = i32
+    sigs = {
+        "b200_ctx_create": [i32, vp, C.POINTER(vp)],
+        "b200_ctx_destroy": [vp],
+        "b200_ctx_synchronize": [vp],
+        "b200_ctx_kernel_launches": [vp, C.POINTER(u64)],
+        "b200_ctx_set_timing": [vp, i32],
+        "b200_csr_upload": [vp, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
+        "b200_csr_upload_idx64": [vp, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
+        "b200_csr_from_device": [vp, u64, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
+        "b200_csr_free": [vp, vp],
+        "b200_csr_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)],
+        "b200_csr_device_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+        "b200_csr_max_value": [vp, vp, C.POINTER(u64)],
+        "b200_csr_download": [vp, vp, vp, vp, vp],
+        "b200_csr_download_idx64": [vp, vp, vp, vp, vp],
+        "b200_csr_download_async": [vp, vp, vp, vp, vp],
+        "b200_spgemm": [vp, vp, vp, C.POINTER(vp), C.POINTER(Stats)],
+        "b200_row_products": [vp, vp, vp, vp],
+        "b200_shard_rows_by_products": [vp, vp, vp, i32, vp],
+        "b200_csr_row_block": [vp, vp, u64, u64, C.POINTER(vp)],
+        "b200_csr_add": [vp, vp, vp, C.POINTER(vp)],
+        "b200_csr_same_pattern": [vp, vp, vp, C.POINTER(i32)],
+    }
+    for name, args in sigs.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = i32
+    _lib = L
+    return L
+
+
+def check(code: int):
+    if code != B200_OK:
+        msg = load().b200_last_error().decode("utf-8", "replace")
+        raise (ShapeMismatch if code == B200_ERR_SHAPE else B200Error)(code, msg)
+
+
+def _vdtype(bits: int):
+    return np.uint32 if bits == 32 else np.uint64
+
+
+class Context:
+    """One engine context = one device + one stream (b200_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        L = load()
+        h = C.c_void_p()
+        check(L.b200_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(load().b200_ctx_synchronize(self._h))
+
+    def set_timing(self, enabled: bool):
+        check(load().b200_ctx_set_timing(self._h, int(enabled)))
+
+    def kernel_launches(self) -> int:
+        v = C.c_uint64()
+        check(load().b200_ctx_kernel_launches(self._h, C.byref(v)))
+        return int(v.value)
+
+    # -- matrices ----------------------------------------------------------------------
+    def upload(self, rows: int, cols: int, row_ptr, col_idx, values) -> "DeviceCsr":
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        vv = np.ascontiguousarray(values)
+        if vv.dtype not in (np.uint32, np.uint64):
+            raise B200Error(B200_ERR_BADARG, f"values must be uint32 or uint64, got {vv.dtype}")
+        bits = 32 if vv.dtype == np.uint32 else 64
+        ci = np.ascontiguousarray(col_idx)
+        h = C.c_void_p()
+        if ci.dtype == np.uint64:   # MAGNUS usize columns
+            check(load().b200_csr_upload_idx64(self._h, rows, cols, rp.ctypes.data, ci.ctypes.data, vv.ctypes.data, bits, C.byref(h)))
+        else:
+            ci = np.ascontiguousarray(ci, dtype=np.uint32)
+            check(load().b200_csr_upload(self._h, rows, cols, rp.ctypes.data, ci.ctypes.data, vv.ctypes.data, bits, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def from_device(self, rows: int, cols: int, nnz: int, d_row_ptr: int, d_col_idx: int, d_values: int, val_bits: int) -> "DeviceCsr":
+        h = C.c_void_p()
+        check(load().b200_csr_from_device(self._h, rows, cols, nnz, d_row_ptr, d_col_idx, d_values, val_bits, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def spgemm(self, a: "DeviceCsr", b: "DeviceCsr", want_stats: bool = False):
+        h = C.c_void_p()
+        st = Stats() if want_stats else None
+        check(load().b200_spgemm(self._h, a._h, b._h, C.byref(h), C.byref(st) if want_stats else None))
+        c = DeviceCsr(self, h)
+        return (c, st) if want_stats else c
+
+    def add(self, a: "DeviceCsr", b: "DeviceCsr") -> "DeviceCsr":
+        h = C.c_void_p()
+        check(load().b200_csr_add(self._h, a._h, b._h, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def same_pattern(self, a: "DeviceCsr", b: "DeviceCsr") -> bool:
+        s = C.c_int()
+        check(load().b200_csr_same_pattern(self._h, a._h, b._h, C.byref(s)))
+        return bool(s.value)
+
+    def row_products(self, a: "DeviceCsr", b: "DeviceCsr") -> np.ndarray:
+        out = np.zeros(a.rows, dtype=np.uint64)
+        check(load().b200_row_products(self._h, a._h, b._h, out.ctypes.data))
+        return out
+
+    def shard_rows_by_products(self, a: "DeviceCsr", b: "DeviceCsr", nparts: int) -> np.ndarray:
+        cuts = np.zeros(nparts + 1, dtype=np.uint64)
+        check(load().b200_shard_rows_by_products(self._h, a._h, b._h, nparts, cuts.ctypes.data))
+        return cuts
+
+    def row_block(self, a: "DeviceCsr", r0: int, r1: int) -> "DeviceCsr":
+        h = C.c_void_p()
+        check(load().b200_csr_row_block(self._h, a._h, r0, r1, C.byref(h)))
+        return DeviceCsr(self, h)
+
+
+class DeviceCsr:
+    """Owning wrapper of a b200_csr handle."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+        r, c, n, b = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        check(load().b200_csr_info(self._h, C.byref(r), C.byref(c), C.byref(n), C.byref(b)))
+        self.rows, self.cols, self.nnz, self.val_bits = int(r.value), int(c.value), int(n.value), int(b.value)
+
+    def free(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            load().b200_csr_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def download(self, idx64: bool = False):
+        rp = np.empty(self.rows + 1, dtype=np.uint64)
+        ci = np.empty(self.nnz, dtype=np.uint64 if idx64 else np.uint32)
+        vv = np.empty(self.nnz, dtype=_vdtype(self.val_bits))
+        f = load().b200_csr_download_idx64 if idx64 else load().b200_csr_download
+        check(f(self.ctx._h, self._h, rp.ctypes.data, ci.ctypes.data, vv.ctypes.data))
+        return rp, ci, vv
+
+    def download_async_into(self, rp: int, ci: int, vv: int):
+        """Raw-pointer variant for pinned buffers (bench end-to-end path)."""
+        check(load().b200_csr_download_async(self.ctx._h, self._h, rp, ci, vv))
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(load().b200_csr_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def max_value(self) -> int:
+        v = C.c_uint64()
+        check(load().b200_csr_max_value(self.ctx._h, self._h, C.byref(v)))
+        return int(v.value)

@@ -1,0 +1,663 @@
+// api.cu -- extern "C" entry points (include/b200_spgemm.h) and host orchestration of the kernels.
+// No CPU fallback anywhere in this file: every compute entry point runs CUDA kernels or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b200_spgemm.h"
+#include "kernels.cuh"
+
+// ---------------------------------------------------------------------------- error plumbing
+static thread_local std::string g_last_error;
+static int set_err(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return set_err(_e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA,       \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr) do { int _r = (expr); if (_r != B200_OK) return _r; } while (0)
+
+extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------- handles
+struct b200_csr {
+    u64 rows, cols, nnz;
+    int val_bits;
+    u64 *d_rp; u32 *d_col; void *d_val;
+    ull *d_maxval;          // device scalar: largest stored value
+    u64 max_row_len;        // host-known upper bound of the longest row
+    b200_ctx *ctx;
+};
+
+struct b200_ctx {
+    int device, num_sms;
+    size_t smem_optin;
+    cudaStream_t stream; bool own_stream;
+    B200Ctrl *d_ctrl, *h_ctrl;
+    // per-row scratch, grown on demand
+    u64 cap_rows; u64 *d_prod; u32 *d_nnz_row; u32 *d_bin_rows; u64 *d_tile_status; u64 cap_tiles;
+    // heavy-row scratch
+    void *d_heavy; size_t cap_heavy;
+    u32 *d_flag;            // small device flag word (+ pinned mirror)
+    u32 *h_flag;
+    cudaEvent_t ev[4];
+    bool timing;
+    u64 launches;
+};
+
+template <typename VT>
+static CsrView<VT> view(const b200_csr *m) {
+    CsrView<VT> v; v.rows = m->rows; v.cols = m->cols; v.nnz = m->nnz; v.rp = m->d_rp; v.col = m->d_col; v.val = (const VT *)m->d_val;
+    return v;
+}
+
+#define LAUNCH_CHECK(ctx)                                                                          \
+    do { (ctx)->launches++; cudaError_t _e = cudaGetLastError();                                   \
+         if (_e != cudaSuccess) return set_err(B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+static int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(B200_ERR_ALLOC, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
+    return B200_OK;
+}
+static void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
+    if (rows > ctx->cap_rows) {
+        dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows);
+        ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->cap_rows = 0;
+        u64 cap = rows + rows / 8 + 1024;
+        TRY(dmalloc(ctx, (void **)&ctx->d_prod, cap * 8));
+        TRY(dmalloc(ctx, (void **)&ctx->d_nnz_row, cap * 4));
+        TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4));
+        ctx->cap_rows = cap;
+    }
+    u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1;
+    if (tiles > ctx->cap_tiles) {
+        dfree(ctx, ctx->d_tile_status); ctx->d_tile_status = nullptr; ctx->cap_tiles = 0;
+        TRY(dmalloc(ctx, (void **)&ctx->d_tile_status, (tiles + 64) * 8));
+        ctx->cap_tiles = tiles + 64;
+    }
+    return B200_OK;
+}
+static int ensure_heavy_scratch(b200_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->cap_heavy) {
+        dfree(ctx, ctx->d_heavy); ctx->d_heavy = nullptr; ctx->cap_heavy = 0;
+        TRY(dmalloc(ctx, &ctx->d_heavy, bytes));
+        ctx->cap_heavy = bytes;
+    }
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------- kernel attribute setup
+template <typename K>
+static void allow_big_smem(K kernel, size_t bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+
+template <typename VT>
+static void setup_kernels_vt(size_t optin) {
+    allow_big_smem(k_sym_hash<VT, false>, optin);
+    allow_big_smem(k_sym_hash<VT, true>, optin);
+    allow_big_smem(k_num_hash<VT, 0, false>, optin); allow_big_smem(k_num_hash<VT, 0, true>, optin);
+    allow_big_smem(k_num_hash<VT, 1, false>, optin); allow_big_smem(k_num_hash<VT, 1, true>, optin);
+}
+
+extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
+    if (!out) return set_err(B200_ERR_BADARG, "b200_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_err(B200_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return set_err(B200_ERR_BADARG, "device %d out of range (0..%d)", device, n - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(B200_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    b200_ctx *ctx = new b200_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device; ctx->num_sms = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CUDA_TRY(cudaMalloc((void **)&ctx->d_ctrl, sizeof(B200Ctrl)));
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl)));
+    CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 64));
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 64));
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    ctx->timing = true;
+    setup_kernels_vt<u32>(ctx->smem_optin);
+    setup_kernels_vt<u64>(ctx->smem_optin);
+    allow_big_smem(k_num_hash<u64, 2, false>, ctx->smem_optin);
+    allow_big_smem(k_num_hash<u64, 2, true>, ctx->smem_optin);
+    cudaGetLastError();
+    *out = ctx;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
+    if (!ctx) return B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_ctrl); cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_synchronize(b200_ctx *ctx) {
+    if (!ctx) return set_err(B200_ERR_BADARG, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+extern "C" int b200_ctx_kernel_launches(b200_ctx *ctx, uint64_t *out) {
+    if (!ctx || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    *out = ctx->launches; return B200_OK;
+}
+extern "C" int b200_ctx_set_timing(b200_ctx *ctx, int enabled) {
+    if (!ctx) return set_err(B200_ERR_BADARG, "ctx is NULL");
+    ctx->timing = enabled != 0; return B200_OK;
+}
+
+// ---------------------------------------------------------------------------- CSR handles
+static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out) {
+    b200_csr *m = new b200_csr();
+    memset(m, 0, sizeof(*m));
+    m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
+    int r = dmalloc(ctx, (void **)&m->d_maxval, 16);
+    if (r == B200_OK) r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8);
+    if (r == B200_OK && alloc_arrays) {
+        r = dmalloc(ctx, (void **)&m->d_col, nnz * 4);
+        if (r == B200_OK) r = dmalloc(ctx, &m->d_val, nnz * (size_t)(val_bits / 8));
+    }
+    if (r != B200_OK) { dfree(ctx, m->d_maxval); dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); delete m; return r; }
+    *out = m;
+    return B200_OK;
+}
+
+extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
+    if (!m) return B200_OK;
+    if (!ctx) ctx = m->ctx;
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval);
+    delete m;
+    return B200_OK;
+}
+
+static int grid_for(u64 n, int threads, int cap) { u64 g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > (u64)cap) g = cap; return (int)g; }
+
+// value max + format check (explicit zeros, column range); synchronises
+static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check) {
+    CUDA_TRY(cudaMemsetAsync(m->d_maxval, 0, 16, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 4, ctx->stream));
+    if (m->nnz) {
+        int g = grid_for(m->nnz, 256, ctx->num_sms * 8);
+        if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag);
+        else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag);
+        LAUNCH_CHECK(ctx);
+    }
+    if (check) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_flag[0]) return set_err(B200_ERR_FORMAT, "CSR holds an explicit zero value or a column index >= cols");
+    }
+    return B200_OK;
+}
+
+static int check_host_rowptr(u64 rows, const uint64_t *row_ptr, u64 *nnz, u64 *max_len) {
+    if (row_ptr[0] != 0) return set_err(B200_ERR_FORMAT, "row_ptr[0] must be 0");
+    u64 ml = 0;
+    for (u64 i = 0; i < rows; i++) {
+        if (row_ptr[i + 1] < row_ptr[i]) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone at row %llu", (ull)i);
+        u64 l = row_ptr[i + 1] - row_ptr[i]; if (l > ml) ml = l;
+    }
+    *nnz = row_ptr[rows]; *max_len = ml;
+    return B200_OK;
+}
+
+static int upload_common(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint64_t *row_ptr, const void *col_idx, bool idx64,
+                         const void *values, int val_bits, b200_csr **out) {
+    if (!ctx || !row_ptr || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (val_bits != 32 && val_bits != 64) return set_err(B200_ERR_BADARG, "val_bits must be 32 or 64, got %d", val_bits);
+    if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "rows/cols must fit in u32 (NodeId)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    u64 nnz = 0, max_len = 0;
+    TRY(check_host_rowptr(rows, row_ptr, &nnz, &max_len));
+    if (nnz && (!col_idx || !values)) return set_err(B200_ERR_BADARG, "NULL col_idx/values with nnz > 0");
+    b200_csr *m = nullptr;
+    TRY(csr_alloc(ctx, rows, cols, nnz, val_bits, true, &m));
+    m->max_row_len = max_len;
+    cudaError_t e = cudaMemcpyAsync(m->d_rp, row_ptr, (rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_val, values, nnz * (size_t)(val_bits / 8), cudaMemcpyHostToDevice, ctx->stream);
+    u64 *tmp = nullptr;
+    if (e == cudaSuccess && nnz) {
+        if (!idx64) e = cudaMemcpyAsync(m->d_col, col_idx, nnz * 4, cudaMemcpyHostToDevice, ctx->stream);
+        else {
+            int r = dmalloc(ctx, (void **)&tmp, nnz * 8);
+            if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
+            e = cudaMemcpyAsync(tmp, col_idx, nnz * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                cudaMemsetAsync(ctx->d_flag + 8, 0, 4, ctx->stream);
+                k_narrow_idx<<<grid_for(nnz, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(nnz, tmp, m->d_col, ctx->d_flag + 8);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+        }
+    }
+    if (e != cudaSuccess) { dfree(ctx, tmp); b200_csr_free(ctx, m); return set_err(B200_ERR_CUDA, "upload copy failed: %s", cudaGetErrorString(e)); }
+    int r = finish_new_csr(ctx, m, true);
+    dfree(ctx, tmp);
+    if (r == B200_OK && idx64 && nnz && ctx->h_flag[8]) r = set_err(B200_ERR_FORMAT, "column index does not fit in u32 (NodeId)");
+    if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
+    *out = m;
+    return B200_OK;
+}
+
+extern "C" int b200_csr_upload(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint64_t *row_ptr, const uint32_t *col_idx,
+                               const void *values, int val_bits, b200_csr **out) {
+    return upload_common(ctx, rows, cols, row_ptr, col_idx, false, values, val_bits, out);
+}
+extern "C" int b200_csr_upload_idx64(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint64_t *row_ptr, const uint64_t *col_idx,
+                                     const void *values, int val_bits, b200_csr **out) {
+    return upload_common(ctx, rows, cols, row_ptr, col_idx, true, values, val_bits, out);
+}
+
+extern "C" int b200_csr_from_device(b200_ctx *ctx, uint64_t rows, uint64_t cols, uint64_t nnz, const void *d_row_ptr,
+                                    const void *d_col_idx, const void *d_values, int val_bits, b200_csr **out) {
+    if (!ctx || !d_row_ptr || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (val_bits != 32 && val_bits != 64) return set_err(B200_ERR_BADARG, "val_bits must be 32 or 64");
+    if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "rows/cols must fit in u32 (NodeId)");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    b200_csr *m = nullptr;
+    TRY(csr_alloc(ctx, rows, cols, nnz, val_bits, true, &m));
+    cudaError_t e = cudaMemcpyAsync(m->d_rp, d_row_ptr, (rows + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_col, d_col_idx, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_val, d_values, nnz * (size_t)(val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { b200_csr_free(ctx, m); return set_err(B200_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+    m->max_row_len = std::min<u64>(nnz, cols);          // bound only; tightened by the first multiply that reads it
+    int r = finish_new_csr(ctx, m, true);
+    if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
+    *out = m;
+    return B200_OK;
+}
+
+extern "C" int b200_csr_info(const b200_csr *m, uint64_t *rows, uint64_t *cols, uint64_t *nnz, int *val_bits) {
+    if (!m) return set_err(B200_ERR_BADARG, "matrix is NULL");
+    if (rows) *rows = m->rows; if (cols) *cols = m->cols; if (nnz) *nnz = m->nnz; if (val_bits) *val_bits = m->val_bits;
+    return B200_OK;
+}
+extern "C" int b200_csr_device_ptrs(const b200_csr *m, void **d_row_ptr, void **d_col_idx, void **d_values) {
+    if (!m) return set_err(B200_ERR_BADARG, "matrix is NULL");
+    if (d_row_ptr) *d_row_ptr = m->d_rp; if (d_col_idx) *d_col_idx = m->d_col; if (d_values) *d_values = m->d_val;
+    return B200_OK;
+}
+extern "C" int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *out) {
+    if (!ctx || !m || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 2, m->d_maxval, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_flag + 2, 8);
+    return B200_OK;
+}
+
+extern "C" int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
+    if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (row_ptr) CUDA_TRY(cudaMemcpyAsync(row_ptr, m->d_rp, (m->rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (col_idx && m->nnz) CUDA_TRY(cudaMemcpyAsync(col_idx, m->d_col, m->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (values && m->nnz) CUDA_TRY(cudaMemcpyAsync(values, m->d_val, m->nnz * (size_t)(m->val_bits / 8), cudaMemcpyDeviceToHost, ctx->stream));
+    return B200_OK;
+}
+extern "C" int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
+    TRY(b200_csr_download_async(ctx, m, row_ptr, col_idx, values));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values) {
+    if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    u64 *tmp = nullptr;
+    if (col_idx && m->nnz) {
+        TRY(dmalloc(ctx, (void **)&tmp, m->nnz * 8));
+        k_widen_idx<<<grid_for(m->nnz, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(m->nnz, m->d_col, tmp);
+        LAUNCH_CHECK(ctx);
+        CUDA_TRY(cudaMemcpyAsync(col_idx, tmp, m->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TRY(b200_csr_download_async(ctx, m, row_ptr, nullptr, values));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, tmp);
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------- SpGEMM
+
+// lanes cooperating on one A entry while walking its B row: ~ the mean B row length
+static int pick_lg(const b200_csr *B, int max_lg) {
+    double avg = B->rows ? (double)B->nnz / (double)B->rows : 1.0;
+    int lg = 0;
+    while (lg < max_lg && (double)(1 << lg) < avg) lg++;
+    return lg;
+}
+
+struct HashCfg { int threads; u32 slots; bool bitmap; size_t smem; int ctas_per_sm; };
+
+template <typename VT>
+static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B) {
+    double avg = A->rows ? (double)A->nnz / (double)A->rows : 0.0;
+    u64 rows = A->rows;
+#define RP_LAUNCH(G)                                                                                              \
+    k_row_products<G><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_rp, \
+                                                                                    ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl)
+    if (avg <= 2.0) RP_LAUNCH(1);
+    else if (avg <= 6.0) RP_LAUNCH(4);
+    else if (avg <= 24.0) RP_LAUNCH(8);
+    else RP_LAUNCH(32);
+#undef RP_LAUNCH
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
+
+template <typename VT>
+static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st) {
+    const u64 rows = A->rows, ncols = B->cols;
+    cudaStream_t s = ctx->stream;
+    const u64 launches0 = ctx->launches;
+    const bool timing = ctx->timing && st;
+    b200_csr *C = nullptr;
+    TRY(csr_alloc(ctx, rows, ncols, 0, A->val_bits, false, &C));
+    CUDA_TRY(cudaMemsetAsync(C->d_maxval, 0, 16, s));
+    if (st) { memset(st, 0, sizeof(*st)); st->rows = rows; st->cols = ncols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; }
+    if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
+        CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8, s));
+        TRY(dmalloc(ctx, (void **)&C->d_col, 0)); TRY(dmalloc(ctx, &C->d_val, 0));
+        if (st) st->bytes_algorithmic = (A->nnz + B->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
+        *out = C;
+        return B200_OK;
+    }
+    int r = ensure_row_scratch(ctx, rows);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    CsrView<VT> vA = view<VT>(A), vB = view<VT>(B);
+    const u32 nwords = (u32)((ncols + 31) / 32);
+    const int lg = pick_lg(B, 5);
+    const u64 p_bound = A->max_row_len * B->max_row_len;                 // host-known bound of the largest P_i
+    const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
+
+    if (timing) cudaEventRecord(ctx->ev[0], s);
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, ntiles * 8, s));
+    // ---- symbolic: product counts, bins, exact nnz per row
+    TRY(launch_row_products<VT>(ctx, A, B));
+    const unsigned row_grid = (unsigned)((rows + 255) / 256);
+    k_bin_scatter<0><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    LAUNCH_CHECK(ctx);
+    {
+        int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        k_sym_tiny<VT><<<g, 256, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
+        const u64 lo = hb == 0 ? 33 : (u64)b200_hash_cap(hb - 1) + 1;
+        if (p_bound < lo) break;                                         // no row can reach this bin
+        const int threads = b200_hash_threads(hb);
+        const u32 slots = b200_hash_slots(hb);
+        const bool bitmap = nwords <= slots && (size_t)nwords * 4 <= ctx->smem_optin - 1024;
+        const size_t smem = bitmap ? (size_t)nwords * 4 : (size_t)slots * 4;
+        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)((ctx->smem_optin) / (smem + 256)))));
+        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * per_sm * 2);
+        if (bitmap) k_sym_hash<VT, true><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+        else k_sym_hash<VT, false><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+        LAUNCH_CHECK(ctx);
+    }
+    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) {
+        // heavy rows: column bitmap, in shared memory when the column space fits, else in global scratch
+        if ((size_t)nwords * 4 <= ctx->smem_optin - 1024) {
+            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
+            k_sym_hash<VT, true><<<g, 1024, (size_t)nwords * 4, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
+        } else {
+            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
+            r = ensure_heavy_scratch(ctx, (size_t)g * nwords * 4);
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            k_sym_heavy<VT><<<g, 1024, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    // ---- row_ptr (decoupled look-back scan) + numeric bins
+    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
+    LAUNCH_CHECK(ctx);
+    k_num_classify<<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl);
+    LAUNCH_CHECK(ctx);
+    k_bin_scatter<1><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    LAUNCH_CHECK(ctx);
+    if (timing) cudaEventRecord(ctx->ev[1], s);
+    // ---- the one host read-back: total nnz, bin sizes, value bounds
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 4, A->d_maxval, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 6, B->d_maxval, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const B200Ctrl hc = *ctx->h_ctrl;
+    u64 maxA, maxB; memcpy(&maxA, ctx->h_flag + 4, 8); memcpy(&maxB, ctx->h_flag + 6, 8);
+    if (hc.error_flag) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "symbolic pass reported an internal error (flag %u)", hc.error_flag); }
+    C->nnz = hc.total_nnz;
+    C->max_row_len = hc.max_row_nnz;
+    r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
+    if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    // accumulator width: prove no overflow from max_row_products * max(A) * max(B)
+    int mode;
+    {
+        unsigned __int128 bound = (unsigned __int128)hc.max_row_products * maxA;
+        bool over64 = (bound >> 64) != 0;
+        if (!over64) { bound *= maxB; over64 = (bound >> 64) != 0; }
+        if (!over64 && (u64)bound < (1ull << 32)) mode = 0;
+        else if (sizeof(VT) == 4) mode = 1;                               // clamped 32-bit products, < 2^32 of them per row
+        else mode = over64 ? 2 : 1;
+    }
+    if (timing) cudaEventRecord(ctx->ev[2], s);
+    // ---- numeric
+    if (hc.num_bin_count[B200_BIN_TINY]) {
+        int g = (int)std::min<u64>(((u64)hc.num_bin_count[B200_BIN_TINY] + 7) / 8, (u64)ctx->num_sms * 32);
+        k_num_tiny<VT><<<g, 256, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, C->d_rp, C->d_col, (VT *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
+        const u32 cnt = hc.num_bin_count[B200_BIN_HASH0 + hb];
+        if (!cnt) continue;
+        const int threads = b200_hash_threads(hb);
+        const u32 slots = b200_hash_slots(hb);
+        const size_t acc_b = mode == 0 ? 4 : 8;
+        const size_t tab = (size_t)slots * (4 + acc_b);
+        const bool bitmap = nwords <= 2 * slots && tab + (size_t)nwords * 8 + 1024 <= ctx->smem_optin;
+        const size_t smem = tab + (bitmap ? (size_t)nwords * 8 : 0);
+        if (smem + 1024 > ctx->smem_optin) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem); }
+        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 256)))));
+        const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
+        const int bin = B200_BIN_HASH0 + hb;
+#define NUM_LAUNCH(MODE, BM) k_num_hash<VT, MODE, BM><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val)
+        if (mode == 0) { if (bitmap) NUM_LAUNCH(0, true); else NUM_LAUNCH(0, false); }
+        else if (mode == 1) { if (bitmap) NUM_LAUNCH(1, true); else NUM_LAUNCH(1, false); }
+        else {
+            if (sizeof(VT) == 8) { if (bitmap) k_num_hash<u64, 2, true><<<g, threads, smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val);
+                                   else k_num_hash<u64, 2, false><<<g, threads, smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val); }
+        }
+#undef NUM_LAUNCH
+        LAUNCH_CHECK(ctx);
+    }
+    if (hc.num_bin_count[B200_BIN_HEAVY]) {
+        const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
+        u64 max_slots = 1; while (max_slots < 2 * hc.max_row_nnz) max_slots <<= 1;
+        const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;
+        size_t budget = (size_t)8 << 30;
+        int g = (int)std::min<u64>(std::min<u64>(cnt, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
+        r = ensure_heavy_scratch(ctx, per_cta * g);
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        unsigned char *base = (unsigned char *)ctx->d_heavy;
+        u64 *s_vals = (u64 *)base;                                            // g * max_slots u64
+        u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
+        u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
+        u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
+        if (mode == 2 && sizeof(VT) == 8)
+            k_num_heavy<u64, 2><<<g, 1024, 0, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, C->d_col, (u64 *)C->d_val);
+        else
+            k_num_heavy<VT, 1><<<g, 1024, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, C->d_col, (VT *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
+    if (timing) cudaEventRecord(ctx->ev[3], s);
+    if (st) {
+        st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
+        st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
+        st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
+        for (int i = 0; i < B200_NBINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.num_bin_count[i]; }
+        if (timing) {
+            CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+            cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&st->ms_numeric, ctx->ev[2], ctx->ev[3]);
+            cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
+        }
+    }
+    *out = C;
+    return B200_OK;
+}
+
+extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C, b200_stats *stats) {
+    if (!ctx || !A || !B || !C) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch: A is %llux%llu, B is %llux%llu", (ull)A->rows, (ull)A->cols, (ull)B->rows, (ull)B->cols);
+    if (A->val_bits != B->val_bits) return set_err(B200_ERR_SHAPE, "value width mismatch: A is u%d, B is u%d", A->val_bits, B->val_bits);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return A->val_bits == 32 ? spgemm_typed<u32>(ctx, A, B, C, stats) : spgemm_typed<u64>(ctx, A, B, C, stats);
+}
+
+// ---------------------------------------------------------------------------- sharding helpers
+extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, uint64_t *host_out) {
+    if (!ctx || !A || !B || !host_out) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (A->rows == 0) return B200_OK;
+    TRY(ensure_row_scratch(ctx, A->rows));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), ctx->stream));
+    TRY(launch_row_products<u32>(ctx, A, B));
+    CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_prod, A->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_shard_rows_by_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int nparts, uint64_t *cuts) {
+    if (!cuts || nparts < 1) return set_err(B200_ERR_BADARG, "bad nparts/cuts");
+    std::vector<uint64_t> p(A ? A->rows : 0);
+    TRY(b200_row_products(ctx, A, B, p.data()));
+    // cut k is the first row whose product prefix reaches k/nparts of the total (+1 per row so empty rows spread too)
+    std::vector<unsigned __int128> pre(p.size() + 1, 0);
+    for (size_t i = 0; i < p.size(); i++) pre[i + 1] = pre[i] + p[i] + 1;
+    const unsigned __int128 total = pre[p.size()];
+    cuts[0] = 0; cuts[nparts] = A->rows;
+    for (int k = 1; k < nparts; k++) {
+        unsigned __int128 target = total * (unsigned)k / (unsigned)nparts;
+        size_t lo = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+        if (lo > p.size()) lo = p.size();
+        cuts[k] = std::max<uint64_t>(lo, cuts[k - 1]);
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t r0, uint64_t r1, b200_csr **out) {
+    if (!ctx || !A || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (r0 > r1 || r1 > A->rows) return set_err(B200_ERR_BADARG, "row range [%llu,%llu) outside 0..%llu", (ull)r0, (ull)r1, (ull)A->rows);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    u64 ends[2];
+    CUDA_TRY(cudaMemcpyAsync(&ends[0], A->d_rp + r0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&ends[1], A->d_rp + r1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const u64 nnz = ends[1] - ends[0], rows = r1 - r0;
+    b200_csr *m = nullptr;
+    TRY(csr_alloc(ctx, rows, A->cols, nnz, A->val_bits, true, &m));
+    k_rebase_rowptr<<<grid_for(rows + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(rows + 1, A->d_rp + r0, ends[0], m->d_rp);
+    ctx->launches++;
+    if (nnz) {
+        cudaMemcpyAsync(m->d_col, A->d_col + ends[0], nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(m->d_val, (const char *)A->d_val + ends[0] * (A->val_bits / 8), nnz * (size_t)(A->val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    m->max_row_len = A->max_row_len;
+    int r = finish_new_csr(ctx, m, false);
+    if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
+    *out = m;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------- add / pattern compare
+template <typename VT>
+static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out) {
+    const u64 rows = A->rows;
+    cudaStream_t s = ctx->stream;
+    b200_csr *C = nullptr;
+    TRY(csr_alloc(ctx, rows, A->cols, 0, A->val_bits, false, &C));
+    CUDA_TRY(cudaMemsetAsync(C->d_maxval, 0, 16, s));
+    if (rows == 0) { TRY(dmalloc(ctx, (void **)&C->d_col, 0)); TRY(dmalloc(ctx, &C->d_val, 0)); CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, 8, s)); *out = C; return B200_OK; }
+    int r = ensure_row_scratch(ctx, rows);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, ntiles * 8, s));
+    const unsigned g = (unsigned)((rows + 255) / 256);
+    k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
+    LAUNCH_CHECK(ctx);
+    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    C->nnz = ctx->h_ctrl->total_nnz; C->max_row_len = ctx->h_ctrl->max_row_nnz;
+    r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
+    if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    k_add_rows<VT, true><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, C->d_rp, C->d_col, (VT *)C->d_val, ctx->d_ctrl);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
+    *out = C;
+    return B200_OK;
+}
+
+extern "C" int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C) {
+    if (!ctx || !A || !B || !C) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->rows != B->rows || A->cols != B->cols) return set_err(B200_ERR_SHAPE, "add: shape mismatch");
+    if (A->val_bits != B->val_bits) return set_err(B200_ERR_SHAPE, "add: value width mismatch");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return A->val_bits == 32 ? add_typed<u32>(ctx, A, B, C) : add_typed<u64>(ctx, A, B, C);
+}
+
+extern "C" int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same) {
+    if (!ctx || !A || !B || !same) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->rows != B->rows || A->cols != B->cols || A->nnz != B->nnz) { *same = 0; return B200_OK; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 64, ctx->stream));
+    k_compare_u64<<<grid_for(A->rows + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(A->rows + 1, A->d_rp, B->d_rp, ctx->d_flag);
+    LAUNCH_CHECK(ctx);
+    if (A->nnz) { k_compare_u32<<<grid_for(A->nnz, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(A->nnz, A->d_col, B->d_col, ctx->d_flag); LAUNCH_CHECK(ctx); }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *same = ctx->h_flag[0] == 0;
+    return B200_OK;
+}

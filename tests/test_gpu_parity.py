@@ -1,0 +1,285 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact row_ptr / col_idx / values (integer path).  Cases follow the reference's own tests
+(src/graph_csr.rs:878-1104, src/graph_magnus.rs:455-697, linalg/src/csr.rs:796-989) plus the bins
+of the engine (tiny / hash / heavy, bitmap-rank and sort emission, 32/64-bit/saturating accumulators).
+"""
+import numpy as np
+import pytest
+
+from sparse_linear_algebra_tests_b200 import B200Matrix, ShapeMismatch, hostgen
+
+pytestmark = pytest.mark.gpu
+
+
+def to_o(O, h):
+    return O.Csr(h.rows, h.cols, h.row_ptr, h.col_idx, h.values)
+
+
+def assert_same(got, want, what=""):
+    assert got.rows == want.rows and got.cols == want.cols, what
+    assert np.array_equal(got.row_ptr, want.row_ptr), f"row_ptr differs {what}"
+    assert np.array_equal(got.col_idx, want.col_idx), f"col_idx differs {what}"
+    assert got.values.dtype == want.values.dtype, what
+    assert np.array_equal(got.values, want.values), f"values differ {what}"
+
+
+def check_product(O, ctx, a_h, b_h, what=""):
+    a, b = B200Matrix.from_host(a_h, ctx), B200Matrix.from_host(b_h, ctx)
+    c = a.matmul(b, want_stats=True)
+    want = O.matmul(to_o(O, a_h), to_o(O, b_h))
+    assert_same(c.to_host(), want, what)
+    assert c.nnz() == want.nnz()
+    assert c.last_stats.products == int(O.row_products(to_o(O, a_h), to_o(O, b_h)).sum())
+    return c
+
+
+def rand_csr(rng, rows, cols, nnz, bits, vmax=3):
+    r = rng.integers(0, rows, size=nnz)
+    c = rng.integers(0, cols, size=nnz)
+    v = rng.integers(1, vmax + 1, size=nnz, dtype=np.uint64)
+    return hostgen.from_coo(rows, cols, r, c, v.astype(hostgen.vdtype(bits)), bits)
+
+
+# ------------------------------------------------------------------ reference KATs through the engine
+@pytest.mark.parametrize("bits", [32, 64])
+def test_identity_matmul(gpu_ctx, bits):
+    m = B200Matrix.from_edges(3, [(0, 1), (1, 2)], bits)
+    r = m.matmul(B200Matrix.identity(3, bits))
+    assert (r.get(0, 1), r.get(1, 2), r.get(0, 2), r.nnz()) == (1, 1, 0, 2)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_path_counting_triangle_diamond(gpu_ctx, bits):
+    m = B200Matrix.from_edges(3, [(0, 1), (1, 2), (2, 0)], bits)
+    m2 = m.matmul(m)
+    assert (m2.get(0, 2), m2.get(1, 0), m2.get(2, 1), m2.nnz()) == (1, 1, 1, 3)
+    m3 = m2.matmul(m)
+    assert (m3.get(0, 0), m3.get(1, 1), m3.get(2, 2)) == (1, 1, 1)
+    d = B200Matrix.from_edges(4, [(0, 1), (0, 2), (1, 3), (2, 3)], bits)
+    assert d.matmul(d).get(0, 3) == 2
+    assert B200Matrix.from_edges(2, [(0, 1), (0, 1)], bits).get(0, 1) == 2
+
+
+def test_matmul_par_agrees_with_seq_10_node(gpu_ctx, oracle):
+    edges = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (9, 0), (0, 5), (1, 6), (2, 7)]
+    a_h = hostgen.from_coo(10, 10, [e[0] for e in edges], [e[1] for e in edges], np.ones(13, np.uint32), 32)
+    check_product(oracle, gpu_ctx, a_h, a_h)
+
+
+def test_dense_2x2(gpu_ctx):
+    a = B200Matrix.from_coo(2, [(0, 0, 1), (0, 1, 2), (1, 0, 3), (1, 1, 4)])
+    b = B200Matrix.from_coo(2, [(0, 0, 5), (0, 1, 6), (1, 0, 7), (1, 1, 8)])
+    c = a.matmul(b)
+    assert [c.get(0, 0), c.get(0, 1), c.get(1, 0), c.get(1, 1)] == [19, 22, 43, 50]
+
+
+def test_shape_mismatch_panics(gpu_ctx):
+    with pytest.raises(ShapeMismatch):
+        B200Matrix.identity(3).matmul(B200Matrix.identity(4))
+    with pytest.raises(AssertionError):
+        B200Matrix.identity(3, 32).matmul(B200Matrix.identity(3, 64))
+
+
+def test_reachability_power_components(gpu_ctx):
+    m = B200Matrix.from_edges(4, [(0, 1), (1, 2), (2, 3)])
+    s, _ = m.reachability_sum()
+    assert all(s.get(i, j) > 0 for i, j in [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)])
+    assert s.get(3, 0) == 0 and s.get(2, 0) == 0
+    n = 64
+    chain = B200Matrix.from_edges(n, [(i, i + 1) for i in range(n - 1)], 32)
+    _, iters = chain.add(B200Matrix.identity(n, 32)).power_until_stable()
+    assert iters <= 8
+    tri2 = B200Matrix.from_edges_undirected(6, [(0, 1), (1, 2), (2, 0), (3, 4), (4, 5), (5, 3)])
+    comp = tri2.connected_components()
+    assert comp[0] == comp[1] == comp[2] and comp[3] == comp[4] == comp[5] and comp[0] != comp[3]
+    assert len(set(B200Matrix.new(5).connected_components())) == 5
+    assert tri2.num_components() == 2
+
+
+# ------------------------------------------------------------------ saturation (graph_csr.rs:931-939 saturates on purpose)
+@pytest.mark.parametrize("bits", [32, 64])
+def test_chain_closure_saturates_like_oracle(gpu_ctx, oracle, bits):
+    n = 64
+    e = [(i, i + 1) for i in range(n - 1)]
+    a_h = hostgen.from_coo(n, n, [x[0] for x in e] + list(range(n)), [x[1] for x in e] + list(range(n)), np.ones(2 * n - 1, hostgen.vdtype(bits)), bits)
+    cur, cur_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    for _ in range(9 if bits == 32 else 12):
+        cur = cur.matmul(cur)
+        cur_o = oracle.matmul(cur_o, cur_o)
+        assert_same(cur.to_host(), cur_o)
+    lim = (1 << bits) - 1
+    if bits == 32:
+        assert int(cur_o.values.max()) == lim
+
+
+@pytest.mark.parametrize("bits,vmax", [(32, 70000), (32, 0xFFFFFFFF), (64, 1 << 33), (64, 1 << 62), (64, 0xFFFFFFFFFFFFFFFF)])
+def test_large_values_all_accumulator_modes(gpu_ctx, oracle, bits, vmax):
+    rng = np.random.default_rng(7)
+    n = 600
+    a_h = rand_csr(rng, n, n, 6000, bits, 3)
+    a_h.values[:] = rng.integers(max(1, vmax // 3), vmax, size=a_h.nnz(), dtype=np.uint64, endpoint=True).astype(a_h.values.dtype)
+    b_h = rand_csr(rng, n, n, 9000, bits, 3)
+    b_h.values[::2] = np.array(vmax, dtype=b_h.values.dtype)
+    c = check_product(oracle, gpu_ctx, a_h, b_h, f"u{bits} vmax={vmax}")
+    if vmax >= (1 << bits) - 1:
+        assert int(c.values.max()) == (1 << bits) - 1
+
+
+# ------------------------------------------------------------------ the benchmark family at oracle-friendly sizes
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("side,epn", [(5, 2), (5, 26), (10, 3), (10, 8), (10, 26), (20, 4)])
+def test_sweep_grid_a_times_a(gpu_ctx, oracle, side, epn, bits):
+    full = hostgen.lattice([side] * 3, True, bits)
+    a_h = full if epn >= 26 else hostgen.thin(full, epn / 26.0)
+    check_product(oracle, gpu_ctx, a_h, a_h, f"side={side} epn={epn}")
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_repeated_exponentiation_chain(gpu_ctx, oracle, bits):
+    a_h = hostgen.reference_bench_instance(12, 3.0, bits)
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k in range(2, 8):
+        p = p.matmul(a)
+        p_o = oracle.matmul_par(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k}")
+
+
+def test_reference_instance_30_first_powers(gpu_ctx, oracle):
+    a_h = hostgen.reference_bench_instance(30, 3.0, 64)
+    assert a_h.nnz() == 81434
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k, nnz in zip(range(2, 6), (251590, 655391, 1574848, 3383207)):
+        p = p.matmul(a)
+        p_o = oracle.matmul_par(p_o, a_o)
+        assert p.nnz() == nnz
+        assert_same(p.to_host(), p_o, f"A^{k}")
+
+
+# ------------------------------------------------------------------ bins and edge cases
+def test_empty_and_degenerate(gpu_ctx, oracle):
+    for bits in (32, 64):
+        z = hostgen.empty(7, bits)
+        i7 = hostgen.identity(7, bits)
+        for x, y in ((z, z), (z, i7), (i7, z)):
+            c = check_product(oracle, gpu_ctx, x, y)
+            assert c.nnz() == 0
+    one = hostgen.from_coo(1, 1, [0], [0], np.array([5], np.uint64), 64)
+    assert check_product(oracle, gpu_ctx, one, one).get(0, 0) == 25
+
+
+def test_rows_pointing_at_empty_b_rows(gpu_ctx, oracle):
+    rng = np.random.default_rng(3)
+    n = 500
+    a_h = rand_csr(rng, n, n, 40000, 64)           # ~80 entries per row
+    b_h = rand_csr(rng, n, n, 300, 64)             # most B rows empty: P <= 32 with deg_A > 32
+    check_product(oracle, gpu_ctx, a_h, b_h)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("n,nnz_a,nnz_b", [(200, 1000, 1000), (3000, 30000, 60000), (20000, 200000, 400000), (400000, 1200000, 2000000)])
+def test_random_graphs(gpu_ctx, oracle, n, nnz_a, nnz_b, bits):
+    rng = np.random.default_rng(n)
+    check_product(oracle, gpu_ctx, rand_csr(rng, n, n, nnz_a, bits), rand_csr(rng, n, n, nnz_b, bits), f"n={n}")
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_ragged_rows_hit_every_hash_bin(gpu_ctx, oracle, bits):
+    """Row lengths 1..20000 against a fairly dense B: exercises every hash bin, bitmap-rank emission
+    (small column space) and the heavy path."""
+    rng = np.random.default_rng(11)
+    n = 30000
+    lens = [1, 2, 5, 20, 33, 64, 100, 200, 400, 800, 1500, 3000, 6000, 12000, 20000, 0, 7]
+    r = np.concatenate([np.full(l, i) for i, l in enumerate(lens)])
+    c = np.concatenate([rng.choice(n, size=l, replace=False) for l in lens])
+    a_h = hostgen.from_coo(n, n, r, c, rng.integers(1, 4, size=r.size, dtype=np.uint64).astype(hostgen.vdtype(bits)), bits)
+    b_h = rand_csr(rng, n, n, 5 * n, bits)
+    c = check_product(oracle, gpu_ctx, a_h, b_h)
+    assert c.last_stats.num_bin_rows[9] > 0, "heavy numeric bin not exercised"
+
+
+def test_wide_column_space_sort_emission_and_global_heavy(gpu_ctx, oracle):
+    """n = 2.5M columns: no shared-memory bitmap anywhere (sort emission, global-bitmap heavy rows)."""
+    rng = np.random.default_rng(5)
+    n = 2_500_000
+    lens = [3, 40, 150, 700, 2500, 9000, 30000]
+    r = np.concatenate([np.full(l, i * 1000) for i, l in enumerate(lens)])
+    c = np.concatenate([rng.choice(n, size=l, replace=False) for l in lens])
+    a_h = hostgen.from_coo(n, n, r, c, np.ones(r.size, np.uint64), 64)
+    b_h = rand_csr(rng, n, n, 4 * n, 64)
+    c = check_product(oracle, gpu_ctx, a_h, b_h)
+    assert c.last_stats.num_bin_rows[9] > 0
+
+
+def test_rectangular_row_block_matches_rows_of_full_product(gpu_ctx, oracle):
+    a_h = hostgen.reference_bench_instance(10, 4.0, 64)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    full = a.matmul(a).to_host()
+    cuts = gpu_ctx.shard_rows_by_products(a.device, a.device, 3)
+    assert cuts[0] == 0 and cuts[-1] == a_h.rows and np.all(np.diff(cuts.astype(np.int64)) >= 0)
+    prods = gpu_ctx.row_products(a.device, a.device)
+    assert np.array_equal(prods, oracle.row_products(to_o(oracle, a_h), to_o(oracle, a_h)))
+    per_part = [int(prods[int(cuts[i]):int(cuts[i + 1])].sum()) for i in range(3)]
+    assert max(per_part) - min(per_part) <= 2 * int(prods.max()) + 3
+    for i in range(3):
+        r0, r1 = int(cuts[i]), int(cuts[i + 1])
+        blk = B200Matrix(gpu_ctx.row_block(a.device, r0, r1))
+        assert_same(blk.to_host(), a_h.row_block(r0, r1))
+        got = blk.matmul(a).to_host()
+        assert_same(got, full.row_block(r0, r1), f"block {i}")
+
+
+def test_magnus_layout_usize_columns_roundtrip(gpu_ctx):
+    a_h = hostgen.reference_bench_instance(6, 3.0, 64)
+    m = B200Matrix.from_parts(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx.astype(np.uint64), a_h.values, gpu_ctx)
+    rp, ci, vv = m.device.download(idx64=True)
+    assert ci.dtype == np.uint64 and np.array_equal(ci, a_h.col_idx) and np.array_equal(rp, a_h.row_ptr) and np.array_equal(vv, a_h.values)
+
+
+def test_upload_rejects_explicit_zero(gpu_ctx):
+    from sparse_linear_algebra_tests_b200 import B200Error
+    with pytest.raises(B200Error):
+        gpu_ctx.upload(2, 2, np.array([0, 1, 2], np.uint64), np.array([0, 1], np.uint32), np.array([1, 0], np.uint64))
+    with pytest.raises(B200Error):
+        gpu_ctx.upload(2, 2, np.array([0, 1, 2], np.uint64), np.array([0, 5], np.uint32), np.array([1, 1], np.uint64))
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_add_matches_oracle(gpu_ctx, oracle, bits):
+    rng = np.random.default_rng(2)
+    a_h, b_h = rand_csr(rng, 3000, 3000, 20000, bits), rand_csr(rng, 3000, 3000, 25000, bits)
+    a_h.values[:50] = np.array((1 << bits) - 1, dtype=a_h.values.dtype)
+    got = B200Matrix.from_host(a_h, gpu_ctx).add(B200Matrix.from_host(b_h, gpu_ctx)).to_host()
+    assert_same(got, oracle.add(to_o(oracle, a_h), to_o(oracle, b_h)))
+
+
+# ------------------------------------------------------------------ size-independent properties at larger scale
+def test_properties_on_full_size_torus(gpu_ctx):
+    """30^3 reference instance up to A^7: nnz matches the reference README table (README.md:42-47, rounded),
+    row sums obey (A^k 1) = A (A^(k-1) 1), symmetry of A^k, sorted unique columns."""
+    a_h = hostgen.reference_bench_instance(30, 3.0, 64)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    p = a
+    readme = {2: "252k", 3: "655k", 4: "1.57M", 5: "3.38M", 6: "6.59M", 7: "11.7M"}
+    exact = {2: 251590, 3: 655391, 4: 1574848, 5: 3383207, 6: 6590100, 7: 11736555}
+    rowsum_prev = np.add.reduceat(a_h.values.astype(np.float64), a_h.row_ptr[:-1].astype(np.int64)) * (np.diff(a_h.row_ptr.astype(np.int64)) > 0)
+    import scipy.sparse as sp
+    a_sp = sp.csr_matrix((a_h.values.astype(np.float64), a_h.col_idx.astype(np.int64), a_h.row_ptr.astype(np.int64)), shape=(a_h.rows, a_h.cols))
+    for k in range(2, 8):
+        p = p.matmul(a)
+        assert p.nnz() == exact[k]
+        s = f"{p.nnz() / 1e3:.0f}k" if p.nnz() < 1e6 else f"{p.nnz() / 1e6:.3g}M"
+        assert s == readme[k]
+        h = p.to_host()
+        lens = np.diff(h.row_ptr.astype(np.int64))
+        rows = np.repeat(np.arange(h.rows), lens)
+        key = rows * h.cols + h.col_idx.astype(np.int64)
+        assert np.all(np.diff(key) > 0), "columns not strictly ascending within rows"
+        rowsum = np.bincount(rows, weights=h.values.astype(np.float64), minlength=h.rows)
+        # A^k 1 = A^(k-1) (A 1); with symmetric A also = A (A^(k-1) 1)
+        assert np.allclose(rowsum, a_sp @ rowsum_prev, rtol=0, atol=0.5)
+        rowsum_prev = rowsum
+        m = sp.csr_matrix((h.values.astype(np.float64), h.col_idx.astype(np.int64), h.row_ptr.astype(np.int64)), shape=(h.rows, h.cols))
+        assert (m != m.T).nnz == 0, "A^k of a symmetric A must be symmetric"
