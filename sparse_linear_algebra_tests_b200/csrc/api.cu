@@ -109,7 +109,11 @@ static int ensure_heavy_scratch(b200_ctx *ctx, size_t bytes) {
 
 // ---------------------------------------------------------------------------- kernel attribute setup
 template <typename K>
-static void allow_big_smem(K kernel, size_t bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+static void allow_big_smem(K kernel, size_t optin) {
+    // static shared memory counts against the opt-in limit: leave 1 KB for it
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - 1024));
+    if (e != cudaSuccess) { fprintf(stderr, "b200: cudaFuncSetAttribute(max dynamic smem) failed: %s\n", cudaGetErrorString(e)); cudaGetLastError(); }
+}
 
 template <typename VT>
 static void setup_kernels_vt(size_t optin) {
