@@ -121,6 +121,7 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_sym_hash<VT, true>, optin);
     allow_big_smem(k_num_hash<VT, 0, false>, optin); allow_big_smem(k_num_hash<VT, 0, true>, optin);
     allow_big_smem(k_num_hash<VT, 1, false>, optin); allow_big_smem(k_num_hash<VT, 1, true>, optin);
+    allow_big_smem(k_num_rank<VT, 0>, optin); allow_big_smem(k_num_rank<VT, 1>, optin);
 }
 
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
@@ -157,6 +158,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     setup_kernels_vt<u64>(ctx->smem_optin);
     allow_big_smem(k_num_hash<u64, 2, false>, ctx->smem_optin);
     allow_big_smem(k_num_hash<u64, 2, true>, ctx->smem_optin);
+    allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
     cudaGetLastError();
     *out = ctx;
     return B200_OK;
@@ -493,14 +495,26 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (!cnt) continue;
         const int threads = b200_hash_threads(hb);
         const u32 slots = b200_hash_slots(hb);
+        const u32 cap = b200_hash_cap(hb);
+        const int bin = B200_BIN_HASH0 + hb;
+        // rank kernel (column bitmap in shared memory) when the column space is small next to the row
+        const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (mode == 0 ? 4 : 8);
+        if (nwords <= 4 * cap && rank_smem + 1024 <= ctx->smem_optin) {
+            const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (rank_smem + 1024)))));
+            const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
+            if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val);
+            else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val);
+            else if (sizeof(VT) == 8) k_num_rank<u64, 2><<<g, threads, rank_smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val);
+            LAUNCH_CHECK(ctx);
+            continue;
+        }
         const size_t acc_b = mode == 0 ? 4 : 8;
         const size_t tab = (size_t)slots * (4 + acc_b);
-        const bool bitmap = nwords <= 2 * slots && tab + (size_t)nwords * 8 + 1024 <= ctx->smem_optin;
-        const size_t smem = tab + (bitmap ? (size_t)nwords * 8 : 0);
+        const bool bitmap = false;
+        const size_t smem = tab;
         if (smem + 1024 > ctx->smem_optin) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem); }
-        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 256)))));
+        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
         const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
-        const int bin = B200_BIN_HASH0 + hb;
 #define NUM_LAUNCH(MODE, BM) k_num_hash<VT, MODE, BM><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val)
         if (mode == 0) { if (bitmap) NUM_LAUNCH(0, true); else NUM_LAUNCH(0, false); }
         else if (mode == 1) { if (bitmap) NUM_LAUNCH(1, true); else NUM_LAUNCH(1, false); }
@@ -511,7 +525,17 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
 #undef NUM_LAUNCH
         LAUNCH_CHECK(ctx);
     }
-    if (hc.num_bin_count[B200_BIN_HEAVY]) {
+    const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)hc.max_row_nnz * (mode == 0 ? 4 : 8);
+    if (hc.num_bin_count[B200_BIN_HEAVY] && hc.max_row_nnz < 65536 && heavy_rank_smem + 1024 <= ctx->smem_optin) {
+        // heavy rows over a small column space: same rank kernel, accumulators sized for the longest row
+        const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
+        const u32 cap = (u32)hc.max_row_nnz;
+        const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * 2);
+        if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (VT *)C->d_val);
+        else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (VT *)C->d_val);
+        else if (sizeof(VT) == 8) k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (u64 *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    } else if (hc.num_bin_count[B200_BIN_HEAVY]) {
         const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
         u64 max_slots = 1; while (max_slots < 2 * hc.max_row_nnz) max_slots <<= 1;
         const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;

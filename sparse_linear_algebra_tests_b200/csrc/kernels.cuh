@@ -469,6 +469,115 @@ __global__ void __launch_bounds__(1024) k_num_hash(CsrView<VT> A, CsrView<VT> B,
     if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
 }
 
+// ---------------------------------------------------------------------------------------
+// 4b. numeric for rows whose whole column space fits a shared-memory bitmap ("rank" kernel).
+// No hash table: walk 1 sets one bit per product column; a prefix popcount over the bitmap
+// words gives every present column its rank (= its position in the sorted output row); walk 2
+// adds each product into acc[rank]; columns are emitted by enumerating the set bits, values by
+// streaming acc[0..nnz).  Shared memory: nwords*6 + cap*4 (MODE 0) bytes -> high occupancy.
+// MODE 1 keeps a 64-bit sum as two u32 words (lo/hi) and propagates the carry with the value
+// returned by the atomic on lo: shared-memory u64 atomicAdd is a CAS spin loop on sm_100
+// (ATOMS.CAST.SPIN.64, measured 7x slower than ATOMS.ADD).
+// ---------------------------------------------------------------------------------------
+template <typename VT, int MODE>
+__global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
+                                                   int bin, u32 cap, u32 nwords, int lg, const u64 *__restrict__ rpC,
+                                                   u32 *__restrict__ colC, VT *__restrict__ valC) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_warp[33];
+    // layout: [acc64 cap (MODE 2)] | lo cap | [hi cap (MODE 1)] | bm nwords | wpre nwords (u16)
+    ull *acc64 = reinterpret_cast<ull *>(smem_raw);
+    u32 *lo = reinterpret_cast<u32 *>(smem_raw + (MODE == 2 ? (size_t)cap * 8 : 0));
+    u32 *hi = lo + (MODE == 2 ? 0 : cap);
+    u32 *bm = hi + (MODE == 1 ? cap : 0);
+    unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
+    const u32 count = ctrl->num_bin_count[bin];
+    const u32 off = bin_offset(ctrl->num_bin_count, bin);
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int G = 1 << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
+    const u32 wpt = (nwords + nt - 1) / nt;                               // bitmap words per thread
+    u64 vmax = 0;
+    for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
+        const u32 row = bin_rows[off + r];
+        const u64 obase = rpC[row];
+        const u32 nnz = (u32)(rpC[row + 1] - obase);
+        for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
+        for (u32 t = tid; t < nnz; t += nt) {
+            if (MODE == 2) acc64[t] = 0; else lo[t] = 0;
+            if (MODE == 1) hi[t] = 0;
+        }
+        __syncthreads();
+        const u64 s = A.rp[row], e = A.rp[row + 1];
+        // ---- walk 1: column bitmap
+        for (u64 ia = s + grp; ia < e; ia += ngrp) {
+            const u32 k = A.col[ia];
+            const u64 bs = B.rp[k], be = B.rp[k + 1];
+            for (u64 jb = bs + sub; jb < be; jb += G) {
+                const u32 c = B.col[jb];
+                atomicOr(&bm[c >> 5], 1u << (c & 31));
+            }
+        }
+        __syncthreads();
+        // ---- ranks: exclusive prefix popcount over the words (each thread owns wpt consecutive words)
+        {
+            const u32 w0 = tid * wpt;
+            u32 mine = 0;
+            for (u32 i = 0; i < wpt; i++) if (w0 + i < nwords) mine += __popc(bm[w0 + i]);
+            u32 total;
+            u32 run = block_excl_scan(mine, s_warp, total);
+            for (u32 i = 0; i < wpt; i++) {
+                if (w0 + i < nwords) {
+                    const u32 w = bm[w0 + i];
+                    wpre[w0 + i] = (unsigned short)run;
+                    // columns come out in ascending order: emit them here
+                    u32 bits = w;
+                    u64 p = obase + run;
+                    while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; colC[p++] = ((w0 + i) << 5) + b; }
+                    run += __popc(w);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- walk 2: accumulate into acc[rank(col)]
+        for (u64 ia = s + grp; ia < e; ia += ngrp) {
+            const u32 k = A.col[ia];
+            const VT a = A.val[ia];
+            const u64 bs = B.rp[k], be = B.rp[k + 1];
+            for (u64 jb = bs + sub; jb < be; jb += G) {
+                const u32 c = B.col[jb];
+                const u32 w = bm[c >> 5];
+                const u32 pos = (u32)wpre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+                if (MODE == 0) {
+                    atomicAdd(&lo[pos], (u32)a * (u32)B.val[jb]);
+                } else if (MODE == 1) {
+                    u64 x;
+                    if (sizeof(VT) == 4) { x = (u64)a * (u64)B.val[jb]; x = x > 0xFFFFFFFFull ? 0xFFFFFFFFull : x; }
+                    else x = (u64)a * (u64)B.val[jb];
+                    const u32 xlo = (u32)x, xhi = (u32)(x >> 32);
+                    const u32 old = atomicAdd(&lo[pos], xlo);
+                    const u32 up = xhi + ((u32)(old + xlo) < xlo ? 1u : 0u);
+                    if (up) atomicAdd(&hi[pos], up);
+                } else {
+                    acc_add<2>((u64 *)&acc64[pos], sat_mul((u64)a, (u64)B.val[jb]));
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 t = tid; t < nnz; t += nt) {
+            u64 v;
+            if (MODE == 0) v = lo[t];
+            else if (MODE == 1) v = ((u64)hi[t] << 32) | lo[t];
+            else v = acc64[t];
+            if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
+            valC[obase + t] = (VT)v;
+            vmax = vmax > v ? vmax : v;
+        }
+        __syncthreads();
+    }
+    vmax = warp_max_u64(vmax);
+    if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
+}
+
 // =======================================================================================
 // 5. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
 // =======================================================================================
