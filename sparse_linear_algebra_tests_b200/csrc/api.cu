@@ -11,6 +11,8 @@
 #include "../../include/b200_spgemm.h"
 #include "kernels.cuh"
 
+#define B200_NAUX 3
+
 // ---------------------------------------------------------------------------- error plumbing
 static thread_local std::string g_last_error;
 static int set_err(int code, const char *fmt, ...) {
@@ -43,6 +45,7 @@ struct b200_csr {
     u64 *d_rp; u32 *d_col; void *d_val;
     ull *d_maxval;          // device scalar: largest stored value
     u64 max_row_len;        // host-known upper bound of the longest row
+    uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
     b200_ctx *ctx;
 };
 
@@ -58,6 +61,7 @@ struct b200_ctx {
     u32 *d_flag;            // small device flag word (+ pinned mirror)
     u32 *h_flag;
     cudaEvent_t ev[4];
+    cudaStream_t aux[B200_NAUX]; cudaEvent_t ev_fork, ev_join[B200_NAUX]; int naux_enabled;
     bool timing;
     u64 launches;
 };
@@ -117,11 +121,9 @@ static void allow_big_smem(K kernel, size_t optin) {
 
 template <typename VT>
 static void setup_kernels_vt(size_t optin) {
-    allow_big_smem(k_sym_hash<VT, false>, optin);
-    allow_big_smem(k_sym_hash<VT, true>, optin);
-    allow_big_smem(k_num_hash<VT, 0, false>, optin); allow_big_smem(k_num_hash<VT, 0, true>, optin);
-    allow_big_smem(k_num_hash<VT, 1, false>, optin); allow_big_smem(k_num_hash<VT, 1, true>, optin);
+    allow_big_smem(k_num_cta<VT, 0>, optin); allow_big_smem(k_num_cta<VT, 1>, optin);
     allow_big_smem(k_num_rank<VT, 0>, optin); allow_big_smem(k_num_rank<VT, 1>, optin);
+    allow_big_smem(k_num_warp<VT, 0>, optin); allow_big_smem(k_num_warp<VT, 1>, optin);
 }
 
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
@@ -153,12 +155,15 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 64));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 64));
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < B200_NAUX; i++) { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : B200_NAUX; }
     ctx->timing = true;
     setup_kernels_vt<u32>(ctx->smem_optin);
     setup_kernels_vt<u64>(ctx->smem_optin);
-    allow_big_smem(k_num_hash<u64, 2, false>, ctx->smem_optin);
-    allow_big_smem(k_num_hash<u64, 2, true>, ctx->smem_optin);
-    allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
+    allow_big_smem(k_sym_cta<false>, ctx->smem_optin); allow_big_smem(k_sym_cta<true>, ctx->smem_optin);
+    allow_big_smem(k_num_cta<u64, 2>, ctx->smem_optin); allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
+    allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
     cudaGetLastError();
     *out = ctx;
     return B200_OK;
@@ -172,6 +177,8 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_ctrl); cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B200_OK;
@@ -210,7 +217,7 @@ static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, b
 extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval);
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc);
     delete m;
     return B200_OK;
 }
@@ -361,23 +368,42 @@ extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_
 }
 
 // ---------------------------------------------------------------------------- SpGEMM
+static int env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
-// lanes cooperating on one A entry while walking its B row: ~ the mean B row length
+// lanes cooperating on one A entry while walking its B row: largest power of two <= mean B row length / 2
 static int pick_lg(const b200_csr *B, int max_lg) {
-    double avg = B->rows ? (double)B->nnz / (double)B->rows : 1.0;
+    const int forced = env_int("B200_LG", -1);
+    if (forced >= 0) return std::min(forced, max_lg);
+    const double avg = B->rows ? (double)B->nnz / (double)B->rows : 1.0;
     int lg = 0;
-    while (lg < max_lg && (double)(1 << lg) < avg) lg++;
+    while (lg < max_lg && (double)(2 << lg) <= avg / 2.0) lg++;
     return lg;
 }
+// threads that own one row of hash bin hb: ~one group per 4 A entries, assuming deg_A ~ cap/2
+static int bin_threads(int hb, int lg) {
+    const int div = std::max(1, env_int("B200_TDIV", 8));
+    long t = ((long)b200_hash_cap(hb) << lg) / div;
+    t = std::max(32L, std::min(1024L, t));
+    long need = (long)b200_hash_slots(hb) / 16;                           // sort path keeps <= 16 slots per thread
+    return (int)std::max(t, std::min(1024L, need));
+}
 
-struct HashCfg { int threads; u32 slots; bool bitmap; size_t smem; int ctas_per_sm; };
+// B row descriptors {start,len}: built once per right operand and cached in the handle
+static int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
+    if (B->d_desc) return B200_OK;
+    if (B->nnz >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "right operand with >= 2^32 stored entries is not supported");
+    b200_csr *Bm = const_cast<b200_csr *>(B);
+    TRY(dmalloc(ctx, (void **)&Bm->d_desc, (B->rows + 1) * sizeof(uint2)));
+    k_build_desc<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, Bm->d_desc);
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
 
-template <typename VT>
 static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B) {
-    double avg = A->rows ? (double)A->nnz / (double)A->rows : 0.0;
-    u64 rows = A->rows;
+    const double avg = A->rows ? (double)A->nnz / (double)A->rows : 0.0;
+    const u64 rows = A->rows;
 #define RP_LAUNCH(G)                                                                                              \
-    k_row_products<G><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_rp, \
+    k_row_products<G><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, \
                                                                                     ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl)
     if (avg <= 2.0) RP_LAUNCH(1);
     else if (avg <= 6.0) RP_LAUNCH(4);
@@ -387,6 +413,26 @@ static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr 
     LAUNCH_CHECK(ctx);
     return B200_OK;
 }
+
+// Independent per-bin kernels are spread over the main stream and a few auxiliary streams.
+struct Fan {
+    b200_ctx *ctx; int next; bool used[B200_NAUX]; bool forked;
+    explicit Fan(b200_ctx *c) : ctx(c), next(0), forked(false) { for (int i = 0; i < B200_NAUX; i++) used[i] = false; }
+    cudaStream_t pick() {
+        const int n = ctx->naux_enabled;
+        if (n == 0) return ctx->stream;
+        const int slot = next++ % (n + 1);
+        if (slot == n) return ctx->stream;
+        if (!forked) { cudaEventRecord(ctx->ev_fork, ctx->stream); forked = true; }
+        if (!used[slot]) { cudaStreamWaitEvent(ctx->aux[slot], ctx->ev_fork, 0); used[slot] = true; }
+        return ctx->aux[slot];
+    }
+    void join() {
+        for (int i = 0; i < B200_NAUX; i++)
+            if (used[i]) { cudaEventRecord(ctx->ev_join[i], ctx->aux[i]); cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0); used[i] = false; }
+        forked = false; next = 0;
+    }
+};
 
 template <typename VT>
 static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st) {
@@ -406,56 +452,64 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         return B200_OK;
     }
     int r = ensure_row_scratch(ctx, rows);
+    if (r == B200_OK) r = ensure_desc(ctx, B);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-    CsrView<VT> vA = view<VT>(A), vB = view<VT>(B);
+    SymArgs sa{A->d_rp, A->d_col, B->d_desc, B->d_col};
+    NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     const u32 nwords = (u32)((ncols + 31) / 32);
     const int lg = pick_lg(B, 5);
     const u64 p_bound = A->max_row_len * B->max_row_len;                 // host-known bound of the largest P_i
     const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
+    const size_t smem_max = ctx->smem_optin - 1024;
+    Fan fan(ctx);
 
     if (timing) cudaEventRecord(ctx->ev[0], s);
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
     CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, ntiles * 8, s));
     // ---- symbolic: product counts, bins, exact nnz per row
-    TRY(launch_row_products<VT>(ctx, A, B));
+    TRY(launch_row_products(ctx, A, B));
     const unsigned row_grid = (unsigned)((rows + 255) / 256);
     k_bin_scatter<0><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
     LAUNCH_CHECK(ctx);
     {
-        int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
-        k_sym_tiny<VT><<<g, 256, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
+        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
         LAUNCH_CHECK(ctx);
     }
-    for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
-        const u64 lo = hb == 0 ? 33 : (u64)b200_hash_cap(hb - 1) + 1;
-        if (p_bound < lo) break;                                         // no row can reach this bin
-        const int threads = b200_hash_threads(hb);
+    if (p_bound > 32 || A->max_row_len > 32) {
+        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
+        k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, std::min(lg, 5), ctx->d_nnz_row);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
+        if (p_bound <= (u64)b200_hash_cap(hb - 1)) break;                // no row can reach this bin
+        const int threads = bin_threads(hb, lg);
         const u32 slots = b200_hash_slots(hb);
-        const bool bitmap = nwords <= slots && (size_t)nwords * 4 <= ctx->smem_optin - 1024;
+        const bool bitmap = nwords <= slots && (size_t)nwords * 4 <= smem_max;
         const size_t smem = bitmap ? (size_t)nwords * 4 : (size_t)slots * 4;
-        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)((ctx->smem_optin) / (smem + 256)))));
+        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * per_sm * 2);
-        if (bitmap) k_sym_hash<VT, true><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
-        else k_sym_hash<VT, false><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+        cudaStream_t bs = fan.pick();
+        if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+        else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
         LAUNCH_CHECK(ctx);
     }
     if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) {
         // heavy rows: column bitmap, in shared memory when the column space fits, else in global scratch
-        if ((size_t)nwords * 4 <= ctx->smem_optin - 1024) {
+        if ((size_t)nwords * 4 <= smem_max) {
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-            k_sym_hash<VT, true><<<g, 1024, (size_t)nwords * 4, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
+            k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
         } else {
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
             r = ensure_heavy_scratch(ctx, (size_t)g * nwords * 4);
-            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-            k_sym_heavy<VT><<<g, 1024, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
+            if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
+            k_sym_heavy<<<g, 1024, 0, s>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
         }
         LAUNCH_CHECK(ctx);
     }
-    // ---- row_ptr (decoupled look-back scan) + numeric bins
-    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
-    LAUNCH_CHECK(ctx);
-    k_num_classify<<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl);
+    fan.join();
+    // ---- row_ptr (decoupled look-back scan, fused numeric-bin histogram), numeric bin lists
+    k_scan_rowptr<true><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, A->d_rp, ctx->d_prod);
     LAUNCH_CHECK(ctx);
     k_bin_scatter<1><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
     LAUNCH_CHECK(ctx);
@@ -482,78 +536,87 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (!over64 && (u64)bound < (1ull << 32)) mode = 0;
         else if (sizeof(VT) == 4) mode = 1;                               // clamped 32-bit products, < 2^32 of them per row
         else mode = over64 ? 2 : 1;
+        const int forced = env_int("B200_FORCE_MODE", -1);                // testing hook: a wider mode is always valid
+        if (forced > mode && forced <= (sizeof(VT) == 8 ? 2 : 1)) mode = forced;
     }
     if (timing) cudaEventRecord(ctx->ev[2], s);
+    u32 *colC = C->d_col; VT *valC = (VT *)C->d_val;
+    NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
     // ---- numeric
     if (hc.num_bin_count[B200_BIN_TINY]) {
-        int g = (int)std::min<u64>(((u64)hc.num_bin_count[B200_BIN_TINY] + 7) / 8, (u64)ctx->num_sms * 32);
-        k_num_tiny<VT><<<g, 256, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, C->d_rp, C->d_col, (VT *)C->d_val);
+        const int g = (int)std::min<u64>(((u64)hc.num_bin_count[B200_BIN_TINY] + 7) / 8, (u64)ctx->num_sms * 32);
+        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, C->d_rp, colC, valC);
         LAUNCH_CHECK(ctx);
     }
-    for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
+    if (hc.num_bin_count[B200_BIN_HASH0] + hc.num_bin_count[B200_BIN_HASH0 + 1]) {
+        const u64 cnt = (u64)hc.num_bin_count[B200_BIN_HASH0] + hc.num_bin_count[B200_BIN_HASH0 + 1];
+        const size_t smem = 8 * (Acc<1>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4);
+        const size_t smem0 = 8 * (Acc<0>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4);
+        const int g = (int)std::min<u64>((cnt + 7) / 8, (u64)ctx->num_sms * 16);
+        cudaStream_t bs = fan.pick();
+        const int wlg = std::min(lg, 5);
+        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem0, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, valC);
+        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, valC);
+        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, (u64 *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
         const u32 cnt = hc.num_bin_count[B200_BIN_HASH0 + hb];
         if (!cnt) continue;
-        const int threads = b200_hash_threads(hb);
+        const int threads = bin_threads(hb, lg);
         const u32 slots = b200_hash_slots(hb);
         const u32 cap = b200_hash_cap(hb);
         const int bin = B200_BIN_HASH0 + hb;
+        cudaStream_t bs = fan.pick();
         // rank kernel (column bitmap in shared memory) when the column space is small next to the row
         const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (mode == 0 ? 4 : 8);
-        if (nwords <= 4 * cap && rank_smem + 1024 <= ctx->smem_optin) {
+        if (nwords <= 4 * cap && rank_smem <= smem_max) {
             const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (rank_smem + 1024)))));
             const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
-            if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val);
-            else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val);
-            else if (sizeof(VT) == 8) k_num_rank<u64, 2><<<g, threads, rank_smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val);
+            if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, valC);
+            else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, valC);
+            else k_num_rank<u64, 2><<<g, threads, rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, (u64 *)C->d_val);
             LAUNCH_CHECK(ctx);
             continue;
         }
-        const size_t acc_b = mode == 0 ? 4 : 8;
-        const size_t tab = (size_t)slots * (4 + acc_b);
-        const bool bitmap = false;
-        const size_t smem = tab;
-        if (smem + 1024 > ctx->smem_optin) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem); }
+        const size_t smem = (size_t)slots * (4 + (mode == 0 ? 4 : 8));
+        if (smem > smem_max) { fan.join(); b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem); }
         const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
         const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
-#define NUM_LAUNCH(MODE, BM) k_num_hash<VT, MODE, BM><<<g, threads, smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (VT *)C->d_val)
-        if (mode == 0) { if (bitmap) NUM_LAUNCH(0, true); else NUM_LAUNCH(0, false); }
-        else if (mode == 1) { if (bitmap) NUM_LAUNCH(1, true); else NUM_LAUNCH(1, false); }
-        else {
-            if (sizeof(VT) == 8) { if (bitmap) k_num_hash<u64, 2, true><<<g, threads, smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val);
-                                   else k_num_hash<u64, 2, false><<<g, threads, smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, bin, slots, nwords, lg, C->d_rp, C->d_col, (u64 *)C->d_val); }
-        }
-#undef NUM_LAUNCH
+        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, valC);
+        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, valC);
+        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, (u64 *)C->d_val);
         LAUNCH_CHECK(ctx);
     }
     const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)hc.max_row_nnz * (mode == 0 ? 4 : 8);
-    if (hc.num_bin_count[B200_BIN_HEAVY] && hc.max_row_nnz < 65536 && heavy_rank_smem + 1024 <= ctx->smem_optin) {
+    if (hc.num_bin_count[B200_BIN_HEAVY] && hc.max_row_nnz < 65536 && heavy_rank_smem <= smem_max) {
         // heavy rows over a small column space: same rank kernel, accumulators sized for the longest row
         const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
         const u32 cap = (u32)hc.max_row_nnz;
         const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * 2);
-        if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (VT *)C->d_val);
-        else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (VT *)C->d_val);
-        else if (sizeof(VT) == 8) k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, C->d_col, (u64 *)C->d_val);
+        cudaStream_t bs = fan.pick();
+        if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, valC);
+        else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, valC);
+        else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, (u64 *)C->d_val);
         LAUNCH_CHECK(ctx);
     } else if (hc.num_bin_count[B200_BIN_HEAVY]) {
         const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
         u64 max_slots = 1; while (max_slots < 2 * hc.max_row_nnz) max_slots <<= 1;
         const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;
-        size_t budget = (size_t)8 << 30;
-        int g = (int)std::min<u64>(std::min<u64>(cnt, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
+        const size_t budget = (size_t)8 << 30;
+        const int g = (int)std::min<u64>(std::min<u64>(cnt, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
         r = ensure_heavy_scratch(ctx, per_cta * g);
-        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
         unsigned char *base = (unsigned char *)ctx->d_heavy;
         u64 *s_vals = (u64 *)base;                                            // g * max_slots u64
         u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
         u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
         u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
-        if (mode == 2 && sizeof(VT) == 8)
-            k_num_heavy<u64, 2><<<g, 1024, 0, s>>>(view<u64>(A), view<u64>(B), ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, C->d_col, (u64 *)C->d_val);
-        else
-            k_num_heavy<VT, 1><<<g, 1024, 0, s>>>(vA, vB, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, C->d_col, (VT *)C->d_val);
+        if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, s>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, colC, (u64 *)C->d_val);
+        else k_num_heavy<VT, 1><<<g, 1024, 0, s>>>(na, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, colC, valC);
         LAUNCH_CHECK(ctx);
     }
+    fan.join();
     CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
     if (timing) cudaEventRecord(ctx->ev[3], s);
     if (st) {
@@ -588,7 +651,8 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     if (A->rows == 0) return B200_OK;
     TRY(ensure_row_scratch(ctx, A->rows));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), ctx->stream));
-    TRY(launch_row_products<u32>(ctx, A, B));
+    TRY(ensure_desc(ctx, B));
+    TRY(launch_row_products(ctx, A, B));
     CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_prod, A->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
@@ -653,7 +717,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);
-    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
+    k_scan_rowptr<false><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

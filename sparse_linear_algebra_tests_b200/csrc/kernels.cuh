@@ -1,15 +1,60 @@
 // kernels.cuh -- device kernels of the SpGEMM engine (sm_100a).
 //
 // Pipeline of one C = A x B (host orchestration in api.cu):
+//   k_build_desc        B row descriptors {start,len} packed in 8 bytes (cached per right operand)
 //   k_row_products      per-row intermediate-product count P_i, symbolic-bin histogram
 //   k_bin_scatter       row ids grouped by bin (device-side counts, no host round trip)
-//   k_sym_tiny/_hash    exact nnz_i per row (distinct output columns)
-//   k_scan_rowptr       hand-written decoupled look-back scan: row_ptr_C (u64), total nnz
-//   k_num_classify      numeric-bin histogram on exact nnz_i, then k_bin_scatter again
-//   k_num_tiny/_hash    values: saturating accumulate, in-row column order, write col/val
-// Heavy rows (beyond a CTA's shared memory) use the *_heavy kernels with a global table.
+//   k_sym_*             exact nnz_i per row (distinct output columns)
+//   k_scan_rowptr       hand-written decoupled look-back scan: row_ptr_C (u64), total nnz,
+//                       fused with the numeric-bin histogram on exact nnz_i
+//   k_num_*             values: saturating accumulate, in-row column order, write col/val
+// Row classes: tiny (warp register merge), warp-hash (one warp per row, several rows per CTA),
+// CTA-hash (+ bitonic sort) or CTA-rank (column bitmap + prefix popcount, no sort), heavy
+// (global-memory table).  All inner loops use 32-bit offsets; 64-bit only for row bases.
 #pragma once
 #include "common.cuh"
+
+// =======================================================================================
+// 0. operand views
+// =======================================================================================
+struct SymArgs {                 // what the symbolic pass touches (value-type independent)
+    const u64 *rpA; const u32 *colA;
+    const uint2 *bdesc;          // per B row: x = first entry (u32), y = length
+    const u32 *colB;
+};
+template <typename VT>
+struct NumArgs {
+    const u64 *rpA; const u32 *colA; const VT *valA;
+    const uint2 *bdesc; const u32 *colB; const VT *valB;
+};
+
+__global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, uint2 *__restrict__ desc) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[i], e = rp[i + 1];
+        desc[i] = make_uint2((u32)s, (u32)(e - s));
+    }
+}
+
+// Walk the intermediate products of one A row.  `ngrp` groups of G lanes each take A entries
+// grp, grp+ngrp, ...; the G lanes of a group stride over that entry's B row.  Two A entries are
+// in flight per iteration so their dependent loads (A.col -> desc -> B.col) overlap.
+template <typename CT, typename P, typename F>
+__device__ __forceinline__ void walk_products(const u32 *__restrict__ Ac, u32 lenA, const uint2 *__restrict__ bdesc, u32 grp,
+                                              u32 ngrp, u32 sub, u32 G, P pre, F f) {
+    for (u32 t = grp; t < lenA; t += 2 * ngrp) {
+        const u32 t1 = t + ngrp;
+        const bool has1 = t1 < lenA;
+        const u32 k0 = Ac[t];
+        const u32 k1 = has1 ? Ac[t1] : k0;
+        const uint2 d0 = bdesc[k0];
+        uint2 d1 = bdesc[k1];
+        if (!has1) d1.y = 0;
+        const CT c0 = pre(t);
+        const CT c1 = pre(has1 ? t1 : t);
+        for (u32 j = sub; j < d0.y; j += G) f(c0, d0.x + j);
+        for (u32 j = sub; j < d1.y; j += G) f(c1, d1.x + j);
+    }
+}
 
 // =======================================================================================
 // 1. product count per row + symbolic-bin histogram
@@ -19,10 +64,16 @@ __device__ __forceinline__ int sym_bin_of(u64 p, u64 dA) {
     if (p <= 32 && dA <= 32) return B200_BIN_TINY;
     return b200_bin_by_size(p);
 }
+// numeric classification on exact nnz (rows with P<=32 and deg_A<=32 stay in the warp-merge bin)
+__device__ __forceinline__ int num_bin_of(u32 nnz, u64 p, u64 dA) {
+    if (nnz == 0) return B200_BIN_NONE;
+    if (p <= 32 && dA <= 32) return B200_BIN_TINY;
+    return b200_bin_by_size(nnz);
+}
 
 template <int G>  // lanes per row (power of two <= 32)
 __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
-                                                      const u64 *__restrict__ rpB, u64 *__restrict__ prod,
+                                                      const uint2 *__restrict__ bdesc, u64 *__restrict__ prod,
                                                       u32 *__restrict__ nnz_row, B200Ctrl *ctrl) {
     __shared__ u32 s_hist[B200_NBINS];
     __shared__ ull s_sum, s_max;
@@ -31,54 +82,32 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
     __syncthreads();
     const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 row = gtid / G;
-    const int sub = threadIdx.x % G;
-    u64 p = 0, s = 0, e = 0;
+    const u32 sub = threadIdx.x % G;
+    u64 p = 0; u32 lenA = 0;
     if (row < rows) {
-        s = rpA[row]; e = rpA[row + 1];
-        for (u64 i = s + sub; i < e; i += G) {
-            u32 c = colA[i];
-            p += rpB[c + 1] - rpB[c];
-        }
+        const u64 s = rpA[row];
+        lenA = (u32)(rpA[row + 1] - s);
+        const u32 *Ac = colA + s;
+        for (u32 i = sub; i < lenA; i += G) p += bdesc[Ac[i]].y;
     }
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1) p += shfl_xor_u64(p, m);
     u64 wsum = 0, wmax = 0;
     if (row < rows && sub == 0) {
         prod[row] = p;
-        int b = sym_bin_of(p, e - s);
+        const int b = sym_bin_of(p, lenA);
         if (b == B200_BIN_NONE) nnz_row[row] = (u32)p;       // 0, or the single B row's length
         else atomicAdd(&s_hist[b], 1u);
         wsum = p; wmax = p;
     }
     wsum = warp_sum_u64(wsum); wmax = warp_max_u64(wmax);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum, (ull)wsum); atomicMax(&s_max, (ull)wmax); }
+    if ((threadIdx.x & 31) == 0) { if (wsum) atomicAdd(&s_sum, (ull)wsum); atomicMax(&s_max, (ull)wmax); }
     __syncthreads();
     if (threadIdx.x < B200_NBINS && s_hist[threadIdx.x]) atomicAdd(&ctrl->sym_bin_count[threadIdx.x], s_hist[threadIdx.x]);
     if (threadIdx.x == 0) {
         if (s_sum) atomicAdd(&ctrl->total_products, s_sum);
-        atomicMax(&ctrl->max_row_products, s_max);
+        if (s_max) atomicMax(&ctrl->max_row_products, s_max);
     }
-}
-
-// numeric classification on exact nnz (rows with P<=32 and deg_A<=32 stay in the warp-merge bin)
-__device__ __forceinline__ int num_bin_of(u32 nnz, u64 p, u64 dA) {
-    if (nnz == 0) return B200_BIN_NONE;
-    if (p <= 32 && dA <= 32) return B200_BIN_TINY;
-    return b200_bin_by_size(nnz);
-}
-
-__global__ void __launch_bounds__(256) k_num_classify(u64 rows, const u64 *__restrict__ rpA, const u64 *__restrict__ prod,
-                                                      const u32 *__restrict__ nnz_row, B200Ctrl *ctrl) {
-    __shared__ u32 s_hist[B200_NBINS];
-    if (threadIdx.x < B200_NBINS) s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < rows) {
-        int b = num_bin_of(nnz_row[row], prod[row], rpA[row + 1] - rpA[row]);
-        if (b != B200_BIN_NONE) atomicAdd(&s_hist[b], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < B200_NBINS && s_hist[threadIdx.x]) atomicAdd(&ctrl->num_bin_count[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 // scatter row ids into their bin's segment of bin_rows; PHASE 0 = symbolic bins, 1 = numeric bins
@@ -91,7 +120,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__rest
     const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     int b = B200_BIN_NONE; u32 local = 0;
     if (row < rows) {
-        u64 dA = rpA[row + 1] - rpA[row];
+        const u64 dA = rpA[row + 1] - rpA[row];
         b = PHASE == 0 ? sym_bin_of(prod[row], dA) : num_bin_of(nnz_row[row], prod[row], dA);
         if (b != B200_BIN_NONE) local = atomicAdd(&s_cnt[b], 1u);
     }
@@ -101,7 +130,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__rest
         u32 *fill = PHASE == 0 ? ctrl->sym_bin_fill : ctrl->num_bin_fill;
         u32 off = 0;
         for (int i = 0; i < (int)threadIdx.x; i++) off += cnt[i];
-        u32 c = s_cnt[threadIdx.x];
+        const u32 c = s_cnt[threadIdx.x];
         s_base[threadIdx.x] = off + (c ? atomicAdd(&fill[threadIdx.x], c) : 0u);
     }
     __syncthreads();
@@ -115,22 +144,92 @@ __device__ __forceinline__ u32 bin_offset(const u32 *cnt, int bin) {
 }
 
 // =======================================================================================
-// 2. tiny rows: one warp per row, <= 32 products held one per lane
+// 2. accumulator storage shared by the numeric kernels
 // =======================================================================================
-// Gathers the row's products into registers: lane p gets product p (column, and the pair of
-// operand values when NUMERIC).  Returns P (same in all lanes).
-template <typename VT, bool NUMERIC>
-__device__ __forceinline__ u32 tiny_gather(const CsrView<VT> &A, const CsrView<VT> &B, u32 row, int lane, u32 &key, VT &val) {
-    const u64 s = A.rp[row];
-    const u32 dA = (u32)(A.rp[row + 1] - s);               // <= 32 by bin construction
-    u32 k = 0, deg = 0; u64 bstart = 0; VT a = 0;
-    if (lane < (int)dA) {
-        k = A.col[s + lane];
-        bstart = B.rp[k];
-        deg = (u32)(B.rp[k + 1] - bstart);
-        if (NUMERIC) a = A.val[s + lane];
+// MODE 0: 32-bit sums (host proved max_row_products*max(A)*max(B) < 2^32)
+// MODE 1: 64-bit sums kept as two u32 words; the carry out of `lo` is recovered from the value
+//         the atomic returns.  (Shared-memory u64 atomicAdd compiles to a CAS spin loop,
+//         ATOMS.CAST.SPIN.64, measured 7x slower than ATOMS.ADD on B200.)  For u32 values the
+//         products are clamped to 2^32-1 first; < 2^32 of them per row cannot wrap 64 bits.
+// MODE 2: u64 saturating multiply + CAS-loop saturating add.
+template <int MODE> struct Acc;
+template <> struct Acc<0> {
+    u32 *lo;
+    static __host__ __device__ size_t bytes(u32 n) { return (size_t)n * 4; }
+    __device__ void bind(unsigned char *base, u32) { lo = reinterpret_cast<u32 *>(base); }
+    __device__ void clear(u32 i) { lo[i] = 0; }
+    template <typename VT> __device__ void add(u32 i, VT a, VT b) { atomicAdd(&lo[i], (u32)a * (u32)b); }
+    __device__ u64 get(u32 i) const { return lo[i]; }
+    __device__ void set(u32 i, u64 x) { lo[i] = (u32)x; }
+};
+template <> struct Acc<1> {
+    u32 *lo, *hi;
+    static __host__ __device__ size_t bytes(u32 n) { return (size_t)n * 8; }
+    __device__ void bind(unsigned char *base, u32 n) { lo = reinterpret_cast<u32 *>(base); hi = lo + n; }
+    __device__ void clear(u32 i) { lo[i] = 0; hi[i] = 0; }
+    template <typename VT> __device__ void add(u32 i, VT a, VT b) {
+        u64 x = (u64)a * (u64)b;
+        if (sizeof(VT) == 4) x = x > 0xFFFFFFFFull ? 0xFFFFFFFFull : x;
+        const u32 xlo = (u32)x, xhi = (u32)(x >> 32);
+        const u32 old = atomicAdd(&lo[i], xlo);
+        const u32 up = xhi + ((u32)(old + xlo) < xlo ? 1u : 0u);
+        if (up) atomicAdd(&hi[i], up);
     }
-    // exclusive scan of deg across lanes
+    __device__ u64 get(u32 i) const { return ((u64)hi[i] << 32) | lo[i]; }
+    __device__ void set(u32 i, u64 x) { lo[i] = (u32)x; hi[i] = (u32)(x >> 32); }
+};
+template <> struct Acc<2> {
+    ull *v;
+    static __host__ __device__ size_t bytes(u32 n) { return (size_t)n * 8; }
+    __device__ void bind(unsigned char *base, u32) { v = reinterpret_cast<ull *>(base); }
+    __device__ void clear(u32 i) { v[i] = 0; }
+    template <typename VT> __device__ void add(u32 i, VT a, VT b) {
+        const ull x = sat_mul((u64)a, (u64)b);
+        ull old = *reinterpret_cast<volatile ull *>(&v[i]), assumed;
+        do {
+            assumed = old;
+            ull s = assumed + x; if (s < assumed) s = ~0ull;
+            if (s == assumed) break;
+            old = atomicCAS(&v[i], assumed, s);
+        } while (old != assumed);
+    }
+    __device__ u64 get(u32 i) const { return v[i]; }
+    __device__ void set(u32 i, u64 x) { v[i] = x; }
+};
+template <typename VT> __device__ __forceinline__ VT emit_val(u64 v) {
+    if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;   // u32 sums accumulated in 64 bits saturate here
+    return (VT)v;
+}
+
+// insert column c into an open-addressing key table; returns the slot.  `fresh` = first insertion.
+__device__ __forceinline__ u32 table_insert(u32 *keys, u32 mask, int shift, u32 c, bool &fresh) {
+    u32 h = b200_hash(c, shift);
+    fresh = false;
+    while (true) {
+        u32 cur = ld_volatile_u32(&keys[h]);
+        if (cur == B200_EMPTY_KEY) {
+            cur = atomicCAS(&keys[h], B200_EMPTY_KEY, c);
+            if (cur == B200_EMPTY_KEY) { fresh = true; return h; }
+        }
+        if (cur == c) return h;
+        h = (h + 1) & mask;
+    }
+}
+
+// =======================================================================================
+// 3. tiny rows: one warp per row, <= 32 products held one per lane
+// =======================================================================================
+template <typename VT, bool NUMERIC>
+__device__ __forceinline__ u32 tiny_gather(const u64 *rpA, const u32 *colA, const VT *valA, const uint2 *bdesc, const u32 *colB,
+                                           const VT *valB, u32 row, int lane, u32 &key, VT &val) {
+    const u64 s = rpA[row];
+    const u32 dA = (u32)(rpA[row + 1] - s);               // <= 32 by bin construction
+    u32 deg = 0, bstart = 0; VT a = 0;
+    if (lane < (int)dA) {
+        const uint2 d = bdesc[colA[s + lane]];
+        bstart = d.x; deg = d.y;
+        if (NUMERIC) a = valA[s + lane];
+    }
     u32 incl = deg;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
@@ -140,19 +239,19 @@ __device__ __forceinline__ u32 tiny_gather(const CsrView<VT> &A, const CsrView<V
     int lo = 0;
 #pragma unroll
     for (int step = 16; step > 0; step >>= 1) {
-        int cand = lo + step;
-        u32 t = __shfl_sync(0xFFFFFFFFu, excl, cand & 31);
+        const int cand = lo + step;
+        const u32 t = __shfl_sync(0xFFFFFFFFu, excl, cand & 31);
         if (cand < (int)dA && t <= (u32)lane) lo = cand;
     }
     const u32 e_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
-    const u64 e_bstart = shfl_u64(bstart, lo);
+    const u32 e_bstart = __shfl_sync(0xFFFFFFFFu, bstart, lo);
     VT e_a = 0;
     if (NUMERIC) e_a = shfl_any(a, lo);
     key = B200_EMPTY_KEY; val = 0;
     if ((u32)lane < P) {
-        const u64 j = e_bstart + ((u32)lane - e_excl);
-        key = B.col[j];
-        if (NUMERIC) val = sat_mul(e_a, B.val[j]);
+        const u32 j = e_bstart + ((u32)lane - e_excl);
+        key = colB[j];
+        if (NUMERIC) val = sat_mul(e_a, valB[j]);
     }
     return P;
 }
@@ -169,7 +268,6 @@ __device__ __forceinline__ void warp_bitonic(u32 &key, VT &val, int lane) {
             if (NUMERIC) ov = shfl_xor_any(val, j);
             const bool up = ((lane & k) == 0);
             const bool lower = ((lane & j) == 0);
-            // lower lane of an ascending pair keeps the min; of a descending pair keeps the max
             const bool take_min = (up == lower);
             const bool swap = take_min ? (ok < key) : (ok > key);
             if (swap) { key = ok; if (NUMERIC) val = ov; }
@@ -177,18 +275,15 @@ __device__ __forceinline__ void warp_bitonic(u32 &key, VT &val, int lane) {
     }
 }
 
-template <typename VT>
-__global__ void __launch_bounds__(256) k_sym_tiny(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows,
-                                                  B200Ctrl *ctrl, u32 *__restrict__ nnz_row) {
+__global__ void __launch_bounds__(256) k_sym_tiny(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 *__restrict__ nnz_row) {
     const u32 count = ctrl->sym_bin_count[B200_BIN_TINY];
-    const u32 off = 0;
     const int lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
     for (u32 r = blockIdx.x * wpb + (threadIdx.x >> 5); r < count; r += gridDim.x * wpb) {
-        const u32 row = bin_rows[off + r];
-        u32 key; VT val;
-        tiny_gather<VT, false>(A, B, row, lane, key, val);
-        warp_bitonic<VT, false>(key, val, lane);
+        const u32 row = bin_rows[r];
+        u32 key; u32 val;
+        tiny_gather<u32, false>(a.rpA, a.colA, nullptr, a.bdesc, a.colB, nullptr, row, lane, key, val);
+        warp_bitonic<u32, false>(key, val, lane);
         const u32 prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
         const bool head = key != B200_EMPTY_KEY && (lane == 0 || prev != key);
         const u32 n = __popc(__ballot_sync(0xFFFFFFFFu, head));
@@ -197,9 +292,8 @@ __global__ void __launch_bounds__(256) k_sym_tiny(CsrView<VT> A, CsrView<VT> B, 
 }
 
 template <typename VT>
-__global__ void __launch_bounds__(256) k_num_tiny(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows,
-                                                  B200Ctrl *ctrl, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
-                                                  VT *__restrict__ valC) {
+__global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
+                                                  const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
     const u32 count = ctrl->num_bin_count[B200_BIN_TINY];
     const int lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
@@ -207,7 +301,7 @@ __global__ void __launch_bounds__(256) k_num_tiny(CsrView<VT> A, CsrView<VT> B, 
     for (u32 r = blockIdx.x * wpb + (threadIdx.x >> 5); r < count; r += gridDim.x * wpb) {
         const u32 row = bin_rows[r];
         u32 key; VT val;
-        tiny_gather<VT, true>(A, B, row, lane, key, val);
+        tiny_gather<VT, true>(a.rpA, a.colA, a.valA, a.bdesc, a.colB, a.valB, row, lane, key, val);
         warp_bitonic<VT, true>(key, val, lane);
         // segmented inclusive scan (saturating) over runs of equal keys; the run's last lane has the total
 #pragma unroll
@@ -230,20 +324,50 @@ __global__ void __launch_bounds__(256) k_num_tiny(CsrView<VT> A, CsrView<VT> B, 
 }
 
 // =======================================================================================
-// 3. hash rows -- symbolic: distinct columns via a shared-memory key table, or via a
-//    shared-memory column bitmap when the whole column space fits (BITMAP)
+// 4. symbolic: distinct output columns per row
 // =======================================================================================
-// One "group" of `blockDim.x` threads owns one row at a time (grid-stride over the bin).
-// Within the group, `1<<lg` lanes cooperate on one A entry and stride over its B row.
-template <typename VT, bool BITMAP>
-__global__ void __launch_bounds__(1024) k_sym_hash(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin,
-                           u32 slots, u32 nwords, int lg, u32 *__restrict__ nnz_row) {
+// 4a. warp per row (8 rows in flight per CTA), 256-slot key table per warp: rows with P <= 128
+#define B200_WARP_SLOTS 256
+__global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
+                                                  int nbins, int lg, u32 *__restrict__ nnz_row) {
+    __shared__ u32 s_keys[8][B200_WARP_SLOTS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 *keys = s_keys[wid];
+    u32 count = 0;
+    for (int b = 0; b < nbins; b++) count += ctrl->sym_bin_count[first_bin + b];
+    const u32 off = bin_offset(ctrl->sym_bin_count, first_bin);
+    const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
+    const int shift = 32 - 8;
+    for (u32 r = blockIdx.x * 8 + wid; r < count; r += gridDim.x * 8) {
+        const u32 row = bin_rows[off + r];
+#pragma unroll
+        for (int i = 0; i < B200_WARP_SLOTS / 32; i++) keys[i * 32 + lane] = B200_EMPTY_KEY;
+        __syncwarp();
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        u32 local = 0;
+        walk_products<int>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [](u32) { return 0; },
+                           [&](int, u32 jb) {
+                               bool fresh;
+                               table_insert(keys, B200_WARP_SLOTS - 1, shift, a.colB[jb], fresh);
+                               local += fresh;
+                           });
+        local = warp_sum_u32(local);
+        if (lane == 0) nnz_row[row] = local;
+        __syncwarp();
+    }
+}
+
+// 4b. CTA per row: key table, or a column bitmap when the whole column space fits shared memory
+template <bool BITMAP>
+__global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
+                                                  u32 nwords, int lg, u32 *__restrict__ nnz_row) {
     extern __shared__ u32 smem[];
     __shared__ u32 s_count;
     const u32 count = ctrl->sym_bin_count[bin];
     const u32 off = bin_offset(ctrl->sym_bin_count, bin);
-    const int nt = blockDim.x, tid = threadIdx.x;
-    const int G = 1 << lg, sub = tid & (G - 1);
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const u32 tabn = BITMAP ? nwords : slots;
     const int shift = 32 - (31 - __clz(slots));
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
@@ -251,32 +375,22 @@ __global__ void __launch_bounds__(1024) k_sym_hash(CsrView<VT> A, CsrView<VT> B,
         for (u32 t = tid; t < tabn; t += nt) smem[t] = BITMAP ? 0u : B200_EMPTY_KEY;
         if (tid == 0) s_count = 0;
         __syncthreads();
-        const u64 s = A.rp[row], e = A.rp[row + 1];
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
         u32 local = 0;
-        for (u64 ia = s + (tid >> lg); ia < e; ia += (nt >> lg)) {
-            const u32 k = A.col[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + sub; jb < be; jb += G) {
-                const u32 c = B.col[jb];
-                if (BITMAP) {
-                    const u32 bit = 1u << (c & 31);
-                    const u32 old = atomicOr(&smem[c >> 5], bit);
-                    local += !(old & bit);
-                } else {
-                    u32 h = b200_hash(c, shift);
-                    while (true) {
-                        u32 cur = ld_volatile_u32(&smem[h]);
-                        if (cur == c) break;
-                        if (cur == B200_EMPTY_KEY) {
-                            cur = atomicCAS(&smem[h], B200_EMPTY_KEY, c);
-                            if (cur == B200_EMPTY_KEY) { local++; break; }
-                            if (cur == c) break;
-                        }
-                        h = (h + 1) & (slots - 1);
-                    }
-                }
-            }
-        }
+        walk_products<int>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [](u32) { return 0; },
+                           [&](int, u32 jb) {
+                               const u32 c = a.colB[jb];
+                               if (BITMAP) {
+                                   const u32 bit = 1u << (c & 31);
+                                   const u32 old = atomicOr(&smem[c >> 5], bit);
+                                   local += !(old & bit);
+                               } else {
+                                   bool fresh;
+                                   table_insert(smem, slots - 1, shift, c, fresh);
+                                   local += fresh;
+                               }
+                           });
         local = warp_sum_u32(local);
         if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
         __syncthreads();
@@ -286,45 +400,8 @@ __global__ void __launch_bounds__(1024) k_sym_hash(CsrView<VT> A, CsrView<VT> B,
 }
 
 // =======================================================================================
-// 4. hash rows -- numeric
+// 5. numeric
 // =======================================================================================
-// MODE 0: 32-bit accumulators (host proved max_row_products*max(A)*max(B) < 2^32)
-// MODE 1: 64-bit accumulators, plain adds (u64: proved < 2^64; u32: products clamped to 2^32-1,
-//         sums of < 2^32 such terms cannot wrap 64 bits, clamp on emit)
-// MODE 2: u64 saturating multiply + CAS-loop saturating add
-template <int MODE> struct AccOf { typedef u64 type; };
-template <> struct AccOf<0> { typedef u32 type; };
-
-template <typename VT, int MODE>
-__device__ __forceinline__ typename AccOf<MODE>::type make_product(VT a, VT b) {
-    if (MODE == 0) return (u32)a * (u32)b;
-    if (MODE == 1) {
-        if (sizeof(VT) == 4) { u64 p = (u64)a * (u64)b; return p > 0xFFFFFFFFull ? 0xFFFFFFFFull : p; }
-        return (u64)a * (u64)b;
-    }
-    return sat_mul((u64)a, (u64)b);
-}
-template <int MODE>
-__device__ __forceinline__ void acc_add(typename AccOf<MODE>::type *p, typename AccOf<MODE>::type x) {
-    if (MODE == 0) atomicAdd((u32 *)p, (u32)x);
-    else if (MODE == 1) atomicAdd((ull *)p, (ull)x);
-    else {
-        ull *q = (ull *)p;
-        ull old = *reinterpret_cast<volatile ull *>(q), assumed;
-        do {
-            assumed = old;
-            ull s = assumed + (ull)x; if (s < assumed) s = ~0ull;
-            if (s == assumed) break;
-            old = atomicCAS(q, assumed, s);
-        } while (old != assumed);
-    }
-}
-template <typename VT, int MODE>
-__device__ __forceinline__ VT emit_val(typename AccOf<MODE>::type v) {
-    if (sizeof(VT) == 4 && MODE == 1) return (VT)(v > 0xFFFFFFFFull ? 0xFFFFFFFFull : v);
-    return (VT)v;
-}
-
 // block-wide exclusive scan of one u32 per thread; returns exclusive prefix, total in `total`
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 &total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -347,121 +424,140 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 
     return r;
 }
 
-// in-shared-memory bitonic sort of n (power of two) key/value pairs
-template <typename AccT>
-__device__ __forceinline__ void smem_bitonic(u32 *keys, AccT *vals, u32 n) {
+// bitonic sort of n (power of two) key/accumulator pairs in shared memory.  WARP: one warp owns the
+// arrays (__syncwarp between stages); otherwise the whole CTA does.
+template <int MODE, bool WARP>
+__device__ __forceinline__ void smem_bitonic(u32 *keys, Acc<MODE> &acc, u32 n) {
+    const u32 me = WARP ? (threadIdx.x & 31) : threadIdx.x;
+    const u32 stride = WARP ? 32 : blockDim.x;
     for (u32 k = 2; k <= n; k <<= 1) {
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+            for (u32 t = me; t < (n >> 1); t += stride) {
                 const u32 i = 2 * t - (t & (j - 1));
                 const u32 l = i + j;
                 const bool up = ((i & k) == 0);
-                const u32 a = keys[i], b = keys[l];
-                if ((a > b) == up) {
-                    keys[i] = b; keys[l] = a;
-                    const AccT va = vals[i]; vals[i] = vals[l]; vals[l] = va;
+                const u32 x = keys[i], y = keys[l];
+                if ((x > y) == up) {
+                    keys[i] = y; keys[l] = x;
+                    const u64 vx = acc.get(i), vy = acc.get(l);
+                    acc.set(i, vy); acc.set(l, vx);
                 }
             }
-            __syncthreads();
+            if (WARP) __syncwarp(); else __syncthreads();
         }
     }
 }
 
-template <typename VT, int MODE, bool BITMAP>
-__global__ void __launch_bounds__(1024) k_num_hash(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin,
-                           u32 slots, u32 nwords, int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
-                           VT *__restrict__ valC) {
-    typedef typename AccOf<MODE>::type AccT;
+// 5a. warp per row (8 rows in flight per CTA): hash accumulate, compact, sort, stream out. nnz <= 128.
+template <typename VT, int MODE>
+__global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
+                                                  int nbins, int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
+                                                  VT *__restrict__ valC) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = Acc<MODE>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4;
+    unsigned char *base = smem_raw + wid * per_warp;
+    Acc<MODE> acc; acc.bind(base, B200_WARP_SLOTS);
+    u32 *keys = reinterpret_cast<u32 *>(base + Acc<MODE>::bytes(B200_WARP_SLOTS));
+    u32 count = 0;
+    for (int b = 0; b < nbins; b++) count += ctrl->num_bin_count[first_bin + b];
+    const u32 off = bin_offset(ctrl->num_bin_count, first_bin);
+    const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
+    const int shift = 32 - 8;
+    constexpr int PER = B200_WARP_SLOTS / 32;
+    u64 vmax = 0;
+    for (u32 r = blockIdx.x * 8 + wid; r < count; r += gridDim.x * 8) {
+        const u32 row = bin_rows[off + r];
+#pragma unroll
+        for (int i = 0; i < PER; i++) { keys[i * 32 + lane] = B200_EMPTY_KEY; acc.clear(i * 32 + lane); }
+        __syncwarp();
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const VT *Av = a.valA + s;
+        walk_products<VT>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [&](u32 t) { return Av[t]; },
+                          [&](VT av, u32 jb) {
+                              bool fresh;
+                              const u32 h = table_insert(keys, B200_WARP_SLOTS - 1, shift, a.colB[jb], fresh);
+                              acc.add(h, av, a.valB[jb]);
+                          });
+        __syncwarp();
+        // compact through registers (slot i*32+lane: conflict-free), then sort the front of the arrays
+        u32 rk[PER]; u64 rv[PER]; u32 mine = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) { rk[i] = keys[i * 32 + lane]; rv[i] = acc.get(i * 32 + lane); mine += rk[i] != B200_EMPTY_KEY; }
+        u32 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        u32 pos = incl - mine;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PER; i++) if (rk[i] != B200_EMPTY_KEY) { keys[pos] = rk[i]; acc.set(pos, rv[i]); pos++; }
+        u32 n2 = 1; while (n2 < total) n2 <<= 1;
+        __syncwarp();
+        for (u32 t = total + lane; t < n2; t += 32) keys[t] = B200_EMPTY_KEY;
+        __syncwarp();
+        smem_bitonic<MODE, true>(keys, acc, n2);
+        const u64 obase = rpC[row];
+        for (u32 t = lane; t < total; t += 32) {
+            const VT v = emit_val<VT>(acc.get(t));
+            colC[obase + t] = keys[t]; valC[obase + t] = v;
+            vmax = vmax > (u64)v ? vmax : (u64)v;
+        }
+        __syncwarp();
+    }
+    vmax = warp_max_u64(vmax);
+    if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
+}
+
+// 5b. CTA per row, hash + sort emission (any column space).  slots = 2 * bin capacity.
+template <typename VT, int MODE>
+__global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
+                                                  int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
-    AccT *vals = reinterpret_cast<AccT *>(smem_raw);                       // slots
-    u32 *keys = reinterpret_cast<u32 *>(vals + slots);                     // slots
-    u32 *bm = keys + slots;                                                // nwords   (BITMAP)
-    u32 *wpre = bm + nwords;                                               // nwords   (BITMAP)
+    Acc<MODE> acc; acc.bind(smem_raw, slots);
+    u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
     const u32 count = ctrl->num_bin_count[bin];
     const u32 off = bin_offset(ctrl->num_bin_count, bin);
-    const int nt = blockDim.x, tid = threadIdx.x;
-    const int G = 1 << lg, sub = tid & (G - 1);
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const int shift = 32 - (31 - __clz(slots));
+    const u32 per = slots / nt;                                             // <= 16 by the bin table
     u64 vmax = 0;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
-        for (u32 t = tid; t < slots; t += nt) { keys[t] = B200_EMPTY_KEY; vals[t] = 0; }
-        if (BITMAP) for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
+        for (u32 t = tid; t < slots; t += nt) { keys[t] = B200_EMPTY_KEY; acc.clear(t); }
         __syncthreads();
-        const u64 s = A.rp[row], e = A.rp[row + 1];
-        for (u64 ia = s + (tid >> lg); ia < e; ia += (nt >> lg)) {
-            const u32 k = A.col[ia];
-            const VT a = A.val[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + sub; jb < be; jb += G) {
-                const u32 c = B.col[jb];
-                const AccT x = make_product<VT, MODE>(a, B.val[jb]);
-                u32 h = b200_hash(c, shift);
-                while (true) {
-                    u32 cur = ld_volatile_u32(&keys[h]);
-                    if (cur == B200_EMPTY_KEY) {
-                        cur = atomicCAS(&keys[h], B200_EMPTY_KEY, c);
-                        if (cur == B200_EMPTY_KEY) {
-                            if (BITMAP) atomicOr(&bm[c >> 5], 1u << (c & 31));
-                            cur = c;
-                        }
-                    }
-                    if (cur == c) { acc_add<MODE>(&vals[h], x); break; }
-                    h = (h + 1) & (slots - 1);
-                }
-            }
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const VT *Av = a.valA + s;
+        walk_products<VT>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [&](u32 t) { return Av[t]; },
+                          [&](VT av, u32 jb) {
+                              bool fresh;
+                              const u32 h = table_insert(keys, slots - 1, shift, a.colB[jb], fresh);
+                              acc.add(h, av, a.valB[jb]);
+                          });
+        __syncthreads();
+        u32 rk[16]; u64 rv[16]; u32 mine = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < (int)per) { rk[i] = keys[i * nt + tid]; rv[i] = acc.get(i * nt + tid); mine += rk[i] != B200_EMPTY_KEY; }
         }
+        u32 total;
+        u32 pos = block_excl_scan(mine, s_warp, total);                  // its barriers order the reads above before the writes below
+#pragma unroll
+        for (int i = 0; i < 16; i++) if (i < (int)per && rk[i] != B200_EMPTY_KEY) { keys[pos] = rk[i]; acc.set(pos, rv[i]); pos++; }
+        u32 n2 = 1; while (n2 < total) n2 <<= 1;
         __syncthreads();
+        for (u32 t = total + tid; t < n2; t += nt) keys[t] = B200_EMPTY_KEY;
+        __syncthreads();
+        smem_bitonic<MODE, false>(keys, acc, n2);
         const u64 obase = rpC[row];
-        if (BITMAP) {
-            // rank of a column = number of set bits below it: prefix popcount over the bitmap words
-            u32 carry = 0;
-            for (u32 base = 0; base < nwords; base += nt) {
-                const u32 w = base + tid < nwords ? bm[base + tid] : 0u;
-                u32 total;
-                const u32 ex = block_excl_scan(__popc(w), s_warp, total);
-                if (base + tid < nwords) wpre[base + tid] = carry + ex;
-                carry += total;
-            }
-            __syncthreads();
-            for (u32 t = tid; t < slots; t += nt) {
-                const u32 c = keys[t];
-                if (c != B200_EMPTY_KEY) {
-                    const u32 w = bm[c >> 5];
-                    const u64 pos = obase + wpre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
-                    const VT v = emit_val<VT, MODE>(vals[t]);
-                    colC[pos] = c; valC[pos] = v;
-                    vmax = vmax > (u64)v ? vmax : (u64)v;
-                }
-            }
-        } else {
-            // compact the occupied slots to the front (through registers), sort by column, stream out
-            const u32 per = slots / nt;                                    // 4 .. 16
-            u32 rk[16]; AccT rv[16]; u32 mine = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (i < (int)per) {
-                    rk[i] = keys[tid * per + i]; rv[i] = vals[tid * per + i];
-                    mine += rk[i] != B200_EMPTY_KEY;
-                }
-            }
-            u32 total;
-            u32 pos = block_excl_scan(mine, s_warp, total);             // contains the barriers that protect the reads above
-            u32 n2 = 1; while (n2 < total) n2 <<= 1;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (i < (int)per && rk[i] != B200_EMPTY_KEY) { keys[pos] = rk[i]; vals[pos] = rv[i]; pos++; }
-            }
-            __syncthreads();
-            for (u32 t = total + tid; t < n2; t += nt) keys[t] = B200_EMPTY_KEY;
-            __syncthreads();
-            smem_bitonic<AccT>(keys, vals, n2);
-            for (u32 t = tid; t < total; t += nt) {
-                const VT v = emit_val<VT, MODE>(vals[t]);
-                colC[obase + t] = keys[t]; valC[obase + t] = v;
-                vmax = vmax > (u64)v ? vmax : (u64)v;
-            }
+        for (u32 t = tid; t < total; t += nt) {
+            const VT v = emit_val<VT>(acc.get(t));
+            colC[obase + t] = keys[t]; valC[obase + t] = v;
+            vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         __syncthreads();
     }
@@ -469,32 +565,24 @@ __global__ void __launch_bounds__(1024) k_num_hash(CsrView<VT> A, CsrView<VT> B,
     if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
 }
 
-// ---------------------------------------------------------------------------------------
-// 4b. numeric for rows whose whole column space fits a shared-memory bitmap ("rank" kernel).
-// No hash table: walk 1 sets one bit per product column; a prefix popcount over the bitmap
-// words gives every present column its rank (= its position in the sorted output row); walk 2
-// adds each product into acc[rank]; columns are emitted by enumerating the set bits, values by
-// streaming acc[0..nnz).  Shared memory: nwords*6 + cap*4 (MODE 0) bytes -> high occupancy.
-// MODE 1 keeps a 64-bit sum as two u32 words (lo/hi) and propagates the carry with the value
-// returned by the atomic on lo: shared-memory u64 atomicAdd is a CAS spin loop on sm_100
-// (ATOMS.CAST.SPIN.64, measured 7x slower than ATOMS.ADD).
-// ---------------------------------------------------------------------------------------
+// 5c. CTA per row, rank emission: the whole column space fits a shared-memory bitmap.
+// No hash table: walk 1 sets one bit per product column; a prefix popcount over the bitmap words
+// gives every present column its rank (= its position in the sorted output row); walk 2 adds each
+// product into acc[rank]; columns are emitted by enumerating the set bits, values by streaming
+// acc[0..nnz).  Shared memory: nwords*6 + cap*(4|8) bytes -> high occupancy.
 template <typename VT, int MODE>
-__global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
-                                                   int bin, u32 cap, u32 nwords, int lg, const u64 *__restrict__ rpC,
-                                                   u32 *__restrict__ colC, VT *__restrict__ valC) {
+__global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 cap,
+                                                   u32 nwords, int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
+                                                   VT *__restrict__ valC) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
-    // layout: [acc64 cap (MODE 2)] | lo cap | [hi cap (MODE 1)] | bm nwords | wpre nwords (u16)
-    ull *acc64 = reinterpret_cast<ull *>(smem_raw);
-    u32 *lo = reinterpret_cast<u32 *>(smem_raw + (MODE == 2 ? (size_t)cap * 8 : 0));
-    u32 *hi = lo + (MODE == 2 ? 0 : cap);
-    u32 *bm = hi + (MODE == 1 ? cap : 0);
+    Acc<MODE> acc; acc.bind(smem_raw, cap);
+    u32 *bm = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(cap));
     unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
     const u32 count = ctrl->num_bin_count[bin];
     const u32 off = bin_offset(ctrl->num_bin_count, bin);
-    const int nt = blockDim.x, tid = threadIdx.x;
-    const int G = 1 << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const u32 wpt = (nwords + nt - 1) / nt;                               // bitmap words per thread
     u64 vmax = 0;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
@@ -502,21 +590,15 @@ __global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B,
         const u64 obase = rpC[row];
         const u32 nnz = (u32)(rpC[row + 1] - obase);
         for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
-        for (u32 t = tid; t < nnz; t += nt) {
-            if (MODE == 2) acc64[t] = 0; else lo[t] = 0;
-            if (MODE == 1) hi[t] = 0;
-        }
+        for (u32 t = tid; t < nnz; t += nt) acc.clear(t);
         __syncthreads();
-        const u64 s = A.rp[row], e = A.rp[row + 1];
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const u32 *Ac = a.colA + s;
+        const VT *Av = a.valA + s;
         // ---- walk 1: column bitmap
-        for (u64 ia = s + grp; ia < e; ia += ngrp) {
-            const u32 k = A.col[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + sub; jb < be; jb += G) {
-                const u32 c = B.col[jb];
-                atomicOr(&bm[c >> 5], 1u << (c & 31));
-            }
-        }
+        walk_products<int>(Ac, lenA, a.bdesc, grp, ngrp, sub, G, [](u32) { return 0; },
+                           [&](int, u32 jb) { const u32 c = a.colB[jb]; atomicOr(&bm[c >> 5], 1u << (c & 31)); });
         __syncthreads();
         // ---- ranks: exclusive prefix popcount over the words (each thread owns wpt consecutive words)
         {
@@ -529,8 +611,7 @@ __global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B,
                 if (w0 + i < nwords) {
                     const u32 w = bm[w0 + i];
                     wpre[w0 + i] = (unsigned short)run;
-                    // columns come out in ascending order: emit them here
-                    u32 bits = w;
+                    u32 bits = w;                                          // columns come out in ascending order: emit them here
                     u64 p = obase + run;
                     while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; colC[p++] = ((w0 + i) << 5) + b; }
                     run += __popc(w);
@@ -539,38 +620,18 @@ __global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B,
         }
         __syncthreads();
         // ---- walk 2: accumulate into acc[rank(col)]
-        for (u64 ia = s + grp; ia < e; ia += ngrp) {
-            const u32 k = A.col[ia];
-            const VT a = A.val[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + sub; jb < be; jb += G) {
-                const u32 c = B.col[jb];
-                const u32 w = bm[c >> 5];
-                const u32 pos = (u32)wpre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
-                if (MODE == 0) {
-                    atomicAdd(&lo[pos], (u32)a * (u32)B.val[jb]);
-                } else if (MODE == 1) {
-                    u64 x;
-                    if (sizeof(VT) == 4) { x = (u64)a * (u64)B.val[jb]; x = x > 0xFFFFFFFFull ? 0xFFFFFFFFull : x; }
-                    else x = (u64)a * (u64)B.val[jb];
-                    const u32 xlo = (u32)x, xhi = (u32)(x >> 32);
-                    const u32 old = atomicAdd(&lo[pos], xlo);
-                    const u32 up = xhi + ((u32)(old + xlo) < xlo ? 1u : 0u);
-                    if (up) atomicAdd(&hi[pos], up);
-                } else {
-                    acc_add<2>((u64 *)&acc64[pos], sat_mul((u64)a, (u64)B.val[jb]));
-                }
-            }
-        }
+        walk_products<VT>(Ac, lenA, a.bdesc, grp, ngrp, sub, G, [&](u32 t) { return Av[t]; },
+                          [&](VT av, u32 jb) {
+                              const u32 c = a.colB[jb];
+                              const u32 w = bm[c >> 5];
+                              const u32 pos = (u32)wpre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+                              acc.add(pos, av, a.valB[jb]);
+                          });
         __syncthreads();
         for (u32 t = tid; t < nnz; t += nt) {
-            u64 v;
-            if (MODE == 0) v = lo[t];
-            else if (MODE == 1) v = ((u64)hi[t] << 32) | lo[t];
-            else v = acc64[t];
-            if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
-            valC[obase + t] = (VT)v;
-            vmax = vmax > v ? vmax : v;
+            const VT v = emit_val<VT>(acc.get(t));
+            valC[obase + t] = v;
+            vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         __syncthreads();
     }
@@ -579,34 +640,30 @@ __global__ void __launch_bounds__(1024) k_num_rank(CsrView<VT> A, CsrView<VT> B,
 }
 
 // =======================================================================================
-// 5. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
+// 6. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
 // =======================================================================================
-template <typename VT>
-__global__ void __launch_bounds__(1024) k_sym_heavy(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows,
-                                                    B200Ctrl *ctrl, u32 nwords, u32 *__restrict__ scratch_bm,
-                                                    u32 *__restrict__ nnz_row) {
+__global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 nwords,
+                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row) {
     __shared__ u32 s_count;
     const u32 count = ctrl->sym_bin_count[B200_BIN_HEAVY];
     const u32 off = bin_offset(ctrl->sym_bin_count, B200_BIN_HEAVY);
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
-    const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, nwarp = nt >> 5, w = tid >> 5;
+    const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
         for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
         if (tid == 0) s_count = 0;
         __syncthreads();
-        const u64 s = A.rp[row], e = A.rp[row + 1];
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
         u32 local = 0;
-        for (u64 ia = s + w; ia < e; ia += nwarp) {                        // a warp per A entry
-            const u32 k = A.col[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + lane; jb < be; jb += 32) {
-                const u32 c = B.col[jb];
-                const u32 bit = 1u << (c & 31);
-                const u32 old = atomicOr(&bm[c >> 5], bit);
-                local += !(old & bit);
-            }
-        }
+        walk_products<int>(a.colA + s, lenA, a.bdesc, tid >> 5, nt >> 5, lane, 32, [](u32) { return 0; },
+                           [&](int, u32 jb) {
+                               const u32 c = a.colB[jb];
+                               const u32 bit = 1u << (c & 31);
+                               const u32 old = atomicOr(&bm[c >> 5], bit);
+                               local += !(old & bit);
+                           });
         local = warp_sum_u32(local);
         if (lane == 0 && local) atomicAdd(&s_count, local);
         __syncthreads();
@@ -615,9 +672,9 @@ __global__ void __launch_bounds__(1024) k_sym_heavy(CsrView<VT> A, CsrView<VT> B
     }
 }
 
-template <typename VT, int MODE>
-__global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B, const u32 *__restrict__ bin_rows,
-                                                    B200Ctrl *ctrl, const u32 *__restrict__ nnz_row, u32 nwords, u64 max_slots,
+template <typename VT, int MODE>   // MODE 1: plain 64-bit global atomics (u32 products clamped); MODE 2: saturating CAS
+__global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
+                                                    const u32 *__restrict__ nnz_row, u32 nwords, u64 max_slots,
                                                     u32 *__restrict__ scratch_bm, u32 *__restrict__ scratch_pre,
                                                     u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals,
                                                     const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
@@ -628,7 +685,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B
     u32 *wpre = scratch_pre + (u64)blockIdx.x * nwords;
     u32 *keys = scratch_keys + (u64)blockIdx.x * max_slots;
     ull *vals = (ull *)(scratch_vals + (u64)blockIdx.x * max_slots);
-    const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, nwarp = nt >> 5, w = tid >> 5;
+    const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     u64 vmax = 0;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
@@ -638,38 +695,43 @@ __global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B
         for (u64 t = tid; t < slots; t += nt) { keys[t] = B200_EMPTY_KEY; vals[t] = 0; }
         for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
         __syncthreads();
-        const u64 s = A.rp[row], e = A.rp[row + 1];
-        for (u64 ia = s + w; ia < e; ia += nwarp) {
-            const u32 k = A.col[ia];
-            const VT a = A.val[ia];
-            const u64 bs = B.rp[k], be = B.rp[k + 1];
-            for (u64 jb = bs + lane; jb < be; jb += 32) {
-                const u32 c = B.col[jb];
-                ull x;
-                if (MODE == 2) x = sat_mul((u64)a, (u64)B.val[jb]);
-                else if (sizeof(VT) == 4) { u64 p = (u64)a * (u64)B.val[jb]; x = p > 0xFFFFFFFFull ? 0xFFFFFFFFull : p; }
-                else x = (u64)a * (u64)B.val[jb];
-                u64 h = ((u64)c * 0x9E3779B97F4A7C15ull) >> shift;
-                while (true) {
-                    u32 cur = ld_volatile_u32(&keys[h]);
-                    if (cur == B200_EMPTY_KEY) {
-                        cur = atomicCAS(&keys[h], B200_EMPTY_KEY, c);
-                        if (cur == B200_EMPTY_KEY) { atomicOr(&bm[c >> 5], 1u << (c & 31)); cur = c; }
-                    }
-                    if (cur == c) {
-                        if (MODE == 2) acc_add<2>((u64 *)&vals[h], (u64)x);
-                        else atomicAdd(&vals[h], x);
-                        break;
-                    }
-                    h = (h + 1) & (slots - 1);
-                }
-            }
-        }
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const VT *Av = a.valA + s;
+        walk_products<VT>(a.colA + s, lenA, a.bdesc, tid >> 5, nt >> 5, lane, 32, [&](u32 t) { return Av[t]; },
+                          [&](VT av, u32 jb) {
+                              const u32 c = a.colB[jb];
+                              ull x;
+                              if (MODE == 2) x = sat_mul((u64)av, (u64)a.valB[jb]);
+                              else if (sizeof(VT) == 4) { u64 p = (u64)av * (u64)a.valB[jb]; x = p > 0xFFFFFFFFull ? 0xFFFFFFFFull : p; }
+                              else x = (u64)av * (u64)a.valB[jb];
+                              u64 h = ((u64)c * 0x9E3779B97F4A7C15ull) >> shift;
+                              while (true) {
+                                  u32 cur = ld_volatile_u32(&keys[h]);
+                                  if (cur == B200_EMPTY_KEY) {
+                                      cur = atomicCAS(&keys[h], B200_EMPTY_KEY, c);
+                                      if (cur == B200_EMPTY_KEY) { atomicOr(&bm[c >> 5], 1u << (c & 31)); cur = c; }
+                                  }
+                                  if (cur == c) {
+                                      if (MODE == 2) {
+                                          ull old = ld_volatile_u64((const u64 *)&vals[h]), assumed;
+                                          do {
+                                              assumed = old;
+                                              ull sum = assumed + x; if (sum < assumed) sum = ~0ull;
+                                              if (sum == assumed) break;
+                                              old = atomicCAS(&vals[h], assumed, sum);
+                                          } while (old != assumed);
+                                      } else atomicAdd(&vals[h], x);
+                                      break;
+                                  }
+                                  h = (h + 1) & (slots - 1);
+                              }
+                          });
         __threadfence_block();
         __syncthreads();
         u32 carry = 0;
         for (u32 base = 0; base < nwords; base += nt) {
-            const u32 wd = base + tid < nwords ? bm[base + tid] : 0u;
+            const u32 wd = base + tid < nwords ? __ldcg(&bm[base + tid]) : 0u;
             u32 total;
             const u32 ex = block_excl_scan(__popc(wd), s_warp, total);
             if (base + tid < nwords) wpre[base + tid] = carry + ex;
@@ -678,11 +740,11 @@ __global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B
         __syncthreads();
         const u64 obase = rpC[row];
         for (u64 t = tid; t < slots; t += nt) {
-            const u32 c = keys[t];
+            const u32 c = __ldcg(&keys[t]);
             if (c != B200_EMPTY_KEY) {
-                const u32 wd = bm[c >> 5];
-                const u64 pos = obase + wpre[c >> 5] + __popc(wd & ((1u << (c & 31)) - 1u));
-                ull v = vals[t];
+                const u32 wd = __ldcg(&bm[c >> 5]);
+                const u64 pos = obase + __ldcg(&wpre[c >> 5]) + __popc(wd & ((1u << (c & 31)) - 1u));
+                ull v = __ldcg(&vals[t]);
                 if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
                 colC[pos] = c; valC[pos] = (VT)v;
                 vmax = vmax > v ? vmax : v;
@@ -695,7 +757,8 @@ __global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B
 }
 
 // =======================================================================================
-// 6. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64)
+// 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64),
+//    fused with the numeric-bin histogram
 // =======================================================================================
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 8
@@ -704,13 +767,17 @@ __global__ void __launch_bounds__(1024) k_num_heavy(CsrView<VT> A, CsrView<VT> B
 #define SCAN_FLAG_PRE (2ull << 62)
 #define SCAN_VAL_MASK ((1ull << 62) - 1)
 
+template <bool CLASSIFY>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
-                                                              u64 *tile_status, B200Ctrl *ctrl) {
+                                                              u64 *tile_status, B200Ctrl *ctrl, const u64 *__restrict__ rpA,
+                                                              const u64 *__restrict__ prod) {
     __shared__ u32 s_tile;
     __shared__ u64 s_wsum[SCAN_THREADS / 32];
     __shared__ u64 s_excl;
+    __shared__ u32 s_hist[B200_NBINS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket, 1u);               // tiles start in ticket order
+    if (CLASSIFY && tid < B200_NBINS) s_hist[tid] = 0;
     __syncthreads();
     const u32 tile = s_tile;
     const u64 base = (u64)tile * SCAN_TILE + (u64)tid * SCAN_ITEMS;
@@ -719,6 +786,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
     for (int i = 0; i < SCAN_ITEMS; i++) {
         item[i] = base + i < rows ? nnz_row[base + i] : 0u;
         tsum += item[i]; tmaxv = item[i] > tmaxv ? item[i] : tmaxv;
+    }
+    if (CLASSIFY) {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < rows && item[i]) {
+                const int b = num_bin_of(item[i], prod[base + i], rpA[base + i + 1] - rpA[base + i]);
+                atomicAdd(&s_hist[b], 1u);
+            }
+        }
     }
     u64 incl = tsum;
 #pragma unroll
@@ -729,7 +805,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
 #pragma unroll
     for (int i = 0; i < SCAN_THREADS / 32; i++) { if (i < w) wbase += s_wsum[i]; agg += s_wsum[i]; }
     const u64 texcl = wbase + incl - tsum;                                   // exclusive within the tile
-    // publish, then look back
+    // publish the tile aggregate, then look back over the predecessors
     if (w == 0) {
         if (lane == 0) {
             const u64 st = (tile == 0 ? SCAN_FLAG_PRE : SCAN_FLAG_AGG) | agg;
@@ -746,7 +822,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
                 } while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0));
                 const u32 pre_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
                 const int first = pre_mask ? __ffs(pre_mask) - 1 : 32;      // nearest tile that knows its full prefix
-                u64 contrib = lane <= first ? (st & SCAN_VAL_MASK) : 0ull;
+                const u64 contrib = lane <= first ? (st & SCAN_VAL_MASK) : 0ull;
                 excl += warp_sum_u64(contrib);
                 if (pre_mask) break;
                 look -= 32;
@@ -764,14 +840,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
         if (base + i < rows) rpC[base + i + 1] = run;
     }
     if (base < rows && base + SCAN_ITEMS >= rows) ctrl->total_nnz = run;   // the thread holding the last row
-    tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, 16)); tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, 8));
-    tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, 4)); tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, 2));
-    tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, 1));
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
     if (lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
+    if (CLASSIFY && tid < B200_NBINS && s_hist[tid]) atomicAdd(&ctrl->num_bin_count[tid], s_hist[tid]);
 }
 
 // =======================================================================================
-// 7. small utilities: value max / zero check on upload, index narrowing, add, pattern compare
+// 8. small utilities: value max / zero check on upload, index narrowing, add, pattern compare
 // =======================================================================================
 template <typename VT>
 __global__ void __launch_bounds__(256) k_value_stats(u64 nnz, const VT *__restrict__ val, const u32 *__restrict__ col, u64 cols,
