@@ -46,6 +46,8 @@ struct b200_csr {
     ull *d_maxval;          // device scalar: largest stored value
     u64 max_row_len;        // host-known upper bound of the longest row
     uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
+    uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
+    u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
     b200_ctx *ctx;
 };
 
@@ -55,7 +57,7 @@ struct b200_ctx {
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
     // per-row scratch, grown on demand
-    u64 cap_rows; u64 *d_prod; u32 *d_nnz_row; u32 *d_bin_rows; u64 *d_tile_status; u64 cap_tiles;
+    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; u64 *d_tile_status; u64 cap_tiles;
     // heavy-row scratch
     void *d_heavy; size_t cap_heavy;
     u32 *d_flag;            // small device flag word (+ pinned mirror)
@@ -65,6 +67,8 @@ struct b200_ctx {
     bool timing;
     u64 launches;
 };
+
+static int host_maxval(b200_ctx *ctx, const b200_csr *m);
 
 template <typename VT>
 static CsrView<VT> view(const b200_csr *m) {
@@ -86,10 +90,11 @@ static void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream)
 
 static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     if (rows > ctx->cap_rows) {
-        dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows);
-        ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->cap_rows = 0;
+        dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tmp_ptr);
+        ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->d_tmp_ptr = nullptr; ctx->cap_rows = 0;
         u64 cap = rows + rows / 8 + 1024;
         TRY(dmalloc(ctx, (void **)&ctx->d_prod, cap * 8));
+        TRY(dmalloc(ctx, (void **)&ctx->d_tmp_ptr, (cap + 1) * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_nnz_row, cap * 4));
         TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4));
         ctx->cap_rows = cap;
@@ -97,7 +102,7 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1;
     if (tiles > ctx->cap_tiles) {
         dfree(ctx, ctx->d_tile_status); ctx->d_tile_status = nullptr; ctx->cap_tiles = 0;
-        TRY(dmalloc(ctx, (void **)&ctx->d_tile_status, (tiles + 64) * 8));
+        TRY(dmalloc(ctx, (void **)&ctx->d_tile_status, 2 * (tiles + 64) * 8));
         ctx->cap_tiles = tiles + 64;
     }
     return B200_OK;
@@ -124,6 +129,8 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_num_cta<VT, 0>, optin); allow_big_smem(k_num_cta<VT, 1>, optin);
     allow_big_smem(k_num_rank<VT, 0>, optin); allow_big_smem(k_num_rank<VT, 1>, optin);
     allow_big_smem(k_num_warp<VT, 0>, optin); allow_big_smem(k_num_warp<VT, 1>, optin);
+    allow_big_smem(k_num_rank_pack<VT, 0, false>, optin); allow_big_smem(k_num_rank_pack<VT, 0, true>, optin);
+    allow_big_smem(k_num_rank_pack<VT, 1, false>, optin); allow_big_smem(k_num_rank_pack<VT, 1, true>, optin);
 }
 
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
@@ -164,6 +171,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     allow_big_smem(k_sym_cta<false>, ctx->smem_optin); allow_big_smem(k_sym_cta<true>, ctx->smem_optin);
     allow_big_smem(k_num_cta<u64, 2>, ctx->smem_optin); allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
+    allow_big_smem(k_sym_pack<false>, ctx->smem_optin); allow_big_smem(k_sym_pack<true>, ctx->smem_optin);
+    allow_big_smem(k_num_rank_pack<u64, 2, false>, ctx->smem_optin); allow_big_smem(k_num_rank_pack<u64, 2, true>, ctx->smem_optin);
     cudaGetLastError();
     *out = ctx;
     return B200_OK;
@@ -173,7 +182,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return B200_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_ctrl); cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
@@ -217,7 +226,7 @@ static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, b
 extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc);
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;
 }
@@ -332,9 +341,8 @@ extern "C" int b200_csr_device_ptrs(const b200_csr *m, void **d_row_ptr, void **
 extern "C" int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *out) {
     if (!ctx || !m || !out) return set_err(B200_ERR_BADARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 2, m->d_maxval, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    memcpy(out, ctx->h_flag + 2, 8);
+    TRY(host_maxval(ctx, m));
+    *out = m->h_maxval;
     return B200_OK;
 }
 
@@ -399,12 +407,38 @@ static int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
     return B200_OK;
 }
 
-static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B) {
+// sector-packed records for low-degree right operands (mean row length <= 4)
+static bool want_pack(const b200_csr *B) {
+    const int forced = env_int("B200_PACK", -1);
+    if (forced >= 0) return forced != 0;
+    return B->rows && (double)B->nnz / (double)B->rows <= 4.0;
+}
+static int ensure_pack(b200_ctx *ctx, const b200_csr *B) {
+    if (B->d_pack) return B200_OK;
+    b200_csr *Bm = const_cast<b200_csr *>(B);
+    TRY(dmalloc(ctx, (void **)&Bm->d_pack, (B->rows + 1) * 2 * sizeof(uint4)));
+    k_build_pack<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, B->d_col, Bm->d_pack);
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
+
+// host copy of a handle's largest value (read back once; products get it from their own final read-back)
+static int host_maxval(b200_ctx *ctx, const b200_csr *m) {
+    if (m->h_maxval_known) return B200_OK;
+    b200_csr *mm = const_cast<b200_csr *>(m);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 2, m->d_maxval, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(&mm->h_maxval, ctx->h_flag + 2, 8);
+    mm->h_maxval_known = true;
+    return B200_OK;
+}
+
+static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, bool onepass) {
     const double avg = A->rows ? (double)A->nnz / (double)A->rows : 0.0;
     const u64 rows = A->rows;
 #define RP_LAUNCH(G)                                                                                              \
-    k_row_products<G><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, \
-                                                                                    ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl)
+    do { if (onepass) k_row_products<G, true><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl); \
+         else k_row_products<G, false><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl); } while (0)
     if (avg <= 2.0) RP_LAUNCH(1);
     else if (avg <= 6.0) RP_LAUNCH(4);
     else if (avg <= 24.0) RP_LAUNCH(8);
@@ -434,6 +468,139 @@ struct Fan {
     }
 };
 
+static int ctas_per_sm(const b200_ctx *ctx, int threads, size_t smem) {
+    return std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
+}
+
+// accumulator width from a proof that no row sum can overflow: rows_bound * max(A) * max(B)
+template <typename VT>
+static int pick_mode(u64 max_row_products, u64 maxA, u64 maxB) {
+    unsigned __int128 bound = (unsigned __int128)max_row_products * maxA;
+    bool over64 = (bound >> 64) != 0;
+    if (!over64) { bound *= maxB; over64 = (bound >> 64) != 0; }
+    int mode;
+    if (!over64 && (u64)bound < (1ull << 32)) mode = 0;
+    else if (sizeof(VT) == 4) mode = 1;                                   // clamped 32-bit products, < 2^32 of them per row
+    else mode = over64 ? 2 : 1;
+    const int forced = env_int("B200_FORCE_MODE", -1);                    // testing hook: a wider mode is always valid
+    if (forced > mode && forced <= (sizeof(VT) == 8 ? 2 : 1)) mode = forced;
+    return mode;
+}
+
+// Launch the numeric kernels of every non-empty bin.  `cnt` = host-known bin sizes (two-pass) or null
+// (one-pass: sizes live on the device only; bins that no row can reach are skipped via p_bound).
+template <typename VT>
+static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const u32 *cnt, u64 rows, u64 p_bound, u64 heavy_cap,
+                          int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan) {
+    const u32 nwords = (u32)((B->cols + 31) / 32);
+    const size_t smem_max = ctx->smem_optin - 1024;
+    NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
+    NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
+    OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt};
+    const size_t accb = mode == 0 ? 4 : 8;
+    auto bin_size = [&](int bin) -> u64 { return cnt ? cnt[bin] : rows; };
+    auto reachable = [&](int hb) { return cnt ? cnt[B200_BIN_HASH0 + hb] != 0 : (hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1)); };
+    if (bin_size(B200_BIN_TINY)) {
+        const int g = (int)std::min<u64>((bin_size(B200_BIN_TINY) + 7) / 8, (u64)ctx->num_sms * 32);
+        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o);
+        LAUNCH_CHECK(ctx);
+    }
+    if (reachable(0) || reachable(1)) {
+        const u64 n01 = cnt ? (u64)cnt[B200_BIN_HASH0] + cnt[B200_BIN_HASH0 + 1] : rows;
+        const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4);
+        const int g = (int)std::min<u64>((n01 + 7) / 8, (u64)ctx->num_sms * 16);
+        cudaStream_t bs = fan.pick();
+        const int wlg = std::min(lg, 5);
+        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o);
+        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o);
+        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o64);
+        LAUNCH_CHECK(ctx);
+    }
+    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
+        if (!reachable(hb)) { if (cnt) continue; else break; }
+        const u64 n = bin_size(B200_BIN_HASH0 + hb);
+        const u32 slots = b200_hash_slots(hb);
+        const u32 cap = b200_hash_cap(hb);
+        const int bin = B200_BIN_HASH0 + hb;
+        cudaStream_t bs = fan.pick();
+        // rank kernel (column bitmap in shared memory) when the column space is small next to the row
+        const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (4 + accb);
+        if (nwords <= 4 * cap && rank_smem <= smem_max) {
+            if (packed) {
+                const int pt = std::max(64, std::min(1024, (int)cap / env_int("B200_NDIV", cnt ? 8 : 16)));
+                const int pg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, rank_smem) * 4);
+#define RANK_PACK(MODE, VTT, NA, OO)                                                                                                  \
+                do { if (bpat) k_num_rank_pack<VTT, MODE, true><<<pg, pt, rank_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, OO); \
+                     else k_num_rank_pack<VTT, MODE, false><<<pg, pt, rank_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, OO); } while (0)
+                if (mode == 0) RANK_PACK(0, VT, na, o);
+                else if (mode == 1) RANK_PACK(1, VT, na, o);
+                else RANK_PACK(2, u64, na64, o64);
+#undef RANK_PACK
+            } else {
+                const int threads = bin_threads(hb, lg);
+                const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, rank_smem) * 4);
+                if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o);
+                else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o);
+                else k_num_rank<u64, 2><<<g, threads, rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o64);
+            }
+            LAUNCH_CHECK(ctx);
+            continue;
+        }
+        const int threads = bin_threads(hb, lg);
+        const size_t smem = (size_t)slots * (4 + accb);
+        if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
+        const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
+        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
+        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
+        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o64);
+        LAUNCH_CHECK(ctx);
+    }
+    const bool heavy = cnt ? cnt[B200_BIN_HEAVY] != 0 : p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
+    if (heavy) {
+        const u64 n = bin_size(B200_BIN_HEAVY);
+        const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)heavy_cap * (4 + accb);
+        if (heavy_cap < 65536 && heavy_rank_smem <= smem_max) {
+            // heavy rows over a small column space: the rank kernel with accumulators sized for the longest row
+            const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * 2);
+            cudaStream_t bs = fan.pick();
+            const u32 cap = (u32)heavy_cap;
+            if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
+            else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
+            else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o64);
+            LAUNCH_CHECK(ctx);
+        } else {
+            u64 max_slots = 1; while (max_slots < 2 * heavy_cap) max_slots <<= 1;
+            const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;
+            const size_t budget = (size_t)8 << 30;
+            const int g = (int)std::min<u64>(std::min<u64>(n, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
+            TRY(ensure_heavy_scratch(ctx, per_cta * g));
+            unsigned char *base = (unsigned char *)ctx->d_heavy;
+            u64 *s_vals = (u64 *)base;                                            // g * max_slots u64
+            u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
+            u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
+            u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
+            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64);
+            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    return B200_OK;
+}
+
+static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwords, Fan &fan) {
+    const size_t smem_max = ctx->smem_optin - 1024;
+    if ((size_t)nwords * 4 <= smem_max) {
+        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
+        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
+    } else {
+        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
+        TRY(ensure_heavy_scratch(ctx, (size_t)g * nwords * 4));
+        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
+    }
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
+
 template <typename VT>
 static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st) {
     const u64 rows = A->rows, ncols = B->cols;
@@ -447,29 +614,121 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
         CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8, s));
         TRY(dmalloc(ctx, (void **)&C->d_col, 0)); TRY(dmalloc(ctx, &C->d_val, 0));
+        C->h_maxval = 0; C->h_maxval_known = true;
         if (st) st->bytes_algorithmic = (A->nnz + B->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
         *out = C;
         return B200_OK;
     }
     int r = ensure_row_scratch(ctx, rows);
     if (r == B200_OK) r = ensure_desc(ctx, B);
+    const bool packed = want_pack(B);
+    if (r == B200_OK && packed) r = ensure_pack(ctx, B);
+    if (r == B200_OK) r = host_maxval(ctx, A);
+    if (r == B200_OK) r = host_maxval(ctx, B);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     SymArgs sa{A->d_rp, A->d_col, B->d_desc, B->d_col};
-    NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     const u32 nwords = (u32)((ncols + 31) / 32);
     const int lg = pick_lg(B, 5);
     const u64 p_bound = A->max_row_len * B->max_row_len;                 // host-known bound of the largest P_i
     const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
     const size_t smem_max = ctx->smem_optin - 1024;
+    const u64 maxA = A->h_maxval, maxB = B->h_maxval;
+    const bool bpat = maxB == 1;
     Fan fan(ctx);
+    void *tmp_col = nullptr, *tmp_val = nullptr;
+    u64 *tile2 = ctx->d_tile_status + ctx->cap_tiles;                     // second status array (bound scan)
+
+    // One-pass (default): numeric kernels write every row at its bound offset prefix(min(P_i, cols)) in a
+    // scratch CSR and report its exact length; a scan of the lengths gives row_ptr and a compaction kernel
+    // moves the rows.  No symbolic pass.  Needs scratch for sum(min(P_i, cols)) entries: the host-known bound
+    // nnz(A) * maxlen(B) is used when it is cheap, else the exact sum is read back first; if even that is
+    // too large for the memory budget the exact two-pass path (symbolic + numeric) runs instead.
+    bool onepass = env_int("B200_TWOPASS", 0) == 0;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t esz = 4 + sizeof(VT);
+    unsigned __int128 hb128 = (unsigned __int128)A->nnz * B->max_row_len;
+    const unsigned __int128 dense128 = (unsigned __int128)rows * ncols;
+    if (dense128 < hb128) hb128 = dense128;
+    const bool cheap_bound = hb128 * esz <= (unsigned __int128)(total_b / 16);
 
     if (timing) cudaEventRecord(ctx->ev[0], s);
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, ntiles * 8, s));
-    // ---- symbolic: product counts, bins, exact nnz per row
-    TRY(launch_row_products(ctx, A, B));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, 2 * ctx->cap_tiles * 8, s));
+    TRY(launch_row_products(ctx, A, B, onepass));
     const unsigned row_grid = (unsigned)((rows + 255) / 256);
-    k_bin_scatter<0><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    u64 tmp_entries = 0;
+    if (onepass) {
+        k_scan_rowptr<false, 1><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, nullptr, ctx->d_tmp_ptr, tile2, ctx->d_ctrl, nullptr, ctx->d_prod, ncols);
+        LAUNCH_CHECK(ctx);
+        if (cheap_bound) tmp_entries = (u64)hb128;
+        else {
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            tmp_entries = ctx->h_ctrl->total_bound;
+            if ((unsigned __int128)tmp_entries * esz > (unsigned __int128)(free_b / 3)) onepass = false;   // scratch would crowd out C
+        }
+    }
+    if (onepass) {
+        k_bin_scatter<0, true><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+        LAUNCH_CHECK(ctx);
+        r = dmalloc(ctx, &tmp_col, tmp_entries * 4);
+        if (r == B200_OK) r = dmalloc(ctx, &tmp_val, tmp_entries * sizeof(VT));
+        if (r != B200_OK) { dfree(ctx, tmp_col); b200_csr_free(ctx, C); return r; }
+        const int mode = pick_mode<VT>(p_bound, maxA, maxB);
+        const u64 heavy_cap = std::min<u64>(p_bound, ncols);
+        if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) && !(heavy_cap < 65536 && (size_t)nwords * 6 + 16 + heavy_cap * 12 <= smem_max)) {
+            // heavy rows that need the global table: size it from their exact nnz (bitmap count first)
+            r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
+            fan.join();
+        }
+        OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count};
+        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan);
+        fan.join();
+        if (r != B200_OK) { dfree(ctx, tmp_col); dfree(ctx, tmp_val); b200_csr_free(ctx, C); return r; }
+        k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0);
+        LAUNCH_CHECK(ctx);
+        if (timing) cudaEventRecord(ctx->ev[1], s);
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const B200Ctrl hc = *ctx->h_ctrl;
+        C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
+        r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
+        if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+        if (r != B200_OK) { dfree(ctx, tmp_col); dfree(ctx, tmp_val); b200_csr_free(ctx, C); return r; }
+        if (timing) cudaEventRecord(ctx->ev[2], s);
+        {
+            const double avg = (double)C->nnz / (double)rows;
+            const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
+            const u64 want = (rows << llg) / 256 + 1;
+            k_compact_rows<VT><<<(unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64), 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg);
+            LAUNCH_CHECK(ctx);
+        }
+        CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
+        dfree(ctx, tmp_col); dfree(ctx, tmp_val);
+        if (timing) cudaEventRecord(ctx->ev[3], s);
+        if (st) {
+            st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
+            st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
+            st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
+            for (int i = 0; i < B200_NBINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
+            if (timing) {
+                CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+                cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[2], ctx->ev[3]);   // one-pass: compaction of the scratch rows
+                cudaEventElapsedTime(&st->ms_numeric, ctx->ev[0], ctx->ev[1]);    // counts + bins + numeric kernels + row_ptr scan
+                cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
+            }
+        }
+        *out = C;
+        return B200_OK;
+    }
+
+    // ---------------- exact two-pass path: symbolic (nnz per row) -> row_ptr -> numeric into the final arrays
+    if (!env_int("B200_TWOPASS", 0)) {                                    // fell back after a one-pass count: redo the bins with the two-pass rule
+        CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
+        TRY(launch_row_products(ctx, A, B, false));
+    }
+    k_bin_scatter<0, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
     LAUNCH_CHECK(ctx);
     {
         const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
@@ -483,140 +742,50 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
     for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
         if (p_bound <= (u64)b200_hash_cap(hb - 1)) break;                // no row can reach this bin
-        const int threads = bin_threads(hb, lg);
         const u32 slots = b200_hash_slots(hb);
-        const bool bitmap = nwords <= slots && (size_t)nwords * 4 <= smem_max;
+        const bool bitmap = nwords <= 4 * b200_hash_cap(hb) && (size_t)nwords * 4 <= smem_max;
         const size_t smem = bitmap ? (size_t)nwords * 4 : (size_t)slots * 4;
-        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
-        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * per_sm * 2);
         cudaStream_t bs = fan.pick();
-        if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
-        else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
-        LAUNCH_CHECK(ctx);
-    }
-    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) {
-        // heavy rows: column bitmap, in shared memory when the column space fits, else in global scratch
-        if ((size_t)nwords * 4 <= smem_max) {
-            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-            k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
+        if (packed) {
+            const int pt = std::max(bitmap ? 64 : 32, std::min(1024, (int)b200_hash_cap(hb) / env_int("B200_SDIV", 8)));
+            const int pg = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, smem) * 2);
+            if (bitmap) k_sym_pack<true><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row);
+            else k_sym_pack<false><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row);
         } else {
-            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
-            r = ensure_heavy_scratch(ctx, (size_t)g * nwords * 4);
-            if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
-            k_sym_heavy<<<g, 1024, 0, s>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
+            const int threads = bin_threads(hb, lg);
+            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
+            if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+            else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
         }
         LAUNCH_CHECK(ctx);
     }
+    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) {
+        r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
+        if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
+    }
     fan.join();
     // ---- row_ptr (decoupled look-back scan, fused numeric-bin histogram), numeric bin lists
-    k_scan_rowptr<true><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, A->d_rp, ctx->d_prod);
+    k_scan_rowptr<true, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, A->d_rp, ctx->d_prod, 0);
     LAUNCH_CHECK(ctx);
-    k_bin_scatter<1><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    k_bin_scatter<1, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
     LAUNCH_CHECK(ctx);
     if (timing) cudaEventRecord(ctx->ev[1], s);
-    // ---- the one host read-back: total nnz, bin sizes, value bounds
+    // ---- the one host read-back: total nnz, bin sizes
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 4, A->d_maxval, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 6, B->d_maxval, 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     const B200Ctrl hc = *ctx->h_ctrl;
-    u64 maxA, maxB; memcpy(&maxA, ctx->h_flag + 4, 8); memcpy(&maxB, ctx->h_flag + 6, 8);
     if (hc.error_flag) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "symbolic pass reported an internal error (flag %u)", hc.error_flag); }
     C->nnz = hc.total_nnz;
     C->max_row_len = hc.max_row_nnz;
     r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
     if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-    // accumulator width: prove no overflow from max_row_products * max(A) * max(B)
-    int mode;
-    {
-        unsigned __int128 bound = (unsigned __int128)hc.max_row_products * maxA;
-        bool over64 = (bound >> 64) != 0;
-        if (!over64) { bound *= maxB; over64 = (bound >> 64) != 0; }
-        if (!over64 && (u64)bound < (1ull << 32)) mode = 0;
-        else if (sizeof(VT) == 4) mode = 1;                               // clamped 32-bit products, < 2^32 of them per row
-        else mode = over64 ? 2 : 1;
-        const int forced = env_int("B200_FORCE_MODE", -1);                // testing hook: a wider mode is always valid
-        if (forced > mode && forced <= (sizeof(VT) == 8 ? 2 : 1)) mode = forced;
-    }
+    const int mode = pick_mode<VT>(hc.max_row_products, maxA, maxB);
     if (timing) cudaEventRecord(ctx->ev[2], s);
-    u32 *colC = C->d_col; VT *valC = (VT *)C->d_val;
-    NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
-    // ---- numeric
-    if (hc.num_bin_count[B200_BIN_TINY]) {
-        const int g = (int)std::min<u64>(((u64)hc.num_bin_count[B200_BIN_TINY] + 7) / 8, (u64)ctx->num_sms * 32);
-        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, C->d_rp, colC, valC);
-        LAUNCH_CHECK(ctx);
-    }
-    if (hc.num_bin_count[B200_BIN_HASH0] + hc.num_bin_count[B200_BIN_HASH0 + 1]) {
-        const u64 cnt = (u64)hc.num_bin_count[B200_BIN_HASH0] + hc.num_bin_count[B200_BIN_HASH0 + 1];
-        const size_t smem = 8 * (Acc<1>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4);
-        const size_t smem0 = 8 * (Acc<0>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4);
-        const int g = (int)std::min<u64>((cnt + 7) / 8, (u64)ctx->num_sms * 16);
-        cudaStream_t bs = fan.pick();
-        const int wlg = std::min(lg, 5);
-        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem0, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, valC);
-        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, valC);
-        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, C->d_rp, colC, (u64 *)C->d_val);
-        LAUNCH_CHECK(ctx);
-    }
-    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
-        const u32 cnt = hc.num_bin_count[B200_BIN_HASH0 + hb];
-        if (!cnt) continue;
-        const int threads = bin_threads(hb, lg);
-        const u32 slots = b200_hash_slots(hb);
-        const u32 cap = b200_hash_cap(hb);
-        const int bin = B200_BIN_HASH0 + hb;
-        cudaStream_t bs = fan.pick();
-        // rank kernel (column bitmap in shared memory) when the column space is small next to the row
-        const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (mode == 0 ? 4 : 8);
-        if (nwords <= 4 * cap && rank_smem <= smem_max) {
-            const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (rank_smem + 1024)))));
-            const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
-            if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, valC);
-            else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, valC);
-            else k_num_rank<u64, 2><<<g, threads, rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, C->d_rp, colC, (u64 *)C->d_val);
-            LAUNCH_CHECK(ctx);
-            continue;
-        }
-        const size_t smem = (size_t)slots * (4 + (mode == 0 ? 4 : 8));
-        if (smem > smem_max) { fan.join(); b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem); }
-        const int per_sm = std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
-        const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * per_sm * 4);
-        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, valC);
-        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, valC);
-        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, C->d_rp, colC, (u64 *)C->d_val);
-        LAUNCH_CHECK(ctx);
-    }
-    const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)hc.max_row_nnz * (mode == 0 ? 4 : 8);
-    if (hc.num_bin_count[B200_BIN_HEAVY] && hc.max_row_nnz < 65536 && heavy_rank_smem <= smem_max) {
-        // heavy rows over a small column space: same rank kernel, accumulators sized for the longest row
-        const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
-        const u32 cap = (u32)hc.max_row_nnz;
-        const int g = (int)std::min<u64>(cnt, (u64)ctx->num_sms * 2);
-        cudaStream_t bs = fan.pick();
-        if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, valC);
-        else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, valC);
-        else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, C->d_rp, colC, (u64 *)C->d_val);
-        LAUNCH_CHECK(ctx);
-    } else if (hc.num_bin_count[B200_BIN_HEAVY]) {
-        const u32 cnt = hc.num_bin_count[B200_BIN_HEAVY];
-        u64 max_slots = 1; while (max_slots < 2 * hc.max_row_nnz) max_slots <<= 1;
-        const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;
-        const size_t budget = (size_t)8 << 30;
-        const int g = (int)std::min<u64>(std::min<u64>(cnt, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
-        r = ensure_heavy_scratch(ctx, per_cta * g);
-        if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
-        unsigned char *base = (unsigned char *)ctx->d_heavy;
-        u64 *s_vals = (u64 *)base;                                            // g * max_slots u64
-        u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
-        u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
-        u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
-        if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, s>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, colC, (u64 *)C->d_val);
-        else k_num_heavy<VT, 1><<<g, 1024, 0, s>>>(na, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, C->d_rp, colC, valC);
-        LAUNCH_CHECK(ctx);
-    }
+    OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->num_bin_count};
+    r = launch_numeric<VT>(ctx, A, B, hc.num_bin_count, rows, p_bound, hc.max_row_nnz, mode, packed, bpat, lg, o, fan);
     fan.join();
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
     if (timing) cudaEventRecord(ctx->ev[3], s);
     if (st) {
@@ -652,7 +821,7 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     TRY(ensure_row_scratch(ctx, A->rows));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), ctx->stream));
     TRY(ensure_desc(ctx, B));
-    TRY(launch_row_products(ctx, A, B));
+    TRY(launch_row_products(ctx, A, B, false));
     CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_prod, A->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
@@ -717,7 +886,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);
-    k_scan_rowptr<false><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr);
+    k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

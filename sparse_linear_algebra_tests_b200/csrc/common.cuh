@@ -57,9 +57,10 @@ struct B200Ctrl {
     u32 sym_bin_fill[B200_NBINS];
     u32 num_bin_count[B200_NBINS];
     u32 num_bin_fill[B200_NBINS];
-    u32 scan_ticket;
+    ull total_bound;          // one-pass mode: sum of per-row bounds min(P_i, cols)
+    u32 scan_ticket[2];
     u32 error_flag;           // set by kernels on impossible states (table overflow)
-    u32 pad[2];
+    u32 pad[1];
 };
 
 // Read-only view of a device CSR.

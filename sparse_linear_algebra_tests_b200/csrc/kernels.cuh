@@ -28,6 +28,16 @@ struct NumArgs {
     const uint2 *bdesc; const u32 *colB; const VT *valB;
 };
 
+// Where a numeric kernel puts its rows.  Two-pass: base = row_ptr_C (exact, from the symbolic pass),
+// bins = numeric bins.  One-pass: base = offsets from the scan of the per-row bounds min(P_i, cols),
+// rows land in a scratch CSR and their exact lengths in nnz_out; bins = the product-count bins.
+template <typename VT>
+struct OutArgs {
+    const u64 *base; u32 *col; VT *val;
+    u32 *nnz_out;                // may be null (two-pass)
+    const u32 *bin_cnt;          // bin sizes to iterate (ctrl->sym_bin_count or ctrl->num_bin_count)
+};
+
 __global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, uint2 *__restrict__ desc) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
         const u64 s = rp[i], e = rp[i + 1];
@@ -59,8 +69,10 @@ __device__ __forceinline__ void walk_products(const u32 *__restrict__ Ac, u32 le
 // =======================================================================================
 // 1. product count per row + symbolic-bin histogram
 // =======================================================================================
+// ONEPASS: the product-count bins drive the numeric kernels directly, so single-entry rows need a bin too
+template <bool ONEPASS = false>
 __device__ __forceinline__ int sym_bin_of(u64 p, u64 dA) {
-    if (p == 0 || dA == 1) return B200_BIN_NONE;           // nnz known: 0, or P (one B row: distinct cols)
+    if (p == 0 || (!ONEPASS && dA == 1)) return B200_BIN_NONE;   // nnz known: 0, or P (one B row: distinct cols)
     if (p <= 32 && dA <= 32) return B200_BIN_TINY;
     return b200_bin_by_size(p);
 }
@@ -71,7 +83,7 @@ __device__ __forceinline__ int num_bin_of(u32 nnz, u64 p, u64 dA) {
     return b200_bin_by_size(nnz);
 }
 
-template <int G>  // lanes per row (power of two <= 32)
+template <int G, bool ONEPASS>  // G lanes per row (power of two <= 32)
 __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
                                                       const uint2 *__restrict__ bdesc, u64 *__restrict__ prod,
                                                       u32 *__restrict__ nnz_row, B200Ctrl *ctrl) {
@@ -95,7 +107,7 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
     u64 wsum = 0, wmax = 0;
     if (row < rows && sub == 0) {
         prod[row] = p;
-        const int b = sym_bin_of(p, lenA);
+        const int b = sym_bin_of<ONEPASS>(p, lenA);
         if (b == B200_BIN_NONE) nnz_row[row] = (u32)p;       // 0, or the single B row's length
         else atomicAdd(&s_hist[b], 1u);
         wsum = p; wmax = p;
@@ -111,7 +123,7 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 }
 
 // scatter row ids into their bin's segment of bin_rows; PHASE 0 = symbolic bins, 1 = numeric bins
-template <int PHASE>
+template <int PHASE, bool ONEPASS>
 __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__restrict__ rpA, const u64 *__restrict__ prod,
                                                      const u32 *__restrict__ nnz_row, B200Ctrl *ctrl, u32 *__restrict__ bin_rows) {
     __shared__ u32 s_cnt[B200_NBINS], s_base[B200_NBINS];
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__rest
     int b = B200_BIN_NONE; u32 local = 0;
     if (row < rows) {
         const u64 dA = rpA[row + 1] - rpA[row];
-        b = PHASE == 0 ? sym_bin_of(prod[row], dA) : num_bin_of(nnz_row[row], prod[row], dA);
+        b = PHASE == 0 ? sym_bin_of<ONEPASS>(prod[row], dA) : num_bin_of(nnz_row[row], prod[row], dA);
         if (b != B200_BIN_NONE) local = atomicAdd(&s_cnt[b], 1u);
     }
     __syncthreads();
@@ -292,9 +304,8 @@ __global__ void __launch_bounds__(256) k_sym_tiny(SymArgs a, const u32 *__restri
 }
 
 template <typename VT>
-__global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
-                                                  const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
-    const u32 count = ctrl->num_bin_count[B200_BIN_TINY];
+__global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, OutArgs<VT> o) {
+    const u32 count = o.bin_cnt[B200_BIN_TINY];
     const int lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
     u64 vmax = 0;
@@ -314,10 +325,11 @@ __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__re
         const bool tail = key != B200_EMPTY_KEY && (lane == 31 || nk != key);
         const u32 tails = __ballot_sync(0xFFFFFFFFu, tail);
         if (tail) {
-            const u64 pos = rpC[row] + __popc(tails & ((1u << lane) - 1u));
-            colC[pos] = key; valC[pos] = val;
+            const u64 pos = o.base[row] + __popc(tails & ((1u << lane) - 1u));
+            o.col[pos] = key; o.val[pos] = val;
             vmax = vmax > (u64)val ? vmax : (u64)val;
         }
+        if (lane == 0 && o.nnz_out) o.nnz_out[row] = __popc(tails);
     }
     vmax = warp_max_u64(vmax);
     if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
@@ -402,6 +414,14 @@ __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restri
 // =======================================================================================
 // 5. numeric
 // =======================================================================================
+// rows [begin,end) of a bin handled by this CTA: contiguous chunks keep consecutive rows (which share
+// most of their B rows in lattice-like graphs) on one SM, so the records stay hot in its L1
+__device__ __forceinline__ void cta_row_range(u32 count, u32 &begin, u32 &end) {
+    const u32 rpc = (count + gridDim.x - 1) / gridDim.x;
+    begin = blockIdx.x * rpc;
+    end = begin + rpc < count ? begin + rpc : count;
+}
+
 // block-wide exclusive scan of one u32 per thread; returns exclusive prefix, total in `total`
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 &total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -451,8 +471,7 @@ __device__ __forceinline__ void smem_bitonic(u32 *keys, Acc<MODE> &acc, u32 n) {
 // 5a. warp per row (8 rows in flight per CTA): hash accumulate, compact, sort, stream out. nnz <= 128.
 template <typename VT, int MODE>
 __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
-                                                  int nbins, int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
-                                                  VT *__restrict__ valC) {
+                                                  int nbins, int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t per_warp = Acc<MODE>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4;
@@ -460,8 +479,8 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
     Acc<MODE> acc; acc.bind(base, B200_WARP_SLOTS);
     u32 *keys = reinterpret_cast<u32 *>(base + Acc<MODE>::bytes(B200_WARP_SLOTS));
     u32 count = 0;
-    for (int b = 0; b < nbins; b++) count += ctrl->num_bin_count[first_bin + b];
-    const u32 off = bin_offset(ctrl->num_bin_count, first_bin);
+    for (int b = 0; b < nbins; b++) count += o.bin_cnt[first_bin + b];
+    const u32 off = bin_offset(o.bin_cnt, first_bin);
     const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
     const int shift = 32 - 8;
     constexpr int PER = B200_WARP_SLOTS / 32;
@@ -498,12 +517,13 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
         for (u32 t = total + lane; t < n2; t += 32) keys[t] = B200_EMPTY_KEY;
         __syncwarp();
         smem_bitonic<MODE, true>(keys, acc, n2);
-        const u64 obase = rpC[row];
+        const u64 obase = o.base[row];
         for (u32 t = lane; t < total; t += 32) {
             const VT v = emit_val<VT>(acc.get(t));
-            colC[obase + t] = keys[t]; valC[obase + t] = v;
+            o.col[obase + t] = keys[t]; o.val[obase + t] = v;
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
+        if (lane == 0 && o.nnz_out) o.nnz_out[row] = total;
         __syncwarp();
     }
     vmax = warp_max_u64(vmax);
@@ -513,13 +533,13 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
 // 5b. CTA per row, hash + sort emission (any column space).  slots = 2 * bin capacity.
 template <typename VT, int MODE>
 __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
-                                                  int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
+                                                  int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
     Acc<MODE> acc; acc.bind(smem_raw, slots);
     u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
-    const u32 count = ctrl->num_bin_count[bin];
-    const u32 off = bin_offset(ctrl->num_bin_count, bin);
+    const u32 count = o.bin_cnt[bin];
+    const u32 off = bin_offset(o.bin_cnt, bin);
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const int shift = 32 - (31 - __clz(slots));
@@ -553,12 +573,13 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
         for (u32 t = total + tid; t < n2; t += nt) keys[t] = B200_EMPTY_KEY;
         __syncthreads();
         smem_bitonic<MODE, false>(keys, acc, n2);
-        const u64 obase = rpC[row];
+        const u64 obase = o.base[row];
         for (u32 t = tid; t < total; t += nt) {
             const VT v = emit_val<VT>(acc.get(t));
-            colC[obase + t] = keys[t]; valC[obase + t] = v;
+            o.col[obase + t] = keys[t]; o.val[obase + t] = v;
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
+        if (tid == 0 && o.nnz_out) o.nnz_out[row] = total;
         __syncthreads();
     }
     vmax = warp_max_u64(vmax);
@@ -568,29 +589,42 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
 // 5c. CTA per row, rank emission: the whole column space fits a shared-memory bitmap.
 // No hash table: walk 1 sets one bit per product column; a prefix popcount over the bitmap words
 // gives every present column its rank (= its position in the sorted output row); walk 2 adds each
-// product into acc[rank]; columns are emitted by enumerating the set bits, values by streaming
-// acc[0..nnz).  Shared memory: nwords*6 + cap*(4|8) bytes -> high occupancy.
+// product into acc[rank] and drops the column into cols[rank]; both arrays are then streamed out
+// with coalesced stores.  Shared memory: nwords*6 + cap*(8|12) bytes.
+// rank phase shared by both rank kernels: fills wpre[] (exclusive prefix popcount per word), returns nnz
+__device__ __forceinline__ u32 rank_prefix(const u32 *bm, unsigned short *wpre, u32 nwords, u32 *s_warp) {
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    const u32 wpt = (nwords + nt - 1) / nt;                               // consecutive bitmap words per thread
+    const u32 w0 = tid * wpt;
+    u32 mine = 0;
+    for (u32 i = 0; i < wpt; i++) if (w0 + i < nwords) mine += __popc(bm[w0 + i]);
+    u32 total;
+    u32 run = block_excl_scan(mine, s_warp, total);
+    for (u32 i = 0; i < wpt; i++) {
+        if (w0 + i < nwords) { wpre[w0 + i] = (unsigned short)run; run += __popc(bm[w0 + i]); }
+    }
+    return total;
+}
+
 template <typename VT, int MODE>
 __global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 cap,
-                                                   u32 nwords, int lg, const u64 *__restrict__ rpC, u32 *__restrict__ colC,
-                                                   VT *__restrict__ valC) {
+                                                   u32 nwords, int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
     Acc<MODE> acc; acc.bind(smem_raw, cap);
-    u32 *bm = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(cap));
+    u32 *cols = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(cap));
+    u32 *bm = cols + cap;
     unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
-    const u32 count = ctrl->num_bin_count[bin];
-    const u32 off = bin_offset(ctrl->num_bin_count, bin);
+    const u32 count = o.bin_cnt[bin];
+    const u32 off = bin_offset(o.bin_cnt, bin);
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
-    const u32 wpt = (nwords + nt - 1) / nt;                               // bitmap words per thread
     u64 vmax = 0;
-    for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
+    u32 r_begin, r_end;
+    cta_row_range(count, r_begin, r_end);
+    for (u32 r = r_begin; r < r_end; r++) {
         const u32 row = bin_rows[off + r];
-        const u64 obase = rpC[row];
-        const u32 nnz = (u32)(rpC[row + 1] - obase);
         for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
-        for (u32 t = tid; t < nnz; t += nt) acc.clear(t);
         __syncthreads();
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
@@ -600,39 +634,186 @@ __global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__r
         walk_products<int>(Ac, lenA, a.bdesc, grp, ngrp, sub, G, [](u32) { return 0; },
                            [&](int, u32 jb) { const u32 c = a.colB[jb]; atomicOr(&bm[c >> 5], 1u << (c & 31)); });
         __syncthreads();
-        // ---- ranks: exclusive prefix popcount over the words (each thread owns wpt consecutive words)
-        {
-            const u32 w0 = tid * wpt;
-            u32 mine = 0;
-            for (u32 i = 0; i < wpt; i++) if (w0 + i < nwords) mine += __popc(bm[w0 + i]);
-            u32 total;
-            u32 run = block_excl_scan(mine, s_warp, total);
-            for (u32 i = 0; i < wpt; i++) {
-                if (w0 + i < nwords) {
-                    const u32 w = bm[w0 + i];
-                    wpre[w0 + i] = (unsigned short)run;
-                    u32 bits = w;                                          // columns come out in ascending order: emit them here
-                    u64 p = obase + run;
-                    while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; colC[p++] = ((w0 + i) << 5) + b; }
-                    run += __popc(w);
-                }
-            }
-        }
+        const u32 nnz = rank_prefix(bm, wpre, nwords, s_warp);
+        for (u32 t = tid; t < nnz; t += nt) acc.clear(t);
         __syncthreads();
         // ---- walk 2: accumulate into acc[rank(col)]
         walk_products<VT>(Ac, lenA, a.bdesc, grp, ngrp, sub, G, [&](u32 t) { return Av[t]; },
                           [&](VT av, u32 jb) {
                               const u32 c = a.colB[jb];
-                              const u32 w = bm[c >> 5];
-                              const u32 pos = (u32)wpre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+                              const u32 pos = (u32)wpre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
+                              cols[pos] = c;                               // same value from every product of this column
                               acc.add(pos, av, a.valB[jb]);
                           });
         __syncthreads();
+        const u64 obase = o.base[row];
         for (u32 t = tid; t < nnz; t += nt) {
             const VT v = emit_val<VT>(acc.get(t));
-            valC[obase + t] = v;
+            o.col[obase + t] = cols[t]; o.val[obase + t] = v;
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
+        if (tid == 0 && o.nnz_out) o.nnz_out[row] = nnz;
+        __syncthreads();
+    }
+    vmax = warp_max_u64(vmax);
+    if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
+}
+
+// =======================================================================================
+// 5d. sector-packed right operand (low-degree B): one 32-byte record per B row
+//     rec[2k] = {start, len, col0, col1}, rec[2k+1] = {col2, col3, col4, col5}
+// One aligned 32-byte fetch (a single L2 sector) returns a B row's length AND its first six
+// columns, instead of a descriptor sector plus a column sector; the dependent-load chain of a
+// product shrinks from A.col -> desc -> B.col to A.col -> record.  Rows longer than six columns
+// continue in B.col.  The numeric rank kernel keeps each thread's records in registers between
+// its two walks, so a row costs one sector per A entry in the whole numeric pass.
+// =======================================================================================
+#define B200_PACK_INLINE 6
+struct PackRec { uint4 a, b; };
+
+__global__ void __launch_bounds__(256) k_build_pack(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col, uint4 *__restrict__ pack) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[i];
+        const u32 len = (u32)(rp[i + 1] - s);
+        u32 c[B200_PACK_INLINE];
+#pragma unroll
+        for (int j = 0; j < B200_PACK_INLINE; j++) c[j] = j < (int)len ? col[s + j] : B200_EMPTY_KEY;
+        pack[2 * i] = make_uint4((u32)s, len, c[0], c[1]);
+        pack[2 * i + 1] = make_uint4(c[2], c[3], c[4], c[5]);
+    }
+}
+__device__ __forceinline__ PackRec load_pack(const uint4 *__restrict__ pack, u32 k) {
+    PackRec r; r.a = __ldg(&pack[2 * (u64)k]); r.b = __ldg(&pack[2 * (u64)k + 1]); return r;
+}
+template <typename F>
+__device__ __forceinline__ void for_each_col(const PackRec &r, const u32 *__restrict__ colB, F f) {
+    const u32 start = r.a.x, len = r.a.y;
+    if (len > 0) f(r.a.z, start);
+    if (len > 1) f(r.a.w, start + 1);
+    if (len > 2) f(r.b.x, start + 2);
+    if (len > 3) f(r.b.y, start + 3);
+    if (len > 4) f(r.b.z, start + 4);
+    if (len > 5) f(r.b.w, start + 5);
+    for (u32 j = B200_PACK_INLINE; j < len; j++) f(colB[start + j], start + j);
+}
+
+template <bool BITMAP>
+__global__ void __launch_bounds__(1024) k_sym_pack(SymArgs a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
+                                                   B200Ctrl *ctrl, int bin, u32 slots, u32 nwords, u32 *__restrict__ nnz_row) {
+    extern __shared__ u32 smem[];
+    __shared__ u32 s_count;
+    const u32 count = ctrl->sym_bin_count[bin];
+    const u32 off = bin_offset(ctrl->sym_bin_count, bin);
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    const u32 tabn = BITMAP ? nwords : slots;
+    const int shift = 32 - (31 - __clz(slots));
+    u32 r_begin, r_end;
+    cta_row_range(count, r_begin, r_end);
+    for (u32 r = r_begin; r < r_end; r++) {
+        const u32 row = bin_rows[off + r];
+        for (u32 t = tid; t < tabn; t += nt) smem[t] = BITMAP ? 0u : B200_EMPTY_KEY;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const u32 *Ac = a.colA + s;
+        u32 local = 0;
+        auto visit = [&](u32 c, u32) {
+            if (BITMAP) {
+                const u32 bit = 1u << (c & 31);
+                const u32 old = atomicOr(&smem[c >> 5], bit);
+                local += !(old & bit);
+            } else {
+                bool fresh;
+                table_insert(smem, slots - 1, shift, c, fresh);
+                local += fresh;
+            }
+        };
+        for (u32 t = tid; t < lenA; t += 2 * nt) {
+            const u32 t1 = t + nt;
+            const bool has1 = t1 < lenA;
+            const u32 k0 = Ac[t], k1 = has1 ? Ac[t1] : 0;
+            const PackRec r0 = load_pack(pack, k0);
+            PackRec r1 = load_pack(pack, has1 ? k1 : k0);
+            if (!has1) r1.a.y = 0;
+            for_each_col(r0, a.colB, visit);
+            for_each_col(r1, a.colB, visit);
+        }
+        local = warp_sum_u32(local);
+        if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
+        __syncthreads();
+        if (tid == 0) nnz_row[row] = s_count;
+        __syncthreads();
+    }
+}
+
+template <typename VT, int MODE, bool BPAT>   // BPAT: every stored value of B is 1 (adjacency pattern): no B.val loads
+__global__ void __launch_bounds__(1024) k_num_rank_pack(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
+                                                        B200Ctrl *ctrl, int bin, u32 cap, u32 nwords, OutArgs<VT> o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_warp[33];
+    Acc<MODE> acc; acc.bind(smem_raw, cap);
+    u32 *cols = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(cap));
+    u32 *bm = cols + cap;
+    unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
+    const u32 count = o.bin_cnt[bin];
+    const u32 off = bin_offset(o.bin_cnt, bin);
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    u64 vmax = 0;
+    u32 r_begin, r_end;
+    cta_row_range(count, r_begin, r_end);
+    for (u32 r = r_begin; r < r_end; r++) {
+        const u32 row = bin_rows[off + r];
+        for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const u32 *Ac = a.colA + s;
+        const VT *Av = a.valA + s;
+        // the first two A entries of every thread stay in registers across both walks
+        PackRec rec[2]; VT av[2];
+        {
+            const u32 t1 = tid + nt;
+            const bool h0 = tid < lenA, h1 = t1 < lenA;
+            const u32 k0 = h0 ? Ac[tid] : 0, k1 = h1 ? Ac[t1] : 0;
+            rec[0] = load_pack(pack, k0); rec[1] = load_pack(pack, k1);
+            if (!h0) rec[0].a.y = 0;
+            if (!h1) rec[1].a.y = 0;
+            av[0] = h0 ? Av[tid] : (VT)0; av[1] = h1 ? Av[t1] : (VT)0;
+        }
+        __syncthreads();
+        // ---- walk 1: column bitmap
+        auto mark = [&](u32 c, u32) { atomicOr(&bm[c >> 5], 1u << (c & 31)); };
+        for_each_col(rec[0], a.colB, mark);
+        for_each_col(rec[1], a.colB, mark);
+        for (u32 t = tid + 2 * nt; t < lenA; t += nt) { const PackRec rr = load_pack(pack, Ac[t]); for_each_col(rr, a.colB, mark); }
+        __syncthreads();
+        const u32 nnz = rank_prefix(bm, wpre, nwords, s_warp);
+        for (u32 t = tid; t < nnz; t += nt) acc.clear(t);
+        __syncthreads();
+        // ---- walk 2: accumulate into acc[rank(col)]
+        auto put = [&](VT x, u32 c, u32 jb) {
+            const u32 pos = (u32)wpre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
+            cols[pos] = c;
+            acc.add(pos, x, BPAT ? (VT)1 : a.valB[jb]);
+        };
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const VT x = av[i];
+            for_each_col(rec[i], a.colB, [&](u32 c, u32 jb) { put(x, c, jb); });
+        }
+        for (u32 t = tid + 2 * nt; t < lenA; t += nt) {
+            const PackRec rr = load_pack(pack, Ac[t]);
+            const VT x = Av[t];
+            for_each_col(rr, a.colB, [&](u32 c, u32 jb) { put(x, c, jb); });
+        }
+        __syncthreads();
+        const u64 obase = o.base[row];
+        for (u32 t = tid; t < nnz; t += nt) {
+            const VT v = emit_val<VT>(acc.get(t));
+            o.col[obase + t] = cols[t]; o.val[obase + t] = v;
+            vmax = vmax > (u64)v ? vmax : (u64)v;
+        }
+        if (tid == 0 && o.nnz_out) o.nnz_out[row] = nnz;
         __syncthreads();
     }
     vmax = warp_max_u64(vmax);
@@ -676,11 +857,10 @@ template <typename VT, int MODE>   // MODE 1: plain 64-bit global atomics (u32 p
 __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
                                                     const u32 *__restrict__ nnz_row, u32 nwords, u64 max_slots,
                                                     u32 *__restrict__ scratch_bm, u32 *__restrict__ scratch_pre,
-                                                    u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals,
-                                                    const u64 *__restrict__ rpC, u32 *__restrict__ colC, VT *__restrict__ valC) {
+                                                    u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o) {
     __shared__ u32 s_warp[33];
-    const u32 count = ctrl->num_bin_count[B200_BIN_HEAVY];
-    const u32 off = bin_offset(ctrl->num_bin_count, B200_BIN_HEAVY);
+    const u32 count = o.bin_cnt[B200_BIN_HEAVY];
+    const u32 off = bin_offset(o.bin_cnt, B200_BIN_HEAVY);
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
     u32 *wpre = scratch_pre + (u64)blockIdx.x * nwords;
     u32 *keys = scratch_keys + (u64)blockIdx.x * max_slots;
@@ -738,7 +918,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
             carry += total;
         }
         __syncthreads();
-        const u64 obase = rpC[row];
+        const u64 obase = o.base[row];
         for (u64 t = tid; t < slots; t += nt) {
             const u32 c = __ldcg(&keys[t]);
             if (c != B200_EMPTY_KEY) {
@@ -746,7 +926,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                 const u64 pos = obase + __ldcg(&wpre[c >> 5]) + __popc(wd & ((1u << (c & 31)) - 1u));
                 ull v = __ldcg(&vals[t]);
                 if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
-                colC[pos] = c; valC[pos] = (VT)v;
+                o.col[pos] = c; o.val[pos] = (VT)v;
                 vmax = vmax > v ? vmax : v;
             }
         }
@@ -767,16 +947,18 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 #define SCAN_FLAG_PRE (2ull << 62)
 #define SCAN_VAL_MASK ((1ull << 62) - 1)
 
-template <bool CLASSIFY>
+// SRC 0: exact nnz per row -> row_ptr_C (CLASSIFY also histograms the numeric bins);
+// SRC 1: per-row bound min(P_i, cols) -> offsets of the one-pass scratch CSR (total in ctrl->total_bound)
+template <bool CLASSIFY, int SRC>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
                                                               u64 *tile_status, B200Ctrl *ctrl, const u64 *__restrict__ rpA,
-                                                              const u64 *__restrict__ prod) {
+                                                              const u64 *__restrict__ prod, u64 ncols) {
     __shared__ u32 s_tile;
     __shared__ u64 s_wsum[SCAN_THREADS / 32];
     __shared__ u64 s_excl;
     __shared__ u32 s_hist[B200_NBINS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket, 1u);               // tiles start in ticket order
+    if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket[SRC], 1u);          // tiles start in ticket order
     if (CLASSIFY && tid < B200_NBINS) s_hist[tid] = 0;
     __syncthreads();
     const u32 tile = s_tile;
@@ -784,7 +966,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
     u32 item[SCAN_ITEMS]; u64 tsum = 0; u32 tmaxv = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        item[i] = base + i < rows ? nnz_row[base + i] : 0u;
+        if (SRC == 0) item[i] = base + i < rows ? nnz_row[base + i] : 0u;
+        else { const u64 pv = base + i < rows ? prod[base + i] : 0ull; item[i] = (u32)(pv < ncols ? pv : ncols); }
         tsum += item[i]; tmaxv = item[i] > tmaxv ? item[i] : tmaxv;
     }
     if (CLASSIFY) {
@@ -839,11 +1022,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
         run += item[i];
         if (base + i < rows) rpC[base + i + 1] = run;
     }
-    if (base < rows && base + SCAN_ITEMS >= rows) ctrl->total_nnz = run;   // the thread holding the last row
+    if (base < rows && base + SCAN_ITEMS >= rows) { if (SRC == 0) ctrl->total_nnz = run; else ctrl->total_bound = run; }   // thread holding the last row
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
-    if (lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
+    if (SRC == 0 && lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
     if (CLASSIFY && tid < B200_NBINS && s_hist[tid]) atomicAdd(&ctrl->num_bin_count[tid], s_hist[tid]);
+}
+
+// one-pass mode: move every row from the scratch CSR (bound offsets) to its exact place
+template <typename VT>
+__global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__restrict__ src_ptr, const u64 *__restrict__ rpC,
+                                                      const u32 *__restrict__ src_col, const VT *__restrict__ src_val,
+                                                      u32 *__restrict__ colC, VT *__restrict__ valC, int lanes_lg) {
+    const u32 L = 1u << lanes_lg;                                           // lanes per row
+    const u64 gthread = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 nsub = ((u64)gridDim.x * blockDim.x) >> lanes_lg;
+    const u32 sub = threadIdx.x & (L - 1);
+    for (u64 row = gthread >> lanes_lg; row < rows; row += nsub) {
+        const u64 d = rpC[row];
+        const u32 n = (u32)(rpC[row + 1] - d);
+        const u64 sbase = src_ptr[row];
+        for (u32 t = sub; t < n; t += L) { colC[d + t] = src_col[sbase + t]; valC[d + t] = src_val[sbase + t]; }
+    }
 }
 
 // =======================================================================================
