@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 SpGEMM engine (driver contract: ONE JSON line on rank 0).
+
+Workload (BASELINE.json configs[1], the reference's bench_repeated_exponentiation,
+src/graph_magnus.rs:699-788): A^2..A^7 on the 30x30x30 Moore torus thinned to ~3 edges/node with
+StdRng::from_seed([42;32]) -- the reference's exact operand (81 434 nnz) -- u64 saturating values,
+A^k = A^(k-1) * A.  One "step" = the whole chain (6 multiplies, 45.8 M intermediate products).
+metric = intermediate products / second (whole job); ms per A^k multiply is reported beside it.
+
+  value     operands resident in HBM, CUDA-event time on the engine's stream (= torch's current
+            stream), L2 flushed between steps, max over ranks
+  e2e       same chain through the public API with HOST buffers: pinned H2D of A, the six multiplies,
+            pinned D2H of every power (row_ptr, col_idx, values), wall clock
+  roofline  the largest multiply of the step (A^7 = A^6 * A): algorithmic bytes over
+            its CUDA-event time, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the CPU restatement of the reference's rayon CsrMatrix::matmul_par (oracle/, OpenMP, all
+            host cores), reference protocol: 1 warm-up + 3 timed multiplies per power, wall clock
+N > 1 (torchrun, one rank per GPU): weak scaling over the natural row sharding -- the torus grows to
+(30*N) x 30 x 30, A is broadcast once over NCCL, rank r keeps its product-balanced row block of every
+power resident and multiplies it by the replicated A; no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "intermediate_products_per_second"
+UNIT = "products/s"
+MAX_POWER = 7
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--side", type=int, default=30)
+    ap.add_argument("--epn", type=float, default=3.0)
+    ap.add_argument("--bits", type=int, default=64, choices=[32, 64])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def workload_config(args, world):
+    dims = [args.side * world, args.side, args.side]
+    return {"workload": f"repeated exponentiation A^2..A^{MAX_POWER} on the {dims[0]}x{dims[1]}x{dims[2]} Moore torus, "
+                        f"~{args.epn:g} e/n, StdRng([42;32]) thinning (graph_magnus.rs:699-788)",
+            "dims": dims, "val_bits": args.bits, "left": "A^(k-1) (resident row block per GPU)", "right": "A (replicated)",
+            "sharding": "contiguous row blocks balanced by intermediate-product count" if world > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write); within a step A^(k-1) is L2-warm from the previous multiply, as in the reference loop"}
+
+
+def build_operand(args, world):
+    from sparse_linear_algebra_tests_b200 import hostgen
+    full = hostgen.lattice([args.side * world, args.side, args.side], True, args.bits)
+    density = args.epn / (full.nnz() / full.rows)
+    return hostgen.thin(full, density, bytes([42] * 32))
+
+
+def algorithmic_bytes(nnz_a, nnz_b, nnz_c, rows_a, rows_b, vbytes):
+    return (nnz_a + nnz_b + nnz_c) * (4 + vbytes) + (rows_a + rows_b + rows_a + 3) * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU (reference arm / baseline)
+def cpu_chain(a_h, iters=3):
+    """Reference protocol on the CPU restatement of CsrMatrix::matmul_par: per power 1 warm-up (kept as the next
+    left operand) + `iters` timed multiplies with the result dropped.  Returns per-power seconds and products."""
+    from oracle import oracle as O
+    nt = O.max_threads()
+    a = O.Csr(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values)
+    p, secs, prods = a, [], []
+    for _k in range(2, MAX_POWER + 1):
+        prods.append(int(O.row_products(p, a).sum()))
+        nxt = O.matmul_par(p, a, nt)
+        secs.append(O.time_matmul(p, a, True, nt, iters))
+        p = nxt
+    return secs, prods, nt
+
+
+def run_reference(args):
+    rank, _lr, world = dist_env()
+    if rank != 0:
+        return
+    a_h = build_operand(args, max(1, args.gpus))                    # same job as the GPU arm at this N (the CPU does all rows)
+    steps = max(1, min(args.steps, 3))                              # bounded: each step already holds 3 timed multiplies per power
+    for _ in range(min(args.warmup, 1)):
+        cpu_chain(a_h, 1)
+    t_steps, prods = [], None
+    for _ in range(steps):
+        secs, prods, nt = cpu_chain(a_h, 3)
+        t_steps.append(sum(secs))
+    t = float(np.mean(t_steps))
+    value = sum(prods) / t
+    cfg = workload_config(args, max(1, args.gpus))
+    cfg["cpu"] = "OpenMP restatement of the reference's rayon matmul_par (Rust toolchain absent: the reference itself cannot be built)"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+           "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
+           "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
+                            "sample": f"full A^2..A^{MAX_POWER} chain, 3 timed multiplies per power, {steps} repetitions"},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from sparse_linear_algebra_tests_b200 import Context, hostgen
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(dev)                                 # the engine runs on this (non-default) torch stream,
+    torch.cuda.set_stream(stream)                                   # so torch.cuda.Event on it brackets every engine kernel
+    ctx = Context(local_rank, stream.cuda_stream)
+    vbytes = args.bits // 8
+    vdt = torch.int32 if args.bits == 32 else torch.int64          # bit containers for NCCL
+
+    # ---- operand: rank 0 builds A, one NCCL broadcast replicates it (the only collective of the job)
+    if rank == 0:
+        a_h = build_operand(args, world)
+        meta = torch.tensor([a_h.rows, a_h.cols, a_h.nnz()], dtype=torch.int64, device=dev)
+    else:
+        a_h, meta = None, torch.zeros(3, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(meta, 0)
+    n_rows, n_cols, n_nnz = (int(x) for x in meta.tolist())
+    if rank == 0:
+        d_rp = torch.from_numpy(a_h.row_ptr.view(np.int64)).to(dev)
+        d_ci = torch.from_numpy(a_h.col_idx.view(np.int32)).to(dev)
+        d_vv = torch.from_numpy(a_h.values.view(np.int32 if args.bits == 32 else np.int64)).to(dev)
+    else:
+        d_rp = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        d_ci = torch.empty(n_nnz, dtype=torch.int32, device=dev)
+        d_vv = torch.empty(n_nnz, dtype=vdt, device=dev)
+    if world > 1:
+        for t in (d_rp, d_ci, d_vv):
+            dist.broadcast(t, 0)
+    torch.cuda.synchronize(dev)
+    A = ctx.from_device(n_rows, n_cols, n_nnz, d_rp.data_ptr(), d_ci.data_ptr(), d_vv.data_ptr(), args.bits)
+    # ---- this rank's row block of the left operand, balanced by intermediate products of A x A
+    if world > 1:
+        cuts = ctx.shard_rows_by_products(A, A, world)
+        r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+        A_blk = ctx.row_block(A, r0, r1)
+    else:
+        r0, r1, A_blk = 0, n_rows, A
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def chain(collect_stats=False):
+        p, stats, keep = A_blk, [], []
+        for _k in range(2, MAX_POWER + 1):
+            if collect_stats:
+                c, st = ctx.spgemm(p, A, True)
+                stats.append(st.as_dict())
+            else:
+                c = ctx.spgemm(p, A)
+            keep.append(c)
+            p = c
+        return keep, stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        powers, _ = chain()
+        del powers
+    # one instrumented pass for per-multiply numbers (events inside the engine; not part of the timed steps)
+    powers, st = chain(True)
+    prods = [s["products"] for s in st]
+    nnzs = [s["nnz_c"] for s in st]
+    del powers
+
+    ctx.set_timing(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = ctx.kernel_launches()
+    step_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                                               # evict L2 between steps (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        powers, _ = chain()
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        del powers
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.set_timing(True)
+
+    my_ms = float(np.mean(step_ms))
+    t_ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(sum(prods)), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t_ms.item())
+    total_products, total_launches = float(tot[0].item()), int(tot[1].item())
+    value = total_products / (ms_per_step * 1e-3)
+
+    # ---- per-multiply detail (rank-local, instrumented pass repeated for a best-of-5)
+    best = [dict(s) for s in st]
+    for _ in range(4):
+        flush.fill_(1)
+        powers, st2 = chain(True)
+        for b, s in zip(best, st2):
+            if s["ms_total"] < b["ms_total"]:
+                b.update(s)
+        del powers
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    top = max(best, key=lambda s: s["bytes_algorithmic"])
+    achieved = top["bytes_algorithmic"] / (top["ms_total"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"all kernels of the largest multiply A^{MAX_POWER} = A^{MAX_POWER - 1} x A "
+                                           "(counts, bins, per-bin numeric, row_ptr scan, compaction)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes": top["bytes_algorithmic"], "ms": top["ms_total"], "traffic": None,
+                "numeric_only_frac": top["bytes_algorithmic"] / (top["ms_numeric"] * 1e-3) / 1e9 / peak if top["ms_numeric"] else None}
+    per_power = [{"power": k, "products": s["products"], "nnz": s["nnz_c"], "ms": s["ms_total"],
+                  "gbs": s["bytes_algorithmic"] / (s["ms_total"] * 1e-3) / 1e9, "launches": s["kernel_launches"]}
+                 for k, s in zip(range(2, MAX_POWER + 1), best)]
+
+    # ---- end to end through the public API with host buffers (pinned H2D of A, pinned D2H of every power)
+    e2e = None
+    a_loc = hostgen.HostCsr(n_rows, n_cols, d_rp.cpu().numpy().view(np.uint64), d_ci.cpu().numpy().view(np.uint32),
+                            d_vv.cpu().numpy().view(np.uint32 if args.bits == 32 else np.uint64))
+    blk = a_loc.row_block(r0, r1)
+    pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8)).pin_memory()
+    h_in = [pin(x) for x in (a_loc.row_ptr, a_loc.col_idx, a_loc.values, blk.row_ptr, blk.col_idx, blk.values)]
+    h_out = [(torch.empty((r1 - r0 + 1) * 8, dtype=torch.uint8).pin_memory(), torch.empty(max(n, 1) * 4, dtype=torch.uint8).pin_memory(),
+              torch.empty(max(n, 1) * vbytes, dtype=torch.uint8).pin_memory()) for n in nnzs]
+    vnp = np.uint32 if args.bits == 32 else np.uint64
+    h2d = sum(int(t.numel()) for t in (h_in[:3] if world == 1 else h_in))
+    d2h = sum(int(a.numel() + b.numel() + c.numel()) for a, b, c in h_out)
+
+    def e2e_step():
+        Af = ctx.upload(n_rows, n_cols, h_in[0].numpy().view(np.uint64), h_in[1].numpy().view(np.uint32), h_in[2].numpy().view(vnp))
+        p = Af if world == 1 else ctx.upload(r1 - r0, n_cols, h_in[3].numpy().view(np.uint64), h_in[4].numpy().view(np.uint32), h_in[5].numpy().view(vnp))
+        keep = []
+        for i in range(MAX_POWER - 1):
+            c = ctx.spgemm(p, Af)
+            c.download_async_into(h_out[i][0].data_ptr(), h_out[i][1].data_ptr(), h_out[i][2].data_ptr())
+            keep.append(c)
+            p = c
+        ctx.synchronize()
+        return keep
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_t = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        keep = e2e_step()
+        e_t.append(time.perf_counter() - t0)
+        del keep
+    e_ms = torch.tensor([float(np.mean(e_t)) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    # the last power read back must equal the resident result (cheap end-to-end sanity: nnz via row_ptr)
+    last_rp = h_out[-1][0].numpy().view(np.uint64)
+    assert int(last_rp[-1]) == nnzs[-1], "end-to-end read-back disagrees with the device result"
+    e2e = {"value": total_products / (float(e_ms.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e_ms.item()),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timing": "wall clock, synchronize on both sides, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cfg = workload_config(args, world)
+    cfg.update({"nodes": n_rows, "nnz_A": n_nnz, "products_per_step": int(total_products), "nnz_per_power_rank0": nnzs,
+                "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
+           "data": "synthetic", "config": cfg, "per_power": per_power, "gpu_launches": total_launches, "wall_s_timed_region": wall,
+           "clocks": clocks, "e2e": e2e, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        secs, cprods, nt = cpu_chain(a_loc, 3)
+        out["cpu_baseline"] = {"value": sum(cprods) / sum(secs), "unit": UNIT, "cores": nt, "kind": "port",
+                               "sample": f"full A^2..A^{MAX_POWER} chain, reference protocol (1 warm-up + 3 timed multiplies per power)",
+                               "ms_per_power": [s * 1e3 for s in secs], "ms_per_step": sum(secs) * 1e3}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

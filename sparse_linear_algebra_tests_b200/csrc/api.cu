@@ -53,13 +53,15 @@ struct b200_csr {
 
 struct b200_ctx {
     int device, num_sms;
-    size_t smem_optin;
+    size_t smem_optin, total_mem;
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
     // per-row scratch, grown on demand
     u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; u64 *d_tile_status; u64 cap_tiles;
     // heavy-row scratch
     void *d_heavy; size_t cap_heavy;
+    // one-pass scratch CSR (bound-offset rows), kept across multiplies so the steady state allocates nothing
+    void *d_tmp_col, *d_tmp_val; size_t cap_tmp_col, cap_tmp_val;
     u32 *d_flag;            // small device flag word (+ pinned mirror)
     u32 *h_flag;
     cudaEvent_t ev[4];
@@ -107,6 +109,21 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     }
     return B200_OK;
 }
+static int ensure_tmp(b200_ctx *ctx, size_t col_bytes, size_t val_bytes) {
+    if (col_bytes > ctx->cap_tmp_col) {
+        dfree(ctx, ctx->d_tmp_col); ctx->d_tmp_col = nullptr; ctx->cap_tmp_col = 0;
+        const size_t want = col_bytes + col_bytes / 4;
+        TRY(dmalloc(ctx, &ctx->d_tmp_col, want));
+        ctx->cap_tmp_col = want;
+    }
+    if (val_bytes > ctx->cap_tmp_val) {
+        dfree(ctx, ctx->d_tmp_val); ctx->d_tmp_val = nullptr; ctx->cap_tmp_val = 0;
+        const size_t want = val_bytes + val_bytes / 4;
+        TRY(dmalloc(ctx, &ctx->d_tmp_val, want));
+        ctx->cap_tmp_val = want;
+    }
+    return B200_OK;
+}
 static int ensure_heavy_scratch(b200_ctx *ctx, size_t bytes) {
     if (bytes > ctx->cap_heavy) {
         dfree(ctx, ctx->d_heavy); ctx->d_heavy = nullptr; ctx->cap_heavy = 0;
@@ -150,7 +167,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
         return set_err(B200_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
     b200_ctx *ctx = new b200_ctx();
     memset(ctx, 0, sizeof(*ctx));
-    ctx->device = device; ctx->num_sms = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->device = device; ctx->num_sms = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin; ctx->total_mem = prop.totalGlobalMem;
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
     else { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     cudaMemPool_t pool;
@@ -182,7 +199,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return B200_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_ctrl); cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
@@ -644,8 +661,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // nnz(A) * maxlen(B) is used when it is cheap, else the exact sum is read back first; if even that is
     // too large for the memory budget the exact two-pass path (symbolic + numeric) runs instead.
     bool onepass = env_int("B200_TWOPASS", 0) == 0;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+    size_t free_b = 0;
+    const size_t total_b = ctx->total_mem;
     const size_t esz = 4 + sizeof(VT);
     unsigned __int128 hb128 = (unsigned __int128)A->nnz * B->max_row_len;
     const unsigned __int128 dense128 = (unsigned __int128)rows * ncols;
@@ -666,15 +683,16 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             tmp_entries = ctx->h_ctrl->total_bound;
+            { size_t tb = 0; cudaMemGetInfo(&free_b, &tb); }
             if ((unsigned __int128)tmp_entries * esz > (unsigned __int128)(free_b / 3)) onepass = false;   // scratch would crowd out C
         }
     }
     if (onepass) {
         k_bin_scatter<0, true><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
         LAUNCH_CHECK(ctx);
-        r = dmalloc(ctx, &tmp_col, tmp_entries * 4);
-        if (r == B200_OK) r = dmalloc(ctx, &tmp_val, tmp_entries * sizeof(VT));
-        if (r != B200_OK) { dfree(ctx, tmp_col); b200_csr_free(ctx, C); return r; }
+        r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        tmp_col = ctx->d_tmp_col; tmp_val = ctx->d_tmp_val;
         const int mode = pick_mode<VT>(p_bound, maxA, maxB);
         const u64 heavy_cap = std::min<u64>(p_bound, ncols);
         if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) && !(heavy_cap < 65536 && (size_t)nwords * 6 + 16 + heavy_cap * 12 <= smem_max)) {
@@ -685,7 +703,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count};
         if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan);
         fan.join();
-        if (r != B200_OK) { dfree(ctx, tmp_col); dfree(ctx, tmp_val); b200_csr_free(ctx, C); return r; }
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
@@ -695,7 +713,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
         r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
         if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
-        if (r != B200_OK) { dfree(ctx, tmp_col); dfree(ctx, tmp_val); b200_csr_free(ctx, C); return r; }
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         if (timing) cudaEventRecord(ctx->ev[2], s);
         {
             const double avg = (double)C->nnz / (double)rows;
@@ -705,7 +723,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             LAUNCH_CHECK(ctx);
         }
         CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
-        dfree(ctx, tmp_col); dfree(ctx, tmp_val);
         if (timing) cudaEventRecord(ctx->ev[3], s);
         if (st) {
             st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
