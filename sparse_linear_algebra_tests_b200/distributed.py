@@ -1,0 +1,157 @@
+"""Multi-GPU orchestration of the SpGEMM path: natural row sharding, one process per GPU.
+
+The reference has no distributed code; the path shards by rows of the LEFT operand
+because row i of C depends only on row i of A and on B (src/graph_csr.rs:433-446):
+
+  * B (the original A of a power chain) is replicated once with a `torch.distributed` broadcast
+    (NCCL over NVLink on GPUs, gloo in the CPU tests);
+  * the left operand is cut into contiguous row blocks balanced by intermediate-product count,
+    not row count (`product_balanced_cuts`);
+  * in repeated exponentiation every rank keeps its row block of A^(k-1) resident and multiplies it
+    by the replicated A: no communication per step (`ShardedPowerChain`);
+  * `allgather_csr` optionally assembles the full C from the row blocks (variable sizes).
+
+Everything here is engine-agnostic plumbing: the multiply itself is `engine.spgemm`, which in the
+product is the CUDA engine (`CudaEngine`, no CPU fallback).  The gloo tests inject a CPU checker.
+"""
+from __future__ import annotations
+
+from typing import Protocol
+
+import numpy as np
+
+from . import hostgen
+
+
+def product_balanced_cuts(row_products: np.ndarray, nparts: int) -> np.ndarray:
+    """cuts[0..nparts]: part k = rows [cuts[k], cuts[k+1]) holds ~1/nparts of sum(P_i + 1).
+
+    Same rule as b200_shard_rows_by_products (csrc/api.cu): prefix of (P_i + 1) -- the +1 spreads
+    empty rows too -- and cut k at the first prefix >= k * total / nparts."""
+    p = np.asarray(row_products, dtype=np.uint64)
+    pre = np.zeros(p.shape[0] + 1, dtype=np.uint64)
+    np.cumsum(p + np.uint64(1), out=pre[1:])
+    total = int(pre[-1])
+    cuts = np.zeros(nparts + 1, dtype=np.uint64)
+    cuts[nparts] = p.shape[0]
+    for k in range(1, nparts):
+        lo = int(np.searchsorted(pre, np.uint64(total * k // nparts), side="left"))
+        cuts[k] = max(min(lo, p.shape[0]), int(cuts[k - 1]))
+    return cuts
+
+
+class Engine(Protocol):
+    def upload(self, h: hostgen.HostCsr): ...
+    def download(self, m) -> hostgen.HostCsr: ...
+    def row_products(self, a, b) -> np.ndarray: ...
+    def row_block(self, a, r0: int, r1: int): ...
+    def spgemm(self, a, b): ...
+
+
+class CudaEngine:
+    """The product engine: libb200spgemm.so through `_native.Context` (raises without a B200)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def upload(self, h):
+        return self.ctx.upload(h.rows, h.cols, h.row_ptr, h.col_idx, h.values)
+
+    def download(self, m):
+        rp, ci, vv = m.download()
+        return hostgen.HostCsr(m.rows, m.cols, rp, ci, vv)
+
+    def row_products(self, a, b):
+        return self.ctx.row_products(a, b)
+
+    def row_block(self, a, r0, r1):
+        return self.ctx.row_block(a, r0, r1)
+
+    def spgemm(self, a, b):
+        return self.ctx.spgemm(a, b)
+
+
+def broadcast_host_csr(h: hostgen.HostCsr | None, src: int = 0, group=None, device="cpu") -> hostgen.HostCsr:
+    """Replicate a CSR from rank `src` (three tensors + a 4-word header); returns the host copy on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    meta = torch.zeros(4, dtype=torch.int64, device=device)
+    if rank == src:
+        meta = torch.tensor([h.rows, h.cols, h.nnz(), h.val_bits], dtype=torch.int64, device=device)
+    dist.broadcast(meta, src, group=group)
+    rows, cols, nnz, bits = (int(x) for x in meta.tolist())
+    vnp = np.int32 if bits == 32 else np.int64
+    if rank == src:
+        t_rp = torch.from_numpy(h.row_ptr.view(np.int64).copy()).to(device)
+        t_ci = torch.from_numpy(h.col_idx.view(np.int32).copy()).to(device)
+        t_vv = torch.from_numpy(h.values.view(vnp).copy()).to(device)
+    else:
+        t_rp = torch.empty(rows + 1, dtype=torch.int64, device=device)
+        t_ci = torch.empty(nnz, dtype=torch.int32, device=device)
+        t_vv = torch.empty(nnz, dtype=torch.int32 if bits == 32 else torch.int64, device=device)
+    for t in (t_rp, t_ci, t_vv):
+        dist.broadcast(t, src, group=group)
+    return hostgen.HostCsr(rows, cols, t_rp.cpu().numpy().view(np.uint64), t_ci.cpu().numpy().view(np.uint32),
+                           t_vv.cpu().numpy().view(np.uint32 if bits == 32 else np.uint64))
+
+
+class ShardedPowerChain:
+    """A^k = A^(k-1) x A with the left operand row-sharded over the ranks and A replicated.
+
+    Rank r owns rows [cuts[r], cuts[r+1]) of every power; `step()` needs no communication."""
+
+    def __init__(self, engine: Engine, a_host: hostgen.HostCsr, rank: int, world: int):
+        self.engine, self.rank, self.world = engine, rank, world
+        self.a = engine.upload(a_host)
+        self.row_products = np.asarray(engine.row_products(self.a, self.a), dtype=np.uint64)
+        self.cuts = product_balanced_cuts(self.row_products, world)
+        self.r0, self.r1 = int(self.cuts[rank]), int(self.cuts[rank + 1])
+        self.block = engine.row_block(self.a, self.r0, self.r1) if world > 1 else self.a
+        self.power = 1
+
+    def step(self):
+        self.block = self.engine.spgemm(self.block, self.a)
+        self.power += 1
+        return self.block
+
+    def local_products(self) -> int:
+        return int(np.asarray(self.engine.row_products(self.block, self.a), dtype=np.uint64).sum())
+
+
+def allgather_csr(block: hostgen.HostCsr, group=None, device="cpu") -> hostgen.HostCsr:
+    """Assemble the full matrix from per-rank row blocks (rank order = row order).  Blocks have different
+    sizes: lengths are gathered first, payloads are padded to the largest block, row_ptr is re-based."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    bits = block.val_bits
+    sizes = torch.tensor([block.rows, block.nnz()], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    rows_l = [int(s[0]) for s in all_sizes]
+    nnz_l = [int(s[1]) for s in all_sizes]
+    mr, mn = max(rows_l) + 1, max(max(nnz_l), 1)
+    vnp, vt = (np.int32, torch.int32) if bits == 32 else (np.int64, torch.int64)
+
+    def padded(arr, n, dt):
+        t = torch.zeros(n, dtype=dt, device=device)
+        t[:arr.shape[0]] = torch.from_numpy(arr.copy()).to(device)
+        return t
+
+    parts = []
+    for arr, n, dt in ((block.row_ptr.view(np.int64), mr, torch.int64), (block.col_idx.view(np.int32), mn, torch.int32),
+                       (block.values.view(vnp), mn, vt)):
+        mine = padded(arr, n, dt)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        parts.append([o.cpu().numpy() for o in out])
+    rp = [np.zeros(1, dtype=np.uint64)]
+    base = 0
+    for r in range(world):
+        local = parts[0][r][:rows_l[r] + 1].view(np.uint64)
+        rp.append(local[1:] + np.uint64(base))
+        base += nnz_l[r]
+    col = np.concatenate([parts[1][r][:nnz_l[r]].view(np.uint32) for r in range(world)])
+    val = np.concatenate([parts[2][r][:nnz_l[r]].view(np.uint32 if bits == 32 else np.uint64) for r in range(world)])
+    return hostgen.HostCsr(sum(rows_l), block.cols, np.concatenate(rp).astype(np.uint64), col, val)

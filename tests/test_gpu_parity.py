@@ -283,3 +283,46 @@ def test_properties_on_full_size_torus(gpu_ctx):
         rowsum_prev = rowsum
         m = sp.csr_matrix((h.values.astype(np.float64), h.col_idx.astype(np.int64), h.row_ptr.astype(np.int64)), shape=(h.rows, h.cols))
         assert (m != m.T).nnz == 0, "A^k of a symmetric A must be symmetric"
+
+
+# ------------------------------------------------------------------ committed golden fixtures (tests/golden/*.npz)
+import glob as _glob
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def _load_golden(path):
+    z = np.load(path)
+    names = sorted({k[:-len("_shape")] for k in z.files if k.endswith("_shape")})
+    return {n: hostgen.HostCsr(int(z[n + "_shape"][0]), int(z[n + "_shape"][1]), z[n + "_row_ptr"], z[n + "_col_idx"], z[n + "_values"]) for n in names}
+
+
+@pytest.mark.parametrize("path", sorted(_glob.glob(_os.path.join(_GOLD, "*.npz"))), ids=_os.path.basename)
+def test_engine_reproduces_golden_fixture(gpu_ctx, path):
+    m = _load_golden(path)
+    up = lambda h: B200Matrix.from_host(h, gpu_ctx)
+    if "AA" in m:
+        assert_same(up(m["A"]).matmul(up(m["A"])).to_host(), m["AA"])
+    elif "A2" in m:
+        a = up(m["A"]); p = a
+        for k in range(2, 6):
+            p = p.matmul(a)
+            assert_same(p.to_host(), m[f"A{k}"], f"A^{k}")
+    else:
+        p = up(m["M0"])
+        for k in range(1, 9):
+            p = p.matmul(p)
+            assert_same(p.to_host(), m[f"M{k}"], f"squaring {k}")
+
+
+def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, monkeypatch):
+    """B200_TWOPASS=1 forces the exact-allocation path (symbolic -> row_ptr -> numeric) used when the one-pass
+    scratch would not fit; both must give the same bytes."""
+    a_h = hostgen.reference_bench_instance(12, 3.0, 64)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    one = a.matmul(a).matmul(a).to_host()
+    monkeypatch.setenv("B200_TWOPASS", "1")
+    two = a.matmul(a).matmul(a).to_host()
+    assert_same(one, two)
+    assert_same(one, oracle.matmul(oracle.matmul(to_o(oracle, a_h), to_o(oracle, a_h)), to_o(oracle, a_h)))

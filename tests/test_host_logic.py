@@ -1,0 +1,88 @@
+"""Host-side logic (no GPU): builders against the oracle's independent C versions, sharding rule, ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from sparse_linear_algebra_tests_b200 import EXPORTS, LIB_PATH, hostgen
+from sparse_linear_algebra_tests_b200.distributed import product_balanced_cuts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def same(h, o):
+    return (h.rows == o.rows and np.array_equal(h.row_ptr, o.row_ptr) and np.array_equal(h.col_idx, o.col_idx)
+            and h.values.dtype == o.values.dtype and np.array_equal(h.values, o.values))
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("dims,torus", [([5], False), ([5], True), ([3, 3], True), ([2, 2, 2], False), ([2, 2, 2], True), ([4, 3], False), ([6, 5, 4], True)])
+def test_lattice_matches_oracle(oracle, dims, torus, bits):
+    assert same(hostgen.lattice(dims, torus, bits), oracle.lattice(dims, torus, bits))
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_thin_and_bench_instance_match_oracle(oracle, bits):
+    for side, epn in ((6, 3.0), (10, 4.0), (12, 8.0)):
+        assert same(hostgen.reference_bench_instance(side, epn, bits), oracle.reference_bench_instance(side, epn, bits))
+    full = hostgen.lattice([7, 7, 7], True, bits)
+    t = hostgen.thin(full, 0.3, bytes(range(32)))
+    assert same(t, oracle.thin_stdrng(oracle.lattice([7, 7, 7], True, bits), bytes(range(32)), 0.3))
+    rows = t.row_of_entry()
+    for r, c, v in zip(rows.tolist(), t.col_idx.tolist(), t.values.tolist()):
+        assert t.get(c, r) == v                                    # thinning preserves symmetry (graph_csr.rs:224)
+
+
+def test_portable_generators_match_oracle(oracle):
+    assert same(hostgen.lattice_csr_xorshift(8, 3.0, 42), oracle.lattice_csr_xorshift(8, 3.0, 42))
+    assert same(hostgen.rmat(9, 8, 0.57, 0.19, 0.19, 42, 64), oracle.rmat(9, 8, 0.57, 0.19, 0.19, 42, 64))
+    assert same(hostgen.rmat(8, 4, 0.45, 0.15, 0.15, 7, 32), oracle.rmat(8, 4, 0.45, 0.15, 0.15, 7, 32))
+
+
+def test_from_coo_semantics(oracle):
+    h = hostgen.from_coo(4, 4, [3, 0, 0, 2, 0], [1, 2, 2, 2, 0], np.array([1, 2, 3, 0, 9], np.uint32), 32)
+    assert (h.get(0, 2), h.get(0, 0), h.get(3, 1), h.nnz()) == (5, 9, 1, 3) and h.row_ptr.tolist() == [0, 2, 2, 2, 3]
+    big = np.array([0xFFFFFFFF, 2], np.uint32)
+    wrap = hostgen.from_coo(1, 1, [0, 0], [0, 0], big, 32)                    # plain += (graph_csr.rs:93) wraps in release
+    sat = hostgen.from_coo(1, 1, [0, 0], [0, 0], big, 32, saturating=True)   # linalg/src/csr.rs:167
+    assert wrap.get(0, 0) == 1 and sat.get(0, 0) == 0xFFFFFFFF
+    assert same(wrap, oracle.from_coo(1, 1, [0, 0], [0, 0], big, 32, False)) and same(sat, oracle.from_coo(1, 1, [0, 0], [0, 0], big, 32, True))
+    with pytest.raises(IndexError):
+        hostgen.from_coo(2, 2, [2], [0], [1])
+
+
+def test_product_balanced_cuts(oracle):
+    a = oracle.reference_bench_instance(10, 3.0, 64)
+    p = oracle.row_products(a, a)
+    for parts in (1, 2, 3, 8):
+        cuts = product_balanced_cuts(p, parts)
+        assert cuts[0] == 0 and cuts[-1] == a.rows and np.all(np.diff(cuts.astype(np.int64)) >= 0)
+        loads = [int(p[int(cuts[i]):int(cuts[i + 1])].sum()) + int(cuts[i + 1] - cuts[i]) for i in range(parts)]
+        assert max(loads) - min(loads) <= 2 * (int(p.max()) + 1)
+    skew = np.array([1000] + [0] * 99, dtype=np.uint64)            # one heavy row: it gets a part of its own
+    cuts = product_balanced_cuts(skew, 4)
+    assert cuts[1] == 1
+
+
+def test_shared_library_loads_and_exports_every_declared_symbol():
+    assert os.path.exists(LIB_PATH), "build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()')"
+    lib = ctypes.CDLL(LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "b200_spgemm.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found in include/b200_spgemm.h"
+    for name in declared:
+        assert hasattr(lib, name), f"libb200spgemm.so does not export {name}"
+    assert sorted(EXPORTS) == declared
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without a CUDA device the context cannot be created."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from sparse_linear_algebra_tests_b200 import B200Error, Context
+    with pytest.raises(B200Error) as e:
+        Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
