@@ -97,7 +97,9 @@ int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *out);
 /* Device handle -> caller-allocated host arrays (sizes from b200_csr_info). */
 int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values);
 int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values);
-/* Asynchronous variant into pinned host memory on the ctx stream (no synchronize). */
+/* Asynchronous variant into pinned host memory: ordered after the work queued on the ctx stream so far, run on
+ * the context's own copy stream so that it overlaps the next multiply; b200_ctx_synchronize waits for it, and
+ * freeing the handle is ordered after it. */
 int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values);
 
 /* C = A x B.  Replaces CsrMatrix::matmul / matmul_par (src/graph_csr.rs:306-346, 350-484),

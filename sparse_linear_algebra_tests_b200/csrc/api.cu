@@ -48,6 +48,7 @@ struct b200_csr {
     uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
     uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
     u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
+    cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
     b200_ctx *ctx;
 };
 
@@ -66,6 +67,7 @@ struct b200_ctx {
     u32 *h_flag;
     cudaEvent_t ev[4];
     cudaStream_t aux[B200_NAUX]; cudaEvent_t ev_fork, ev_join[B200_NAUX]; int naux_enabled;
+    cudaStream_t copy; cudaEvent_t ev_ready;   // D2H stream: downloads overlap the next multiply
     bool timing;
     u64 launches;
 };
@@ -181,6 +183,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < B200_NAUX; i++) { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : B200_NAUX; }
     ctx->timing = true;
     setup_kernels_vt<u32>(ctx->smem_optin);
@@ -198,6 +202,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
 extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return B200_OK;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
     cudaStreamSynchronize(ctx->stream);
@@ -205,6 +210,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
+    cudaStreamDestroy(ctx->copy); cudaEventDestroy(ctx->ev_ready);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B200_OK;
@@ -213,6 +219,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
 extern "C" int b200_ctx_synchronize(b200_ctx *ctx) {
     if (!ctx) return set_err(B200_ERR_BADARG, "ctx is NULL");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy));
     return B200_OK;
 }
 extern "C" int b200_ctx_kernel_launches(b200_ctx *ctx, uint64_t *out) {
@@ -243,6 +250,7 @@ static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, b
 extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
+    if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
     dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;
@@ -250,10 +258,15 @@ extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
 
 static int grid_for(u64 n, int threads, int cap) { u64 g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > (u64)cap) g = cap; return (int)g; }
 
-// value max + format check (explicit zeros, column range); synchronises
-static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check) {
+// value max + format check (explicit zeros, column range); synchronises when `check`.  `device_rowptr`: the
+// row_ptr never passed through the host, so its sanity and the longest row are established on the device too.
+static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr = false) {
     CUDA_TRY(cudaMemsetAsync(m->d_maxval, 0, 16, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 32, ctx->stream));
+    if (device_rowptr && m->rows) {
+        k_rowptr_stats<<<grid_for(m->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(m->rows, m->nnz, m->d_rp, ctx->d_flag + 4, ctx->d_flag);
+        LAUNCH_CHECK(ctx);
+    }
     if (m->nnz) {
         int g = grid_for(m->nnz, 256, ctx->num_sms * 8);
         if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag);
@@ -263,7 +276,9 @@ static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check) {
     if (check) {
         CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 64, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_flag[0] & 2u) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone from 0 to nnz");
         if (ctx->h_flag[0]) return set_err(B200_ERR_FORMAT, "CSR holds an explicit zero value or a column index >= cols");
+        if (device_rowptr) m->max_row_len = ctx->h_flag[4];
     }
     return B200_OK;
 }
@@ -338,8 +353,8 @@ extern "C" int b200_csr_from_device(b200_ctx *ctx, uint64_t rows, uint64_t cols,
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_col, d_col_idx, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_val, d_values, nnz * (size_t)(val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
     if (e != cudaSuccess) { b200_csr_free(ctx, m); return set_err(B200_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e)); }
-    m->max_row_len = std::min<u64>(nnz, cols);          // bound only; tightened by the first multiply that reads it
-    int r = finish_new_csr(ctx, m, true);
+    m->max_row_len = std::min<u64>(nnz, cols);          // bound; replaced by the exact longest row below
+    int r = finish_new_csr(ctx, m, true, true);
     if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
     *out = m;
     return B200_OK;
@@ -366,14 +381,20 @@ extern "C" int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *ou
 extern "C" int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
     if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (row_ptr) CUDA_TRY(cudaMemcpyAsync(row_ptr, m->d_rp, (m->rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (col_idx && m->nnz) CUDA_TRY(cudaMemcpyAsync(col_idx, m->d_col, m->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (values && m->nnz) CUDA_TRY(cudaMemcpyAsync(values, m->d_val, m->nnz * (size_t)(m->val_bits / 8), cudaMemcpyDeviceToHost, ctx->stream));
+    // the copies run on the context's copy stream, after everything queued on the compute stream so far
+    b200_csr *mm = const_cast<b200_csr *>(m);
+    if (!mm->ev_copy) CUDA_TRY(cudaEventCreateWithFlags(&mm->ev_copy, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ctx->ev_ready, 0));
+    if (row_ptr) CUDA_TRY(cudaMemcpyAsync(row_ptr, m->d_rp, (m->rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy));
+    if (col_idx && m->nnz) CUDA_TRY(cudaMemcpyAsync(col_idx, m->d_col, m->nnz * 4, cudaMemcpyDeviceToHost, ctx->copy));
+    if (values && m->nnz) CUDA_TRY(cudaMemcpyAsync(values, m->d_val, m->nnz * (size_t)(m->val_bits / 8), cudaMemcpyDeviceToHost, ctx->copy));
+    CUDA_TRY(cudaEventRecord(mm->ev_copy, ctx->copy));
     return B200_OK;
 }
 extern "C" int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
     TRY(b200_csr_download_async(ctx, m, row_ptr, col_idx, values));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy));
     return B200_OK;
 }
 extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values) {
@@ -388,6 +409,7 @@ extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_
     }
     TRY(b200_csr_download_async(ctx, m, row_ptr, nullptr, values));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy));
     dfree(ctx, tmp);
     return B200_OK;
 }
@@ -880,7 +902,7 @@ extern "C" int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t r0,
         cudaMemcpyAsync(m->d_val, (const char *)A->d_val + ends[0] * (A->val_bits / 8), nnz * (size_t)(A->val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
     }
     m->max_row_len = A->max_row_len;
-    int r = finish_new_csr(ctx, m, false);
+    int r = finish_new_csr(ctx, m, true, true);
     if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
     *out = m;
     return B200_OK;

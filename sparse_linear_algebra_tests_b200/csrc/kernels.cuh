@@ -1062,6 +1062,21 @@ __global__ void __launch_bounds__(256) k_value_stats(u64 nnz, const VT *__restri
     if ((threadIdx.x & 31) == 0) { if (m) atomicMax(maxval, (ull)m); if (z) atomicOr(bad, 1u); }
 }
 
+// longest row + row_ptr sanity for handles adopted from device arrays (the host never sees their row_ptr)
+__global__ void __launch_bounds__(256) k_rowptr_stats(u64 rows, u64 nnz, const u64 *__restrict__ rp, u32 *max_len, u32 *bad) {
+    u32 m = 0, z = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[i], e = rp[i + 1];
+        z |= (e < s) | (e > nnz) | (i == 0 && s != 0) | (i + 1 == rows && e != nnz);
+        const u64 l = e - s;
+        m = l > m && e >= s ? (u32)(l > 0xFFFFFFFFull ? 0xFFFFFFFFull : l) : m;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, k));
+    z = __any_sync(0xFFFFFFFFu, z);
+    if ((threadIdx.x & 31) == 0) { if (m) atomicMax(max_len, m); if (z) atomicOr(bad, 2u); }
+}
+
 __global__ void __launch_bounds__(256) k_narrow_idx(u64 n, const u64 *__restrict__ in, u32 *__restrict__ out, u32 *bad) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const u64 v = in[i];

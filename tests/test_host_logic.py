@@ -35,6 +35,14 @@ def test_thin_and_bench_instance_match_oracle(oracle, bits):
         assert t.get(c, r) == v                                    # thinning preserves symmetry (graph_csr.rs:224)
 
 
+@pytest.mark.parametrize("dims", [[5, 4, 3], [6, 6, 6], [7, 3], [9]])
+def test_thinned_torus_equals_lattice_then_thin(dims):
+    """The large-instance builder (200^3 config) skips the full-lattice COO sort but must give the same matrix."""
+    for bits, density, seed in ((32, 3.0 / 26.0, bytes([42] * 32)), (64, 0.4, bytes(range(32)))):
+        want = hostgen.thin(hostgen.lattice(dims, True, bits), density, seed)
+        assert same(hostgen.thinned_torus(dims, density, seed, bits), want)
+
+
 def test_portable_generators_match_oracle(oracle):
     assert same(hostgen.lattice_csr_xorshift(8, 3.0, 42), oracle.lattice_csr_xorshift(8, 3.0, 42))
     assert same(hostgen.rmat(9, 8, 0.57, 0.19, 0.19, 42, 64), oracle.rmat(9, 8, 0.57, 0.19, 0.19, 42, 64))
