@@ -70,7 +70,27 @@ struct b200_ctx {
     cudaStream_t copy; cudaEvent_t ev_ready;   // D2H stream: downloads overlap the next multiply
     bool timing;
     u64 launches;
+    // developer timeline (B200_TRACE=1): an event after every launch, on the stream it went to
+    bool trace; cudaStream_t cur_stream;
+    std::vector<std::pair<int, cudaEvent_t>> *marks;
 };
+static void trace_mark(b200_ctx *ctx, int line) {
+    cudaEvent_t e; cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->cur_stream ? ctx->cur_stream : ctx->stream);
+    ctx->marks->push_back(std::make_pair(line, e));
+    ctx->cur_stream = nullptr;
+}
+static void trace_dump(b200_ctx *ctx, const char *what) {
+    if (!ctx->trace || ctx->marks->empty()) return;
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[b200 trace] %s\n", what);
+    for (size_t i = 0; i < ctx->marks->size(); i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, (*ctx->marks)[0].second, (*ctx->marks)[i].second);
+        fprintf(stderr, "   line %4d done at %8.1f us\n", (*ctx->marks)[i].first, ms * 1e3f);
+    }
+    for (auto &m : *ctx->marks) cudaEventDestroy(m.second);
+    ctx->marks->clear();
+}
 
 static int host_maxval(b200_ctx *ctx, const b200_csr *m);
 
@@ -81,7 +101,7 @@ static CsrView<VT> view(const b200_csr *m) {
 }
 
 #define LAUNCH_CHECK(ctx)                                                                          \
-    do { (ctx)->launches++; cudaError_t _e = cudaGetLastError();                                   \
+    do { (ctx)->launches++; if ((ctx)->trace) trace_mark(ctx, __LINE__); cudaError_t _e = cudaGetLastError(); \
          if (_e != cudaSuccess) return set_err(B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
 static int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
@@ -150,8 +170,13 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_num_warp<VT, 0>, optin); allow_big_smem(k_num_warp<VT, 1>, optin);
     allow_big_smem(k_num_rank_pack<VT, 0, false>, optin); allow_big_smem(k_num_rank_pack<VT, 0, true>, optin);
     allow_big_smem(k_num_rank_pack<VT, 1, false>, optin); allow_big_smem(k_num_rank_pack<VT, 1, true>, optin);
+    allow_big_smem(k_num_expand<VT, 0, false, false>, optin); allow_big_smem(k_num_expand<VT, 0, false, true>, optin);
+    allow_big_smem(k_num_expand<VT, 0, true, false>, optin); allow_big_smem(k_num_expand<VT, 0, true, true>, optin);
+    allow_big_smem(k_num_expand<VT, 1, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, false, true>, optin);
+    allow_big_smem(k_num_expand<VT, 1, true, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, true>, optin);
 }
 
+static int env_int_early(const char *name) { const char *v = getenv(name); return v && *v ? atoi(v) : 0; }
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     if (!out) return set_err(B200_ERR_BADARG, "b200_ctx_create: out is NULL");
     int n = 0;
@@ -187,6 +212,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : B200_NAUX; }
     ctx->timing = true;
+    ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
     setup_kernels_vt<u32>(ctx->smem_optin);
     setup_kernels_vt<u64>(ctx->smem_optin);
     allow_big_smem(k_sym_cta<false>, ctx->smem_optin); allow_big_smem(k_sym_cta<true>, ctx->smem_optin);
@@ -194,6 +220,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_sym_pack<false>, ctx->smem_optin); allow_big_smem(k_sym_pack<true>, ctx->smem_optin);
     allow_big_smem(k_num_rank_pack<u64, 2, false>, ctx->smem_optin); allow_big_smem(k_num_rank_pack<u64, 2, true>, ctx->smem_optin);
+    allow_big_smem(k_num_expand<u64, 2, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true>, ctx->smem_optin);
+    allow_big_smem(k_num_expand<u64, 2, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true>, ctx->smem_optin);
     cudaGetLastError();
     *out = ctx;
     return B200_OK;
@@ -496,6 +524,7 @@ struct Fan {
         if (n == 0) return ctx->stream;
         const int slot = next++ % (n + 1);
         if (slot == n) return ctx->stream;
+        ctx->cur_stream = ctx->aux[slot];
         if (!forked) { cudaEventRecord(ctx->ev_fork, ctx->stream); forked = true; }
         if (!used[slot]) { cudaStreamWaitEvent(ctx->aux[slot], ctx->ev_fork, 0); used[slot] = true; }
         return ctx->aux[slot];
@@ -539,12 +568,42 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     const size_t accb = mode == 0 ? 4 : 8;
     auto bin_size = [&](int bin) -> u64 { return cnt ? cnt[bin] : rows; };
     auto reachable = [&](int hb) { return cnt ? cnt[B200_BIN_HASH0 + hb] != 0 : (hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1)); };
-    if (bin_size(B200_BIN_TINY)) {
+    auto do_tiny = [&]() -> int {
+        if (!bin_size(B200_BIN_TINY)) return B200_OK;
         const int g = (int)std::min<u64>((bin_size(B200_BIN_TINY) + 7) / 8, (u64)ctx->num_sms * 32);
         k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o);
         LAUNCH_CHECK(ctx);
-    }
-    if (reachable(0) || reachable(1)) {
+        return B200_OK;
+    };
+    // one-pass bins are cut on the product count P <= cap: expand the products into shared memory once and run every
+    // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
+    auto launch_expand = [&](int bin, int nb, u32 cap, u64 n, cudaStream_t bs) -> bool {
+        if (cnt || !env_int("B200_EXPAND", 1)) return false;
+        const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
+        const u32 nw4 = (nwords + 3) / 4;
+        const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
+        const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
+        if (ex_smem > smem_max || nw4 > 8 * (size_t)pcap) return false;
+        const int et = std::max(32, std::min(512, (int)pcap / std::max(1, env_int("B200_EDIV", 8))));
+        const int eg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * 4);
+        if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
+#define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
+        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); \
+                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); }   \
+             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO);         \
+                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); } } while (0)
+        if (mode == 0) EXPAND(0, VT, na, o);
+        else if (mode == 1) EXPAND(1, VT, na, o);
+        else EXPAND(2, u64, na64, o64);
+#undef EXPAND
+        return true;
+    };
+    auto do_small = [&]() -> int {
+        if (!(reachable(0) || reachable(1))) return B200_OK;
+        if (!cnt && env_int("B200_EXPAND_SMALL", 1) && launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), rows, fan.pick())) {
+            LAUNCH_CHECK(ctx);
+            return B200_OK;
+        }
         const u64 n01 = cnt ? (u64)cnt[B200_BIN_HASH0] + cnt[B200_BIN_HASH0 + 1] : rows;
         const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4);
         const int g = (int)std::min<u64>((n01 + 7) / 8, (u64)ctx->num_sms * 16);
@@ -554,14 +613,16 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
         else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o);
         else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o64);
         LAUNCH_CHECK(ctx);
-    }
-    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
-        if (!reachable(hb)) { if (cnt) continue; else break; }
+        return B200_OK;
+    };
+    auto do_bin = [&](int hb) -> int {
+        if (!reachable(hb)) return B200_OK;
         const u64 n = bin_size(B200_BIN_HASH0 + hb);
         const u32 slots = b200_hash_slots(hb);
         const u32 cap = b200_hash_cap(hb);
         const int bin = B200_BIN_HASH0 + hb;
         cudaStream_t bs = fan.pick();
+        if (launch_expand(bin, 1, cap, n, bs)) { LAUNCH_CHECK(ctx); return B200_OK; }
         // rank kernel (column bitmap in shared memory) when the column space is small next to the row
         const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (4 + accb);
         if (nwords <= 4 * cap && rank_smem <= smem_max) {
@@ -583,7 +644,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
                 else k_num_rank<u64, 2><<<g, threads, rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o64);
             }
             LAUNCH_CHECK(ctx);
-            continue;
+            return B200_OK;
         }
         const int threads = bin_threads(hb, lg);
         const size_t smem = (size_t)slots * (4 + accb);
@@ -593,7 +654,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
         else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
         else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o64);
         LAUNCH_CHECK(ctx);
-    }
+        return B200_OK;
+    };
+    // the longest rows first: the big kernels start while the host is still queueing the small ones
     const bool heavy = cnt ? cnt[B200_BIN_HEAVY] != 0 : p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
     if (heavy) {
         const u64 n = bin_size(B200_BIN_HEAVY);
@@ -623,6 +686,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
             LAUNCH_CHECK(ctx);
         }
     }
+    for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) TRY(do_bin(hb));
+    TRY(do_small());
+    TRY(do_tiny());
     return B200_OK;
 }
 
@@ -692,6 +758,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool cheap_bound = hb128 * esz <= (unsigned __int128)(total_b / 16);
 
     if (timing) cudaEventRecord(ctx->ev[0], s);
+    if (ctx->trace) trace_mark(ctx, __LINE__);
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
     CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, 2 * ctx->cap_tiles * 8, s));
     TRY(launch_row_products(ctx, A, B, onepass));
@@ -737,6 +804,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         if (timing) cudaEventRecord(ctx->ev[2], s);
+        if (ctx->trace) trace_mark(ctx, __LINE__);
         {
             const double avg = (double)C->nnz / (double)rows;
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
@@ -758,6 +826,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
             }
         }
+        trace_dump(ctx, "one-pass multiply");
         *out = C;
         return B200_OK;
     }

@@ -171,6 +171,7 @@ template <> struct Acc<0> {
     __device__ void bind(unsigned char *base, u32) { lo = reinterpret_cast<u32 *>(base); }
     __device__ void clear(u32 i) { lo[i] = 0; }
     template <typename VT> __device__ void add(u32 i, VT a, VT b) { atomicAdd(&lo[i], (u32)a * (u32)b); }
+    __device__ void addv(u32 i, u64 x) { atomicAdd(&lo[i], (u32)x); }                 // x: an already formed product
     __device__ u64 get(u32 i) const { return lo[i]; }
     __device__ void set(u32 i, u64 x) { lo[i] = (u32)x; }
 };
@@ -187,6 +188,12 @@ template <> struct Acc<1> {
         const u32 up = xhi + ((u32)(old + xlo) < xlo ? 1u : 0u);
         if (up) atomicAdd(&hi[i], up);
     }
+    __device__ void addv(u32 i, u64 x) {
+        const u32 xlo = (u32)x, xhi = (u32)(x >> 32);
+        const u32 old = atomicAdd(&lo[i], xlo);
+        const u32 up = xhi + ((u32)(old + xlo) < xlo ? 1u : 0u);
+        if (up) atomicAdd(&hi[i], up);
+    }
     __device__ u64 get(u32 i) const { return ((u64)hi[i] << 32) | lo[i]; }
     __device__ void set(u32 i, u64 x) { lo[i] = (u32)x; hi[i] = (u32)(x >> 32); }
 };
@@ -197,6 +204,15 @@ template <> struct Acc<2> {
     __device__ void clear(u32 i) { v[i] = 0; }
     template <typename VT> __device__ void add(u32 i, VT a, VT b) {
         const ull x = sat_mul((u64)a, (u64)b);
+        ull old = *reinterpret_cast<volatile ull *>(&v[i]), assumed;
+        do {
+            assumed = old;
+            ull s = assumed + x; if (s < assumed) s = ~0ull;
+            if (s == assumed) break;
+            old = atomicCAS(&v[i], assumed, s);
+        } while (old != assumed);
+    }
+    __device__ void addv(u32 i, u64 x) {
         ull old = *reinterpret_cast<volatile ull *>(&v[i]), assumed;
         do {
             assumed = old;
@@ -683,7 +699,12 @@ __global__ void __launch_bounds__(256) k_build_pack(u64 rows, const u64 *__restr
     }
 }
 __device__ __forceinline__ PackRec load_pack(const uint4 *__restrict__ pack, u32 k) {
-    PackRec r; r.a = __ldg(&pack[2 * (u64)k]); r.b = __ldg(&pack[2 * (u64)k + 1]); return r;
+    // one 256-bit read-only load (LDG.E.256 on sm_100): a single L1 request per record instead of two
+    PackRec r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                 : "l"(pack + 2 * (u64)k));
+    return r;
 }
 template <typename F>
 __device__ __forceinline__ void for_each_col(const PackRec &r, const u32 *__restrict__ colB, F f) {
@@ -818,6 +839,236 @@ __global__ void __launch_bounds__(1024) k_num_rank_pack(NumArgs<VT> a, const uin
     }
     vmax = warp_max_u64(vmax);
     if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
+}
+
+// =======================================================================================
+// 5e. expand-then-rank (one-pass numeric, medium rows): CTA per row, every phase after the expansion
+//     runs one PRODUCT (or one output entry) per thread, so no lane idles on a short B row.
+//       expand : thread per A entry; warp scan of the B-row lengths hands every entry a slice of the
+//                row's product buffer in shared memory; the entry's columns (from its sector-packed
+//                record) and its product values a_ik*b_kj are written there, and each column is
+//                marked in the row's column bitmap (atomicOr) while it is still in a register
+//       rank   : prefix popcount over the bitmap, 128-bit shared loads, four words per thread-step
+//       accum  : thread per product -> acc[rank(col)] += value, cols[rank(col)] = col
+//       emit   : thread per output entry, coalesced stores; accumulators and bitmap are cleared on the
+//                way out so the next row starts clean
+//     Shared memory: pcap*(4+pv) + ncap*(4+acc) + 6*nwords bytes (pcap = bin's product capacity).
+// =======================================================================================
+template <int MODE, typename VT> struct PVal { typedef u64 type; };
+template <typename VT> struct PVal<0, VT> { typedef u32 type; };
+template <> struct PVal<1, u32> { typedef u32 type; };
+
+template <int MODE, typename VT>
+__device__ __forceinline__ typename PVal<MODE, VT>::type product_value(VT a, VT b) {
+    if (MODE == 0) return (typename PVal<MODE, VT>::type)((u32)a * (u32)b);
+    if (MODE == 2) return (typename PVal<MODE, VT>::type)sat_mul((u64)a, (u64)b);
+    u64 x = (u64)a * (u64)b;
+    if (sizeof(VT) == 4) x = x > 0xFFFFFFFFull ? 0xFFFFFFFFull : x;
+    return (typename PVal<MODE, VT>::type)x;
+}
+// exclusive prefix popcount of the bitmap, four words per step (nw4 = number of uint4 groups); returns nnz.
+// Prefixes are stored as four u16 per group (a row handled here has < 65536 entries).
+__device__ __forceinline__ u32 rank_prefix_v4(const uint4 *bm4, uint2 *wpre4, u32 nw4, u32 *s_warp) {
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    if (nw4 <= nt) {                                                        // one group per thread: no loops
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (tid < nw4) w = bm4[tid];
+        const u32 c0 = __popc(w.x), c1 = __popc(w.y), c2 = __popc(w.z), c3 = __popc(w.w);
+        u32 total;
+        const u32 p0 = block_excl_scan(c0 + c1 + c2 + c3, s_warp, total);
+        const u32 p1 = p0 + c0, p2 = p1 + c1, p3 = p2 + c2;
+        if (tid < nw4) wpre4[tid] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+        return total;
+    }
+    const u32 per = (nw4 + nt - 1) / nt;
+    const u32 g0 = tid * per;
+    u32 mine = 0;
+#pragma unroll 1
+    for (u32 i = 0; i < per; i++) {
+        if (g0 + i < nw4) { const uint4 w = bm4[g0 + i]; mine += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
+    }
+    u32 total;
+    u32 run = block_excl_scan(mine, s_warp, total);
+#pragma unroll 1
+    for (u32 i = 0; i < per; i++) {
+        if (g0 + i < nw4) {
+            const uint4 w = bm4[g0 + i];
+            const u32 p0 = run, p1 = p0 + __popc(w.x), p2 = p1 + __popc(w.y), p3 = p2 + __popc(w.z);
+            wpre4[g0 + i] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+            run = p3 + __popc(w.w);
+        }
+    }
+    return total;
+}
+
+// B row of one A entry as the expansion sees it: where it starts, how long it is, and (packed B) its first columns
+struct BRowRef { u32 start, len; uint4 ca, cb; };
+template <bool PACK>
+__device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, const uint2 *__restrict__ bdesc, u32 k) {
+    BRowRef b;
+    if (PACK) { const PackRec r = load_pack(pack, k); b.start = r.a.x; b.len = r.a.y; b.ca = r.a; b.cb = r.b; }
+    else { const uint2 d = bdesc[k]; b.start = d.x; b.len = d.y; b.ca = make_uint4(0, 0, 0, 0); b.cb = b.ca; }
+    return b;
+}
+
+#define B200_EXPAND_PRE 2   // A entries per thread whose loads are issued one row ahead
+#define B200_EXPAND_ILP 4   // products each thread keeps in flight in the mark / accumulate loops
+
+template <typename VT, int MODE, bool PACK, bool BPAT>
+__global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
+                                                    B200Ctrl *ctrl, int bin, int nbins, u32 pcap, u32 ncap, u32 nw4, OutArgs<VT> o) {
+    typedef typename PVal<MODE, VT>::type PV;
+    constexpr bool PAIR = sizeof(PV) == 4;       // products kept as {col, value} pairs: one 64-bit shared access each
+    constexpr int E = B200_EXPAND_PRE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_warp[33];
+    __shared__ u32 s_P;
+    u32 count = 0;
+    for (int b = 0; b < nbins; b++) count += o.bin_cnt[bin + b];            // consecutive bins share one launch
+    u32 r_begin, r_end;
+    cta_row_range(count, r_begin, r_end);
+    if (r_begin >= r_end) return;
+    // layout: bitmap | word prefixes | products ({col,val} pairs, or values then cols) | accumulators | output cols
+    uint4 *bm4 = reinterpret_cast<uint4 *>(smem_raw);
+    u32 *bm = reinterpret_cast<u32 *>(smem_raw);
+    uint2 *wpre4 = reinterpret_cast<uint2 *>(smem_raw + (size_t)nw4 * 16);
+    const unsigned short *wpre = reinterpret_cast<const unsigned short *>(wpre4);
+    unsigned char *p8 = smem_raw + (size_t)nw4 * 24;
+    uint2 *pp = reinterpret_cast<uint2 *>(p8);                               // PAIR
+    u64 *pv = reinterpret_cast<u64 *>(p8);                                   // !PAIR
+    unsigned char *q8 = p8 + (size_t)pcap * 8;
+    Acc<MODE> acc; acc.bind(q8, ncap);
+    u32 *pc = reinterpret_cast<u32 *>(q8 + Acc<MODE>::bytes(ncap));          // !PAIR only
+    u32 *cols = PAIR ? pc : pc + pcap;
+    const u32 off = bin_offset(o.bin_cnt, bin);
+    const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
+    for (u32 t = tid; t < ncap; t += nt) acc.clear(t);
+    if (tid == 0) s_P = 0;
+
+    auto put = [&](u32 dst, VT av, u32 c, u32 jb) {
+        const PV x = BPAT ? (PV)av : product_value<MODE, VT>(av, a.valB[jb]);
+        if (PAIR) pp[dst] = make_uint2(c, (u32)x);
+        else { pc[dst] = c; pv[dst] = (u64)x; }
+        atomicOr(&bm[c >> 5], __funnelshift_l(0u, 1u, c));                   // mark the column while it is in a register
+    };
+    // products of one warp's 32 A entries -> a slice of the product buffer
+    auto expand32 = [&](bool valid, VT av, const BRowRef &b) {
+        const u32 len = valid ? b.len : 0u;
+        u32 incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += x; }
+        u32 wbase = 0;
+        if (lane == 31) wbase = atomicAdd(&s_P, incl);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+        const u32 dst = wbase + incl - len;
+        if (PACK) {
+            if (len > 0) put(dst, av, b.ca.z, b.start);
+            if (len > 1) put(dst + 1, av, b.ca.w, b.start + 1);
+            if (len > 2) put(dst + 2, av, b.cb.x, b.start + 2);
+            if (len > 3) put(dst + 3, av, b.cb.y, b.start + 3);
+            if (len > 4) put(dst + 4, av, b.cb.z, b.start + 4);
+            if (len > 5) put(dst + 5, av, b.cb.w, b.start + 5);
+            for (u32 j = B200_PACK_INLINE; j < len; j++) put(dst + j, av, a.colB[b.start + j], b.start + j);
+        } else {
+            for (u32 j = 0; j < len; j++) put(dst + j, av, a.colB[b.start + j], b.start + j);
+        }
+    };
+
+    // ---- software pipeline over the CTA's rows: row ids two rows ahead, A entries and B row records one row ahead
+    u32 row = bin_rows[off + r_begin];
+    u64 rs = a.rpA[row];
+    u32 lenA = (u32)(a.rpA[row + 1] - rs);
+    u32 row_n = 0, lenA_n = 0; u64 rs_n = 0;
+    if (r_begin + 1 < r_end) { row_n = bin_rows[off + r_begin + 1]; rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); }
+    VT av[E]; BRowRef br[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const u32 t = tid + e * nt;
+        av[e] = 0; br[e].start = 0; br[e].len = 0; br[e].ca = make_uint4(0, 0, 0, 0); br[e].cb = br[e].ca;
+        if (t < lenA) { av[e] = a.valA[rs + t]; br[e] = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
+    }
+    __syncthreads();
+    u64 vmax = 0;
+    for (u32 r = r_begin; r < r_end; r++) {
+        const bool has_next = r + 1 < r_end;
+        const u64 obase = o.base[row];
+        // ---- expand: one A entry per thread, whole warps iterate together
+        const u32 lenA_w = (lenA + 31u) & ~31u;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const u32 t = tid + e * nt;
+            if (t - lane < lenA_w) expand32(t < lenA, av[e], br[e]);        // warp-uniform condition
+        }
+        for (u32 t = tid + E * nt; t < lenA_w; t += nt) {
+            const bool valid = t < lenA;
+            VT x = 0; BRowRef b; b.start = 0; b.len = 0; b.ca = make_uint4(0, 0, 0, 0); b.cb = b.ca;
+            if (valid) { x = a.valA[rs + t]; b = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
+            expand32(valid, x, b);
+        }
+        // next row: A entries now, their B rows after the mark phase (the column indices have arrived by then)
+        u32 kn[E]; VT avn[E];
+        u32 row_nn = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const u32 t = tid + e * nt;
+            kn[e] = 0; avn[e] = 0;
+            if (has_next && t < lenA_n) { kn[e] = a.colA[rs_n + t]; avn[e] = a.valA[rs_n + t]; }
+        }
+        if (r + 2 < r_end) row_nn = bin_rows[off + r + 2];
+        __syncthreads();
+        const u32 P = s_P;
+        const u32 nnz = rank_prefix_v4(bm4, wpre4, nw4, s_warp);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const u32 t = tid + e * nt;
+            br[e].len = 0;
+            if (has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
+            av[e] = avn[e];
+        }
+        u64 rs_nn = 0; u32 lenA_nn = 0;
+        if (r + 2 < r_end) { rs_nn = a.rpA[row_nn]; lenA_nn = (u32)(a.rpA[row_nn + 1] - rs_nn); }
+        __syncthreads();
+        // ---- accumulate at the column's rank
+        for (u32 p0 = tid; p0 < P; p0 += B200_EXPAND_ILP * nt) {
+            u32 c[B200_EXPAND_ILP], pos[B200_EXPAND_ILP]; u64 x[B200_EXPAND_ILP];
+#pragma unroll
+            for (int j = 0; j < B200_EXPAND_ILP; j++) {
+                const u32 p = p0 + j * nt;
+                c[j] = B200_EMPTY_KEY; x[j] = 0;
+                if (p < P) { if (PAIR) { const uint2 q = pp[p]; c[j] = q.x; x[j] = q.y; } else { c[j] = pc[p]; x[j] = pv[p]; } }
+            }
+#pragma unroll
+            for (int j = 0; j < B200_EXPAND_ILP; j++) {
+                const u32 cc = c[j] != B200_EMPTY_KEY ? c[j] : 0u;          // padding lanes read word 0
+                const u32 w = cc >> 5;
+                pos[j] = (u32)wpre[w] + __popc(bm[w] & (__funnelshift_l(0u, 1u, cc) - 1u));
+            }
+#pragma unroll
+            for (int j = 0; j < B200_EXPAND_ILP; j++)
+                if (c[j] != B200_EMPTY_KEY) { cols[pos[j]] = c[j]; acc.addv(pos[j], x[j]); }
+        }
+        __syncthreads();
+        // ---- emit (coalesced), leaving accumulators, bitmap and the product counter clean
+        for (u32 t0 = tid; t0 < nnz; t0 += 2 * nt) {
+            const u32 t1 = t0 + nt;
+            const bool h1 = t1 < nnz;
+            const u32 c0 = cols[t0], c1 = h1 ? cols[t1] : 0u;
+            const VT v0 = emit_val<VT>(acc.get(t0)), v1 = h1 ? emit_val<VT>(acc.get(t1)) : (VT)0;
+            acc.clear(t0);
+            o.col[obase + t0] = c0; o.val[obase + t0] = v0;
+            if (h1) { acc.clear(t1); o.col[obase + t1] = c1; o.val[obase + t1] = v1; }
+            const u64 m = (u64)(v0 > v1 ? v0 : v1);
+            vmax = vmax > m ? vmax : m;
+        }
+        for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { s_P = 0; if (o.nnz_out) o.nnz_out[row] = nnz; }
+        __syncthreads();
+        row = row_n; rs = rs_n; lenA = lenA_n;
+        row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn;
+    }
+    vmax = warp_max_u64(vmax);
+    if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
 }
 
 // =======================================================================================
