@@ -58,7 +58,9 @@ struct b200_ctx {
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
     // per-row scratch, grown on demand
-    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; u64 *d_tile_status; u64 cap_tiles;
+    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows;
+    // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
+    unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
     // heavy-row scratch
     void *d_heavy; size_t cap_heavy;
     // one-pass scratch CSR (bound-offset rows), kept across multiplies so the steady state allocates nothing
@@ -69,6 +71,7 @@ struct b200_ctx {
     cudaStream_t aux[B200_NAUX]; cudaEvent_t ev_fork, ev_join[B200_NAUX]; int naux_enabled;
     cudaStream_t copy; cudaEvent_t ev_ready;   // D2H stream: downloads overlap the next multiply
     bool timing;
+    u32 epoch;              // multiplies reported through the pinned mirror so far
     u64 launches;
     // developer timeline (B200_TRACE=1): an event after every launch, on the stream it went to
     bool trace; cudaStream_t cur_stream;
@@ -112,6 +115,7 @@ static int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
 }
 static void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
+#define B200_CTRL_BYTES 512
 static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     if (rows > ctx->cap_rows) {
         dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tmp_ptr);
@@ -120,16 +124,24 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
         TRY(dmalloc(ctx, (void **)&ctx->d_prod, cap * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_tmp_ptr, (cap + 1) * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_nnz_row, cap * 4));
-        TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4));
+        TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4 * (B200_BIN_HEAVY + 1)));   // every bin has its own list
         ctx->cap_rows = cap;
     }
-    u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1;
-    if (tiles > ctx->cap_tiles) {
-        dfree(ctx, ctx->d_tile_status); ctx->d_tile_status = nullptr; ctx->cap_tiles = 0;
-        TRY(dmalloc(ctx, (void **)&ctx->d_tile_status, 2 * (tiles + 64) * 8));
-        ctx->cap_tiles = tiles + 64;
+    const u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1, tiles_pre = rows / 8 + 2;  // pre-pass: >= 8 rows per CTA
+    if (!ctx->d_scan || tiles > ctx->cap_tiles || tiles_pre > ctx->cap_tiles_pre) {
+        dfree(ctx, ctx->d_scan); ctx->d_scan = nullptr;
+        const u64 ct = tiles + 64, cp = tiles_pre + tiles_pre / 8 + 1024;
+        TRY(dmalloc(ctx, (void **)&ctx->d_scan, B200_CTRL_BYTES + (ct + cp) * 8));
+        ctx->d_ctrl = (B200Ctrl *)ctx->d_scan;
+        ctx->d_tile_status = (u64 *)(ctx->d_scan + B200_CTRL_BYTES);
+        ctx->d_tile_pre = ctx->d_tile_status + ct;
+        ctx->cap_tiles = ct; ctx->cap_tiles_pre = cp;
     }
     return B200_OK;
+}
+// zero the control block and the scan status words a multiply over `rows` rows will use
+static cudaError_t reset_scan(b200_ctx *ctx, u64 tiles_pre) {
+    return cudaMemsetAsync(ctx->d_scan, 0, B200_CTRL_BYTES + (ctx->cap_tiles + tiles_pre) * 8, ctx->stream);
 }
 static int ensure_tmp(b200_ctx *ctx, size_t col_bytes, size_t val_bytes) {
     if (col_bytes > ctx->cap_tmp_col) {
@@ -201,8 +213,9 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_ctrl, sizeof(B200Ctrl)));
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl)));
+    static_assert(sizeof(B200Ctrl) <= B200_CTRL_BYTES, "control block outgrew its slot");
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));   // + the epoch word the final scan publishes
+    memset(ctx->h_ctrl, 0, sizeof(B200Ctrl) + 64);
     CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 64));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 64));
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -232,9 +245,9 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tile_status); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_ctrl); cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
+    cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
@@ -515,6 +528,27 @@ static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr 
     return B200_OK;
 }
 
+// The final scan's last CTA writes the control block and then the epoch word into pinned host memory; polling that word
+// costs a PCIe write latency instead of a memcpy + stream synchronise.  A stream query every so often catches a failed
+// launch (the word would never arrive).
+static int wait_for_report(b200_ctx *ctx, u32 epoch) {
+    volatile u32 *word = reinterpret_cast<volatile u32 *>(ctx->h_ctrl) + sizeof(B200Ctrl) / 4;
+    for (u64 spins = 1; *word != epoch; spins++) {
+        if ((spins & 0xFFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+            if (q != cudaSuccess) return set_err(B200_ERR_CUDA, "multiply failed on the device: %s", cudaGetErrorString(q));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));                  // finished: the report must be there now
+            if (*word != epoch) return set_err(B200_ERR_CUDA, "the row_ptr scan finished without reporting (epoch %u)", epoch);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __sync_synchronize();
+    return B200_OK;
+}
+
 // Independent per-bin kernels are spread over the main stream and a few auxiliary streams.
 struct Fan {
     b200_ctx *ctx; int next; bool used[B200_NAUX]; bool forked;
@@ -564,7 +598,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     const size_t smem_max = ctx->smem_optin - 1024;
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
-    OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt};
+    OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt, o.bin_stride};
     const size_t accb = mode == 0 ? 4 : 8;
     auto bin_size = [&](int bin) -> u64 { return cnt ? cnt[bin] : rows; };
     auto reachable = [&](int hb) { return cnt ? cnt[B200_BIN_HASH0 + hb] != 0 : (hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1)); };
@@ -686,9 +720,20 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
             LAUNCH_CHECK(ctx);
         }
     }
-    for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) TRY(do_bin(hb));
-    TRY(do_small());
-    TRY(do_tiny());
+    // launch order: the bin that holds the row of mean size first (it carries most of the work), then outwards from
+    // it, larger bins before smaller; the host-side estimate of the mean is nnz(A)/rows * nnz(B)/rows(B)
+    const double meanP = (A->rows ? (double)A->nnz / (double)A->rows : 0.0) * (B->rows ? (double)B->nnz / (double)B->rows : 0.0);
+    int center = -1;                                                       // -1: tiny, 1: small (hash bins 0-1), 2..: hash bin
+    if (meanP > 32.0) { center = 1; while (center < B200_NUM_HASH_BINS - 1 && meanP > (double)b200_hash_cap(center)) center++; }
+    auto run = [&](int id) -> int { return id < 0 ? do_tiny() : id <= 1 ? do_small() : do_bin(id); };
+    const int ids[B200_NUM_HASH_BINS] = {-1, 1, 2, 3, 4, 5, 6, 7};          // ascending row size
+    int ci = 0;
+    for (int i = 0; i < B200_NUM_HASH_BINS; i++) if (ids[i] == center) ci = i;
+    TRY(run(ids[ci]));
+    for (int d = 1; d < B200_NUM_HASH_BINS; d++) {
+        if (ci + d < B200_NUM_HASH_BINS) TRY(run(ids[ci + d]));
+        if (ci - d >= 0) TRY(run(ids[ci - d]));
+    }
     return B200_OK;
 }
 
@@ -696,11 +741,11 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
     const size_t smem_max = ctx->smem_optin - 1024;
     if ((size_t)nwords * 4 <= smem_max) {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row);
+        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows);
     } else {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
         TRY(ensure_heavy_scratch(ctx, (size_t)g * nwords * 4));
-        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row);
+        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row, (u32)ctx->cap_rows);
     }
     LAUNCH_CHECK(ctx);
     return B200_OK;
@@ -741,7 +786,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool bpat = maxB == 1;
     Fan fan(ctx);
     void *tmp_col = nullptr, *tmp_val = nullptr;
-    u64 *tile2 = ctx->d_tile_status + ctx->cap_tiles;                     // second status array (bound scan)
 
     // One-pass (default): numeric kernels write every row at its bound offset prefix(min(P_i, cols)) in a
     // scratch CSR and report its exact length; a scan of the lengths gives row_ptr and a compaction kernel
@@ -759,13 +803,19 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
 
     if (timing) cudaEventRecord(ctx->ev[0], s);
     if (ctx->trace) trace_mark(ctx, __LINE__);
-    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, 2 * ctx->cap_tiles * 8, s));
-    TRY(launch_row_products(ctx, A, B, onepass));
     const unsigned row_grid = (unsigned)((rows + 255) / 256);
+    const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
     u64 tmp_entries = 0;
     if (onepass) {
-        k_scan_rowptr<false, 1><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, nullptr, ctx->d_tmp_ptr, tile2, ctx->d_ctrl, nullptr, ctx->d_prod, ncols);
+        // one launch: product counts, bins, scratch offsets (look-back scan of min(P_i, cols))
+        const double avgA = (double)A->nnz / (double)rows;
+        const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
+        const u64 tiles_pre = (rows + (256 / G) - 1) / (256 / G);
+        CUDA_TRY(reset_scan(ctx, tiles_pre));
+#define PREPASS(GG) k_prepass<GG><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_desc, ncols, ctx->d_prod, ctx->d_nnz_row, \
+                                                                   ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl, ctx->d_bin_rows, bstride)
+        if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
+#undef PREPASS
         LAUNCH_CHECK(ctx);
         if (cheap_bound) tmp_entries = (u64)hb128;
         else {
@@ -777,8 +827,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         }
     }
     if (onepass) {
-        k_bin_scatter<0, true><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
-        LAUNCH_CHECK(ctx);
         r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         tmp_col = ctx->d_tmp_col; tmp_val = ctx->d_tmp_val;
@@ -789,15 +837,17 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
             fan.join();
         }
-        OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count};
+        OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride};
         if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan);
         fan.join();
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-        k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0);
+        const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
+        k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0,
+                                                                          ctx->h_ctrl, epoch);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        r = wait_for_report(ctx, epoch);
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const B200Ctrl hc = *ctx->h_ctrl;
         C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
         r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
@@ -832,11 +882,9 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
 
     // ---------------- exact two-pass path: symbolic (nnz per row) -> row_ptr -> numeric into the final arrays
-    if (!env_int("B200_TWOPASS", 0)) {                                    // fell back after a one-pass count: redo the bins with the two-pass rule
-        CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
-        TRY(launch_row_products(ctx, A, B, false));
-    }
-    k_bin_scatter<0, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    CUDA_TRY(reset_scan(ctx, 0));                                         // (also after a one-pass count that did not fit: redo the bins)
+    TRY(launch_row_products(ctx, A, B, false));
+    k_bin_scatter<0, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows, bstride);
     LAUNCH_CHECK(ctx);
     {
         const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
@@ -845,7 +893,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
     if (p_bound > 32 || A->max_row_len > 32) {
         const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
-        k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, std::min(lg, 5), ctx->d_nnz_row);
+        k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, std::min(lg, 5), ctx->d_nnz_row, bstride);
         LAUNCH_CHECK(ctx);
     }
     for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
@@ -857,13 +905,13 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (packed) {
             const int pt = std::max(bitmap ? 64 : 32, std::min(1024, (int)b200_hash_cap(hb) / env_int("B200_SDIV", 8)));
             const int pg = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, smem) * 2);
-            if (bitmap) k_sym_pack<true><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row);
-            else k_sym_pack<false><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row);
+            if (bitmap) k_sym_pack<true><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row, bstride);
+            else k_sym_pack<false><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row, bstride);
         } else {
             const int threads = bin_threads(hb, lg);
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
-            if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
-            else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row);
+            if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
+            else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -875,7 +923,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // ---- row_ptr (decoupled look-back scan, fused numeric-bin histogram), numeric bin lists
     k_scan_rowptr<true, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, A->d_rp, ctx->d_prod, 0);
     LAUNCH_CHECK(ctx);
-    k_bin_scatter<1, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows);
+    k_bin_scatter<1, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows, bstride);
     LAUNCH_CHECK(ctx);
     if (timing) cudaEventRecord(ctx->ev[1], s);
     // ---- the one host read-back: total nnz, bin sizes
@@ -890,7 +938,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     const int mode = pick_mode<VT>(hc.max_row_products, maxA, maxB);
     if (timing) cudaEventRecord(ctx->ev[2], s);
-    OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->num_bin_count};
+    OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->num_bin_count, bstride};
     r = launch_numeric<VT>(ctx, A, B, hc.num_bin_count, rows, p_bound, hc.max_row_nnz, mode, packed, bpat, lg, o, fan);
     fan.join();
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
@@ -927,7 +975,7 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (A->rows == 0) return B200_OK;
     TRY(ensure_row_scratch(ctx, A->rows));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), ctx->stream));
+    CUDA_TRY(reset_scan(ctx, 0));
     TRY(ensure_desc(ctx, B));
     TRY(launch_row_products(ctx, A, B, false));
     CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_prod, A->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -989,8 +1037,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     int r = ensure_row_scratch(ctx, rows);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
-    CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(B200Ctrl), s));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_tile_status, 0, ntiles * 8, s));
+    CUDA_TRY(reset_scan(ctx, 0));
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);

@@ -60,7 +60,7 @@ struct B200Ctrl {
     ull total_bound;          // one-pass mode: sum of per-row bounds min(P_i, cols)
     u32 scan_ticket[2];
     u32 error_flag;           // set by kernels on impossible states (table overflow)
-    u32 pad[1];
+    u32 scan_done;            // CTAs of the final row_ptr scan that have finished (the last one reports to the host)
 };
 
 // Read-only view of a device CSR.

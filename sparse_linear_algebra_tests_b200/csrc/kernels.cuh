@@ -14,6 +14,14 @@
 #pragma once
 #include "common.cuh"
 
+// decoupled look-back scans (k_prepass, k_scan_rowptr): tile status = 2 flag bits + 62-bit value
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_FLAG_AGG (1ull << 62)
+#define SCAN_FLAG_PRE (2ull << 62)
+#define SCAN_VAL_MASK ((1ull << 62) - 1)
+
 // =======================================================================================
 // 0. operand views
 // =======================================================================================
@@ -36,6 +44,7 @@ struct OutArgs {
     const u64 *base; u32 *col; VT *val;
     u32 *nnz_out;                // may be null (two-pass)
     const u32 *bin_cnt;          // bin sizes to iterate (ctrl->sym_bin_count or ctrl->num_bin_count)
+    u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
 };
 
 __global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, uint2 *__restrict__ desc) {
@@ -122,10 +131,104 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
     }
 }
 
+// One-pass pre-pass, one launch: product count P_i per row, totals, the bin lists (block-wise reservation in every
+// bin's own list, so a CTA's rows stay consecutive) and -- through a decoupled look-back over the CTAs in ticket
+// order -- the scratch offsets prefix(min(P_i, cols)) that the numeric kernels write their rows at.
+template <int G>
+__global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
+                                                 const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
+                                                 u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
+                                                 B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride) {
+    constexpr int RPC = 256 / G;                                            // rows per CTA
+    __shared__ u32 s_tile, s_cnt[B200_NBINS], s_base[B200_NBINS];
+    __shared__ u64 s_bound[RPC], s_wsum[8], s_excl;
+    __shared__ ull s_sum, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) { s_tile = atomicAdd(&ctrl->scan_ticket[1], 1u); s_sum = 0; s_max = 0; }
+    if (tid < B200_NBINS) s_cnt[tid] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 row = (u64)tile * RPC + tid / G;
+    const u32 sub = tid % G;
+    u64 p = 0; u32 lenA = 0;
+    if (row < rows) {
+        const u64 s = rpA[row];
+        lenA = (u32)(rpA[row + 1] - s);
+        const u32 *Ac = colA + s;
+        for (u32 i = sub; i < lenA; i += G) p += bdesc[Ac[i]].y;
+    }
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1) p += shfl_xor_u64(p, m);
+    int b = B200_BIN_NONE; u32 local = 0;
+    u64 wsum = 0, wmax = 0;
+    if (sub == 0) {
+        u64 bound = 0;
+        if (row < rows) {
+            prod[row] = p;
+            bound = p < ncols ? p : ncols;
+            b = sym_bin_of<true>(p, lenA);
+            if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;               // the two smallest hash bins share a list
+            if (b == B200_BIN_NONE) nnz_row[row] = 0;
+            else local = atomicAdd(&s_cnt[b], 1u);
+            wsum = p; wmax = p;
+        }
+        s_bound[tid / G] = bound;
+    }
+    wsum = warp_sum_u64(wsum); wmax = warp_max_u64(wmax);
+    if (lane == 0) { if (wsum) atomicAdd(&s_sum, (ull)wsum); atomicMax(&s_max, (ull)wmax); }
+    __syncthreads();
+    // ---- exclusive scan of the bounds inside the CTA (row order), aggregate, look-back
+    const u64 mine = tid < RPC ? s_bound[tid] : 0ull;
+    u64 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 t = shfl_up_u64(incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_wsum[w] = incl;
+    if (tid < B200_NBINS) { const u32 c = s_cnt[tid]; s_base[tid] = c ? atomicAdd(&ctrl->sym_bin_count[tid], c) : 0u; }
+    __syncthreads();
+    u64 wbase = 0, agg = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { if (i < w) wbase += s_wsum[i]; agg += s_wsum[i]; }
+    if (w == 0) {
+        if (lane == 0) atomicExch((ull *)&tile_status[tile], (ull)((tile == 0 ? SCAN_FLAG_PRE : SCAN_FLAG_AGG) | agg));
+        u64 excl = 0;
+        if (tile > 0) {
+            int look = (int)tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                u64 st;
+                do { st = idx >= 0 ? ld_volatile_u64(&tile_status[idx]) : SCAN_FLAG_PRE; } while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0));
+                const u32 pre_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+                const int first = pre_mask ? __ffs(pre_mask) - 1 : 32;
+                excl += warp_sum_u64(lane <= first ? (st & SCAN_VAL_MASK) : 0ull);
+                if (pre_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch((ull *)&tile_status[tile], (ull)(SCAN_FLAG_PRE | (excl + agg)));
+        }
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    if (tid < RPC) {
+        const u64 r = (u64)tile * RPC + tid;
+        if (r < rows) {
+            const u64 run = s_excl + wbase + incl;
+            tmp_ptr[r + 1] = run;
+            if (r + 1 == rows) ctrl->total_bound = run;
+        }
+        if (r == 0) tmp_ptr[0] = 0;
+    }
+    if (b != B200_BIN_NONE) bin_rows[(u64)b * bin_stride + s_base[b] + local] = (u32)row;
+    if (tid == 0) {
+        if (s_sum) atomicAdd(&ctrl->total_products, s_sum);
+        if (s_max) atomicMax(&ctrl->max_row_products, s_max);
+    }
+}
+
 // scatter row ids into their bin's segment of bin_rows; PHASE 0 = symbolic bins, 1 = numeric bins
 template <int PHASE, bool ONEPASS>
 __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__restrict__ rpA, const u64 *__restrict__ prod,
-                                                     const u32 *__restrict__ nnz_row, B200Ctrl *ctrl, u32 *__restrict__ bin_rows) {
+                                                     const u32 *__restrict__ nnz_row, B200Ctrl *ctrl, u32 *__restrict__ bin_rows,
+                                                     u32 bin_stride) {
     __shared__ u32 s_cnt[B200_NBINS], s_base[B200_NBINS];
     if (threadIdx.x < B200_NBINS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -138,21 +241,19 @@ __global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__rest
     }
     __syncthreads();
     if (threadIdx.x < B200_NBINS) {
-        const u32 *cnt = PHASE == 0 ? ctrl->sym_bin_count : ctrl->num_bin_count;
         u32 *fill = PHASE == 0 ? ctrl->sym_bin_fill : ctrl->num_bin_fill;
-        u32 off = 0;
-        for (int i = 0; i < (int)threadIdx.x; i++) off += cnt[i];
         const u32 c = s_cnt[threadIdx.x];
-        s_base[threadIdx.x] = off + (c ? atomicAdd(&fill[threadIdx.x], c) : 0u);
+        s_base[threadIdx.x] = c ? atomicAdd(&fill[threadIdx.x], c) : 0u;
     }
     __syncthreads();
-    if (b != B200_BIN_NONE) bin_rows[s_base[b] + local] = (u32)row;
+    if (b != B200_BIN_NONE) bin_rows[(u64)b * bin_stride + s_base[b] + local] = (u32)row;
 }
 
-__device__ __forceinline__ u32 bin_offset(const u32 *cnt, int bin) {
-    u32 off = 0;
-    for (int i = 0; i < bin; i++) off += cnt[i];
-    return off;
+// r-th row of the run of `nbins` consecutive bins starting at first_bin (every bin has its own list)
+__device__ __forceinline__ u32 bin_row_at(const u32 *__restrict__ bin_rows, const u32 *cnt, u32 stride, int first_bin, int nbins, u32 r) {
+    int b = first_bin;
+    while (nbins > 1 && r >= cnt[b]) { r -= cnt[b]; b++; nbins--; }
+    return bin_rows[(u64)b * stride + r];
 }
 
 // =======================================================================================
@@ -357,17 +458,16 @@ __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__re
 // 4a. warp per row (8 rows in flight per CTA), 256-slot key table per warp: rows with P <= 128
 #define B200_WARP_SLOTS 256
 __global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
-                                                  int nbins, int lg, u32 *__restrict__ nnz_row) {
+                                                  int nbins, int lg, u32 *__restrict__ nnz_row, u32 bin_stride) {
     __shared__ u32 s_keys[8][B200_WARP_SLOTS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u32 *keys = s_keys[wid];
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += ctrl->sym_bin_count[first_bin + b];
-    const u32 off = bin_offset(ctrl->sym_bin_count, first_bin);
     const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
     const int shift = 32 - 8;
     for (u32 r = blockIdx.x * 8 + wid; r < count; r += gridDim.x * 8) {
-        const u32 row = bin_rows[off + r];
+        const u32 row = bin_row_at(bin_rows, ctrl->sym_bin_count, bin_stride, first_bin, nbins, r);
 #pragma unroll
         for (int i = 0; i < B200_WARP_SLOTS / 32; i++) keys[i * 32 + lane] = B200_EMPTY_KEY;
         __syncwarp();
@@ -389,11 +489,11 @@ __global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restri
 // 4b. CTA per row: key table, or a column bitmap when the whole column space fits shared memory
 template <bool BITMAP>
 __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
-                                                  u32 nwords, int lg, u32 *__restrict__ nnz_row) {
+                                                  u32 nwords, int lg, u32 *__restrict__ nnz_row, u32 bin_stride) {
     extern __shared__ u32 smem[];
     __shared__ u32 s_count;
     const u32 count = ctrl->sym_bin_count[bin];
-    const u32 off = bin_offset(ctrl->sym_bin_count, bin);
+    const u64 off = (u64)bin * bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const u32 tabn = BITMAP ? nwords : slots;
@@ -496,13 +596,12 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
     u32 *keys = reinterpret_cast<u32 *>(base + Acc<MODE>::bytes(B200_WARP_SLOTS));
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += o.bin_cnt[first_bin + b];
-    const u32 off = bin_offset(o.bin_cnt, first_bin);
     const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
     const int shift = 32 - 8;
     constexpr int PER = B200_WARP_SLOTS / 32;
     u64 vmax = 0;
     for (u32 r = blockIdx.x * 8 + wid; r < count; r += gridDim.x * 8) {
-        const u32 row = bin_rows[off + r];
+        const u32 row = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, first_bin, nbins, r);
 #pragma unroll
         for (int i = 0; i < PER; i++) { keys[i * 32 + lane] = B200_EMPTY_KEY; acc.clear(i * 32 + lane); }
         __syncwarp();
@@ -555,7 +654,7 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
     Acc<MODE> acc; acc.bind(smem_raw, slots);
     u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
     const u32 count = o.bin_cnt[bin];
-    const u32 off = bin_offset(o.bin_cnt, bin);
+    const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const int shift = 32 - (31 - __clz(slots));
@@ -632,7 +731,7 @@ __global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__r
     u32 *bm = cols + cap;
     unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
     const u32 count = o.bin_cnt[bin];
-    const u32 off = bin_offset(o.bin_cnt, bin);
+    const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     u64 vmax = 0;
@@ -720,11 +819,12 @@ __device__ __forceinline__ void for_each_col(const PackRec &r, const u32 *__rest
 
 template <bool BITMAP>
 __global__ void __launch_bounds__(1024) k_sym_pack(SymArgs a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
-                                                   B200Ctrl *ctrl, int bin, u32 slots, u32 nwords, u32 *__restrict__ nnz_row) {
+                                                   B200Ctrl *ctrl, int bin, u32 slots, u32 nwords, u32 *__restrict__ nnz_row,
+                                                   u32 bin_stride) {
     extern __shared__ u32 smem[];
     __shared__ u32 s_count;
     const u32 count = ctrl->sym_bin_count[bin];
-    const u32 off = bin_offset(ctrl->sym_bin_count, bin);
+    const u64 off = (u64)bin * bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 tabn = BITMAP ? nwords : slots;
     const int shift = 32 - (31 - __clz(slots));
@@ -778,7 +878,7 @@ __global__ void __launch_bounds__(1024) k_num_rank_pack(NumArgs<VT> a, const uin
     u32 *bm = cols + cap;
     unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
     const u32 count = o.bin_cnt[bin];
-    const u32 off = bin_offset(o.bin_cnt, bin);
+    const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     u64 vmax = 0;
     u32 r_begin, r_end;
@@ -940,7 +1040,6 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     Acc<MODE> acc; acc.bind(q8, ncap);
     u32 *pc = reinterpret_cast<u32 *>(q8 + Acc<MODE>::bytes(ncap));          // !PAIR only
     u32 *cols = PAIR ? pc : pc + pcap;
-    const u32 off = bin_offset(o.bin_cnt, bin);
     const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
     for (u32 t = tid; t < ncap; t += nt) acc.clear(t);
@@ -976,11 +1075,11 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     };
 
     // ---- software pipeline over the CTA's rows: row ids two rows ahead, A entries and B row records one row ahead
-    u32 row = bin_rows[off + r_begin];
+    u32 row = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin);
     u64 rs = a.rpA[row];
     u32 lenA = (u32)(a.rpA[row + 1] - rs);
     u32 row_n = 0, lenA_n = 0; u64 rs_n = 0;
-    if (r_begin + 1 < r_end) { row_n = bin_rows[off + r_begin + 1]; rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); }
+    if (r_begin + 1 < r_end) { row_n = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin + 1); rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); }
     VT av[E]; BRowRef br[E];
 #pragma unroll
     for (int e = 0; e < E; e++) {
@@ -1015,7 +1114,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             kn[e] = 0; avn[e] = 0;
             if (has_next && t < lenA_n) { kn[e] = a.colA[rs_n + t]; avn[e] = a.valA[rs_n + t]; }
         }
-        if (r + 2 < r_end) row_nn = bin_rows[off + r + 2];
+        if (r + 2 < r_end) row_nn = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r + 2);
         __syncthreads();
         const u32 P = s_P;
         const u32 nnz = rank_prefix_v4(bm4, wpre4, nw4, s_warp);
@@ -1075,10 +1174,10 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
 // 6. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
 // =======================================================================================
 __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 nwords,
-                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row) {
+                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row, u32 bin_stride) {
     __shared__ u32 s_count;
     const u32 count = ctrl->sym_bin_count[B200_BIN_HEAVY];
-    const u32 off = bin_offset(ctrl->sym_bin_count, B200_BIN_HEAVY);
+    const u64 off = (u64)B200_BIN_HEAVY * bin_stride;
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
     const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
@@ -1111,7 +1210,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                                                     u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o) {
     __shared__ u32 s_warp[33];
     const u32 count = o.bin_cnt[B200_BIN_HEAVY];
-    const u32 off = bin_offset(o.bin_cnt, B200_BIN_HEAVY);
+    const u64 off = (u64)B200_BIN_HEAVY * o.bin_stride;
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
     u32 *wpre = scratch_pre + (u64)blockIdx.x * nwords;
     u32 *keys = scratch_keys + (u64)blockIdx.x * max_slots;
@@ -1191,20 +1290,15 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 // 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64),
 //    fused with the numeric-bin histogram
 // =======================================================================================
-#define SCAN_THREADS 256
-#define SCAN_ITEMS 8
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
-#define SCAN_FLAG_AGG (1ull << 62)
-#define SCAN_FLAG_PRE (2ull << 62)
-#define SCAN_VAL_MASK ((1ull << 62) - 1)
 
 // SRC 0: exact nnz per row -> row_ptr_C (CLASSIFY also histograms the numeric bins);
 // SRC 1: per-row bound min(P_i, cols) -> offsets of the one-pass scratch CSR (total in ctrl->total_bound)
 template <bool CLASSIFY, int SRC>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
                                                               u64 *tile_status, B200Ctrl *ctrl, const u64 *__restrict__ rpA,
-                                                              const u64 *__restrict__ prod, u64 ncols) {
-    __shared__ u32 s_tile;
+                                                              const u64 *__restrict__ prod, u64 ncols,
+                                                              B200Ctrl *host_mirror = nullptr, u32 epoch = 0) {
+    __shared__ u32 s_tile, s_last;
     __shared__ u64 s_wsum[SCAN_THREADS / 32];
     __shared__ u64 s_excl;
     __shared__ u32 s_hist[B200_NBINS];
@@ -1278,6 +1372,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
     for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
     if (SRC == 0 && lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
     if (CLASSIFY && tid < B200_NBINS && s_hist[tid]) atomicAdd(&ctrl->num_bin_count[tid], s_hist[tid]);
+    // Report to the host without a stream synchronise: the last CTA to finish copies the control block into pinned
+    // host memory and then publishes the epoch word the host is polling.
+    if (host_mirror) {
+        __syncthreads();
+        if (tid == 0) { __threadfence(); s_last = atomicAdd(&ctrl->scan_done, 1u) == gridDim.x - 1 ? 1u : 0u; }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const volatile u32 *src = reinterpret_cast<const volatile u32 *>(ctrl);
+            volatile u32 *dst = reinterpret_cast<volatile u32 *>(host_mirror);
+            for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) dst[i] = src[i];
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) { dst[sizeof(B200Ctrl) / 4] = epoch; __threadfence_system(); }
+        }
+    }
 }
 
 // one-pass mode: move every row from the scratch CSR (bound offsets) to its exact place
