@@ -155,7 +155,13 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         const u64 s = rpA[row];
         lenA = (u32)(rpA[row + 1] - s);
         const u32 *Ac = colA + s;
-        for (u32 i = sub; i < lenA; i += G) p += bdesc[Ac[i]].y;
+        u32 i = sub;
+        for (; i + 3 * G < lenA; i += 4 * G) {                               // four independent gathers in flight
+            const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
+            const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
+            p += (u64)d0 + d1 + d2 + d3;
+        }
+        for (; i < lenA; i += G) p += bdesc[Ac[i]].y;
     }
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1) p += shfl_xor_u64(p, m);
@@ -1403,7 +1409,14 @@ __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__res
         const u64 d = rpC[row];
         const u32 n = (u32)(rpC[row + 1] - d);
         const u64 sbase = src_ptr[row];
-        for (u32 t = sub; t < n; t += L) { colC[d + t] = src_col[sbase + t]; valC[d + t] = src_val[sbase + t]; }
+        u32 t = sub;
+        for (; t + 3 * L < n; t += 4 * L) {                                  // eight loads in flight per lane
+            const u32 c0 = src_col[sbase + t], c1 = src_col[sbase + t + L], c2 = src_col[sbase + t + 2 * L], c3 = src_col[sbase + t + 3 * L];
+            const VT v0 = src_val[sbase + t], v1 = src_val[sbase + t + L], v2 = src_val[sbase + t + 2 * L], v3 = src_val[sbase + t + 3 * L];
+            colC[d + t] = c0; colC[d + t + L] = c1; colC[d + t + 2 * L] = c2; colC[d + t + 3 * L] = c3;
+            valC[d + t] = v0; valC[d + t + L] = v1; valC[d + t + 2 * L] = v2; valC[d + t + 3 * L] = v3;
+        }
+        for (; t < n; t += L) { colC[d + t] = src_col[sbase + t]; valC[d + t] = src_val[sbase + t]; }
     }
 }
 
