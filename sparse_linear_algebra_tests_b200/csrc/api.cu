@@ -46,6 +46,7 @@ struct b200_csr {
     ull *d_maxval;          // device scalar: largest stored value
     u64 max_row_len;        // host-known upper bound of the longest row
     uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
+    uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (one-pass pre-pass)
     uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
     u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
     cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
@@ -58,7 +59,7 @@ struct b200_ctx {
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
     // per-row scratch, grown on demand
-    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows;
+    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint2 *d_win;
     // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
     unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
     // heavy-row scratch
@@ -118,13 +119,14 @@ static void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream)
 #define B200_CTRL_BYTES 512
 static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     if (rows > ctx->cap_rows) {
-        dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tmp_ptr);
-        ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->d_tmp_ptr = nullptr; ctx->cap_rows = 0;
+        dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_win);
+        ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->d_tmp_ptr = nullptr; ctx->d_win = nullptr; ctx->cap_rows = 0;
         u64 cap = rows + rows / 8 + 1024;
         TRY(dmalloc(ctx, (void **)&ctx->d_prod, cap * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_tmp_ptr, (cap + 1) * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_nnz_row, cap * 4));
-        TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4 * (B200_BIN_HEAVY + 1)));   // every bin has its own list
+        TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4 * (B200_BIN_WIDE0 + B200_NUM_HASH_BINS)));   // every bin has its own list
+        TRY(dmalloc(ctx, (void **)&ctx->d_win, cap * sizeof(uint2)));
         ctx->cap_rows = cap;
     }
     const u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1, tiles_pre = rows / 8 + 2;  // pre-pass: >= 8 rows per CTA
@@ -245,7 +247,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
@@ -292,7 +294,7 @@ extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
     if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_pack);
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;
 }
@@ -482,7 +484,8 @@ static int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
     if (B->nnz >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "right operand with >= 2^32 stored entries is not supported");
     b200_csr *Bm = const_cast<b200_csr *>(B);
     TRY(dmalloc(ctx, (void **)&Bm->d_desc, (B->rows + 1) * sizeof(uint2)));
-    k_build_desc<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, Bm->d_desc);
+    TRY(dmalloc(ctx, (void **)&Bm->d_span, (B->rows + 1) * sizeof(uint4)));
+    k_build_desc<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, B->d_col, Bm->d_desc, Bm->d_span);
     LAUNCH_CHECK(ctx);
     return B200_OK;
 }
@@ -593,7 +596,7 @@ static int pick_mode(u64 max_row_products, u64 maxA, u64 maxB) {
 // (one-pass: sizes live on the device only; bins that no row can reach are skipped via p_bound).
 template <typename VT>
 static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const u32 *cnt, u64 rows, u64 p_bound, u64 heavy_cap,
-                          int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan) {
+                          int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps) {
     const u32 nwords = (u32)((B->cols + 31) / 32);
     const size_t smem_max = ctx->smem_optin - 1024;
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
@@ -611,57 +614,79 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     };
     // one-pass bins are cut on the product count P <= cap: expand the products into shared memory once and run every
     // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
-    auto launch_expand = [&](int bin, int nb, u32 cap, u64 n, cudaStream_t bs) -> bool {
-        if (cnt || !env_int("B200_EXPAND", 1)) return false;
+    const u32 nw4_full = (nwords + 3) / 4;
+    auto launch_expand = [&](int bin, int nb, u32 cap, u32 nw4, u64 n, cudaStream_t bs) -> bool {
+        if (cnt || nw4 == 0) return false;
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
-        const u32 nw4 = (nwords + 3) / 4;
         const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
         const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
-        if (ex_smem > smem_max || nw4 > 8 * (size_t)pcap) return false;
-        const int et = std::max(32, std::min(512, (int)pcap / std::max(1, env_int("B200_EDIV", 8))));
+        if (ex_smem > smem_max) return false;
+        // threads: ~8 products or ~8 bitmap groups each, whichever asks for more
+        const int et = std::max(32, std::min(512, (int)std::max<u32>(pcap, nw4) / std::max(1, env_int("B200_EDIV", 8)) / 32 * 32));
         const int eg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * 4);
         if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
 #define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
-        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); \
-                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); }   \
-             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO);         \
-                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, OO); } } while (0)
+        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); \
+                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); }   \
+             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO);         \
+                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); } } while (0)
         if (mode == 0) EXPAND(0, VT, na, o);
         else if (mode == 1) EXPAND(1, VT, na, o);
         else EXPAND(2, u64, na64, o64);
 #undef EXPAND
         return true;
     };
-    auto do_small = [&]() -> int {
-        if (!(reachable(0) || reachable(1))) return B200_OK;
-        if (!cnt && env_int("B200_EXPAND_SMALL", 1) && launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), rows, fan.pick())) {
-            LAUNCH_CHECK(ctx);
-            return B200_OK;
-        }
-        const u64 n01 = cnt ? (u64)cnt[B200_BIN_HASH0] + cnt[B200_BIN_HASH0 + 1] : rows;
+    // hash + in-row sort kernels (any column space): warp per row for the two smallest bins, CTA per row above
+    auto launch_warp_hash = [&](int first_bin, int nb, u64 n, cudaStream_t bs) -> int {
         const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4);
-        const int g = (int)std::min<u64>((n01 + 7) / 8, (u64)ctx->num_sms * 16);
-        cudaStream_t bs = fan.pick();
+        const int g = (int)std::min<u64>((n + 7) / 8, (u64)ctx->num_sms * 16);
         const int wlg = std::min(lg, 5);
-        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o);
-        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o);
-        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, wlg, o64);
+        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o);
+        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o);
+        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o64);
         LAUNCH_CHECK(ctx);
         return B200_OK;
+    };
+    auto launch_cta_hash = [&](int bin, int hb, u64 n, cudaStream_t bs) -> int {
+        const u32 slots = b200_hash_slots(hb);
+        const int threads = bin_threads(hb, lg);
+        const size_t smem = (size_t)slots * (4 + accb);
+        if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
+        const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
+        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
+        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
+        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o64);
+        LAUNCH_CHECK(ctx);
+        return B200_OK;
+    };
+    auto do_small = [&]() -> int {
+        if (!(reachable(0) || reachable(1))) return B200_OK;
+        if (!cnt) {
+            // one-pass: bins 0 and 1 share list HASH0+1; rows whose column window exceeds the bitmap are on the wide list
+            if (launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1], rows, fan.pick())) LAUNCH_CHECK(ctx);
+            if (caps.cap[1] < nw4_full) TRY(launch_warp_hash(B200_BIN_WIDE0 + 1, 1, rows, fan.pick()));
+            return B200_OK;
+        }
+        return launch_warp_hash(B200_BIN_HASH0, 2, (u64)cnt[B200_BIN_HASH0] + cnt[B200_BIN_HASH0 + 1], fan.pick());
     };
     auto do_bin = [&](int hb) -> int {
         if (!reachable(hb)) return B200_OK;
         const u64 n = bin_size(B200_BIN_HASH0 + hb);
-        const u32 slots = b200_hash_slots(hb);
         const u32 cap = b200_hash_cap(hb);
         const int bin = B200_BIN_HASH0 + hb;
         cudaStream_t bs = fan.pick();
-        if (launch_expand(bin, 1, cap, n, bs)) { LAUNCH_CHECK(ctx); return B200_OK; }
-        // rank kernel (column bitmap in shared memory) when the column space is small next to the row
+        if (!cnt) {
+            // one-pass: rows whose column window fits the bin's bitmap -> k_num_expand, the others (wide list) -> hash + sort
+            bool used = false;
+            if (launch_expand(bin, 1, cap, caps.cap[hb], n, bs)) { LAUNCH_CHECK(ctx); used = true; }
+            if (caps.cap[hb] < nw4_full) TRY(launch_cta_hash(B200_BIN_WIDE0 + hb, hb, n, used ? fan.pick() : bs));
+            return B200_OK;
+        }
+        // two-pass (bins cut on exact nnz): rank kernel when the whole column space fits a shared-memory bitmap
         const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (4 + accb);
         if (nwords <= 4 * cap && rank_smem <= smem_max) {
             if (packed) {
-                const int pt = std::max(64, std::min(1024, (int)cap / env_int("B200_NDIV", cnt ? 8 : 16)));
+                const int pt = std::max(64, std::min(1024, (int)cap / env_int("B200_NDIV", 8)));
                 const int pg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, rank_smem) * 4);
 #define RANK_PACK(MODE, VTT, NA, OO)                                                                                                  \
                 do { if (bpat) k_num_rank_pack<VTT, MODE, true><<<pg, pt, rank_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, OO); \
@@ -680,15 +705,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
             LAUNCH_CHECK(ctx);
             return B200_OK;
         }
-        const int threads = bin_threads(hb, lg);
-        const size_t smem = (size_t)slots * (4 + accb);
-        if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
-        const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
-        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
-        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
-        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o64);
-        LAUNCH_CHECK(ctx);
-        return B200_OK;
+        return launch_cta_hash(bin, hb, n, bs);
     };
     // the longest rows first: the big kernels start while the host is still queueing the small ones
     const bool heavy = cnt ? cnt[B200_BIN_HEAVY] != 0 : p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
@@ -806,14 +823,33 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const unsigned row_grid = (unsigned)((rows + 255) / 256);
     const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
     u64 tmp_entries = 0;
+    const int mode1 = pick_mode<VT>(p_bound, maxA, maxB);                 // one-pass accumulator width (host-side bound)
+    // Per hash bin: the largest column window (in 128-column groups) its k_num_expand bitmap holds.  Narrow column
+    // spaces fit whole; otherwise a bin with capacity P gets a window of 384*P columns (at most 512 K columns): on the
+    // 100^3 torus wider windows lost to hash + sort (the per-row prefix over a mostly empty bitmap dominates).
+    // Rows beyond the window take the hash + sort kernels.
+    WinCaps caps;
+    {
+        const u32 nw4_full = (nwords + 3) / 4;
+        const size_t accb1 = mode1 == 0 ? 4 : 8, pvb1 = (mode1 == 0 || sizeof(VT) == 4) ? 4 : 8;
+        const int forced = env_int("B200_WINCAP", -1);                    // testing hook: force a small window (0: hash only)
+        for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
+            const u64 pcap = b200_hash_cap(hb == 0 ? 1 : hb), ncap = std::min<u64>(pcap, ncols);
+            const size_t fixed = pcap * (4 + pvb1) + ncap * (4 + accb1);
+            u64 want = std::min<u64>(nw4_full, std::max<u64>(256, std::min<u64>(4096, (u64)env_int("B200_WINMUL", 3) * pcap)));
+            if (forced >= 0) want = std::min<u64>(want, (u64)forced);
+            const u64 fit = fixed + 24 * 32 <= smem_max ? (smem_max - fixed) / 24 : 0;
+            caps.cap[hb] = env_int("B200_EXPAND", 1) ? (u32)std::min<u64>(want, fit) : 0u;
+        }
+    }
     if (onepass) {
-        // one launch: product counts, bins, scratch offsets (look-back scan of min(P_i, cols))
+        // one launch: product counts, column windows, bins, scratch offsets (look-back scan of min(P_i, cols))
         const double avgA = (double)A->nnz / (double)rows;
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
         const u64 tiles_pre = (rows + (256 / G) - 1) / (256 / G);
         CUDA_TRY(reset_scan(ctx, tiles_pre));
-#define PREPASS(GG) k_prepass<GG><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_desc, ncols, ctx->d_prod, ctx->d_nnz_row, \
-                                                                   ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl, ctx->d_bin_rows, bstride)
+#define PREPASS(GG) k_prepass<GG><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_span, ncols, ctx->d_prod, ctx->d_nnz_row, \
+                                                                   ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl, ctx->d_bin_rows, bstride, ctx->d_win, caps)
         if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
 #undef PREPASS
         LAUNCH_CHECK(ctx);
@@ -830,7 +866,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         tmp_col = ctx->d_tmp_col; tmp_val = ctx->d_tmp_val;
-        const int mode = pick_mode<VT>(p_bound, maxA, maxB);
+        const int mode = mode1;
         const u64 heavy_cap = std::min<u64>(p_bound, ncols);
         if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) && !(heavy_cap < 65536 && (size_t)nwords * 6 + 16 + heavy_cap * 12 <= smem_max)) {
             // heavy rows that need the global table: size it from their exact nnz (bitmap count first)
@@ -838,7 +874,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
         }
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride};
-        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan);
+        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
         fan.join();
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
@@ -868,7 +904,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
             st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
             st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-            for (int i = 0; i < B200_NBINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
+            for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
             if (timing) {
                 CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
                 cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[2], ctx->ev[3]);   // one-pass: compaction of the scratch rows
@@ -939,7 +975,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const int mode = pick_mode<VT>(hc.max_row_products, maxA, maxB);
     if (timing) cudaEventRecord(ctx->ev[2], s);
     OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->num_bin_count, bstride};
-    r = launch_numeric<VT>(ctx, A, B, hc.num_bin_count, rows, p_bound, hc.max_row_nnz, mode, packed, bpat, lg, o, fan);
+    r = launch_numeric<VT>(ctx, A, B, hc.num_bin_count, rows, p_bound, hc.max_row_nnz, mode, packed, bpat, lg, o, fan, caps);
     fan.join();
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
@@ -948,7 +984,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
         st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
         st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-        for (int i = 0; i < B200_NBINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.num_bin_count[i]; }
+        for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.num_bin_count[i]; }
         if (timing) {
             CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
             cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);

@@ -8,7 +8,7 @@ typedef uint64_t u64;
 typedef unsigned long long ull;
 
 #define B200_EMPTY_KEY 0xFFFFFFFFu
-#define B200_NBINS 16
+#define B200_NBINS 24
 #define B200_WARP 32
 
 // ---------------------------------------------------------------------------------------
@@ -25,7 +25,9 @@ typedef unsigned long long ull;
 #define B200_BIN_HASH0 1
 #define B200_NUM_HASH_BINS 8
 #define B200_BIN_HEAVY 9
+#define B200_BIN_WIDE0 10   // one-pass: hash bin hb's rows whose column window is too wide for the bin's bitmap -> list 10 + hb
 #define B200_BIN_NONE 0xFF
+#define B200_STAT_BINS 16   // bins reported in b200_stats
 
 // slots per hash bin; a row goes to the first bin whose capacity covers it.
 __host__ __device__ __forceinline__ u32 b200_hash_slots(int hb) { return 128u << hb; }          // 128 .. 16384

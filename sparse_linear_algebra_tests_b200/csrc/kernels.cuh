@@ -47,12 +47,19 @@ struct OutArgs {
     u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
 };
 
-__global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, uint2 *__restrict__ desc) {
+// desc = {first entry, length}; span = {length, first column, last column, -} (what the one-pass pre-pass gathers: the
+// product count and the column window of a row of C follow from these alone because B's rows are sorted)
+__global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col,
+                                                    uint2 *__restrict__ desc, uint4 *__restrict__ span) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
         const u64 s = rp[i], e = rp[i + 1];
         desc[i] = make_uint2((u32)s, (u32)(e - s));
+        span[i] = e > s ? make_uint4((u32)(e - s), col[s], col[e - 1], 0u) : make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
     }
 }
+
+// per hash bin: how many 128-column groups the bin's shared-memory bitmap holds (0: the bin has no bitmap kernel)
+struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; };
 
 // Walk the intermediate products of one A row.  `ngrp` groups of G lanes each take A entries
 // grp, grp+ngrp, ...; the G lanes of a group stride over that entry's B row.  Two A entries are
@@ -136,9 +143,10 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 // order -- the scratch offsets prefix(min(P_i, cols)) that the numeric kernels write their rows at.
 template <int G>
 __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
-                                                 const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
+                                                 const uint4 *__restrict__ bspan, u64 ncols, u64 *__restrict__ prod,
                                                  u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
-                                                 B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride) {
+                                                 B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride,
+                                                 uint2 *__restrict__ win, WinCaps caps) {
     constexpr int RPC = 256 / G;                                            // rows per CTA
     __shared__ u32 s_tile, s_cnt[B200_NBINS], s_base[B200_NBINS];
     __shared__ u64 s_bound[RPC], s_wsum[8], s_excl;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
     const u32 tile = s_tile;
     const u64 row = (u64)tile * RPC + tid / G;
     const u32 sub = tid % G;
-    u64 p = 0; u32 lenA = 0;
+    u64 p = 0; u32 lenA = 0, cmin = 0xFFFFFFFFu, cmax = 0;
     if (row < rows) {
         const u64 s = rpA[row];
         lenA = (u32)(rpA[row + 1] - s);
@@ -158,13 +166,19 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         u32 i = sub;
         for (; i + 3 * G < lenA; i += 4 * G) {                               // four independent gathers in flight
             const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
-            const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
-            p += (u64)d0 + d1 + d2 + d3;
+            const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
+            p += (u64)d0.x + d1.x + d2.x + d3.x;
+            cmin = min(min(cmin, d0.y), min(min(d1.y, d2.y), d3.y));
+            cmax = max(max(cmax, d0.z), max(max(d1.z, d2.z), d3.z));
         }
-        for (; i < lenA; i += G) p += bdesc[Ac[i]].y;
+        for (; i < lenA; i += G) { const uint4 d = bspan[Ac[i]]; p += d.x; cmin = min(cmin, d.y); cmax = max(cmax, d.z); }
     }
 #pragma unroll
-    for (int m = G / 2; m > 0; m >>= 1) p += shfl_xor_u64(p, m);
+    for (int m = G / 2; m > 0; m >>= 1) {
+        p += shfl_xor_u64(p, m);
+        cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, m));
+        cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
+    }
     int b = B200_BIN_NONE; u32 local = 0;
     u64 wsum = 0, wmax = 0;
     if (sub == 0) {
@@ -174,6 +188,13 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
             bound = p < ncols ? p : ncols;
             b = sym_bin_of<true>(p, lenA);
             if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;               // the two smallest hash bins share a list
+            if (b != B200_BIN_NONE) {
+                // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
+                const u32 base = cmin & ~127u;
+                const u32 groups = (cmax - base) / 128u + 1u;
+                win[row] = make_uint2(base, groups);
+                if (b >= B200_BIN_HASH0 && b < B200_BIN_HEAVY && groups > caps.cap[b - B200_BIN_HASH0]) b = B200_BIN_WIDE0 + (b - B200_BIN_HASH0);
+            }
             if (b == B200_BIN_NONE) nnz_row[row] = 0;
             else local = atomicAdd(&s_cnt[b], 1u);
             wsum = p; wmax = p;
@@ -1022,7 +1043,8 @@ __device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, con
 
 template <typename VT, int MODE, bool PACK, bool BPAT>
 __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
-                                                    B200Ctrl *ctrl, int bin, int nbins, u32 pcap, u32 ncap, u32 nw4, OutArgs<VT> o) {
+                                                    B200Ctrl *ctrl, int bin, int nbins, u32 pcap, u32 ncap, u32 nw4,
+                                                    const uint2 *__restrict__ win, OutArgs<VT> o) {
     typedef typename PVal<MODE, VT>::type PV;
     constexpr bool PAIR = sizeof(PV) == 4;       // products kept as {col, value} pairs: one 64-bit shared access each
     constexpr int E = B200_EXPAND_PRE;
@@ -1050,12 +1072,14 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
     for (u32 t = tid; t < ncap; t += nt) acc.clear(t);
     if (tid == 0) s_P = 0;
+    // the row's column window: bitmap word 0 is column word `wbase` (a multiple of four), `groups` 128-column groups long
+    u32 wbase = 0, groups = nw4;
 
     auto put = [&](u32 dst, VT av, u32 c, u32 jb) {
         const PV x = BPAT ? (PV)av : product_value<MODE, VT>(av, a.valB[jb]);
         if (PAIR) pp[dst] = make_uint2(c, (u32)x);
         else { pc[dst] = c; pv[dst] = (u64)x; }
-        atomicOr(&bm[c >> 5], __funnelshift_l(0u, 1u, c));                   // mark the column while it is in a register
+        atomicOr(&bm[(c >> 5) - wbase], __funnelshift_l(0u, 1u, c));         // mark the column while it is in a register
     };
     // products of one warp's 32 A entries -> a slice of the product buffer
     auto expand32 = [&](bool valid, VT av, const BRowRef &b) {
@@ -1063,10 +1087,10 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         u32 incl = len;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += x; }
-        u32 wbase = 0;
-        if (lane == 31) wbase = atomicAdd(&s_P, incl);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-        const u32 dst = wbase + incl - len;
+        u32 pbase = 0;
+        if (lane == 31) pbase = atomicAdd(&s_P, incl);
+        pbase = __shfl_sync(0xFFFFFFFFu, pbase, 31);
+        const u32 dst = pbase + incl - len;
         if (PACK) {
             if (len > 0) put(dst, av, b.ca.z, b.start);
             if (len > 1) put(dst + 1, av, b.ca.w, b.start + 1);
@@ -1084,8 +1108,11 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     u32 row = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin);
     u64 rs = a.rpA[row];
     u32 lenA = (u32)(a.rpA[row + 1] - rs);
+    uint2 wn = win[row];
+    wbase = wn.x >> 5; groups = wn.y;
     u32 row_n = 0, lenA_n = 0; u64 rs_n = 0;
-    if (r_begin + 1 < r_end) { row_n = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin + 1); rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); }
+    wn = make_uint2(0, 0);
+    if (r_begin + 1 < r_end) { row_n = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin + 1); rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); wn = win[row_n]; }
     VT av[E]; BRowRef br[E];
 #pragma unroll
     for (int e = 0; e < E; e++) {
@@ -1123,7 +1150,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         if (r + 2 < r_end) row_nn = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r + 2);
         __syncthreads();
         const u32 P = s_P;
-        const u32 nnz = rank_prefix_v4(bm4, wpre4, nw4, s_warp);
+        const u32 nnz = rank_prefix_v4(bm4, wpre4, groups, s_warp);
 #pragma unroll
         for (int e = 0; e < E; e++) {
             const u32 t = tid + e * nt;
@@ -1131,8 +1158,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             if (has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
             av[e] = avn[e];
         }
-        u64 rs_nn = 0; u32 lenA_nn = 0;
-        if (r + 2 < r_end) { rs_nn = a.rpA[row_nn]; lenA_nn = (u32)(a.rpA[row_nn + 1] - rs_nn); }
+        u64 rs_nn = 0; u32 lenA_nn = 0; uint2 wnn = make_uint2(0, 0);
+        if (r + 2 < r_end) { rs_nn = a.rpA[row_nn]; lenA_nn = (u32)(a.rpA[row_nn + 1] - rs_nn); wnn = win[row_nn]; }
         __syncthreads();
         // ---- accumulate at the column's rank
         for (u32 p0 = tid; p0 < P; p0 += B200_EXPAND_ILP * nt) {
@@ -1145,8 +1172,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             }
 #pragma unroll
             for (int j = 0; j < B200_EXPAND_ILP; j++) {
-                const u32 cc = c[j] != B200_EMPTY_KEY ? c[j] : 0u;          // padding lanes read word 0
-                const u32 w = cc >> 5;
+                const u32 cc = c[j] != B200_EMPTY_KEY ? c[j] : wbase << 5;  // padding lanes read word 0
+                const u32 w = (cc >> 5) - wbase;
                 pos[j] = (u32)wpre[w] + __popc(bm[w] & (__funnelshift_l(0u, 1u, cc) - 1u));
             }
 #pragma unroll
@@ -1166,11 +1193,11 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             const u64 m = (u64)(v0 > v1 ? v0 : v1);
             vmax = vmax > m ? vmax : m;
         }
-        for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
+        for (u32 t = tid; t < groups; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_P = 0; if (o.nnz_out) o.nnz_out[row] = nnz; }
         __syncthreads();
-        row = row_n; rs = rs_n; lenA = lenA_n;
-        row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn;
+        row = row_n; rs = rs_n; lenA = lenA_n; wbase = wn.x >> 5; groups = wn.y;
+        row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn; wn = wnn;
     }
     vmax = warp_max_u64(vmax);
     if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);

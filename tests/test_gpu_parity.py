@@ -326,3 +326,32 @@ def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, monkeypatch):
     two = a.matmul(a).matmul(a).to_host()
     assert_same(one, two)
     assert_same(one, oracle.matmul(oracle.matmul(to_o(oracle, a_h), to_o(oracle, a_h)), to_o(oracle, a_h)))
+
+
+# ------------------------------------------------------------------ column windows: bitmap path vs hash path of the one-pass numeric
+@pytest.mark.parametrize("wincap", ["0", "1", "3", "16"])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_column_window_split_is_bit_identical(gpu_ctx, oracle, monkeypatch, wincap, bits):
+    """Rows whose column window exceeds their bin's shared-memory bitmap leave k_num_expand for the hash + sort kernels.
+    B200_WINCAP shrinks the window (in 128-column groups; 0 = hash only) so that both lists are populated on a small
+    torus; every split must give the reference's bytes."""
+    monkeypatch.setenv("B200_WINCAP", wincap)
+    a_h = hostgen.reference_bench_instance(12, 3.0, bits)
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k in range(2, 6):
+        p = p.matmul(a)
+        p_o = oracle.matmul(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k} wincap={wincap}")
+
+
+def test_window_of_a_banded_matrix_far_from_column_zero(gpu_ctx, oracle):
+    """The bitmap is relative to the row's first column (a multiple of 128): a band placed at large column indices in a
+    wide, rectangular right operand must land in the same places."""
+    rng = np.random.default_rng(11)
+    rows, inner, cols = 300, 500, 3_000_000
+    a_h = rand_csr(rng, rows, inner, 9000, 64, 5)
+    r = rng.integers(0, inner, size=20000)
+    c = 2_900_000 + (r * 37 + rng.integers(0, 900, size=20000)) % 90_000          # banded, near the right edge
+    b_h = hostgen.from_coo(inner, cols, r, c, rng.integers(1, 4, size=20000).astype(np.uint64), 64)
+    check_product(oracle, gpu_ctx, a_h, b_h, "band at columns 2.9M..3.0M")
