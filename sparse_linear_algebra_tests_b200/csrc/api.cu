@@ -234,6 +234,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     allow_big_smem(k_num_cta<u64, 2>, ctx->smem_optin); allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_sym_pack<false>, ctx->smem_optin); allow_big_smem(k_sym_pack<true>, ctx->smem_optin);
+    allow_big_smem(k_sym_expand<false>, ctx->smem_optin); allow_big_smem(k_sym_expand<true>, ctx->smem_optin);
     allow_big_smem(k_num_rank_pack<u64, 2, false>, ctx->smem_optin); allow_big_smem(k_num_rank_pack<u64, 2, true>, ctx->smem_optin);
     allow_big_smem(k_num_expand<u64, 2, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true>, ctx->smem_optin);
     allow_big_smem(k_num_expand<u64, 2, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true>, ctx->smem_optin);
@@ -768,6 +769,55 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
     return B200_OK;
 }
 
+// Exact mode, first half: distinct-column counts for every list the one-pass pre-pass produced (the lists and the
+// kernels mirror launch_numeric's: tiny / window bitmap / hash, heavy), so that C can be allocated at its exact size.
+static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const SymArgs &sa, u64 rows, u64 p_bound, bool packed, int lg,
+                         Fan &fan, const WinCaps &caps) {
+    const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = (nwords + 3) / 4;
+    const u32 bstride = (u32)ctx->cap_rows;
+    const size_t smem_max = ctx->smem_optin - 1024;
+    auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
+    auto count_expand = [&](int bin, int nb, u32 pcap, u32 nw4) -> int {
+        if (nw4 == 0) return B200_OK;
+        const size_t smem = (size_t)nw4 * 16;
+        const int t = std::max(32, std::min(512, (int)std::max<u32>(pcap / 2, nw4) / 8 / 32 * 32));
+        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4);
+        cudaStream_t bs = fan.pick();
+        if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, ctx->d_nnz_row, bstride);
+        else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, ctx->d_nnz_row, bstride);
+        LAUNCH_CHECK(ctx);
+        return B200_OK;
+    };
+    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan));
+    for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) {
+        if (!reachable(hb)) continue;
+        TRY(count_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb]));
+        if (caps.cap[hb] < nw4_full) {
+            const u32 slots = b200_hash_slots(hb);
+            const int threads = bin_threads(hb, lg);
+            const size_t smem = (size_t)slots * 4;
+            if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
+            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
+            k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    if (reachable(0) || reachable(1)) {
+        TRY(count_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1]));
+        if (caps.cap[1] < nw4_full) {
+            const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
+            k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_WIDE0 + 1, 1, std::min(lg, 5), ctx->d_nnz_row, bstride);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    {
+        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
+        LAUNCH_CHECK(ctx);
+    }
+    return B200_OK;
+}
+
 template <typename VT>
 static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st) {
     const u64 rows = A->rows, ncols = B->cols;
@@ -853,14 +903,57 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
 #undef PREPASS
         LAUNCH_CHECK(ctx);
-        if (cheap_bound) tmp_entries = (u64)hb128;
-        else {
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            tmp_entries = ctx->h_ctrl->total_bound;
-            { size_t tb = 0; cudaMemGetInfo(&free_b, &tb); }
-            if ((unsigned __int128)tmp_entries * esz > (unsigned __int128)(free_b / 3)) onepass = false;   // scratch would crowd out C
+        // Exact mode: count every row's distinct columns first (same lists, count-only kernels), allocate C at its exact
+        // size and let the numeric kernels write it once at the final offsets -- no scratch CSR, no compaction, DRAM
+        // traffic close to the algorithmic bytes.  Measured on the 30^3 chain the count pass costs more (~100 us at A^7)
+        // than the compaction it saves (~64 us), so the scratch path stays the default while its host-known bound
+        // nnz(A) * maxlen(B) entries fits 1/16 of device memory (B200_EXACT_MB overrides the limit); beyond that the
+        // exact mode runs and memory stays at the size of C.
+        const int exact_env = env_int("B200_EXACT", -1);
+        const int exact_mb = env_int("B200_EXACT_MB", -1);
+        const bool exact = exact_env >= 0 ? exact_env != 0
+                                          : (!cheap_bound || (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20)));
+        if (exact) {
+            r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps);
+            fan.join();
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
+            k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0,
+                                                                              ctx->h_ctrl, epoch);
+            LAUNCH_CHECK(ctx);
+            if (timing) cudaEventRecord(ctx->ev[1], s);
+            r = wait_for_report(ctx, epoch);
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            const B200Ctrl hc = *ctx->h_ctrl;
+            C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz;
+            r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
+            if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            if (timing) cudaEventRecord(ctx->ev[2], s);
+            if (ctx->trace) trace_mark(ctx, __LINE__);
+            OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
+            r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps);
+            fan.join();
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
+            if (timing) cudaEventRecord(ctx->ev[3], s);
+            if (st) {
+                st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
+                st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
+                st->acc_mode = mode1; st->kernel_launches = (int32_t)(ctx->launches - launches0);
+                for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
+                if (timing) {
+                    CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+                    cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan
+                    cudaEventElapsedTime(&st->ms_numeric, ctx->ev[2], ctx->ev[3]);    // numeric kernels into the final arrays
+                    cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
+                }
+            }
+            trace_dump(ctx, "exact multiply");
+            *out = C;
+            return B200_OK;
         }
+        tmp_entries = (u64)hb128;
     }
     if (onepass) {
         r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));

@@ -1203,6 +1203,68 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
 }
 
+// 5f. count-only twin of k_num_expand (exact mode: C is written once, at its final offsets): the same expansion, but a
+//     product only marks its column; the row's nnz is the popcount of its window.  Shared memory: the bitmap alone.
+template <bool PACK>
+__global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
+                                                    B200Ctrl *ctrl, int bin, int nbins, u32 nw4, const uint2 *__restrict__ win,
+                                                    u32 *__restrict__ nnz_row, u32 bin_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_warp[33];
+    u32 count = 0;
+    for (int b = 0; b < nbins; b++) count += ctrl->sym_bin_count[bin + b];
+    u32 r_begin, r_end;
+    cta_row_range(count, r_begin, r_end);
+    if (r_begin >= r_end) return;
+    uint4 *bm4 = reinterpret_cast<uint4 *>(smem_raw);
+    u32 *bm = reinterpret_cast<u32 *>(smem_raw);
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (u32 r = r_begin; r < r_end; r++) {
+        const u32 row = bin_row_at(bin_rows, ctrl->sym_bin_count, bin_stride, bin, nbins, r);
+        const u64 s = a.rpA[row];
+        const u32 lenA = (u32)(a.rpA[row + 1] - s);
+        const uint2 wn = win[row];
+        const u32 wbase = wn.x >> 5, groups = wn.y;
+        auto mark = [&](u32 c) { atomicOr(&bm[(c >> 5) - wbase], __funnelshift_l(0u, 1u, c)); };
+        // two A entries per thread and iteration so that their dependent loads overlap
+        for (u32 t = tid; t < lenA; t += 2 * nt) {
+            const u32 t1 = t + nt;
+            const bool h1 = t1 < lenA;
+            const u32 k0 = a.colA[s + t], k1 = h1 ? a.colA[s + t1] : k0;
+            const BRowRef b0 = load_brow<PACK>(pack, a.bdesc, k0);
+            BRowRef b1 = load_brow<PACK>(pack, a.bdesc, k1);
+            if (!h1) b1.len = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const BRowRef &b = e ? b1 : b0;
+                if (PACK) {
+                    if (b.len > 0) mark(b.ca.z);
+                    if (b.len > 1) mark(b.ca.w);
+                    if (b.len > 2) mark(b.cb.x);
+                    if (b.len > 3) mark(b.cb.y);
+                    if (b.len > 4) mark(b.cb.z);
+                    if (b.len > 5) mark(b.cb.w);
+                    for (u32 j = B200_PACK_INLINE; j < b.len; j++) mark(a.colB[b.start + j]);
+                } else {
+                    for (u32 j = 0; j < b.len; j++) mark(a.colB[b.start + j]);
+                }
+            }
+        }
+        __syncthreads();
+        u32 mine = 0;
+        for (u32 g = tid; g < groups; g += nt) {
+            const uint4 w = bm4[g];
+            mine += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+            bm4[g] = make_uint4(0, 0, 0, 0);
+        }
+        u32 total;
+        block_excl_scan(mine, s_warp, total);                              // ends on a barrier: the bitmap is clean for the next row
+        if (tid == 0) nnz_row[row] = total;
+    }
+}
+
 // =======================================================================================
 // 6. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
 // =======================================================================================

@@ -355,3 +355,41 @@ def test_window_of_a_banded_matrix_far_from_column_zero(gpu_ctx, oracle):
     c = 2_900_000 + (r * 37 + rng.integers(0, 900, size=20000)) % 90_000          # banded, near the right edge
     b_h = hostgen.from_coo(inner, cols, r, c, rng.integers(1, 4, size=20000).astype(np.uint64), 64)
     check_product(oracle, gpu_ctx, a_h, b_h, "band at columns 2.9M..3.0M")
+
+
+# ------------------------------------------------------------------ exact mode (count pass, C written once) vs one-pass scratch + compaction
+@pytest.mark.parametrize("exact", ["0", "1"])
+@pytest.mark.parametrize("bits", [32, 64])
+def test_exact_and_scratch_modes_give_the_same_bytes(gpu_ctx, oracle, monkeypatch, exact, bits):
+    """B200_EXACT=1: every list gets a count kernel first and the numeric kernels write C at its final offsets;
+    B200_EXACT=0: rows go to a scratch CSR at bound offsets and are compacted.  The engine picks by size; both are
+    forced here over the torus chain, ragged rows through every bin including the heavy one, and a wide column space."""
+    monkeypatch.setenv("B200_EXACT", exact)
+    a_h = hostgen.reference_bench_instance(12, 3.0, bits)
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k in range(2, 6):
+        p = p.matmul(a)
+        p_o = oracle.matmul(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k} exact={exact}")
+    rng = np.random.default_rng(3)
+    n = 30000
+    lens = [1, 2, 5, 20, 33, 64, 100, 200, 400, 800, 1500, 3000, 6000, 12000, 0, 7]
+    r = np.concatenate([np.full(l, i) for i, l in enumerate(lens)])
+    c = np.concatenate([rng.choice(n, size=l, replace=False) for l in lens])
+    ragged = hostgen.from_coo(n, n, r, c, rng.integers(1, 4, size=r.size, dtype=np.uint64).astype(hostgen.vdtype(bits)), bits)
+    check_product(oracle, gpu_ctx, ragged, rand_csr(rng, n, n, 5 * n, bits), f"ragged exact={exact}")
+    wide_n = 1_500_000
+    lens = [3, 40, 150, 700, 2500, 9000]
+    r = np.concatenate([np.full(l, i * 1000) for i, l in enumerate(lens)])
+    c = np.concatenate([rng.choice(wide_n, size=l, replace=False) for l in lens])
+    wide = hostgen.from_coo(wide_n, wide_n, r, c, np.ones(r.size, hostgen.vdtype(bits)), bits)
+    check_product(oracle, gpu_ctx, wide, rand_csr(rng, wide_n, wide_n, 3 * wide_n, bits), f"wide exact={exact}")
+
+
+def test_exact_mode_saturating_values(gpu_ctx, oracle, monkeypatch):
+    monkeypatch.setenv("B200_EXACT", "1")
+    rng = np.random.default_rng(9)
+    a_h = rand_csr(rng, 500, 500, 6000, 64, 3)
+    a_h.values[:] = rng.integers(1 << 61, 1 << 63, size=a_h.nnz(), dtype=np.uint64)
+    check_product(oracle, gpu_ctx, a_h, a_h, "u64 saturation, exact mode")
