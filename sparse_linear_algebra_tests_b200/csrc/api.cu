@@ -172,8 +172,11 @@ static int ensure_heavy_scratch(b200_ctx *ctx, size_t bytes) {
 // ---------------------------------------------------------------------------- kernel attribute setup
 template <typename K>
 static void allow_big_smem(K kernel, size_t optin) {
-    // static shared memory counts against the opt-in limit: leave 1 KB for it
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - 1024));
+    // static shared memory counts against the opt-in limit
+    cudaFuncAttributes fa;
+    size_t stat = 1024;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) stat = fa.sharedSizeBytes; else cudaGetLastError();
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - stat));
     if (e != cudaSuccess) { fprintf(stderr, "b200: cudaFuncSetAttribute(max dynamic smem) failed: %s\n", cudaGetErrorString(e)); cudaGetLastError(); }
 }
 
@@ -621,7 +624,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
         const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
         const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
-        if (ex_smem > smem_max) return false;
+        if (ex_smem + (packed ? 0 : sizeof(EnumSmem)) > smem_max) return false;
         // threads: ~8 products or ~8 bitmap groups each, whichever asks for more
         const int et = std::max(32, std::min(512, (int)std::max<u32>(pcap, nw4) / std::max(1, env_int("B200_EDIV", 8)) / 32 * 32));
         const int eg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * 4);
@@ -860,7 +863,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // nnz(A) * maxlen(B) is used when it is cheap, else the exact sum is read back first; if even that is
     // too large for the memory budget the exact two-pass path (symbolic + numeric) runs instead.
     bool onepass = env_int("B200_TWOPASS", 0) == 0;
-    size_t free_b = 0;
     const size_t total_b = ctx->total_mem;
     const size_t esz = 4 + sizeof(VT);
     unsigned __int128 hb128 = (unsigned __int128)A->nnz * B->max_row_len;
@@ -888,7 +890,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const size_t fixed = pcap * (4 + pvb1) + ncap * (4 + accb1);
             u64 want = std::min<u64>(nw4_full, std::max<u64>(256, std::min<u64>(4096, (u64)env_int("B200_WINMUL", 3) * pcap)));
             if (forced >= 0) want = std::min<u64>(want, (u64)forced);
-            const u64 fit = fixed + 24 * 32 <= smem_max ? (smem_max - fixed) / 24 : 0;
+            const size_t avail = smem_max - (packed ? 0 : sizeof(EnumSmem));    // the balanced expansion keeps its tile in static shared memory
+            const u64 fit = fixed + 24 * 32 <= avail ? (avail - fixed) / 24 : 0;
             caps.cap[hb] = env_int("B200_EXPAND", 1) ? (u32)std::min<u64>(want, fit) : 0u;
         }
     }

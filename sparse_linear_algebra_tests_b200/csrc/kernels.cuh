@@ -372,6 +372,62 @@ __device__ __forceinline__ u32 table_insert(u32 *keys, u32 mask, int shift, u32 
     }
 }
 
+// block-wide exclusive scan of one u32 per thread; returns exclusive prefix, total in `total`
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        u32 x = lane < nw ? s_warp[lane] : 0, xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, xi, d); if (lane >= d) xi += t; }
+        s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const u32 r = s_warp[w] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+// Balanced enumeration of one A row's intermediate products by a whole CTA.  A tile of blockDim.x A entries is
+// loaded (one per thread), a block scan of their B-row lengths lays the tile's products out on a line, and thread q
+// takes products q, q + blockDim.x, ...: a binary search in the scanned lengths finds the entry, the remainder the
+// position inside its B row.  Every thread gets the same number of products whatever the row lengths are (a single
+// long B row no longer pins one lane group while the rest of the CTA waits at the barrier), and consecutive threads
+// read consecutive B entries.  f(p, jb, a_ik): p = running product index in the row, jb = index into B's arrays.
+struct EnumSmem { u32 pre[1025]; u32 start[1024]; u64 av[1024]; };
+template <bool NEEDED> struct EnumStore { EnumSmem s; };                   // kernels that enumerate only in some variants
+template <> struct EnumStore<false> { u32 s; };
+template <typename VT, bool NUMERIC, typename F>
+__device__ __forceinline__ u32 enumerate_products(const u32 *__restrict__ Ac, const VT *__restrict__ Av, u32 lenA,
+                                                  const uint2 *__restrict__ bdesc, EnumSmem &es, u32 *s_warp, F f) {
+    const u32 nt = blockDim.x, tid = threadIdx.x;
+    u32 done = 0;
+    for (u32 base = 0; base < lenA; base += nt) {
+        const u32 t = base + tid;
+        u32 len = 0, start = 0; u64 av = 0;
+        if (t < lenA) { const uint2 d = bdesc[Ac[t]]; start = d.x; len = d.y; if (NUMERIC) av = (u64)Av[t]; }
+        u32 total;
+        const u32 ex = block_excl_scan(len, s_warp, total);
+        es.pre[tid] = ex; es.start[tid] = start;
+        if (NUMERIC) es.av[tid] = av;
+        __syncthreads();
+        for (u32 q = tid; q < total; q += nt) {
+            u32 lo = 0, hi = nt;                                            // last entry e with pre[e] <= q (its B row is not empty)
+            while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (es.pre[mid] <= q) lo = mid; else hi = mid; }
+            f(done + q, es.start[lo] + (q - es.pre[lo]), NUMERIC ? (VT)es.av[lo] : (VT)0);
+        }
+        done += total;
+        __syncthreads();
+    }
+    return done;
+}
+
 // =======================================================================================
 // 3. tiny rows: one warp per row, <= 32 products held one per lane
 // =======================================================================================
@@ -518,11 +574,11 @@ template <bool BITMAP>
 __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
                                                   u32 nwords, int lg, u32 *__restrict__ nnz_row, u32 bin_stride) {
     extern __shared__ u32 smem[];
-    __shared__ u32 s_count;
+    __shared__ u32 s_count, s_warp[33];
+    __shared__ EnumSmem s_enum;
     const u32 count = ctrl->sym_bin_count[bin];
     const u64 off = (u64)bin * bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
-    const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const u32 tabn = BITMAP ? nwords : slots;
     const int shift = 32 - (31 - __clz(slots));
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
@@ -533,8 +589,8 @@ __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restri
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
         u32 local = 0;
-        walk_products<int>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [](u32) { return 0; },
-                           [&](int, u32 jb) {
+        enumerate_products<u32, false>(a.colA + s, (const u32 *)nullptr, lenA, a.bdesc, s_enum, s_warp,
+                           [&](u32, u32 jb, u32) {
                                const u32 c = a.colB[jb];
                                if (BITMAP) {
                                    const u32 bit = 1u << (c & 31);
@@ -563,28 +619,6 @@ __device__ __forceinline__ void cta_row_range(u32 count, u32 &begin, u32 &end) {
     const u32 rpc = (count + gridDim.x - 1) / gridDim.x;
     begin = blockIdx.x * rpc;
     end = begin + rpc < count ? begin + rpc : count;
-}
-
-// block-wide exclusive scan of one u32 per thread; returns exclusive prefix, total in `total`
-__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 &total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    u32 incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        u32 x = lane < nw ? s_warp[lane] : 0, xi = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, xi, d); if (lane >= d) xi += t; }
-        s_warp[lane] = xi - x;
-        if (lane == 31) s_warp[32] = xi;
-    }
-    __syncthreads();
-    total = s_warp[32];
-    const u32 r = s_warp[w] + incl - v;
-    __syncthreads();
-    return r;
 }
 
 // bitonic sort of n (power of two) key/accumulator pairs in shared memory.  WARP: one warp owns the
@@ -678,12 +712,12 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
                                                   int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
+    __shared__ EnumSmem s_enum;
     Acc<MODE> acc; acc.bind(smem_raw, slots);
     u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
     const u32 count = o.bin_cnt[bin];
     const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
-    const u32 G = 1u << lg, sub = tid & (G - 1), grp = tid >> lg, ngrp = nt >> lg;
     const int shift = 32 - (31 - __clz(slots));
     const u32 per = slots / nt;                                             // <= 16 by the bin table
     u64 vmax = 0;
@@ -694,8 +728,8 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
         const VT *Av = a.valA + s;
-        walk_products<VT>(a.colA + s, lenA, a.bdesc, grp, ngrp, sub, G, [&](u32 t) { return Av[t]; },
-                          [&](VT av, u32 jb) {
+        enumerate_products<VT, true>(a.colA + s, Av, lenA, a.bdesc, s_enum, s_warp,
+                          [&](u32, u32 jb, VT av) {
                               bool fresh;
                               const u32 h = table_insert(keys, slots - 1, shift, a.colB[jb], fresh);
                               acc.add(h, av, a.valB[jb]);
@@ -1051,6 +1085,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
     __shared__ u32 s_P;
+    __shared__ EnumStore<!PACK> s_enum;                                     // only the non-packed expansion needs it
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += o.bin_cnt[bin + b];            // consecutive bins share one launch
     u32 r_begin, r_end;
@@ -1118,25 +1153,32 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     for (int e = 0; e < E; e++) {
         const u32 t = tid + e * nt;
         av[e] = 0; br[e].start = 0; br[e].len = 0; br[e].ca = make_uint4(0, 0, 0, 0); br[e].cb = br[e].ca;
-        if (t < lenA) { av[e] = a.valA[rs + t]; br[e] = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
+        if (PACK && t < lenA) { av[e] = a.valA[rs + t]; br[e] = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
     }
     __syncthreads();
     u64 vmax = 0;
     for (u32 r = r_begin; r < r_end; r++) {
         const bool has_next = r + 1 < r_end;
         const u64 obase = o.base[row];
-        // ---- expand: one A entry per thread, whole warps iterate together
-        const u32 lenA_w = (lenA + 31u) & ~31u;
+        if constexpr (PACK) {
+            // ---- expand: one A entry per thread, whole warps iterate together
+            const u32 lenA_w = (lenA + 31u) & ~31u;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            const u32 t = tid + e * nt;
-            if (t - lane < lenA_w) expand32(t < lenA, av[e], br[e]);        // warp-uniform condition
-        }
-        for (u32 t = tid + E * nt; t < lenA_w; t += nt) {
-            const bool valid = t < lenA;
-            VT x = 0; BRowRef b; b.start = 0; b.len = 0; b.ca = make_uint4(0, 0, 0, 0); b.cb = b.ca;
-            if (valid) { x = a.valA[rs + t]; b = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
-            expand32(valid, x, b);
+            for (int e = 0; e < E; e++) {
+                const u32 t = tid + e * nt;
+                if (t - lane < lenA_w) expand32(t < lenA, av[e], br[e]);    // warp-uniform condition
+            }
+            for (u32 t = tid + E * nt; t < lenA_w; t += nt) {
+                const bool valid = t < lenA;
+                VT x = 0; BRowRef b; b.start = 0; b.len = 0; b.ca = make_uint4(0, 0, 0, 0); b.cb = b.ca;
+                if (valid) { x = a.valA[rs + t]; b = load_brow<PACK>(pack, a.bdesc, a.colA[rs + t]); }
+                expand32(valid, x, b);
+            }
+        } else {
+            // ---- expand (B rows of any length): balanced enumeration, product p lands in slot p
+            const u32 P = enumerate_products<VT, true>(a.colA + rs, a.valA + rs, lenA, a.bdesc, s_enum.s, s_warp,
+                                                       [&](u32 p, u32 jb, VT x) { put(p, x, a.colB[jb], jb); });
+            if (tid == 0) s_P = P;
         }
         // next row: A entries now, their B rows after the mark phase (the column indices have arrived by then)
         u32 kn[E]; VT avn[E];
@@ -1145,7 +1187,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         for (int e = 0; e < E; e++) {
             const u32 t = tid + e * nt;
             kn[e] = 0; avn[e] = 0;
-            if (has_next && t < lenA_n) { kn[e] = a.colA[rs_n + t]; avn[e] = a.valA[rs_n + t]; }
+            if (PACK && has_next && t < lenA_n) { kn[e] = a.colA[rs_n + t]; avn[e] = a.valA[rs_n + t]; }
         }
         if (r + 2 < r_end) row_nn = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r + 2);
         __syncthreads();
@@ -1155,7 +1197,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         for (int e = 0; e < E; e++) {
             const u32 t = tid + e * nt;
             br[e].len = 0;
-            if (has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
+            if (PACK && has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
             av[e] = avn[e];
         }
         u64 rs_nn = 0; u32 lenA_nn = 0; uint2 wnn = make_uint2(0, 0);
@@ -1211,6 +1253,7 @@ __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__re
                                                     u32 *__restrict__ nnz_row, u32 bin_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
+    __shared__ EnumStore<!PACK> s_enum;
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += ctrl->sym_bin_count[bin + b];
     u32 r_begin, r_end;
@@ -1228,8 +1271,12 @@ __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__re
         const uint2 wn = win[row];
         const u32 wbase = wn.x >> 5, groups = wn.y;
         auto mark = [&](u32 c) { atomicOr(&bm[(c >> 5) - wbase], __funnelshift_l(0u, 1u, c)); };
-        // two A entries per thread and iteration so that their dependent loads overlap
-        for (u32 t = tid; t < lenA; t += 2 * nt) {
+        if constexpr (!PACK) {
+            enumerate_products<u32, false>(a.colA + s, (const u32 *)nullptr, lenA, a.bdesc, s_enum.s, s_warp,
+                                           [&](u32, u32 jb, u32) { mark(a.colB[jb]); });
+        }
+        // packed B: two A entries per thread and iteration so that their dependent loads overlap
+        for (u32 t = tid; PACK && t < lenA; t += 2 * nt) {
             const u32 t1 = t + nt;
             const bool h1 = t1 < lenA;
             const u32 k0 = a.colA[s + t], k1 = h1 ? a.colA[s + t1] : k0;
@@ -1270,7 +1317,8 @@ __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__re
 // =======================================================================================
 __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 nwords,
                                                     u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row, u32 bin_stride) {
-    __shared__ u32 s_count;
+    __shared__ u32 s_count, s_warp[33];
+    __shared__ EnumSmem s_enum;
     const u32 count = ctrl->sym_bin_count[B200_BIN_HEAVY];
     const u64 off = (u64)B200_BIN_HEAVY * bin_stride;
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
@@ -1283,8 +1331,8 @@ __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__rest
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
         u32 local = 0;
-        walk_products<int>(a.colA + s, lenA, a.bdesc, tid >> 5, nt >> 5, lane, 32, [](u32) { return 0; },
-                           [&](int, u32 jb) {
+        enumerate_products<u32, false>(a.colA + s, (const u32 *)nullptr, lenA, a.bdesc, s_enum, s_warp,
+                           [&](u32, u32 jb, u32) {
                                const u32 c = a.colB[jb];
                                const u32 bit = 1u << (c & 31);
                                const u32 old = atomicOr(&bm[c >> 5], bit);
@@ -1304,6 +1352,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                                                     u32 *__restrict__ scratch_bm, u32 *__restrict__ scratch_pre,
                                                     u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o) {
     __shared__ u32 s_warp[33];
+    __shared__ EnumSmem s_enum;
     const u32 count = o.bin_cnt[B200_BIN_HEAVY];
     const u64 off = (u64)B200_BIN_HEAVY * o.bin_stride;
     u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
@@ -1323,8 +1372,8 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
         const VT *Av = a.valA + s;
-        walk_products<VT>(a.colA + s, lenA, a.bdesc, tid >> 5, nt >> 5, lane, 32, [&](u32 t) { return Av[t]; },
-                          [&](VT av, u32 jb) {
+        enumerate_products<VT, true>(a.colA + s, Av, lenA, a.bdesc, s_enum, s_warp,
+                          [&](u32, u32 jb, VT av) {
                               const u32 c = a.colB[jb];
                               ull x;
                               if (MODE == 2) x = sat_mul((u64)av, (u64)a.valB[jb]);
