@@ -49,13 +49,16 @@ typedef struct b200_stats {
     uint64_t max_row_products;
     uint64_t max_row_nnz;
     uint64_t bytes_algorithmic; /* (nnzA+nnzB+nnzC)*(4+sizeof(Val)) + (rowsA+rowsB+rowsC+3)*8 */
-    float    ms_symbolic;       /* product count + binning + exact nnz/row + row_ptr scan       */
-    float    ms_numeric;        /* per-bin numeric kernels                                       */
-    float    ms_total;          /* first kernel to last kernel, incl. the one host read-back     */
-    int32_t  acc_mode;          /* 0: 32-bit accumulators proved safe, 1: 64-bit, 2: saturating  */
-    int32_t  kernel_launches;   /* kernels launched by this multiply                             */
-    uint32_t sym_bin_rows[16];  /* rows per symbolic bin                                         */
-    uint32_t num_bin_rows[16];  /* rows per numeric bin                                          */
+    float    ms_symbolic;       /* exact mode: pre-pass + count kernels + row_ptr scan;
+                                   scratch mode: compaction of the scratch rows into C                          */
+    float    ms_numeric;        /* exact mode: numeric kernels writing C;
+                                   scratch mode: pre-pass + numeric kernels + row_ptr scan                      */
+    float    ms_total;          /* first kernel to last kernel, incl. the host's read of nnz in the middle      */
+    int32_t  acc_mode;          /* 0: 32-bit accumulators proved safe, 1: 64-bit, 2: saturating                 */
+    int32_t  kernel_launches;   /* kernels launched by this multiply                                            */
+    uint32_t sym_bin_rows[16];  /* rows per pre-pass list: [0] tiny, [1..8] bitmap bins (P <= 64<<hb; 1 and 2
+                                   share list 2), [9] heavy, [10..15] hash lists of bins 0..5 (window too wide)  */
+    uint32_t num_bin_rows[16];  /* same lists (kept for layout compatibility)                                   */
 } b200_stats;
 
 const char *b200_last_error(void);

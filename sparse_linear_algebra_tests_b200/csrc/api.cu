@@ -185,8 +185,6 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_num_cta<VT, 0>, optin); allow_big_smem(k_num_cta<VT, 1>, optin);
     allow_big_smem(k_num_rank<VT, 0>, optin); allow_big_smem(k_num_rank<VT, 1>, optin);
     allow_big_smem(k_num_warp<VT, 0>, optin); allow_big_smem(k_num_warp<VT, 1>, optin);
-    allow_big_smem(k_num_rank_pack<VT, 0, false>, optin); allow_big_smem(k_num_rank_pack<VT, 0, true>, optin);
-    allow_big_smem(k_num_rank_pack<VT, 1, false>, optin); allow_big_smem(k_num_rank_pack<VT, 1, true>, optin);
     allow_big_smem(k_num_expand<VT, 0, false, false>, optin); allow_big_smem(k_num_expand<VT, 0, false, true>, optin);
     allow_big_smem(k_num_expand<VT, 0, true, false>, optin); allow_big_smem(k_num_expand<VT, 0, true, true>, optin);
     allow_big_smem(k_num_expand<VT, 1, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, false, true>, optin);
@@ -236,9 +234,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     allow_big_smem(k_sym_cta<false>, ctx->smem_optin); allow_big_smem(k_sym_cta<true>, ctx->smem_optin);
     allow_big_smem(k_num_cta<u64, 2>, ctx->smem_optin); allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
-    allow_big_smem(k_sym_pack<false>, ctx->smem_optin); allow_big_smem(k_sym_pack<true>, ctx->smem_optin);
     allow_big_smem(k_sym_expand<false>, ctx->smem_optin); allow_big_smem(k_sym_expand<true>, ctx->smem_optin);
-    allow_big_smem(k_num_rank_pack<u64, 2, false>, ctx->smem_optin); allow_big_smem(k_num_rank_pack<u64, 2, true>, ctx->smem_optin);
     allow_big_smem(k_num_expand<u64, 2, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true>, ctx->smem_optin);
     allow_big_smem(k_num_expand<u64, 2, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true>, ctx->smem_optin);
     cudaGetLastError();
@@ -520,12 +516,10 @@ static int host_maxval(b200_ctx *ctx, const b200_csr *m) {
     return B200_OK;
 }
 
-static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, bool onepass) {
+static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B) {
     const double avg = A->rows ? (double)A->nnz / (double)A->rows : 0.0;
     const u64 rows = A->rows;
-#define RP_LAUNCH(G)                                                                                              \
-    do { if (onepass) k_row_products<G, true><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl); \
-         else k_row_products<G, false><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl); } while (0)
+#define RP_LAUNCH(G) k_row_products<G><<<(unsigned)((rows * G + 255) / 256), 256, 0, ctx->stream>>>(rows, A->d_rp, A->d_col, B->d_desc, ctx->d_prod)
     if (avg <= 2.0) RP_LAUNCH(1);
     else if (avg <= 6.0) RP_LAUNCH(4);
     else if (avg <= 24.0) RP_LAUNCH(8);
@@ -596,10 +590,10 @@ static int pick_mode(u64 max_row_products, u64 maxA, u64 maxB) {
     return mode;
 }
 
-// Launch the numeric kernels of every non-empty bin.  `cnt` = host-known bin sizes (two-pass) or null
-// (one-pass: sizes live on the device only; bins that no row can reach are skipped via p_bound).
+// Launch the numeric kernels of every list the pre-pass filled.  The list sizes live on the device only, so grids are
+// sized from `rows` and bins that no row can reach (p_bound) are skipped.
 template <typename VT>
-static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const u32 *cnt, u64 rows, u64 p_bound, u64 heavy_cap,
+static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u64 rows, u64 p_bound, u64 heavy_cap,
                           int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps) {
     const u32 nwords = (u32)((B->cols + 31) / 32);
     const size_t smem_max = ctx->smem_optin - 1024;
@@ -607,12 +601,10 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
     OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt, o.bin_stride};
     const size_t accb = mode == 0 ? 4 : 8;
-    auto bin_size = [&](int bin) -> u64 { return cnt ? cnt[bin] : rows; };
-    auto reachable = [&](int hb) { return cnt ? cnt[B200_BIN_HASH0 + hb] != 0 : (hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1)); };
+    auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto do_tiny = [&]() -> int {
-        if (!bin_size(B200_BIN_TINY)) return B200_OK;
-        const int g = (int)std::min<u64>((bin_size(B200_BIN_TINY) + 7) / 8, (u64)ctx->num_sms * 32);
-        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o);
+        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o, bpat);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
@@ -620,7 +612,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
     const u32 nw4_full = (nwords + 3) / 4;
     auto launch_expand = [&](int bin, int nb, u32 cap, u32 nw4, u64 n, cudaStream_t bs) -> bool {
-        if (cnt || nw4 == 0) return false;
+        if (nw4 == 0) return false;
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
         const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
         const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
@@ -665,56 +657,24 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, c
     };
     auto do_small = [&]() -> int {
         if (!(reachable(0) || reachable(1))) return B200_OK;
-        if (!cnt) {
-            // one-pass: bins 0 and 1 share list HASH0+1; rows whose column window exceeds the bitmap are on the wide list
-            if (launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1], rows, fan.pick())) LAUNCH_CHECK(ctx);
-            if (caps.cap[1] < nw4_full) TRY(launch_warp_hash(B200_BIN_WIDE0 + 1, 1, rows, fan.pick()));
-            return B200_OK;
-        }
-        return launch_warp_hash(B200_BIN_HASH0, 2, (u64)cnt[B200_BIN_HASH0] + cnt[B200_BIN_HASH0 + 1], fan.pick());
+        // bins 0 and 1 share list HASH0+1; rows whose column window exceeds the bitmap are on the wide list
+        if (launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1], rows, fan.pick())) LAUNCH_CHECK(ctx);
+        if (caps.cap[1] < nw4_full) TRY(launch_warp_hash(B200_BIN_WIDE0 + 1, 1, rows, fan.pick()));
+        return B200_OK;
     };
     auto do_bin = [&](int hb) -> int {
         if (!reachable(hb)) return B200_OK;
-        const u64 n = bin_size(B200_BIN_HASH0 + hb);
-        const u32 cap = b200_hash_cap(hb);
-        const int bin = B200_BIN_HASH0 + hb;
+        // rows whose column window fits the bin's bitmap -> k_num_expand, the others (wide list) -> hash + sort
         cudaStream_t bs = fan.pick();
-        if (!cnt) {
-            // one-pass: rows whose column window fits the bin's bitmap -> k_num_expand, the others (wide list) -> hash + sort
-            bool used = false;
-            if (launch_expand(bin, 1, cap, caps.cap[hb], n, bs)) { LAUNCH_CHECK(ctx); used = true; }
-            if (caps.cap[hb] < nw4_full) TRY(launch_cta_hash(B200_BIN_WIDE0 + hb, hb, n, used ? fan.pick() : bs));
-            return B200_OK;
-        }
-        // two-pass (bins cut on exact nnz): rank kernel when the whole column space fits a shared-memory bitmap
-        const size_t rank_smem = (size_t)nwords * 6 + 16 + (size_t)cap * (4 + accb);
-        if (nwords <= 4 * cap && rank_smem <= smem_max) {
-            if (packed) {
-                const int pt = std::max(64, std::min(1024, (int)cap / env_int("B200_NDIV", 8)));
-                const int pg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, rank_smem) * 4);
-#define RANK_PACK(MODE, VTT, NA, OO)                                                                                                  \
-                do { if (bpat) k_num_rank_pack<VTT, MODE, true><<<pg, pt, rank_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, OO); \
-                     else k_num_rank_pack<VTT, MODE, false><<<pg, pt, rank_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, OO); } while (0)
-                if (mode == 0) RANK_PACK(0, VT, na, o);
-                else if (mode == 1) RANK_PACK(1, VT, na, o);
-                else RANK_PACK(2, u64, na64, o64);
-#undef RANK_PACK
-            } else {
-                const int threads = bin_threads(hb, lg);
-                const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, rank_smem) * 4);
-                if (mode == 0) k_num_rank<VT, 0><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o);
-                else if (mode == 1) k_num_rank<VT, 1><<<g, threads, rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o);
-                else k_num_rank<u64, 2><<<g, threads, rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, cap, nwords, lg, o64);
-            }
-            LAUNCH_CHECK(ctx);
-            return B200_OK;
-        }
-        return launch_cta_hash(bin, hb, n, bs);
+        bool used = false;
+        if (launch_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb], rows, bs)) { LAUNCH_CHECK(ctx); used = true; }
+        if (caps.cap[hb] < nw4_full) TRY(launch_cta_hash(B200_BIN_WIDE0 + hb, hb, rows, used ? fan.pick() : bs));
+        return B200_OK;
     };
     // the longest rows first: the big kernels start while the host is still queueing the small ones
-    const bool heavy = cnt ? cnt[B200_BIN_HEAVY] != 0 : p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
+    const bool heavy = p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
     if (heavy) {
-        const u64 n = bin_size(B200_BIN_HEAVY);
+        const u64 n = rows;
         const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)heavy_cap * (4 + accb);
         if (heavy_cap < 65536 && heavy_rank_smem <= smem_max) {
             // heavy rows over a small column space: the rank kernel with accumulators sized for the longest row
@@ -857,12 +817,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     Fan fan(ctx);
     void *tmp_col = nullptr, *tmp_val = nullptr;
 
-    // One-pass (default): numeric kernels write every row at its bound offset prefix(min(P_i, cols)) in a
-    // scratch CSR and report its exact length; a scan of the lengths gives row_ptr and a compaction kernel
-    // moves the rows.  No symbolic pass.  Needs scratch for sum(min(P_i, cols)) entries: the host-known bound
-    // nnz(A) * maxlen(B) is used when it is cheap, else the exact sum is read back first; if even that is
-    // too large for the memory budget the exact two-pass path (symbolic + numeric) runs instead.
-    bool onepass = env_int("B200_TWOPASS", 0) == 0;
+    // Two ways to place the rows of C (both start with the one-launch pre-pass):
+    //   scratch (default): numeric kernels write every row at its bound offset prefix(min(P_i, cols)) in a scratch CSR
+    //     and report its exact length; a scan of the lengths gives row_ptr and a compaction kernel moves the rows;
+    //   exact: a count pass gives every row's exact length first, C is allocated at its exact size and written once.
+    // The scratch needs sum(min(P_i, cols)) entries; its host-known bound nnz(A) * maxlen(B) decides (see below).
     const size_t total_b = ctx->total_mem;
     const size_t esz = 4 + sizeof(VT);
     unsigned __int128 hb128 = (unsigned __int128)A->nnz * B->max_row_len;
@@ -895,7 +854,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             caps.cap[hb] = env_int("B200_EXPAND", 1) ? (u32)std::min<u64>(want, fit) : 0u;
         }
     }
-    if (onepass) {
+    {
         // one launch: product counts, column windows, bins, scratch offsets (look-back scan of min(P_i, cols))
         const double avgA = (double)A->nnz / (double)rows;
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
@@ -912,7 +871,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         // than the compaction it saves (~64 us), so the scratch path stays the default while its host-known bound
         // nnz(A) * maxlen(B) entries fits 1/16 of device memory (B200_EXACT_MB overrides the limit); beyond that the
         // exact mode runs and memory stays at the size of C.
-        const int exact_env = env_int("B200_EXACT", -1);
+        const int exact_env = env_int("B200_TWOPASS", 0) ? 1 : env_int("B200_EXACT", -1);   // B200_TWOPASS: older name of the switch
         const int exact_mb = env_int("B200_EXACT_MB", -1);
         const bool exact = exact_env >= 0 ? exact_env != 0
                                           : (!cheap_bound || (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20)));
@@ -921,8 +880,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
-            k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0,
-                                                                              ctx->h_ctrl, epoch);
+            k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, ctx->h_ctrl, epoch);
             LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(ctx->ev[1], s);
             r = wait_for_report(ctx, epoch);
@@ -935,7 +893,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             if (timing) cudaEventRecord(ctx->ev[2], s);
             if (ctx->trace) trace_mark(ctx, __LINE__);
             OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
-            r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps);
+            r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
@@ -958,7 +916,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         }
         tmp_entries = (u64)hb128;
     }
-    if (onepass) {
+    {
         r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         tmp_col = ctx->d_tmp_col; tmp_val = ctx->d_tmp_val;
@@ -970,12 +928,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
         }
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride};
-        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, nullptr, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
+        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
         fan.join();
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
-        k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0,
-                                                                          ctx->h_ctrl, epoch);
+        k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, ctx->h_ctrl, epoch);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
         r = wait_for_report(ctx, epoch);
@@ -1013,83 +970,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         return B200_OK;
     }
 
-    // ---------------- exact two-pass path: symbolic (nnz per row) -> row_ptr -> numeric into the final arrays
-    CUDA_TRY(reset_scan(ctx, 0));                                         // (also after a one-pass count that did not fit: redo the bins)
-    TRY(launch_row_products(ctx, A, B, false));
-    k_bin_scatter<0, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows, bstride);
-    LAUNCH_CHECK(ctx);
-    {
-        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
-        k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
-        LAUNCH_CHECK(ctx);
-    }
-    if (p_bound > 32 || A->max_row_len > 32) {
-        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
-        k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0, 2, std::min(lg, 5), ctx->d_nnz_row, bstride);
-        LAUNCH_CHECK(ctx);
-    }
-    for (int hb = 2; hb < B200_NUM_HASH_BINS; hb++) {
-        if (p_bound <= (u64)b200_hash_cap(hb - 1)) break;                // no row can reach this bin
-        const u32 slots = b200_hash_slots(hb);
-        const bool bitmap = nwords <= 4 * b200_hash_cap(hb) && (size_t)nwords * 4 <= smem_max;
-        const size_t smem = bitmap ? (size_t)nwords * 4 : (size_t)slots * 4;
-        cudaStream_t bs = fan.pick();
-        if (packed) {
-            const int pt = std::max(bitmap ? 64 : 32, std::min(1024, (int)b200_hash_cap(hb) / env_int("B200_SDIV", 8)));
-            const int pg = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, pt, smem) * 2);
-            if (bitmap) k_sym_pack<true><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row, bstride);
-            else k_sym_pack<false><<<pg, pt, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, ctx->d_nnz_row, bstride);
-        } else {
-            const int threads = bin_threads(hb, lg);
-            const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
-            if (bitmap) k_sym_cta<true><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
-            else k_sym_cta<false><<<g, threads, smem, bs>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HASH0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
-        }
-        LAUNCH_CHECK(ctx);
-    }
-    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) {
-        r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
-        if (r != B200_OK) { fan.join(); b200_csr_free(ctx, C); return r; }
-    }
-    fan.join();
-    // ---- row_ptr (decoupled look-back scan, fused numeric-bin histogram), numeric bin lists
-    k_scan_rowptr<true, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, A->d_rp, ctx->d_prod, 0);
-    LAUNCH_CHECK(ctx);
-    k_bin_scatter<1, false><<<row_grid, 256, 0, s>>>(rows, A->d_rp, ctx->d_prod, ctx->d_nnz_row, ctx->d_ctrl, ctx->d_bin_rows, bstride);
-    LAUNCH_CHECK(ctx);
-    if (timing) cudaEventRecord(ctx->ev[1], s);
-    // ---- the one host read-back: total nnz, bin sizes
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    const B200Ctrl hc = *ctx->h_ctrl;
-    if (hc.error_flag) { b200_csr_free(ctx, C); return set_err(B200_ERR_CUDA, "symbolic pass reported an internal error (flag %u)", hc.error_flag); }
-    C->nnz = hc.total_nnz;
-    C->max_row_len = hc.max_row_nnz;
-    r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
-    if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
-    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-    const int mode = pick_mode<VT>(hc.max_row_products, maxA, maxB);
-    if (timing) cudaEventRecord(ctx->ev[2], s);
-    OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->num_bin_count, bstride};
-    r = launch_numeric<VT>(ctx, A, B, hc.num_bin_count, rows, p_bound, hc.max_row_nnz, mode, packed, bpat, lg, o, fan, caps);
-    fan.join();
-    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-    CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
-    if (timing) cudaEventRecord(ctx->ev[3], s);
-    if (st) {
-        st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
-        st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
-        st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-        for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.num_bin_count[i]; }
-        if (timing) {
-            CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
-            cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);
-            cudaEventElapsedTime(&st->ms_numeric, ctx->ev[2], ctx->ev[3]);
-            cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
-        }
-    }
-    *out = C;
-    return B200_OK;
+    return set_err(B200_ERR_CUDA, "internal: no numeric path selected");
 }
 
 extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C, b200_stats *stats) {
@@ -1107,9 +988,8 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (A->rows == 0) return B200_OK;
     TRY(ensure_row_scratch(ctx, A->rows));
-    CUDA_TRY(reset_scan(ctx, 0));
     TRY(ensure_desc(ctx, B));
-    TRY(launch_row_products(ctx, A, B, false));
+    TRY(launch_row_products(ctx, A, B));
     CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_prod, A->rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
@@ -1173,7 +1053,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);
-    k_scan_rowptr<false, 0><<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, nullptr, nullptr, 0);
+    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

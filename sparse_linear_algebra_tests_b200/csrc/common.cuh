@@ -56,9 +56,6 @@ struct B200Ctrl {
     ull max_row_nnz;
     ull max_val_out;          // running max of emitted C values
     u32 sym_bin_count[B200_NBINS];
-    u32 sym_bin_fill[B200_NBINS];
-    u32 num_bin_count[B200_NBINS];
-    u32 num_bin_fill[B200_NBINS];
     ull total_bound;          // one-pass mode: sum of per-row bounds min(P_i, cols)
     u32 scan_ticket[2];
     u32 error_flag;           // set by kernels on impossible states (table overflow)

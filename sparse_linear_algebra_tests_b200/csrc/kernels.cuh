@@ -1,16 +1,15 @@
 // kernels.cuh -- device kernels of the SpGEMM engine (sm_100a).
 //
 // Pipeline of one C = A x B (host orchestration in api.cu):
-//   k_build_desc        B row descriptors {start,len} packed in 8 bytes (cached per right operand)
-//   k_row_products      per-row intermediate-product count P_i, symbolic-bin histogram
-//   k_bin_scatter       row ids grouped by bin (device-side counts, no host round trip)
-//   k_sym_*             exact nnz_i per row (distinct output columns)
-//   k_scan_rowptr       hand-written decoupled look-back scan: row_ptr_C (u64), total nnz,
-//                       fused with the numeric-bin histogram on exact nnz_i
+//   k_build_desc / k_build_pack   per right operand, cached: row descriptors, column spans, sector-packed rows
+//   k_prepass           product count P_i and column window per row, bin lists, scratch offsets (look-back scan)
+//   k_sym_*             exact mode only: distinct output columns per row (count-only twins of the numeric kernels)
 //   k_num_*             values: saturating accumulate, in-row column order, write col/val
-// Row classes: tiny (warp register merge), warp-hash (one warp per row, several rows per CTA),
-// CTA-hash (+ bitonic sort) or CTA-rank (column bitmap + prefix popcount, no sort), heavy
-// (global-memory table).  All inner loops use 32-bit offsets; 64-bit only for row bases.
+//   k_scan_rowptr       decoupled look-back scan of the exact row lengths -> row_ptr_C (u64); reports to the host
+//   k_compact_rows      scratch mode only: rows from their bound offsets to their exact places
+// Row classes: tiny (warp register merge), window-bitmap rank (k_num_expand: CTA per row, no sort), hash + bitonic sort
+// (warp or CTA per row, any column space), heavy (global-memory table).  All inner loops use 32-bit offsets; 64-bit only
+// for row bases.
 #pragma once
 #include "common.cuh"
 
@@ -36,14 +35,14 @@ struct NumArgs {
     const uint2 *bdesc; const u32 *colB; const VT *valB;
 };
 
-// Where a numeric kernel puts its rows.  Two-pass: base = row_ptr_C (exact, from the symbolic pass),
-// bins = numeric bins.  One-pass: base = offsets from the scan of the per-row bounds min(P_i, cols),
-// rows land in a scratch CSR and their exact lengths in nnz_out; bins = the product-count bins.
+// Where a numeric kernel puts its rows.  Exact mode: base = row_ptr_C (from the count pass), nnz_out = null.
+// Scratch mode: base = offsets from the scan of the per-row bounds min(P_i, cols), rows land in a scratch CSR and their
+// exact lengths in nnz_out.  Either way the rows to process come from the pre-pass's per-bin lists.
 template <typename VT>
 struct OutArgs {
     const u64 *base; u32 *col; VT *val;
-    u32 *nnz_out;                // may be null (two-pass)
-    const u32 *bin_cnt;          // bin sizes to iterate (ctrl->sym_bin_count or ctrl->num_bin_count)
+    u32 *nnz_out;                // may be null (exact mode)
+    const u32 *bin_cnt;          // list sizes (ctrl->sym_bin_count)
     u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
 };
 
@@ -85,57 +84,30 @@ __device__ __forceinline__ void walk_products(const u32 *__restrict__ Ac, u32 le
 // =======================================================================================
 // 1. product count per row + symbolic-bin histogram
 // =======================================================================================
-// ONEPASS: the product-count bins drive the numeric kernels directly, so single-entry rows need a bin too
-template <bool ONEPASS = false>
+// bin of a row by its product count P (rows without products need no kernel)
 __device__ __forceinline__ int sym_bin_of(u64 p, u64 dA) {
-    if (p == 0 || (!ONEPASS && dA == 1)) return B200_BIN_NONE;   // nnz known: 0, or P (one B row: distinct cols)
+    if (p == 0) return B200_BIN_NONE;
     if (p <= 32 && dA <= 32) return B200_BIN_TINY;
     return b200_bin_by_size(p);
 }
-// numeric classification on exact nnz (rows with P<=32 and deg_A<=32 stay in the warp-merge bin)
-__device__ __forceinline__ int num_bin_of(u32 nnz, u64 p, u64 dA) {
-    if (nnz == 0) return B200_BIN_NONE;
-    if (p <= 32 && dA <= 32) return B200_BIN_TINY;
-    return b200_bin_by_size(nnz);
-}
 
-template <int G, bool ONEPASS>  // G lanes per row (power of two <= 32)
+// Per-row intermediate-product counts only (b200_row_products / product-balanced sharding); G lanes per row.
+template <int G>
 __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
-                                                      const uint2 *__restrict__ bdesc, u64 *__restrict__ prod,
-                                                      u32 *__restrict__ nnz_row, B200Ctrl *ctrl) {
-    __shared__ u32 s_hist[B200_NBINS];
-    __shared__ ull s_sum, s_max;
-    if (threadIdx.x < B200_NBINS) s_hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_sum = 0; s_max = 0; }
-    __syncthreads();
+                                                      const uint2 *__restrict__ bdesc, u64 *__restrict__ prod) {
     const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 row = gtid / G;
     const u32 sub = threadIdx.x % G;
-    u64 p = 0; u32 lenA = 0;
+    u64 p = 0;
     if (row < rows) {
         const u64 s = rpA[row];
-        lenA = (u32)(rpA[row + 1] - s);
+        const u32 lenA = (u32)(rpA[row + 1] - s);
         const u32 *Ac = colA + s;
         for (u32 i = sub; i < lenA; i += G) p += bdesc[Ac[i]].y;
     }
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1) p += shfl_xor_u64(p, m);
-    u64 wsum = 0, wmax = 0;
-    if (row < rows && sub == 0) {
-        prod[row] = p;
-        const int b = sym_bin_of<ONEPASS>(p, lenA);
-        if (b == B200_BIN_NONE) nnz_row[row] = (u32)p;       // 0, or the single B row's length
-        else atomicAdd(&s_hist[b], 1u);
-        wsum = p; wmax = p;
-    }
-    wsum = warp_sum_u64(wsum); wmax = warp_max_u64(wmax);
-    if ((threadIdx.x & 31) == 0) { if (wsum) atomicAdd(&s_sum, (ull)wsum); atomicMax(&s_max, (ull)wmax); }
-    __syncthreads();
-    if (threadIdx.x < B200_NBINS && s_hist[threadIdx.x]) atomicAdd(&ctrl->sym_bin_count[threadIdx.x], s_hist[threadIdx.x]);
-    if (threadIdx.x == 0) {
-        if (s_sum) atomicAdd(&ctrl->total_products, s_sum);
-        if (s_max) atomicMax(&ctrl->max_row_products, s_max);
-    }
+    if (row < rows && sub == 0) prod[row] = p;
 }
 
 // One-pass pre-pass, one launch: product count P_i per row, totals, the bin lists (block-wise reservation in every
@@ -186,7 +158,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         if (row < rows) {
             prod[row] = p;
             bound = p < ncols ? p : ncols;
-            b = sym_bin_of<true>(p, lenA);
+            b = sym_bin_of(p, lenA);
             if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;               // the two smallest hash bins share a list
             if (b != B200_BIN_NONE) {
                 // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
@@ -249,31 +221,6 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         if (s_sum) atomicAdd(&ctrl->total_products, s_sum);
         if (s_max) atomicMax(&ctrl->max_row_products, s_max);
     }
-}
-
-// scatter row ids into their bin's segment of bin_rows; PHASE 0 = symbolic bins, 1 = numeric bins
-template <int PHASE, bool ONEPASS>
-__global__ void __launch_bounds__(256) k_bin_scatter(u64 rows, const u64 *__restrict__ rpA, const u64 *__restrict__ prod,
-                                                     const u32 *__restrict__ nnz_row, B200Ctrl *ctrl, u32 *__restrict__ bin_rows,
-                                                     u32 bin_stride) {
-    __shared__ u32 s_cnt[B200_NBINS], s_base[B200_NBINS];
-    if (threadIdx.x < B200_NBINS) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    int b = B200_BIN_NONE; u32 local = 0;
-    if (row < rows) {
-        const u64 dA = rpA[row + 1] - rpA[row];
-        b = PHASE == 0 ? sym_bin_of<ONEPASS>(prod[row], dA) : num_bin_of(nnz_row[row], prod[row], dA);
-        if (b != B200_BIN_NONE) local = atomicAdd(&s_cnt[b], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < B200_NBINS) {
-        u32 *fill = PHASE == 0 ? ctrl->sym_bin_fill : ctrl->num_bin_fill;
-        const u32 c = s_cnt[threadIdx.x];
-        s_base[threadIdx.x] = c ? atomicAdd(&fill[threadIdx.x], c) : 0u;
-    }
-    __syncthreads();
-    if (b != B200_BIN_NONE) bin_rows[(u64)b * bin_stride + s_base[b] + local] = (u32)row;
 }
 
 // r-th row of the run of `nbins` consecutive bins starting at first_bin (every bin has its own list)
@@ -428,12 +375,41 @@ __device__ __forceinline__ u32 enumerate_products(const u32 *__restrict__ Ac, co
     return done;
 }
 
+// Sector-packed right operand (low-degree B): one 32-byte record per B row,
+//     rec[2k] = {start, len, col0, col1}, rec[2k+1] = {col2, col3, col4, col5}.
+// One aligned 32-byte fetch (a single L2 sector, one LDG.E.256) returns a B row's length AND its first six columns,
+// instead of a descriptor sector plus a column sector; the dependent-load chain of a product shrinks from
+// A.col -> desc -> B.col to A.col -> record.  Rows longer than six columns continue in B.col.
+#define B200_PACK_INLINE 6
+struct PackRec { uint4 a, b; };
+
+__global__ void __launch_bounds__(256) k_build_pack(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col, uint4 *__restrict__ pack) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[i];
+        const u32 len = (u32)(rp[i + 1] - s);
+        u32 c[B200_PACK_INLINE];
+#pragma unroll
+        for (int j = 0; j < B200_PACK_INLINE; j++) c[j] = j < (int)len ? col[s + j] : B200_EMPTY_KEY;
+        pack[2 * i] = make_uint4((u32)s, len, c[0], c[1]);
+        pack[2 * i + 1] = make_uint4(c[2], c[3], c[4], c[5]);
+    }
+}
+__device__ __forceinline__ PackRec load_pack(const uint4 *__restrict__ pack, u32 k) {
+    // one 256-bit read-only load (LDG.E.256 on sm_100): a single L1 request per record instead of two
+    PackRec r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                 : "l"(pack + 2 * (u64)k));
+    return r;
+}
 // =======================================================================================
 // 3. tiny rows: one warp per row, <= 32 products held one per lane
 // =======================================================================================
 template <typename VT, bool NUMERIC>
 __device__ __forceinline__ u32 tiny_gather(const u64 *rpA, const u32 *colA, const VT *valA, const uint2 *bdesc, const u32 *colB,
-                                           const VT *valB, u32 row, int lane, u32 &key, VT &val) {
+                                           const VT *valB, u32 row, int lane, u32 &key, VT &val, bool bpat = false) {
+    // (a sector-packed record per entry was tried here: the 32-byte gathers and six shuffles cost more than the
+    //  descriptor + column gathers they replace -- 100^3 torus A^2 0.79 -> 0.87 ms -- so tiny rows keep bdesc/colB)
     const u64 s = rpA[row];
     const u32 dA = (u32)(rpA[row + 1] - s);               // <= 32 by bin construction
     u32 deg = 0, bstart = 0; VT a = 0;
@@ -463,7 +439,7 @@ __device__ __forceinline__ u32 tiny_gather(const u64 *rpA, const u32 *colA, cons
     if ((u32)lane < P) {
         const u32 j = e_bstart + ((u32)lane - e_excl);
         key = colB[j];
-        if (NUMERIC) val = sat_mul(e_a, valB[j]);
+        if (NUMERIC) val = bpat ? e_a : sat_mul(e_a, valB[j]);
     }
     return P;
 }
@@ -504,7 +480,8 @@ __global__ void __launch_bounds__(256) k_sym_tiny(SymArgs a, const u32 *__restri
 }
 
 template <typename VT>
-__global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, OutArgs<VT> o) {
+__global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, OutArgs<VT> o,
+                                                  bool bpat = false) {
     const u32 count = o.bin_cnt[B200_BIN_TINY];
     const int lane = threadIdx.x & 31;
     const u32 wpb = blockDim.x >> 5;
@@ -512,7 +489,7 @@ __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__re
     for (u32 r = blockIdx.x * wpb + (threadIdx.x >> 5); r < count; r += gridDim.x * wpb) {
         const u32 row = bin_rows[r];
         u32 key; VT val;
-        tiny_gather<VT, true>(a.rpA, a.colA, a.valA, a.bdesc, a.colB, a.valB, row, lane, key, val);
+        tiny_gather<VT, true>(a.rpA, a.colA, a.valA, a.bdesc, a.colB, a.valB, row, lane, key, val, bpat);
         warp_bitonic<VT, true>(key, val, lane);
         // segmented inclusive scan (saturating) over runs of equal keys; the run's last lane has the total
 #pragma unroll
@@ -821,173 +798,6 @@ __global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__r
                               cols[pos] = c;                               // same value from every product of this column
                               acc.add(pos, av, a.valB[jb]);
                           });
-        __syncthreads();
-        const u64 obase = o.base[row];
-        for (u32 t = tid; t < nnz; t += nt) {
-            const VT v = emit_val<VT>(acc.get(t));
-            o.col[obase + t] = cols[t]; o.val[obase + t] = v;
-            vmax = vmax > (u64)v ? vmax : (u64)v;
-        }
-        if (tid == 0 && o.nnz_out) o.nnz_out[row] = nnz;
-        __syncthreads();
-    }
-    vmax = warp_max_u64(vmax);
-    if ((tid & 31) == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
-}
-
-// =======================================================================================
-// 5d. sector-packed right operand (low-degree B): one 32-byte record per B row
-//     rec[2k] = {start, len, col0, col1}, rec[2k+1] = {col2, col3, col4, col5}
-// One aligned 32-byte fetch (a single L2 sector) returns a B row's length AND its first six
-// columns, instead of a descriptor sector plus a column sector; the dependent-load chain of a
-// product shrinks from A.col -> desc -> B.col to A.col -> record.  Rows longer than six columns
-// continue in B.col.  The numeric rank kernel keeps each thread's records in registers between
-// its two walks, so a row costs one sector per A entry in the whole numeric pass.
-// =======================================================================================
-#define B200_PACK_INLINE 6
-struct PackRec { uint4 a, b; };
-
-__global__ void __launch_bounds__(256) k_build_pack(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col, uint4 *__restrict__ pack) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (u64)gridDim.x * blockDim.x) {
-        const u64 s = rp[i];
-        const u32 len = (u32)(rp[i + 1] - s);
-        u32 c[B200_PACK_INLINE];
-#pragma unroll
-        for (int j = 0; j < B200_PACK_INLINE; j++) c[j] = j < (int)len ? col[s + j] : B200_EMPTY_KEY;
-        pack[2 * i] = make_uint4((u32)s, len, c[0], c[1]);
-        pack[2 * i + 1] = make_uint4(c[2], c[3], c[4], c[5]);
-    }
-}
-__device__ __forceinline__ PackRec load_pack(const uint4 *__restrict__ pack, u32 k) {
-    // one 256-bit read-only load (LDG.E.256 on sm_100): a single L1 request per record instead of two
-    PackRec r;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
-                 : "l"(pack + 2 * (u64)k));
-    return r;
-}
-template <typename F>
-__device__ __forceinline__ void for_each_col(const PackRec &r, const u32 *__restrict__ colB, F f) {
-    const u32 start = r.a.x, len = r.a.y;
-    if (len > 0) f(r.a.z, start);
-    if (len > 1) f(r.a.w, start + 1);
-    if (len > 2) f(r.b.x, start + 2);
-    if (len > 3) f(r.b.y, start + 3);
-    if (len > 4) f(r.b.z, start + 4);
-    if (len > 5) f(r.b.w, start + 5);
-    for (u32 j = B200_PACK_INLINE; j < len; j++) f(colB[start + j], start + j);
-}
-
-template <bool BITMAP>
-__global__ void __launch_bounds__(1024) k_sym_pack(SymArgs a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
-                                                   B200Ctrl *ctrl, int bin, u32 slots, u32 nwords, u32 *__restrict__ nnz_row,
-                                                   u32 bin_stride) {
-    extern __shared__ u32 smem[];
-    __shared__ u32 s_count;
-    const u32 count = ctrl->sym_bin_count[bin];
-    const u64 off = (u64)bin * bin_stride;
-    const u32 nt = blockDim.x, tid = threadIdx.x;
-    const u32 tabn = BITMAP ? nwords : slots;
-    const int shift = 32 - (31 - __clz(slots));
-    u32 r_begin, r_end;
-    cta_row_range(count, r_begin, r_end);
-    for (u32 r = r_begin; r < r_end; r++) {
-        const u32 row = bin_rows[off + r];
-        for (u32 t = tid; t < tabn; t += nt) smem[t] = BITMAP ? 0u : B200_EMPTY_KEY;
-        if (tid == 0) s_count = 0;
-        __syncthreads();
-        const u64 s = a.rpA[row];
-        const u32 lenA = (u32)(a.rpA[row + 1] - s);
-        const u32 *Ac = a.colA + s;
-        u32 local = 0;
-        auto visit = [&](u32 c, u32) {
-            if (BITMAP) {
-                const u32 bit = 1u << (c & 31);
-                const u32 old = atomicOr(&smem[c >> 5], bit);
-                local += !(old & bit);
-            } else {
-                bool fresh;
-                table_insert(smem, slots - 1, shift, c, fresh);
-                local += fresh;
-            }
-        };
-        for (u32 t = tid; t < lenA; t += 2 * nt) {
-            const u32 t1 = t + nt;
-            const bool has1 = t1 < lenA;
-            const u32 k0 = Ac[t], k1 = has1 ? Ac[t1] : 0;
-            const PackRec r0 = load_pack(pack, k0);
-            PackRec r1 = load_pack(pack, has1 ? k1 : k0);
-            if (!has1) r1.a.y = 0;
-            for_each_col(r0, a.colB, visit);
-            for_each_col(r1, a.colB, visit);
-        }
-        local = warp_sum_u32(local);
-        if ((tid & 31) == 0 && local) atomicAdd(&s_count, local);
-        __syncthreads();
-        if (tid == 0) nnz_row[row] = s_count;
-        __syncthreads();
-    }
-}
-
-template <typename VT, int MODE, bool BPAT>   // BPAT: every stored value of B is 1 (adjacency pattern): no B.val loads
-__global__ void __launch_bounds__(1024) k_num_rank_pack(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
-                                                        B200Ctrl *ctrl, int bin, u32 cap, u32 nwords, OutArgs<VT> o) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ u32 s_warp[33];
-    Acc<MODE> acc; acc.bind(smem_raw, cap);
-    u32 *cols = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(cap));
-    u32 *bm = cols + cap;
-    unsigned short *wpre = reinterpret_cast<unsigned short *>(bm + nwords);
-    const u32 count = o.bin_cnt[bin];
-    const u64 off = (u64)bin * o.bin_stride;
-    const u32 nt = blockDim.x, tid = threadIdx.x;
-    u64 vmax = 0;
-    u32 r_begin, r_end;
-    cta_row_range(count, r_begin, r_end);
-    for (u32 r = r_begin; r < r_end; r++) {
-        const u32 row = bin_rows[off + r];
-        for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
-        const u64 s = a.rpA[row];
-        const u32 lenA = (u32)(a.rpA[row + 1] - s);
-        const u32 *Ac = a.colA + s;
-        const VT *Av = a.valA + s;
-        // the first two A entries of every thread stay in registers across both walks
-        PackRec rec[2]; VT av[2];
-        {
-            const u32 t1 = tid + nt;
-            const bool h0 = tid < lenA, h1 = t1 < lenA;
-            const u32 k0 = h0 ? Ac[tid] : 0, k1 = h1 ? Ac[t1] : 0;
-            rec[0] = load_pack(pack, k0); rec[1] = load_pack(pack, k1);
-            if (!h0) rec[0].a.y = 0;
-            if (!h1) rec[1].a.y = 0;
-            av[0] = h0 ? Av[tid] : (VT)0; av[1] = h1 ? Av[t1] : (VT)0;
-        }
-        __syncthreads();
-        // ---- walk 1: column bitmap
-        auto mark = [&](u32 c, u32) { atomicOr(&bm[c >> 5], 1u << (c & 31)); };
-        for_each_col(rec[0], a.colB, mark);
-        for_each_col(rec[1], a.colB, mark);
-        for (u32 t = tid + 2 * nt; t < lenA; t += nt) { const PackRec rr = load_pack(pack, Ac[t]); for_each_col(rr, a.colB, mark); }
-        __syncthreads();
-        const u32 nnz = rank_prefix(bm, wpre, nwords, s_warp);
-        for (u32 t = tid; t < nnz; t += nt) acc.clear(t);
-        __syncthreads();
-        // ---- walk 2: accumulate into acc[rank(col)]
-        auto put = [&](VT x, u32 c, u32 jb) {
-            const u32 pos = (u32)wpre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
-            cols[pos] = c;
-            acc.add(pos, x, BPAT ? (VT)1 : a.valB[jb]);
-        };
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const VT x = av[i];
-            for_each_col(rec[i], a.colB, [&](u32 c, u32 jb) { put(x, c, jb); });
-        }
-        for (u32 t = tid + 2 * nt; t < lenA; t += nt) {
-            const PackRec rr = load_pack(pack, Ac[t]);
-            const VT x = Av[t];
-            for_each_col(rr, a.colB, [&](u32 c, u32 jb) { put(x, c, jb); });
-        }
         __syncthreads();
         const u64 obase = o.base[row];
         for (u32 t = tid; t < nnz; t += nt) {
@@ -1431,42 +1241,25 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 }
 
 // =======================================================================================
-// 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64),
-//    fused with the numeric-bin histogram
+// 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64); its last CTA reports to the host
 // =======================================================================================
 
-// SRC 0: exact nnz per row -> row_ptr_C (CLASSIFY also histograms the numeric bins);
-// SRC 1: per-row bound min(P_i, cols) -> offsets of the one-pass scratch CSR (total in ctrl->total_bound)
-template <bool CLASSIFY, int SRC>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
-                                                              u64 *tile_status, B200Ctrl *ctrl, const u64 *__restrict__ rpA,
-                                                              const u64 *__restrict__ prod, u64 ncols,
+                                                              u64 *tile_status, B200Ctrl *ctrl,
                                                               B200Ctrl *host_mirror = nullptr, u32 epoch = 0) {
     __shared__ u32 s_tile, s_last;
     __shared__ u64 s_wsum[SCAN_THREADS / 32];
     __shared__ u64 s_excl;
-    __shared__ u32 s_hist[B200_NBINS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket[SRC], 1u);          // tiles start in ticket order
-    if (CLASSIFY && tid < B200_NBINS) s_hist[tid] = 0;
+    if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket[0], 1u);            // tiles start in ticket order
     __syncthreads();
     const u32 tile = s_tile;
     const u64 base = (u64)tile * SCAN_TILE + (u64)tid * SCAN_ITEMS;
     u32 item[SCAN_ITEMS]; u64 tsum = 0; u32 tmaxv = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (SRC == 0) item[i] = base + i < rows ? nnz_row[base + i] : 0u;
-        else { const u64 pv = base + i < rows ? prod[base + i] : 0ull; item[i] = (u32)(pv < ncols ? pv : ncols); }
+        item[i] = base + i < rows ? nnz_row[base + i] : 0u;
         tsum += item[i]; tmaxv = item[i] > tmaxv ? item[i] : tmaxv;
-    }
-    if (CLASSIFY) {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            if (base + i < rows && item[i]) {
-                const int b = num_bin_of(item[i], prod[base + i], rpA[base + i + 1] - rpA[base + i]);
-                atomicAdd(&s_hist[b], 1u);
-            }
-        }
     }
     u64 incl = tsum;
 #pragma unroll
@@ -1511,11 +1304,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
         run += item[i];
         if (base + i < rows) rpC[base + i + 1] = run;
     }
-    if (base < rows && base + SCAN_ITEMS >= rows) { if (SRC == 0) ctrl->total_nnz = run; else ctrl->total_bound = run; }   // thread holding the last row
+    if (base < rows && base + SCAN_ITEMS >= rows) ctrl->total_nnz = run;      // thread holding the last row
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
-    if (SRC == 0 && lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
-    if (CLASSIFY && tid < B200_NBINS && s_hist[tid]) atomicAdd(&ctrl->num_bin_count[tid], s_hist[tid]);
+    if (lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
     // Report to the host without a stream synchronise: the last CTA to finish copies the control block into pinned
     // host memory and then publishes the epoch word the host is polling.
     if (host_mirror) {

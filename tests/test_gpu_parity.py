@@ -317,8 +317,8 @@ def test_engine_reproduces_golden_fixture(gpu_ctx, path):
 
 
 def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, monkeypatch):
-    """B200_TWOPASS=1 forces the exact-allocation path (symbolic -> row_ptr -> numeric) used when the one-pass
-    scratch would not fit; both must give the same bytes."""
+    """B200_TWOPASS=1 (older name of B200_EXACT=1) forces the exact-allocation path (counts -> row_ptr -> numeric) used
+    when the scratch CSR would not fit; both must give the same bytes."""
     a_h = hostgen.reference_bench_instance(12, 3.0, 64)
     a = B200Matrix.from_host(a_h, gpu_ctx)
     one = a.matmul(a).matmul(a).to_host()
