@@ -604,7 +604,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto do_tiny = [&]() -> int {
         const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
-        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o, bpat);
+        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o, bpat, B->cols <= (1ull << 27), mode == 0);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };

@@ -405,19 +405,16 @@ __device__ __forceinline__ PackRec load_pack(const uint4 *__restrict__ pack, u32
 // =======================================================================================
 // 3. tiny rows: one warp per row, <= 32 products held one per lane
 // =======================================================================================
+// One tiny row per warp.  The caller has already loaded the row's A entries (lane < dA holds column k and value a):
+// the kernels below run a software pipeline over their rows -- row ids two rows ahead, row_ptr / output base and the
+// A entries one row ahead -- so that an iteration only waits for its own desc -> B.col gathers.
 template <typename VT, bool NUMERIC>
-__device__ __forceinline__ u32 tiny_gather(const u64 *rpA, const u32 *colA, const VT *valA, const uint2 *bdesc, const u32 *colB,
-                                           const VT *valB, u32 row, int lane, u32 &key, VT &val, bool bpat = false) {
+__device__ __forceinline__ u32 tiny_gather(u32 dA, u32 k, VT a, const uint2 *bdesc, const u32 *colB, const VT *valB, int lane,
+                                           u32 &key, VT &val, bool bpat = false) {
     // (a sector-packed record per entry was tried here: the 32-byte gathers and six shuffles cost more than the
     //  descriptor + column gathers they replace -- 100^3 torus A^2 0.79 -> 0.87 ms -- so tiny rows keep bdesc/colB)
-    const u64 s = rpA[row];
-    const u32 dA = (u32)(rpA[row + 1] - s);               // <= 32 by bin construction
-    u32 deg = 0, bstart = 0; VT a = 0;
-    if (lane < (int)dA) {
-        const uint2 d = bdesc[colA[s + lane]];
-        bstart = d.x; deg = d.y;
-        if (NUMERIC) a = valA[s + lane];
-    }
+    u32 deg = 0, bstart = 0;
+    if (lane < (int)dA) { const uint2 d = bdesc[k]; bstart = d.x; deg = d.y; }
     u32 incl = deg;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
@@ -463,50 +460,104 @@ __device__ __forceinline__ void warp_bitonic(u32 &key, VT &val, int lane) {
     }
 }
 
+// pipeline state of one warp's row stream (see tiny_gather)
+struct TinyRow { u32 row, dA, k; u64 base; };
+
 __global__ void __launch_bounds__(256) k_sym_tiny(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 *__restrict__ nnz_row) {
     const u32 count = ctrl->sym_bin_count[B200_BIN_TINY];
     const int lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
-    for (u32 r = blockIdx.x * wpb + (threadIdx.x >> 5); r < count; r += gridDim.x * wpb) {
-        const u32 row = bin_rows[r];
+    const u32 wpb = blockDim.x >> 5, stride = gridDim.x * wpb;
+    u32 r = blockIdx.x * wpb + (threadIdx.x >> 5);
+    if (r >= count) return;
+    TinyRow cur, nxt;
+    cur.row = bin_rows[r];
+    { const u64 s = a.rpA[cur.row]; cur.dA = (u32)(a.rpA[cur.row + 1] - s); cur.k = lane < (int)cur.dA ? a.colA[s + lane] : 0u; }
+    nxt.row = r + stride < count ? bin_rows[r + stride] : 0u;
+    for (; r < count; r += stride) {
+        const u32 row_nn = r + 2 * stride < count ? bin_rows[r + 2 * stride] : 0u;
         u32 key; u32 val;
-        tiny_gather<u32, false>(a.rpA, a.colA, nullptr, a.bdesc, a.colB, nullptr, row, lane, key, val);
+        tiny_gather<u32, false>(cur.dA, cur.k, 0u, a.bdesc, a.colB, nullptr, lane, key, val);
+        u64 s_n = 0; nxt.dA = 0;
+        if (r + stride < count) { s_n = a.rpA[nxt.row]; nxt.dA = (u32)(a.rpA[nxt.row + 1] - s_n); }
         warp_bitonic<u32, false>(key, val, lane);
         const u32 prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
         const bool head = key != B200_EMPTY_KEY && (lane == 0 || prev != key);
         const u32 n = __popc(__ballot_sync(0xFFFFFFFFu, head));
-        if (lane == 0) nnz_row[row] = n;
+        if (lane == 0) nnz_row[cur.row] = n;
+        nxt.k = lane < (int)nxt.dA ? a.colA[s_n + lane] : 0u;
+        cur = nxt; nxt.row = row_nn;
     }
 }
 
 template <typename VT>
 __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, OutArgs<VT> o,
-                                                  bool bpat = false) {
+                                                  bool bpat, bool narrow, bool v32) {
     const u32 count = o.bin_cnt[B200_BIN_TINY];
     const int lane = threadIdx.x & 31;
-    const u32 wpb = blockDim.x >> 5;
+    const u32 wpb = blockDim.x >> 5, stride = gridDim.x * wpb;
+    u32 r = blockIdx.x * wpb + (threadIdx.x >> 5);
+    if (r >= count) return;
     u64 vmax = 0;
-    for (u32 r = blockIdx.x * wpb + (threadIdx.x >> 5); r < count; r += gridDim.x * wpb) {
-        const u32 row = bin_rows[r];
+    TinyRow cur, nxt;
+    VT av = 0, av_n = 0;
+    cur.row = bin_rows[r];
+    {
+        const u64 s = a.rpA[cur.row];
+        cur.dA = (u32)(a.rpA[cur.row + 1] - s); cur.base = o.base[cur.row];
+        cur.k = 0;
+        if (lane < (int)cur.dA) { cur.k = a.colA[s + lane]; av = a.valA[s + lane]; }
+    }
+    nxt.row = r + stride < count ? bin_rows[r + stride] : 0u;
+    for (; r < count; r += stride) {
+        const u32 row_nn = r + 2 * stride < count ? bin_rows[r + 2 * stride] : 0u;
         u32 key; VT val;
-        tiny_gather<VT, true>(a.rpA, a.colA, a.valA, a.bdesc, a.colB, a.valB, row, lane, key, val, bpat);
-        warp_bitonic<VT, true>(key, val, lane);
+        tiny_gather<VT, true>(cur.dA, cur.k, av, a.bdesc, a.colB, a.valB, lane, key, val, bpat);
+        // next row's row_ptr and output base (its id arrived an iteration ago)
+        u64 s_n = 0; nxt.dA = 0; nxt.base = 0;
+        if (r + stride < count) { s_n = a.rpA[nxt.row]; nxt.dA = (u32)(a.rpA[nxt.row + 1] - s_n); nxt.base = o.base[nxt.row]; }
+        // The kernel is shuffle-bound (sort + segmented scan), so shuffle as little as possible.  Column indices below 2^27
+        // are sorted packed with their source lane in one 32-bit word (one SHFL per stage instead of one per key plus one
+        // or two per value) and the value is fetched from its source lane afterwards; when the host proved that row sums
+        // stay below 2^32 (accumulator mode 0) the segmented scan also runs on 32-bit values.
+        if (narrow) {
+            u32 packed = key == B200_EMPTY_KEY ? B200_EMPTY_KEY : (key << 5) | (u32)lane, none = 0;
+            warp_bitonic<u32, false>(packed, none, lane);
+            key = packed == B200_EMPTY_KEY ? B200_EMPTY_KEY : packed >> 5;
+            val = shfl_any(val, (int)(packed & 31u));
+        } else {
+            warp_bitonic<VT, true>(key, val, lane);
+        }
         // segmented inclusive scan (saturating) over runs of equal keys; the run's last lane has the total
+        if (v32) {
+            u32 v = (u32)val;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u32 pk = __shfl_up_sync(0xFFFFFFFFu, key, d);
-            const VT pv = shfl_up_any(val, d);
-            if (lane >= d && pk == key) val = sat_add(val, pv);
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 pk = __shfl_up_sync(0xFFFFFFFFu, key, d);
+                const u32 pv = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if (lane >= d && pk == key) v += pv;
+            }
+            val = (VT)v;
+        } else {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 pk = __shfl_up_sync(0xFFFFFFFFu, key, d);
+                const VT pv = shfl_up_any(val, d);
+                if (lane >= d && pk == key) val = sat_add(val, pv);
+            }
         }
         const u32 nk = __shfl_down_sync(0xFFFFFFFFu, key, 1);
         const bool tail = key != B200_EMPTY_KEY && (lane == 31 || nk != key);
         const u32 tails = __ballot_sync(0xFFFFFFFFu, tail);
         if (tail) {
-            const u64 pos = o.base[row] + __popc(tails & ((1u << lane) - 1u));
+            const u64 pos = cur.base + __popc(tails & ((1u << lane) - 1u));
             o.col[pos] = key; o.val[pos] = val;
             vmax = vmax > (u64)val ? vmax : (u64)val;
         }
-        if (lane == 0 && o.nnz_out) o.nnz_out[row] = __popc(tails);
+        if (lane == 0 && o.nnz_out) o.nnz_out[cur.row] = __popc(tails);
+        // next row's A entries (its row_ptr was fetched before the sort)
+        nxt.k = 0; av_n = 0;
+        if (lane < (int)nxt.dA) { nxt.k = a.colA[s_n + lane]; av_n = a.valA[s_n + lane]; }
+        cur = nxt; av = av_n; nxt.row = row_nn;
     }
     vmax = warp_max_u64(vmax);
     if (lane == 0 && vmax) atomicMax(&ctrl->max_val_out, (ull)vmax);
