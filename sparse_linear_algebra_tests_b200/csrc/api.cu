@@ -860,9 +860,14 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
         const u64 tiles_pre = (rows + (256 / G) - 1) / (256 / G);
         CUDA_TRY(reset_scan(ctx, tiles_pre));
-#define PREPASS(GG) k_prepass<GG><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_span, ncols, ctx->d_prod, ctx->d_nnz_row, \
-                                                                   ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl, ctx->d_bin_rows, bstride, ctx->d_win, caps)
+        bool windows = false;                                             // column windows only matter when some bin's bitmap is narrower than B
+        for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < (nwords + 3) / 4;
+#define PREPASS1(GG, WW) k_prepass<GG, WW><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_span, B->d_desc, ncols, ctx->d_prod, \
+                                                                             ctx->d_nnz_row, ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl,   \
+                                                                             ctx->d_bin_rows, bstride, ctx->d_win, caps)
+#define PREPASS(GG) do { if (windows) PREPASS1(GG, true); else PREPASS1(GG, false); } while (0)
         if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
+#undef PREPASS1
 #undef PREPASS
         LAUNCH_CHECK(ctx);
         // Exact mode: count every row's distinct columns first (same lists, count-only kernels), allocate C at its exact

@@ -113,9 +113,11 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 // One-pass pre-pass, one launch: product count P_i per row, totals, the bin lists (block-wise reservation in every
 // bin's own list, so a CTA's rows stay consecutive) and -- through a decoupled look-back over the CTAs in ticket
 // order -- the scratch offsets prefix(min(P_i, cols)) that the numeric kernels write their rows at.
-template <int G>
+// WINDOWS = false (the whole column space fits every bin's bitmap): lengths come from the 8-byte descriptors and every
+// row gets the full window -- half the gather bytes, no min/max reductions.
+template <int G, bool WINDOWS>
 __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
-                                                 const uint4 *__restrict__ bspan, u64 ncols, u64 *__restrict__ prod,
+                                                 const uint4 *__restrict__ bspan, const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
                                                  u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
                                                  B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride,
                                                  uint2 *__restrict__ win, WinCaps caps) {
@@ -138,19 +140,30 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         u32 i = sub;
         for (; i + 3 * G < lenA; i += 4 * G) {                               // four independent gathers in flight
             const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
-            const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
-            p += (u64)d0.x + d1.x + d2.x + d3.x;
-            cmin = min(min(cmin, d0.y), min(min(d1.y, d2.y), d3.y));
-            cmax = max(max(cmax, d0.z), max(max(d1.z, d2.z), d3.z));
+            if (WINDOWS) {
+                const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
+                p += (u64)d0.x + d1.x + d2.x + d3.x;
+                cmin = min(min(cmin, d0.y), min(min(d1.y, d2.y), d3.y));
+                cmax = max(max(cmax, d0.z), max(max(d1.z, d2.z), d3.z));
+            } else {
+                const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
+                p += (u64)d0 + d1 + d2 + d3;
+            }
         }
-        for (; i < lenA; i += G) { const uint4 d = bspan[Ac[i]]; p += d.x; cmin = min(cmin, d.y); cmax = max(cmax, d.z); }
+        for (; i < lenA; i += G) {
+            if (WINDOWS) { const uint4 d = bspan[Ac[i]]; p += d.x; cmin = min(cmin, d.y); cmax = max(cmax, d.z); }
+            else p += bdesc[Ac[i]].y;
+        }
     }
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1) {
         p += shfl_xor_u64(p, m);
-        cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, m));
-        cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
+        if (WINDOWS) {
+            cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, m));
+            cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
+        }
     }
+    if (!WINDOWS) { cmin = 0; cmax = ncols ? (u32)(ncols - 1) : 0u; }
     int b = B200_BIN_NONE; u32 local = 0;
     u64 wsum = 0, wmax = 0;
     if (sub == 0) {
@@ -934,7 +947,7 @@ __device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, con
 }
 
 #define B200_EXPAND_PRE 2   // A entries per thread whose loads are issued one row ahead
-#define B200_EXPAND_ILP 4   // products each thread keeps in flight in the mark / accumulate loops
+#define B200_EXPAND_ILP 2   // products each thread keeps in flight in the mark / accumulate loops
 
 template <typename VT, int MODE, bool PACK, bool BPAT>
 __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
