@@ -4,7 +4,8 @@ Same inherent-method surface as `MagnusMatrix` (src/graph_magnus.rs:16-448) and 
 (src/graph_csr.rs:55-657): new, identity, from_edges, from_edges_undirected, from_adjacency,
 random, lattice, thin, get, nnz, matmul (+ matmul_par / matmul_seq aliases), add,
 reachability_sum, power_until_stable, connected_components[_uf], num_components, print, and the
-`NDIndex` view (ndim, dim, get_opt; einsum-dyn/src/lib.rs:126-154).  The matrix lives on the GPU
+`NDIndex` / `Sparse2D` views (ndim, dim, get_opt, n_rows, row_nnz, row_entry;
+einsum-dyn/src/lib.rs:126-154, einsum-dyn/src/sparse.rs:42-55).  The matrix lives on the GPU
 (a `b200_csr` handle); `matmul`/`add` never leave the device.  Builders run on the host exactly
 like the reference's and upload once.  Shape mismatch raises `ShapeMismatch` (an AssertionError),
 matching the reference's `assert_eq!` panic.
@@ -169,6 +170,19 @@ class B200Matrix:
 
     def set(self, _ix, _v):
         raise TypeError("B200Matrix is immutable after construction")
+
+    # Sparse2D<u64> (einsum-dyn/src/sparse.rs:42-55; CsrMatrix's impl at src/graph_csr.rs:861-871)
+    def n_rows(self) -> int:
+        return self._dev.rows
+
+    def row_nnz(self, row: int) -> int:
+        h = self.to_host()
+        return int(h.row_ptr[row + 1]) - int(h.row_ptr[row])
+
+    def row_entry(self, row: int, idx: int):
+        h = self.to_host()
+        p = int(h.row_ptr[row]) + idx
+        return int(h.col_idx[p]), int(h.values[p])
 
     # ------------------------------------------------------------------ arithmetic (device)
     def matmul(self, other: "B200Matrix", want_stats: bool = False) -> "B200Matrix":

@@ -393,3 +393,21 @@ def test_exact_mode_saturating_values(gpu_ctx, oracle, monkeypatch):
     a_h = rand_csr(rng, 500, 500, 6000, 64, 3)
     a_h.values[:] = rng.integers(1 << 61, 1 << 63, size=a_h.nnz(), dtype=np.uint64)
     check_product(oracle, gpu_ctx, a_h, a_h, "u64 saturation, exact mode")
+
+
+# ------------------------------------------------------------------ einsum front-end (src/graph_csr.rs:1593-1631: einsum == matmul)
+def test_einsum_ab_bc_ac_equals_matmul(gpu_ctx, oracle):
+    from sparse_linear_algebra_tests_b200 import einsum_sparse_driven, einsum_sparse_hash
+    edges = [(0, 1), (0, 2), (1, 2), (1, 3), (2, 3), (3, 4), (4, 5), (5, 0), (2, 5)]
+    a = B200Matrix.from_edges(6, edges, 64)
+    want = a.matmul(a).to_host()
+    assert_same(einsum_sparse_driven("ab,bc->ac", a, a).to_host(), want)
+    assert_same(einsum_sparse_hash("ij,jk->ik", a, a).to_host(), want)
+    assert_same(want, oracle.matmul(to_o(oracle, a.to_host()), to_o(oracle, a.to_host())))
+    with pytest.raises(AssertionError):
+        einsum_sparse_driven("ab,cb->ac", a, a)                      # needs a transpose: not the row-wise arrangement
+    # Sparse2D view of the result (einsum-dyn/src/sparse.rs:42-55)
+    c = a.matmul(a)
+    assert c.n_rows() == 6 and sum(c.row_nnz(r) for r in range(6)) == c.nnz()
+    col, val = c.row_entry(0, 0)
+    assert c.get(0, col) == val

@@ -94,3 +94,16 @@ def test_engine_fails_loudly_without_a_gpu():
     with pytest.raises(B200Error) as e:
         Context(0)
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_einsum_spec_validation_needs_no_gpu():
+    """Spec handling of the einsum front-end (einsum-dyn/src/sparse.rs:81-112): malformed specs are InvalidSpec, specs
+    that are well-formed but not the matmul arrangement panic."""
+    from sparse_linear_algebra_tests_b200.einsum import InvalidSpec, parse_matmul_spec
+    assert parse_matmul_spec("ab,bc->ac") == ("a", "b", "b", "c", "ac")
+    assert parse_matmul_spec(" ij , jk -> ik ") == ("i", "j", "j", "k", "ik")
+    for bad in ("ab,bc", "ab->ab", "ab,bc,cd->ad", "a1,bc->ac", "ab,bc->ad"):
+        with pytest.raises(InvalidSpec):
+            parse_matmul_spec(bad)
+    with pytest.raises(AssertionError):
+        parse_matmul_spec("abc,cd->abd")
