@@ -471,7 +471,7 @@ static int pick_lg(const b200_csr *B, int max_lg) {
 }
 // threads that own one row of hash bin hb: ~one group per 4 A entries, assuming deg_A ~ cap/2
 static int bin_threads(int hb, int lg) {
-    const int div = std::max(1, env_int("B200_TDIV", 8));
+    const int div = std::max(1, env_int("B200_TDIV", 32));
     long t = ((long)b200_hash_cap(hb) << lg) / div;
     t = std::max(32L, std::min(1024L, t));
     long need = (long)b200_hash_slots(hb) / 16;                           // sort path keeps <= 16 slots per thread

@@ -686,6 +686,28 @@ __device__ __forceinline__ void smem_bitonic(u32 *keys, Acc<MODE> &acc, u32 n) {
     }
 }
 
+// Bitonic sort of n (power of two) packed 64-bit words (column << 32 | table slot) by the whole CTA.  The payload travels
+// inside the word, so a compare-exchange is two 64-bit loads and at most two stores (the accumulators stay where the hash
+// put them).  Pair t of a stage always belongs to 64-element block t / 32 and the loop below gives warp w the pairs
+// 32w .. 32w+31 (+ multiples of blockDim), so all stages with k <= 64 are warp-local: __syncwarp instead of a CTA barrier.
+__device__ __forceinline__ void smem_bitonic_words(u64 *w, u32 n) {
+    const u32 tid = threadIdx.x, nt = blockDim.x;
+    for (u32 k = 2; k <= n; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 t = tid; t < (n >> 1); t += nt) {
+                const u32 i = 2 * t - (t & (j - 1));
+                const u32 l = i + j;
+                const bool up = ((i & k) == 0);
+                const u64 x = w[i], y = w[l];
+                if ((x > y) == up) { w[i] = y; w[l] = x; }
+            }
+            if (k <= 64) __syncwarp(); else __syncthreads();
+        }
+        if (k == 64) __syncthreads();                                       // the next stage crosses the warps' blocks
+    }
+    __syncthreads();
+}
+
 // 5a. warp per row (8 rows in flight per CTA): hash accumulate, compact, sort, stream out. nnz <= 128.
 template <typename VT, int MODE>
 __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
@@ -776,24 +798,28 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
                               acc.add(h, av, a.valB[jb]);
                           });
         __syncthreads();
-        u32 rk[16]; u64 rv[16]; u32 mine = 0;
+        // order the row: packed (column << 32 | slot) words are gathered at the front of the key array and sorted; the
+        // accumulators stay in their hash slots and are read through the word's low half on the way out
+        u32 rk[16]; u32 mine = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            if (i < (int)per) { rk[i] = keys[i * nt + tid]; rv[i] = acc.get(i * nt + tid); mine += rk[i] != B200_EMPTY_KEY; }
+            if (i < (int)per) { rk[i] = keys[i * nt + tid]; mine += rk[i] != B200_EMPTY_KEY; }
         }
         u32 total;
-        u32 pos = block_excl_scan(mine, s_warp, total);                  // its barriers order the reads above before the writes below
+        u32 pos = block_excl_scan(mine, s_warp, total);                  // its barriers order the key reads above before the words below
+        u64 *words = reinterpret_cast<u64 *>(keys);                      // n2 <= cap = slots / 2 words fit the key array exactly
 #pragma unroll
-        for (int i = 0; i < 16; i++) if (i < (int)per && rk[i] != B200_EMPTY_KEY) { keys[pos] = rk[i]; acc.set(pos, rv[i]); pos++; }
+        for (int i = 0; i < 16; i++)
+            if (i < (int)per && rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * nt + tid);
         u32 n2 = 1; while (n2 < total) n2 <<= 1;
+        for (u32 t = total + tid; t < n2; t += nt) words[t] = ~0ull;
         __syncthreads();
-        for (u32 t = total + tid; t < n2; t += nt) keys[t] = B200_EMPTY_KEY;
-        __syncthreads();
-        smem_bitonic<MODE, false>(keys, acc, n2);
+        smem_bitonic_words(words, n2);
         const u64 obase = o.base[row];
         for (u32 t = tid; t < total; t += nt) {
-            const VT v = emit_val<VT>(acc.get(t));
-            o.col[obase + t] = keys[t]; o.val[obase + t] = v;
+            const u64 wd = words[t];
+            const VT v = emit_val<VT>(acc.get((u32)wd));
+            o.col[obase + t] = (u32)(wd >> 32); o.val[obase + t] = v;
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         if (tid == 0 && o.nnz_out) o.nnz_out[row] = total;
