@@ -46,7 +46,8 @@ struct b200_csr {
     ull *d_maxval;          // device scalar: largest stored value
     u64 max_row_len;        // host-known upper bound of the longest row
     uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
-    uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (one-pass pre-pass)
+    uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (pre-pass: plain column windows)
+    uint4 *d_cspan;         // square operands: {len, min, max} of (col - row + n/2) mod n (pre-pass: circular windows)
     uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
     u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
     cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
@@ -59,7 +60,7 @@ struct b200_ctx {
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
     // per-row scratch, grown on demand
-    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint2 *d_win;
+    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint4 *d_win;
     // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
     unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
     // heavy-row scratch
@@ -126,7 +127,7 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
         TRY(dmalloc(ctx, (void **)&ctx->d_tmp_ptr, (cap + 1) * 8));
         TRY(dmalloc(ctx, (void **)&ctx->d_nnz_row, cap * 4));
         TRY(dmalloc(ctx, (void **)&ctx->d_bin_rows, cap * 4 * (B200_BIN_WIDE0 + B200_NUM_HASH_BINS)));   // every bin has its own list
-        TRY(dmalloc(ctx, (void **)&ctx->d_win, cap * sizeof(uint2)));
+        TRY(dmalloc(ctx, (void **)&ctx->d_win, cap * sizeof(uint4)));
         ctx->cap_rows = cap;
     }
     const u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1, tiles_pre = rows / 8 + 2;  // pre-pass: >= 8 rows per CTA
@@ -294,7 +295,7 @@ extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
     if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_pack);
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_cspan); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;
 }
@@ -490,6 +491,16 @@ static int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
     return B200_OK;
 }
 
+// circular column spans of a square right operand (see k_build_cspan), cached like the descriptors
+static int ensure_cspan(b200_ctx *ctx, const b200_csr *B) {
+    if (B->d_cspan || B->rows != B->cols) return B200_OK;
+    b200_csr *Bm = const_cast<b200_csr *>(B);
+    TRY(dmalloc(ctx, (void **)&Bm->d_cspan, (B->rows + 1) * sizeof(uint4)));
+    k_build_cspan<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, B->d_col, Bm->d_cspan);
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
+
 // sector-packed records for low-degree right operands (mean row length <= 4)
 static bool want_pack(const b200_csr *B) {
     const int forced = env_int("B200_PACK", -1);
@@ -622,10 +633,10 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         const int eg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * 4);
         if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
 #define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
-        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); \
-                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); }   \
-             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO);         \
-                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, OO); } } while (0)
+        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); \
+                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); }   \
+             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO);         \
+                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); } } while (0)
         if (mode == 0) EXPAND(0, VT, na, o);
         else if (mode == 1) EXPAND(1, VT, na, o);
         else EXPAND(2, u64, na64, o64);
@@ -746,8 +757,8 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         const int t = std::max(32, std::min(512, (int)std::max<u32>(pcap / 2, nw4) / 8 / 32 * 32));
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4);
         cudaStream_t bs = fan.pick();
-        if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, ctx->d_nnz_row, bstride);
-        else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, ctx->d_nnz_row, bstride);
+        if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
+        else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
@@ -860,12 +871,16 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
         const u64 tiles_pre = (rows + (256 / G) - 1) / (256 / G);
         CUDA_TRY(reset_scan(ctx, tiles_pre));
-        bool windows = false;                                             // column windows only matter when some bin's bitmap is narrower than B
+        // column windows only matter when some bin's bitmap is narrower than B; square operands get circular windows
+        bool windows = false;
         for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < (nwords + 3) / 4;
-#define PREPASS1(GG, WW) k_prepass<GG, WW><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, B->d_span, B->d_desc, ncols, ctx->d_prod, \
-                                                                             ctx->d_nnz_row, ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl,   \
+        const bool circular = windows && B->rows == B->cols && env_int("B200_CIRCULAR", 1);
+        if (circular) { r = ensure_cspan(ctx, B); if (r != B200_OK) { b200_csr_free(ctx, C); return r; } }
+        const int wmode = !windows ? 0 : circular ? 2 : 1;
+#define PREPASS1(GG, WW) k_prepass<GG, WW><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, WW == 2 ? B->d_cspan : B->d_span, B->d_desc, ncols,   \
+                                                                             ctx->d_prod, ctx->d_nnz_row, ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl,   \
                                                                              ctx->d_bin_rows, bstride, ctx->d_win, caps)
-#define PREPASS(GG) do { if (windows) PREPASS1(GG, true); else PREPASS1(GG, false); } while (0)
+#define PREPASS(GG) do { if (wmode == 2) PREPASS1(GG, 2); else if (wmode == 1) PREPASS1(GG, 1); else PREPASS1(GG, 0); } while (0)
         if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
 #undef PREPASS1
 #undef PREPASS

@@ -57,6 +57,26 @@ __global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restr
     }
 }
 
+// Circular spans (square B only): for B row k the offsets of its columns from the diagonal, u = (c - k + n/2) mod n,
+// as {length, min u, max u}.  A torus row that wraps around the end of the index space has a plain span of ~n columns but
+// a circular span as narrow as any other row's.  Rows longer than 64 entries are not scanned: they get the full circle
+// (any row of C that touches them is sent to the hash kernels, where long, spread-out rows belong anyway).
+__global__ void __launch_bounds__(256) k_build_cspan(u64 n, const u64 *__restrict__ rp, const u32 *__restrict__ col, uint4 *__restrict__ cspan) {
+    const u32 half = (u32)(n / 2);
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[k], e = rp[k + 1];
+        const u32 len = (u32)(e - s);
+        u32 umin = 0xFFFFFFFFu, umax = 0;
+        if (len > 64) { umin = 0; umax = (u32)(n - 1); }
+        else for (u64 j = s; j < e; j++) {
+            long long t = (long long)col[j] - (long long)k + (long long)half;
+            if (t < 0) t += (long long)n; else if (t >= (long long)n) t -= (long long)n;
+            umin = min(umin, (u32)t); umax = max(umax, (u32)t);
+        }
+        cspan[k] = make_uint4(len, umin, umax, 0u);
+    }
+}
+
 // per hash bin: how many 128-column groups the bin's shared-memory bitmap holds (0: the bin has no bitmap kernel)
 struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; };
 
@@ -113,15 +133,19 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 // One-pass pre-pass, one launch: product count P_i per row, totals, the bin lists (block-wise reservation in every
 // bin's own list, so a CTA's rows stay consecutive) and -- through a decoupled look-back over the CTAs in ticket
 // order -- the scratch offsets prefix(min(P_i, cols)) that the numeric kernels write their rows at.
-// WINDOWS = false (the whole column space fits every bin's bitmap): lengths come from the 8-byte descriptors and every
-// row gets the full window -- half the gather bytes, no min/max reductions.
-template <int G, bool WINDOWS>
+// WMODE 0 (the whole column space fits every bin's bitmap): lengths come from the 8-byte descriptors and every row gets
+// the full window -- half the gather bytes, no min/max reductions.  WMODE 1: plain window [cmin, cmax] from the sorted B
+// rows' first/last columns.  WMODE 2 (square B, `bspan` holds circular spans): columns are measured from a per-row
+// reference ref = the row's first A column, d(c) = (c - ref + n/2) mod n, so rows that wrap around the index space keep
+// a narrow window; win = {window base in d (multiple of 128), 128-column groups, rot = (ref - n/2) mod n, 0}.
+template <int G, int WMODE>
 __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
                                                  const uint4 *__restrict__ bspan, const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
                                                  u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
                                                  B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride,
-                                                 uint2 *__restrict__ win, WinCaps caps) {
+                                                 uint4 *__restrict__ win, WinCaps caps) {
     constexpr int RPC = 256 / G;                                            // rows per CTA
+    constexpr bool WINDOWS = WMODE != 0;
     __shared__ u32 s_tile, s_cnt[B200_NBINS], s_base[B200_NBINS];
     __shared__ u64 s_bound[RPC], s_wsum[8], s_excl;
     __shared__ ull s_sum, s_max;
@@ -132,26 +156,38 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
     const u32 tile = s_tile;
     const u64 row = (u64)tile * RPC + tid / G;
     const u32 sub = tid % G;
-    u64 p = 0; u32 lenA = 0, cmin = 0xFFFFFFFFu, cmax = 0;
+    u64 p = 0; u32 lenA = 0, cmin = 0xFFFFFFFFu, cmax = 0, rot = 0;
     if (row < rows) {
         const u64 s = rpA[row];
         lenA = (u32)(rpA[row + 1] - s);
         const u32 *Ac = colA + s;
+        const long long n = (long long)ncols, half = n / 2;
+        const long long ref = WMODE == 2 && lenA ? (long long)Ac[0] : 0;
+        if (WMODE == 2) { long long t = ref - half; if (t < 0) t += n; rot = (u32)t; }
+        // one entry's contribution to the window: plain [first, last], or its circular span shifted by (k - ref)
+        auto widen = [&](u32 k, const uint4 &d) {
+            if (d.x == 0) return;
+            if (WMODE == 1) { cmin = min(cmin, d.y); cmax = max(cmax, d.z); return; }
+            long long kap = (long long)k - ref + half;                       // (k - ref + n/2) mod n
+            if (kap < 0) kap += n; else if (kap >= n) kap -= n;
+            const long long lo = kap + (long long)d.y - half, hi = kap + (long long)d.z - half;
+            if (lo < 0 || hi >= n) { cmin = 0; cmax = (u32)(n - 1); }         // offsets add up past half the circle: full window
+            else { cmin = min(cmin, (u32)lo); cmax = max(cmax, (u32)hi); }
+        };
         u32 i = sub;
         for (; i + 3 * G < lenA; i += 4 * G) {                               // four independent gathers in flight
             const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
             if (WINDOWS) {
                 const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
                 p += (u64)d0.x + d1.x + d2.x + d3.x;
-                cmin = min(min(cmin, d0.y), min(min(d1.y, d2.y), d3.y));
-                cmax = max(max(cmax, d0.z), max(max(d1.z, d2.z), d3.z));
+                widen(k0, d0); widen(k1, d1); widen(k2, d2); widen(k3, d3);
             } else {
                 const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
                 p += (u64)d0 + d1 + d2 + d3;
             }
         }
         for (; i < lenA; i += G) {
-            if (WINDOWS) { const uint4 d = bspan[Ac[i]]; p += d.x; cmin = min(cmin, d.y); cmax = max(cmax, d.z); }
+            if (WINDOWS) { const u32 k = Ac[i]; const uint4 d = bspan[k]; p += d.x; widen(k, d); }
             else p += bdesc[Ac[i]].y;
         }
     }
@@ -177,7 +213,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
                 // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
                 const u32 base = cmin & ~127u;
                 const u32 groups = (cmax - base) / 128u + 1u;
-                win[row] = make_uint2(base, groups);
+                win[row] = make_uint4(base, groups, rot, 0u);
                 if (b >= B200_BIN_HASH0 && b < B200_BIN_HEAVY && groups > caps.cap[b - B200_BIN_HASH0]) b = B200_BIN_WIDE0 + (b - B200_BIN_HASH0);
             }
             if (b == B200_BIN_NONE) nnz_row[row] = 0;
@@ -662,30 +698,6 @@ __device__ __forceinline__ void cta_row_range(u32 count, u32 &begin, u32 &end) {
     end = begin + rpc < count ? begin + rpc : count;
 }
 
-// bitonic sort of n (power of two) key/accumulator pairs in shared memory.  WARP: one warp owns the
-// arrays (__syncwarp between stages); otherwise the whole CTA does.
-template <int MODE, bool WARP>
-__device__ __forceinline__ void smem_bitonic(u32 *keys, Acc<MODE> &acc, u32 n) {
-    const u32 me = WARP ? (threadIdx.x & 31) : threadIdx.x;
-    const u32 stride = WARP ? 32 : blockDim.x;
-    for (u32 k = 2; k <= n; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = me; t < (n >> 1); t += stride) {
-                const u32 i = 2 * t - (t & (j - 1));
-                const u32 l = i + j;
-                const bool up = ((i & k) == 0);
-                const u32 x = keys[i], y = keys[l];
-                if ((x > y) == up) {
-                    keys[i] = y; keys[l] = x;
-                    const u64 vx = acc.get(i), vy = acc.get(l);
-                    acc.set(i, vy); acc.set(l, vx);
-                }
-            }
-            if (WARP) __syncwarp(); else __syncthreads();
-        }
-    }
-}
-
 // Bitonic sort of n (power of two) packed 64-bit words (column << 32 | table slot) by the whole CTA.  The payload travels
 // inside the word, so a compare-exchange is two 64-bit loads and at most two stores (the accumulators stay where the hash
 // put them).  Pair t of a stage always belongs to 64-element block t / 32 and the loop below gives warp w the pairs
@@ -739,27 +751,39 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
                               acc.add(h, av, a.valB[jb]);
                           });
         __syncwarp();
-        // compact through registers (slot i*32+lane: conflict-free), then sort the front of the arrays
-        u32 rk[PER]; u64 rv[PER]; u32 mine = 0;
+        // order the row: packed (column << 32 | slot) words gathered through registers at the front of the key array
+        // (<= 128 of them fit its 1 KB exactly), sorted by the warp; the accumulators stay in their hash slots
+        u32 rk[PER]; u32 mine = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) { rk[i] = keys[i * 32 + lane]; rv[i] = acc.get(i * 32 + lane); mine += rk[i] != B200_EMPTY_KEY; }
+        for (int i = 0; i < PER; i++) { rk[i] = keys[i * 32 + lane]; mine += rk[i] != B200_EMPTY_KEY; }
         u32 incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
         const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u32 pos = incl - mine;
         __syncwarp();
+        u64 *words = reinterpret_cast<u64 *>(keys);
 #pragma unroll
-        for (int i = 0; i < PER; i++) if (rk[i] != B200_EMPTY_KEY) { keys[pos] = rk[i]; acc.set(pos, rv[i]); pos++; }
+        for (int i = 0; i < PER; i++) if (rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * 32 + lane);
         u32 n2 = 1; while (n2 < total) n2 <<= 1;
+        for (u32 t = total + lane; t < n2; t += 32) words[t] = ~0ull;
         __syncwarp();
-        for (u32 t = total + lane; t < n2; t += 32) keys[t] = B200_EMPTY_KEY;
-        __syncwarp();
-        smem_bitonic<MODE, true>(keys, acc, n2);
+        for (u32 k = 2; k <= n2; k <<= 1) {
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 t = lane; t < (n2 >> 1); t += 32) {
+                    const u32 i = 2 * t - (t & (j - 1));
+                    const u32 l = i + j;
+                    const u64 x = words[i], y = words[l];
+                    if ((x > y) == ((i & k) == 0)) { words[i] = y; words[l] = x; }
+                }
+                __syncwarp();
+            }
+        }
         const u64 obase = o.base[row];
         for (u32 t = lane; t < total; t += 32) {
-            const VT v = emit_val<VT>(acc.get(t));
-            o.col[obase + t] = keys[t]; o.val[obase + t] = v;
+            const u64 wd = words[t];
+            const VT v = emit_val<VT>(acc.get((u32)wd));
+            o.col[obase + t] = (u32)(wd >> 32); o.val[obase + t] = v;
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         if (lane == 0 && o.nnz_out) o.nnz_out[row] = total;
@@ -978,7 +1002,7 @@ __device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, con
 template <typename VT, int MODE, bool PACK, bool BPAT>
 __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
                                                     B200Ctrl *ctrl, int bin, int nbins, u32 pcap, u32 ncap, u32 nw4,
-                                                    const uint2 *__restrict__ win, OutArgs<VT> o) {
+                                                    const uint4 *__restrict__ win, u32 ncols, OutArgs<VT> o) {
     typedef typename PVal<MODE, VT>::type PV;
     constexpr bool PAIR = sizeof(PV) == 4;       // products kept as {col, value} pairs: one 64-bit shared access each
     constexpr int E = B200_EXPAND_PRE;
@@ -1007,14 +1031,17 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
     for (u32 t = tid; t < ncap; t += nt) acc.clear(t);
     if (tid == 0) s_P = 0;
-    // the row's column window: bitmap word 0 is column word `wbase` (a multiple of four), `groups` 128-column groups long
-    u32 wbase = 0, groups = nw4;
+    // The row's column window.  Columns are first rotated, d = (c - rot) mod ncols (rot = 0 unless the pre-pass built
+    // circular windows), then bitmap word 0 is d-word `wbase` (a multiple of four), `groups` 128-column groups long.
+    u32 wbase = 0, groups = nw4, rot = 0;
+    auto dcol = [&](u32 c) -> u32 { return c >= rot ? c - rot : c - rot + ncols; };
 
     auto put = [&](u32 dst, VT av, u32 c, u32 jb) {
         const PV x = BPAT ? (PV)av : product_value<MODE, VT>(av, a.valB[jb]);
         if (PAIR) pp[dst] = make_uint2(c, (u32)x);
         else { pc[dst] = c; pv[dst] = (u64)x; }
-        atomicOr(&bm[(c >> 5) - wbase], __funnelshift_l(0u, 1u, c));         // mark the column while it is in a register
+        const u32 d = dcol(c);
+        atomicOr(&bm[(d >> 5) - wbase], __funnelshift_l(0u, 1u, d));         // mark the column while it is in a register
     };
     // products of one warp's 32 A entries -> a slice of the product buffer
     auto expand32 = [&](bool valid, VT av, const BRowRef &b) {
@@ -1043,10 +1070,10 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     u32 row = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin);
     u64 rs = a.rpA[row];
     u32 lenA = (u32)(a.rpA[row + 1] - rs);
-    uint2 wn = win[row];
-    wbase = wn.x >> 5; groups = wn.y;
+    uint4 wn = win[row];
+    wbase = wn.x >> 5; groups = wn.y; rot = wn.z;
     u32 row_n = 0, lenA_n = 0; u64 rs_n = 0;
-    wn = make_uint2(0, 0);
+    wn = make_uint4(0, 0, 0, 0);
     if (r_begin + 1 < r_end) { row_n = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin + 1); rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); wn = win[row_n]; }
     VT av[E]; BRowRef br[E];
 #pragma unroll
@@ -1100,7 +1127,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             if (PACK && has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
             av[e] = avn[e];
         }
-        u64 rs_nn = 0; u32 lenA_nn = 0; uint2 wnn = make_uint2(0, 0);
+        u64 rs_nn = 0; u32 lenA_nn = 0; uint4 wnn = make_uint4(0, 0, 0, 0);
         if (r + 2 < r_end) { rs_nn = a.rpA[row_nn]; lenA_nn = (u32)(a.rpA[row_nn + 1] - rs_nn); wnn = win[row_nn]; }
         __syncthreads();
         // ---- accumulate at the column's rank
@@ -1114,31 +1141,42 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             }
 #pragma unroll
             for (int j = 0; j < B200_EXPAND_ILP; j++) {
-                const u32 cc = c[j] != B200_EMPTY_KEY ? c[j] : wbase << 5;  // padding lanes read word 0
-                const u32 w = (cc >> 5) - wbase;
-                pos[j] = (u32)wpre[w] + __popc(bm[w] & (__funnelshift_l(0u, 1u, cc) - 1u));
+                const u32 dd = c[j] != B200_EMPTY_KEY ? dcol(c[j]) : wbase << 5;   // padding lanes read word 0
+                const u32 w = (dd >> 5) - wbase;
+                pos[j] = (u32)wpre[w] + __popc(bm[w] & (__funnelshift_l(0u, 1u, dd) - 1u));
             }
 #pragma unroll
             for (int j = 0; j < B200_EXPAND_ILP; j++)
                 if (c[j] != B200_EMPTY_KEY) { cols[pos[j]] = c[j]; acc.addv(pos[j], x[j]); }
         }
         __syncthreads();
-        // ---- emit (coalesced), leaving accumulators, bitmap and the product counter clean
+        // ---- emit (coalesced), leaving accumulators, bitmap and the product counter clean.  Ranks are in d order; with a
+        // rotated window the entries whose column is below `rot` (d >= ncols - rot) belong in FRONT of the others: the
+        // row is written rotated by r0 = number of entries with d < ncols - rot.
+        u32 r0 = nnz;
+        if (rot) {
+            const u32 split = ncols - rot;                                   // first d that maps to a column below rot
+            const u32 wlo = wbase << 5, whi = wlo + (groups << 7);
+            if (split <= wlo) r0 = 0;
+            else if (split < whi) { const u32 sw = (split >> 5) - wbase; r0 = (u32)wpre[sw] + __popc(bm[sw] & (__funnelshift_l(0u, 1u, split) - 1u)); }
+        }
+        const u32 shift_hi = nnz - r0;                                       // d-rank t -> t - r0 (t >= r0) or t + shift_hi
         for (u32 t0 = tid; t0 < nnz; t0 += 2 * nt) {
             const u32 t1 = t0 + nt;
             const bool h1 = t1 < nnz;
             const u32 c0 = cols[t0], c1 = h1 ? cols[t1] : 0u;
             const VT v0 = emit_val<VT>(acc.get(t0)), v1 = h1 ? emit_val<VT>(acc.get(t1)) : (VT)0;
+            const u32 q0 = t0 >= r0 ? t0 - r0 : t0 + shift_hi, q1 = t1 >= r0 ? t1 - r0 : t1 + shift_hi;
             acc.clear(t0);
-            o.col[obase + t0] = c0; o.val[obase + t0] = v0;
-            if (h1) { acc.clear(t1); o.col[obase + t1] = c1; o.val[obase + t1] = v1; }
+            o.col[obase + q0] = c0; o.val[obase + q0] = v0;
+            if (h1) { acc.clear(t1); o.col[obase + q1] = c1; o.val[obase + q1] = v1; }
             const u64 m = (u64)(v0 > v1 ? v0 : v1);
             vmax = vmax > m ? vmax : m;
         }
         for (u32 t = tid; t < groups; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_P = 0; if (o.nnz_out) o.nnz_out[row] = nnz; }
         __syncthreads();
-        row = row_n; rs = rs_n; lenA = lenA_n; wbase = wn.x >> 5; groups = wn.y;
+        row = row_n; rs = rs_n; lenA = lenA_n; wbase = wn.x >> 5; groups = wn.y; rot = wn.z;
         row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn; wn = wnn;
     }
     vmax = warp_max_u64(vmax);
@@ -1149,8 +1187,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
 //     product only marks its column; the row's nnz is the popcount of its window.  Shared memory: the bitmap alone.
 template <bool PACK>
 __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
-                                                    B200Ctrl *ctrl, int bin, int nbins, u32 nw4, const uint2 *__restrict__ win,
-                                                    u32 *__restrict__ nnz_row, u32 bin_stride) {
+                                                    B200Ctrl *ctrl, int bin, int nbins, u32 nw4, const uint4 *__restrict__ win,
+                                                    u32 ncols, u32 *__restrict__ nnz_row, u32 bin_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
     __shared__ EnumStore<!PACK> s_enum;
@@ -1168,9 +1206,9 @@ __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__re
         const u32 row = bin_row_at(bin_rows, ctrl->sym_bin_count, bin_stride, bin, nbins, r);
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
-        const uint2 wn = win[row];
-        const u32 wbase = wn.x >> 5, groups = wn.y;
-        auto mark = [&](u32 c) { atomicOr(&bm[(c >> 5) - wbase], __funnelshift_l(0u, 1u, c)); };
+        const uint4 wn = win[row];
+        const u32 wbase = wn.x >> 5, groups = wn.y, rot = wn.z;
+        auto mark = [&](u32 c) { const u32 d = c >= rot ? c - rot : c - rot + ncols; atomicOr(&bm[(d >> 5) - wbase], __funnelshift_l(0u, 1u, d)); };
         if constexpr (!PACK) {
             enumerate_products<u32, false>(a.colA + s, (const u32 *)nullptr, lenA, a.bdesc, s_enum.s, s_warp,
                                            [&](u32, u32 jb, u32) { mark(a.colB[jb]); });

@@ -411,3 +411,40 @@ def test_einsum_ab_bc_ac_equals_matmul(gpu_ctx, oracle):
     assert c.n_rows() == 6 and sum(c.row_nnz(r) for r in range(6)) == c.nnz()
     col, val = c.row_entry(0, 0)
     assert c.get(0, col) == val
+
+
+# ------------------------------------------------------------------ circular column windows (torus rows that wrap around the index space)
+@pytest.mark.parametrize("circular", ["1", "0"])
+@pytest.mark.parametrize("wincap", ["2", "8", "64"])
+def test_circular_windows_on_a_long_torus(gpu_ctx, oracle, monkeypatch, circular, wincap):
+    """48 x 6 x 6 torus (1728 columns = 14 groups of 128): with a window of a few groups only rows away from the ends of
+    the index space fit a plain window; measured from the row's own reference column every row does.  The rows that wrap
+    come out of the kernel rotated and must land in ascending column order; both settings must give the reference bytes."""
+    monkeypatch.setenv("B200_WINCAP", wincap)
+    monkeypatch.setenv("B200_CIRCULAR", circular)
+    full = hostgen.lattice([48, 6, 6], True, 64)
+    a_h = hostgen.thin(full, 0.2, bytes([7] * 32))
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k in range(2, 6):
+        p = p.matmul(a, want_stats=True)
+        p_o = oracle.matmul(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k} circular={circular} wincap={wincap}")
+    # rectangular row block (a GPU's share in the multi-GPU run) against the replicated square operand
+    blk = B200Matrix(gpu_ctx.row_block(a.device, 0, 300))
+    got = blk.matmul(a).matmul(a).to_host()
+    want = oracle.matmul(oracle.matmul(to_o(oracle, a_h.row_block(0, 300)), a_o), a_o)
+    assert_same(got, want, "row block")
+
+
+def test_circular_window_exact_mode(gpu_ctx, oracle, monkeypatch):
+    monkeypatch.setenv("B200_WINCAP", "4")
+    monkeypatch.setenv("B200_EXACT", "1")
+    full = hostgen.lattice([40, 5, 5], True, 32)
+    a_h = hostgen.thin(full, 0.25, bytes([9] * 32))
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p, p_o = a, a_o
+    for k in range(2, 5):
+        p = p.matmul(a)
+        p_o = oracle.matmul(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k}")

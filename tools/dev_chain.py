@@ -8,14 +8,24 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--side", type=int, default=30); ap.add_argument("--epn", type=float, default=3.0)
 ap.add_argument("--steps", type=int, default=7); ap.add_argument("--bits", type=int, default=64)
 ap.add_argument("--check", type=int, default=1); ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--block", type=int, default=0, help="with --xmul N: multiply only rank 0's row block (the per-GPU work of the N-GPU run)")
+ap.add_argument("--xmul", type=int, default=1, help="torus is (side*xmul) x side x side: the weak-scaling workload of bench.py --gpus xmul, on one GPU")
 args = ap.parse_args()
 ctx = Context(0); set_default_context(ctx)
-a_h = hostgen.reference_bench_instance(args.side, args.epn, args.bits)
+if args.xmul == 1:
+    a_h = hostgen.reference_bench_instance(args.side, args.epn, args.bits)
+else:
+    full = hostgen.lattice([args.side * args.xmul, args.side, args.side], True, args.bits)
+    a_h = hostgen.thin(full, args.epn / (full.nnz() / full.rows), bytes([42] * 32))
 a = B200Matrix.from_host(a_h)
+if args.block:                                     # rank 0's share of bench.py --gpus xmul: the first 1/xmul of the rows (by products)
+    cuts = ctx.shard_rows_by_products(a.device, a.device, args.xmul)
+    p0 = B200Matrix(ctx.row_block(a.device, 0, int(cuts[1])))
+    args.check = 0
 if args.check:
     from oracle import oracle as O
     a_o = O.Csr(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values); p_o = a_o
-p = a
+p = p0 if args.block else a
 print(f"side={args.side} n={a.n} nnz={a.nnz()} bits={args.bits}")
 for k in range(2, args.steps + 1):
     best = None
