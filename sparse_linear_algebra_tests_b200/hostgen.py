@@ -182,14 +182,16 @@ def stdrng_f64_unit(seed: bytes, n: int) -> np.ndarray:
     return (stdrng_u64(seed, n) >> U64(12)).astype(np.float64) * (1.0 / 4503599627370496.0)
 
 
-def thin(a: HostCsr, density: float, seed: bytes = bytes([42] * 32)) -> HostCsr:
+def thin(a: HostCsr, density: float, seed: bytes = bytes([42] * 32), skip: int = 0) -> HostCsr:
     """src/graph_csr.rs:225-247 with StdRng::from_seed(seed): entries visited row-major; one draw per
-    entry with r <= c (short-circuit `&&`, :235); a kept (r,c) also keeps its mirror (c,r) when stored."""
+    entry with r <= c (short-circuit `&&`, :235); a kept (r,c) also keeps its mirror (c,r) when stored.
+    `skip` = draws already taken from the same generator (the sweep of bench_matmul_magnus shares one StdRng across
+    its grid, src/graph_magnus.rs:800-821); this call consumes `draws_of_thin(a)` more."""
     rows = a.row_of_entry()
     cols = a.col_idx.astype(np.int64)
     upper = rows <= cols
     nu = int(upper.sum())
-    draws = stdrng_f64_unit(seed, nu)
+    draws = stdrng_f64_unit(seed, skip + nu)[skip:]
     keep_u = np.zeros(a.nnz(), dtype=bool)
     keep_u[np.flatnonzero(upper)] = draws < density
     kr, kc, kv = rows[keep_u], cols[keep_u], a.values[keep_u]
@@ -205,6 +207,11 @@ def thin(a: HostCsr, density: float, seed: bytes = bytes([42] * 32)) -> HostCsr:
     c = np.concatenate([kc, mc[present]])
     v = np.concatenate([kv, mv])
     return from_coo(a.rows, a.cols, r, c, v, a.val_bits)
+
+
+def draws_of_thin(a: HostCsr) -> int:
+    """Generator outputs one `thin` of `a` consumes: one per stored entry on or above the diagonal."""
+    return int((a.row_of_entry() <= a.col_idx.astype(np.int64)).sum())
 
 
 def thinned_torus(dims, density: float, seed: bytes = bytes([42] * 32), val_bits: int = 32) -> HostCsr:
