@@ -869,7 +869,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         // one launch: product counts, column windows, bins, scratch offsets (look-back scan of min(P_i, cols))
         const double avgA = (double)A->nnz / (double)rows;
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
-        const u64 tiles_pre = (rows + (256 / G) - 1) / (256 / G);
+        const u64 tile_rows = std::max(256 / G, B200_PREPASS_MIN_ROWS);   // B200_PREPASS_ROWS(G)
+        const u64 tiles_pre = (rows + tile_rows - 1) / tile_rows;
         CUDA_TRY(reset_scan(ctx, tiles_pre));
         // column windows only matter when some bin's bitmap is narrower than B; square operands get circular windows
         bool windows = false;

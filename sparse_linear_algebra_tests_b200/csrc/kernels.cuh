@@ -138,95 +138,104 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 // rows' first/last columns.  WMODE 2 (square B, `bspan` holds circular spans): columns are measured from a per-row
 // reference ref = the row's first A column, d(c) = (c - ref + n/2) mod n, so rows that wrap around the index space keep
 // a narrow window; win = {window base in d (multiple of 128), 128-column groups, rot = (ref - n/2) mod n, 0}.
+#define B200_PREPASS_MIN_ROWS 32
+#define B200_PREPASS_ROWS(G) ((256 / (G)) > B200_PREPASS_MIN_ROWS ? (256 / (G)) : B200_PREPASS_MIN_ROWS)   // rows per CTA
 template <int G, int WMODE>
 __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict__ rpA, const u32 *__restrict__ colA,
                                                  const uint4 *__restrict__ bspan, const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
                                                  u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
                                                  B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride,
                                                  uint4 *__restrict__ win, WinCaps caps) {
-    constexpr int RPC = 256 / G;                                            // rows per CTA
+    // G lanes per row, 256/G rows per step, enough (unrolled) steps for >= 32 rows per CTA (16, 64 and 128 measured slower): ncu showed half of this
+    // kernel's stall samples at the barrier behind the look-back when every CTA was a tile of 8 rows (3375 tiles for
+    // the 30^3 torus); fewer, larger tiles shorten that chain and the unrolled steps keep several rows' gathers in flight.
+    constexpr int RPS = 256 / G;                                            // rows per step
+    constexpr int TILE = B200_PREPASS_ROWS(G);
+    constexpr int STEPS = TILE / RPS;
     constexpr bool WINDOWS = WMODE != 0;
-    __shared__ u32 s_tile, s_cnt[B200_NBINS], s_base[B200_NBINS];
-    __shared__ u64 s_bound[RPC], s_wsum[8], s_excl;
+    __shared__ u32 s_tile, s_cnt[B200_NBINS], s_base[B200_NBINS], s_binloc[TILE];
+    __shared__ u64 s_bound[TILE], s_wsum[8], s_excl;
     __shared__ ull s_sum, s_max;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) { s_tile = atomicAdd(&ctrl->scan_ticket[1], 1u); s_sum = 0; s_max = 0; }
     if (tid < B200_NBINS) s_cnt[tid] = 0;
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 row = (u64)tile * RPC + tid / G;
     const u32 sub = tid % G;
-    u64 p = 0; u32 lenA = 0, cmin = 0xFFFFFFFFu, cmax = 0, rot = 0;
-    if (row < rows) {
-        const u64 s = rpA[row];
-        lenA = (u32)(rpA[row + 1] - s);
-        const u32 *Ac = colA + s;
-        const long long n = (long long)ncols, half = n / 2;
-        const long long ref = WMODE == 2 && lenA ? (long long)Ac[0] : 0;
-        if (WMODE == 2) { long long t = ref - half; if (t < 0) t += n; rot = (u32)t; }
-        // one entry's contribution to the window: plain [first, last], or its circular span shifted by (k - ref)
-        auto widen = [&](u32 k, const uint4 &d) {
-            if (d.x == 0) return;
-            if (WMODE == 1) { cmin = min(cmin, d.y); cmax = max(cmax, d.z); return; }
-            long long kap = (long long)k - ref + half;                       // (k - ref + n/2) mod n
-            if (kap < 0) kap += n; else if (kap >= n) kap -= n;
-            const long long lo = kap + (long long)d.y - half, hi = kap + (long long)d.z - half;
-            if (lo < 0 || hi >= n) { cmin = 0; cmax = (u32)(n - 1); }         // offsets add up past half the circle: full window
-            else { cmin = min(cmin, (u32)lo); cmax = max(cmax, (u32)hi); }
-        };
-        u32 i = sub;
-        for (; i + 3 * G < lenA; i += 4 * G) {                               // four independent gathers in flight
-            const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
-            if (WINDOWS) {
-                const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
-                p += (u64)d0.x + d1.x + d2.x + d3.x;
-                widen(k0, d0); widen(k1, d1); widen(k2, d2); widen(k3, d3);
-            } else {
-                const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
-                p += (u64)d0 + d1 + d2 + d3;
-            }
-        }
-        for (; i < lenA; i += G) {
-            if (WINDOWS) { const u32 k = Ac[i]; const uint4 d = bspan[k]; p += d.x; widen(k, d); }
-            else p += bdesc[Ac[i]].y;
-        }
-    }
-#pragma unroll
-    for (int m = G / 2; m > 0; m >>= 1) {
-        p += shfl_xor_u64(p, m);
-        if (WINDOWS) {
-            cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, m));
-            cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
-        }
-    }
-    if (!WINDOWS) { cmin = 0; cmax = ncols ? (u32)(ncols - 1) : 0u; }
-    int b = B200_BIN_NONE; u32 local = 0;
+    const long long n = (long long)ncols, half = n / 2;
     u64 wsum = 0, wmax = 0;
-    if (sub == 0) {
-        u64 bound = 0;
+#pragma unroll
+    for (int step = 0; step < STEPS; step++) {
+        const u32 lrow = step * RPS + tid / G;                               // row inside the tile
+        const u64 row = (u64)tile * TILE + lrow;
+        u64 p = 0; u32 lenA = 0, cmin = 0xFFFFFFFFu, cmax = 0, rot = 0;
         if (row < rows) {
-            prod[row] = p;
-            bound = p < ncols ? p : ncols;
-            b = sym_bin_of(p, lenA);
-            if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;               // the two smallest hash bins share a list
-            if (b != B200_BIN_NONE) {
-                // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
-                const u32 base = cmin & ~127u;
-                const u32 groups = (cmax - base) / 128u + 1u;
-                win[row] = make_uint4(base, groups, rot, 0u);
-                if (b >= B200_BIN_HASH0 && b < B200_BIN_HEAVY && groups > caps.cap[b - B200_BIN_HASH0]) b = B200_BIN_WIDE0 + (b - B200_BIN_HASH0);
+            const u64 s = rpA[row];
+            lenA = (u32)(rpA[row + 1] - s);
+            const u32 *Ac = colA + s;
+            const long long ref = WMODE == 2 && lenA ? (long long)Ac[0] : 0;
+            if (WMODE == 2) { long long t = ref - half; if (t < 0) t += n; rot = (u32)t; }
+            // one entry's contribution to the window: plain [first, last], or its circular span shifted by (k - ref)
+            auto widen = [&](u32 k, const uint4 &d) {
+                if (d.x == 0) return;
+                if (WMODE == 1) { cmin = min(cmin, d.y); cmax = max(cmax, d.z); return; }
+                long long kap = (long long)k - ref + half;                   // (k - ref + n/2) mod n
+                if (kap < 0) kap += n; else if (kap >= n) kap -= n;
+                const long long lo = kap + (long long)d.y - half, hi = kap + (long long)d.z - half;
+                if (lo < 0 || hi >= n) { cmin = 0; cmax = (u32)(n - 1); }     // offsets add up past half the circle: full window
+                else { cmin = min(cmin, (u32)lo); cmax = max(cmax, (u32)hi); }
+            };
+            u32 i = sub;
+            for (; i + 3 * G < lenA; i += 4 * G) {                           // four independent gathers in flight
+                const u32 k0 = Ac[i], k1 = Ac[i + G], k2 = Ac[i + 2 * G], k3 = Ac[i + 3 * G];
+                if (WINDOWS) {
+                    const uint4 d0 = bspan[k0], d1 = bspan[k1], d2 = bspan[k2], d3 = bspan[k3];
+                    p += (u64)d0.x + d1.x + d2.x + d3.x;
+                    widen(k0, d0); widen(k1, d1); widen(k2, d2); widen(k3, d3);
+                } else {
+                    const u32 d0 = bdesc[k0].y, d1 = bdesc[k1].y, d2 = bdesc[k2].y, d3 = bdesc[k3].y;
+                    p += (u64)d0 + d1 + d2 + d3;
+                }
             }
-            if (b == B200_BIN_NONE) nnz_row[row] = 0;
-            else local = atomicAdd(&s_cnt[b], 1u);
-            wsum = p; wmax = p;
+            for (; i < lenA; i += G) {
+                if (WINDOWS) { const u32 k = Ac[i]; const uint4 d = bspan[k]; p += d.x; widen(k, d); }
+                else p += bdesc[Ac[i]].y;
+            }
         }
-        s_bound[tid / G] = bound;
+#pragma unroll
+        for (int m = G / 2; m > 0; m >>= 1) {
+            p += shfl_xor_u64(p, m);
+            if (WINDOWS) {
+                cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, m));
+                cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
+            }
+        }
+        if (!WINDOWS) { cmin = 0; cmax = ncols ? (u32)(ncols - 1) : 0u; }
+        if (sub == 0) {
+            u64 bound = 0; u32 binloc = (u32)B200_BIN_NONE << 24;
+            if (row < rows) {
+                prod[row] = p;
+                bound = p < ncols ? p : ncols;
+                int b = sym_bin_of(p, lenA);
+                if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;           // the two smallest hash bins share a list
+                if (b != B200_BIN_NONE) {
+                    // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
+                    const u32 base = cmin & ~127u;
+                    const u32 groups = (cmax - base) / 128u + 1u;
+                    win[row] = make_uint4(base, groups, rot, 0u);
+                    if (b >= B200_BIN_HASH0 && b < B200_BIN_HEAVY && groups > caps.cap[b - B200_BIN_HASH0]) b = B200_BIN_WIDE0 + (b - B200_BIN_HASH0);
+                    binloc = ((u32)b << 24) | atomicAdd(&s_cnt[b], 1u);
+                } else nnz_row[row] = 0;
+                wsum += p; wmax = wmax > p ? wmax : p;
+            }
+            s_bound[lrow] = bound; s_binloc[lrow] = binloc;
+        }
     }
     wsum = warp_sum_u64(wsum); wmax = warp_max_u64(wmax);
     if (lane == 0) { if (wsum) atomicAdd(&s_sum, (ull)wsum); atomicMax(&s_max, (ull)wmax); }
     __syncthreads();
     // ---- exclusive scan of the bounds inside the CTA (row order), aggregate, look-back
-    const u64 mine = tid < RPC ? s_bound[tid] : 0ull;
+    const u64 mine = tid < TILE ? s_bound[tid] : 0ull;
     u64 incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const u64 t = shfl_up_u64(incl, d); if (lane >= d) incl += t; }
@@ -256,16 +265,17 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
         if (lane == 0) s_excl = excl;
     }
     __syncthreads();
-    if (tid < RPC) {
-        const u64 r = (u64)tile * RPC + tid;
+    if (tid < TILE) {
+        const u64 r = (u64)tile * TILE + tid;
         if (r < rows) {
             const u64 run = s_excl + wbase + incl;
             tmp_ptr[r + 1] = run;
             if (r + 1 == rows) ctrl->total_bound = run;
+            const u32 bl = s_binloc[tid], b = bl >> 24;
+            if (b != B200_BIN_NONE) bin_rows[(u64)b * bin_stride + s_base[b] + (bl & 0xFFFFFFu)] = (u32)r;
         }
         if (r == 0) tmp_ptr[0] = 0;
     }
-    if (b != B200_BIN_NONE) bin_rows[(u64)b * bin_stride + s_base[b] + local] = (u32)row;
     if (tid == 0) {
         if (s_sum) atomicAdd(&ctrl->total_products, s_sum);
         if (s_max) atomicMax(&ctrl->max_row_products, s_max);
