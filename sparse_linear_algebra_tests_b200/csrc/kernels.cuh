@@ -1007,6 +1007,7 @@ __device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, con
 }
 
 #define B200_EXPAND_PRE 2   // A entries per thread whose loads are issued one row ahead
+#define B200_EXPAND_REC_EARLY 1   // 1: next row's B records are fetched right after the rank phase (live across accumulate + emit)
 #define B200_EXPAND_ILP 2   // products each thread keeps in flight in the mark / accumulate loops
 
 template <typename VT, int MODE, bool PACK, bool BPAT>
@@ -1130,6 +1131,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         __syncthreads();
         const u32 P = s_P;
         const u32 nnz = rank_prefix_v4(bm4, wpre4, groups, s_warp);
+#if B200_EXPAND_REC_EARLY
 #pragma unroll
         for (int e = 0; e < E; e++) {
             const u32 t = tid + e * nt;
@@ -1137,6 +1139,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             if (PACK && has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
             av[e] = avn[e];
         }
+#endif
         u64 rs_nn = 0; u32 lenA_nn = 0; uint4 wnn = make_uint4(0, 0, 0, 0);
         if (r + 2 < r_end) { rs_nn = a.rpA[row_nn]; lenA_nn = (u32)(a.rpA[row_nn + 1] - rs_nn); wnn = win[row_nn]; }
         __syncthreads();
@@ -1183,6 +1186,17 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             const u64 m = (u64)(v0 > v1 ? v0 : v1);
             vmax = vmax > m ? vmax : m;
         }
+#if !B200_EXPAND_REC_EARLY
+        // next row's B records: issued only now, so that their 16 registers are not live across the accumulate and emit
+        // loops (63 -> fewer registers: one more CTA per SM); the clear below and the barrier cover part of their latency
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const u32 t = tid + e * nt;
+            br[e].len = 0;
+            if (PACK && has_next && t < lenA_n) br[e] = load_brow<PACK>(pack, a.bdesc, kn[e]);
+            av[e] = avn[e];
+        }
+#endif
         for (u32 t = tid; t < groups; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_P = 0; if (o.nnz_out) o.nnz_out[row] = nnz; }
         __syncthreads();
