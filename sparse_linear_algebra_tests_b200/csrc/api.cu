@@ -43,7 +43,8 @@ struct b200_csr {
     u64 rows, cols, nnz;
     int val_bits;
     u64 *d_rp; u32 *d_col; void *d_val;
-    ull *d_maxval;          // device scalar: largest stored value
+    ull *d_maxval;          // device scalar: largest stored value (lives behind row_ptr, same allocation)
+    bool val_shares_col;    // values live in the col_idx allocation (products: one allocation per multiply)
     u64 max_row_len;        // host-known upper bound of the longest row
     uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
     uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (pre-pass: plain column windows)
@@ -227,7 +228,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
-    { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : B200_NAUX; }
+    // one auxiliary stream measured as good as three, with half the event calls
+    { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : 1; }
     ctx->timing = true;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
     setup_kernels_vt<u32>(ctx->smem_optin);
@@ -276,17 +278,22 @@ extern "C" int b200_ctx_set_timing(b200_ctx *ctx, int enabled) {
 }
 
 // ---------------------------------------------------------------------------- CSR handles
+// col_idx and values of m->nnz entries in ONE allocation (values behind the columns, 256-byte aligned)
+static int alloc_entries(b200_ctx *ctx, b200_csr *m) {
+    const size_t col_bytes = ((size_t)m->nnz * 4 + 255) & ~(size_t)255;
+    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)m->nnz * (size_t)(m->val_bits / 8)));
+    m->d_val = (unsigned char *)m->d_col + col_bytes;
+    m->val_shares_col = true;
+    return B200_OK;
+}
 static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out) {
     b200_csr *m = new b200_csr();
     memset(m, 0, sizeof(*m));
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
-    int r = dmalloc(ctx, (void **)&m->d_maxval, 16);
-    if (r == B200_OK) r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8);
-    if (r == B200_OK && alloc_arrays) {
-        r = dmalloc(ctx, (void **)&m->d_col, nnz * 4);
-        if (r == B200_OK) r = dmalloc(ctx, &m->d_val, nnz * (size_t)(val_bits / 8));
-    }
-    if (r != B200_OK) { dfree(ctx, m->d_maxval); dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); delete m; return r; }
+    int r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8 + 16);           // row_ptr + the max-value scalar
+    if (r == B200_OK) m->d_maxval = (ull *)(m->d_rp + rows + 1);
+    if (r == B200_OK && alloc_arrays) r = alloc_entries(ctx, m);
+    if (r != B200_OK) { dfree(ctx, m->d_rp); delete m; return r; }
     *out = m;
     return B200_OK;
 }
@@ -295,7 +302,8 @@ extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
     if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); dfree(ctx, m->d_val); dfree(ctx, m->d_maxval); dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_cspan); dfree(ctx, m->d_pack);
+    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); if (!m->val_shares_col) dfree(ctx, m->d_val);
+    dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_cspan); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;
 }
@@ -800,11 +808,10 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool timing = ctx->timing && st;
     b200_csr *C = nullptr;
     TRY(csr_alloc(ctx, rows, ncols, 0, A->val_bits, false, &C));
-    CUDA_TRY(cudaMemsetAsync(C->d_maxval, 0, 16, s));
     if (st) { memset(st, 0, sizeof(*st)); st->rows = rows; st->cols = ncols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; }
     if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
-        CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8, s));
-        TRY(dmalloc(ctx, (void **)&C->d_col, 0)); TRY(dmalloc(ctx, &C->d_val, 0));
+        CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8 + 16, s));   // row_ptr and the max-value scalar behind it
+        TRY(alloc_entries(ctx, C));
         C->h_maxval = 0; C->h_maxval_known = true;
         if (st) st->bytes_algorithmic = (A->nnz + B->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
         *out = C;
@@ -888,14 +895,26 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         LAUNCH_CHECK(ctx);
         // Exact mode: count every row's distinct columns first (same lists, count-only kernels), allocate C at its exact
         // size and let the numeric kernels write it once at the final offsets -- no scratch CSR, no compaction, DRAM
-        // traffic close to the algorithmic bytes.  Measured on the 30^3 chain the count pass costs more (~100 us at A^7)
-        // than the compaction it saves (~64 us), so the scratch path stays the default while its host-known bound
-        // nnz(A) * maxlen(B) entries fits 1/16 of device memory (B200_EXACT_MB overrides the limit); beyond that the
-        // exact mode runs and memory stays at the size of C.
+        // traffic close to the algorithmic bytes.  Measured (30^3 A^7: count pass ~100 us vs ~64 us of compaction; 200^3
+        // A^5: 135 vs 101 ms) the scratch path is faster, so it stays the default while the scratch fits: decided from the
+        // host-known bound nnz(A) * maxlen(B) when that is small (1/16 of device memory), else from the pre-pass's exact
+        // figure.  B200_EXACT / B200_EXACT_MB override.
         const int exact_env = env_int("B200_TWOPASS", 0) ? 1 : env_int("B200_EXACT", -1);   // B200_TWOPASS: older name of the switch
         const int exact_mb = env_int("B200_EXACT_MB", -1);
-        const bool exact = exact_env >= 0 ? exact_env != 0
-                                          : (!cheap_bound || (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20)));
+        bool exact = exact_env >= 0 ? exact_env != 0 : (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20));
+        tmp_entries = (u64)hb128;
+        if (exact_env < 0 && !exact && !cheap_bound) {
+            // the host-side bound is too loose to decide: read the pre-pass's exact scratch size sum(min(P_i, cols)) (one
+            // small synchronous copy; multiplies of this size run for milliseconds) and keep the faster scratch path while
+            // it fits a third of the free memory
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            tmp_entries = ctx->h_ctrl->total_bound;
+            size_t free_b = 0, tot_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+            const size_t reusable = ctx->cap_tmp_col + ctx->cap_tmp_val;      // scratch the context already owns
+            exact = (unsigned __int128)tmp_entries * esz > (unsigned __int128)((free_b + reusable) / 3);
+        }
         if (exact) {
             r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps);
             fan.join();
@@ -908,8 +927,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             const B200Ctrl hc = *ctx->h_ctrl;
             C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz;
-            r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
-            if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+            r = alloc_entries(ctx, C);
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             if (timing) cudaEventRecord(ctx->ev[2], s);
             if (ctx->trace) trace_mark(ctx, __LINE__);
@@ -935,7 +953,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             *out = C;
             return B200_OK;
         }
-        tmp_entries = (u64)hb128;
     }
     {
         r = ensure_tmp(ctx, tmp_entries * 4, tmp_entries * sizeof(VT));
@@ -960,8 +977,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const B200Ctrl hc = *ctx->h_ctrl;
         C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
-        r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
-        if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+        r = alloc_entries(ctx, C);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         if (timing) cudaEventRecord(ctx->ev[2], s);
         if (ctx->trace) trace_mark(ctx, __LINE__);
@@ -969,10 +985,10 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const double avg = (double)C->nnz / (double)rows;
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
             const u64 want = (rows << llg) / 256 + 1;
-            k_compact_rows<VT><<<(unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64), 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg);
+            k_compact_rows<VT><<<(unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64), 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg,
+                                                                                                      &ctx->d_ctrl->max_val_out, C->d_maxval);
             LAUNCH_CHECK(ctx);
         }
-        CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));
         if (timing) cudaEventRecord(ctx->ev[3], s);
         if (st) {
             st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
@@ -1066,7 +1082,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     b200_csr *C = nullptr;
     TRY(csr_alloc(ctx, rows, A->cols, 0, A->val_bits, false, &C));
     CUDA_TRY(cudaMemsetAsync(C->d_maxval, 0, 16, s));
-    if (rows == 0) { TRY(dmalloc(ctx, (void **)&C->d_col, 0)); TRY(dmalloc(ctx, &C->d_val, 0)); CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, 8, s)); *out = C; return B200_OK; }
+    if (rows == 0) { TRY(alloc_entries(ctx, C)); CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, 8, s)); *out = C; return B200_OK; }
     int r = ensure_row_scratch(ctx, rows);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
@@ -1079,8 +1095,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     C->nnz = ctx->h_ctrl->total_nnz; C->max_row_len = ctx->h_ctrl->max_row_nnz;
-    r = dmalloc(ctx, (void **)&C->d_col, C->nnz * 4);
-    if (r == B200_OK) r = dmalloc(ctx, &C->d_val, C->nnz * sizeof(VT));
+    r = alloc_entries(ctx, C);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     k_add_rows<VT, true><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, C->d_rp, C->d_col, (VT *)C->d_val, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);

@@ -1482,7 +1482,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
 template <typename VT>
 __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__restrict__ src_ptr, const u64 *__restrict__ rpC,
                                                       const u32 *__restrict__ src_col, const VT *__restrict__ src_val,
-                                                      u32 *__restrict__ colC, VT *__restrict__ valC, int lanes_lg) {
+                                                      u32 *__restrict__ colC, VT *__restrict__ valC, int lanes_lg,
+                                                      const ull *max_val_src, ull *max_val_dst) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *max_val_dst = *max_val_src;    // the product's max-value scalar rides along
     const u32 L = 1u << lanes_lg;                                           // lanes per row
     const u64 gthread = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 nsub = ((u64)gridDim.x * blockDim.x) >> lanes_lg;

@@ -107,3 +107,22 @@ def test_einsum_spec_validation_needs_no_gpu():
             parse_matmul_spec(bad)
     with pytest.raises(AssertionError):
         parse_matmul_spec("abc,cd->abd")
+
+
+def test_thin_with_a_shared_generator_consumes_the_stream_in_order():
+    """bench_matmul_magnus thins every grid point with ONE StdRng (src/graph_magnus.rs:800-821): `skip` continues the
+    stream where the previous thin stopped, one draw per stored entry with r <= c."""
+    full = hostgen.lattice([5, 5, 5], True, 64)
+    n = hostgen.draws_of_thin(full)
+    assert n == int((full.row_of_entry() <= full.col_idx.astype(np.int64)).sum()) and n == full.nnz() // 2    # no diagonal in a lattice
+    seed = bytes([42] * 32)
+    stream = hostgen.stdrng_f64_unit(seed, 2 * n)
+    first, second = hostgen.thin(full, 0.3, seed), hostgen.thin(full, 0.3, seed, skip=n)
+    rows, cols = full.row_of_entry(), full.col_idx.astype(np.int64)
+    upper = np.flatnonzero(rows <= cols)
+    for got, draws in ((first, stream[:n]), (second, stream[n:])):
+        kept = upper[draws < 0.3]
+        want = {(int(rows[i]), int(cols[i])) for i in kept} | {(int(cols[i]), int(rows[i])) for i in kept}
+        have = set(zip(got.row_of_entry().tolist(), got.col_idx.tolist()))
+        assert have == want
+    assert not same(first, second)
