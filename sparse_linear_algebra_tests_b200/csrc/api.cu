@@ -622,7 +622,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     const size_t accb = mode == 0 ? 4 : 8;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto do_tiny = [&]() -> int {
-        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        const int g = (int)std::min<u64>((rows + 31) / 32, (u64)ctx->num_sms * 32);   // >= 4 rows per warp: the software pipeline needs a row stream
         k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o, bpat, B->cols <= (1ull << 27), mode == 0);
         LAUNCH_CHECK(ctx);
         return B200_OK;
@@ -638,7 +638,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         if (ex_smem + (packed ? 0 : sizeof(EnumSmem)) > smem_max) return false;
         // threads: ~8 products or ~8 bitmap groups each, whichever asks for more
         const int et = std::max(32, std::min(512, (int)std::max<u32>(pcap, nw4) / std::max(1, env_int("B200_EDIV", 8)) / 32 * 32));
-        const int eg = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * 4);
+        // a CTA should see several rows (one bitmap/accumulator clear and one pipeline fill per CTA): at most rows/8 CTAs
+        const u64 gdiv = (u64)std::max(1, env_int("B200_GDIV", 8)), gmul = (u64)std::max(1, env_int("B200_GMUL", 4));
+        const int eg = (int)std::max<u64>(1, std::min<u64>((n + gdiv - 1) / gdiv, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * gmul));
         if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
 #define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
         do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); \
@@ -793,7 +795,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         }
     }
     {
-        const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 32);
+        const int g = (int)std::min<u64>((rows + 31) / 32, (u64)ctx->num_sms * 32);   // >= 4 rows per warp: the software pipeline needs a row stream
         k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
         LAUNCH_CHECK(ctx);
     }
