@@ -765,7 +765,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         if (nw4 == 0) return B200_OK;
         const size_t smem = (size_t)nw4 * 16;
         const int t = std::max(32, std::min(512, (int)std::max<u32>(pcap / 2, nw4) / 8 / 32 * 32));
-        const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4);
+        const int g = (int)std::max<u64>(1, std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4));
         cudaStream_t bs = fan.pick();
         if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
         else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
