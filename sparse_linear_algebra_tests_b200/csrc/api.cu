@@ -51,6 +51,10 @@ struct b200_csr {
     uint4 *d_cspan;         // square operands: {len, min, max} of (col - row + n/2) mod n (pre-pass: circular windows)
     uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
     u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
+    // circular column range: every stored column is (cr_start + o) mod cols for some o < cr_len (cr_len = cols: unknown / everything)
+    u32 cr_start; u64 cr_len;
+    // square operands used on the right: signed offsets (c - k) of all entries lie in [cs_lo, cs_hi]; cs_state 0 unknown, 1 known, 2 none
+    long long cs_lo, cs_hi; int cs_state;
     cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
     b200_ctx *ctx;
 };
@@ -290,6 +294,7 @@ static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, b
     b200_csr *m = new b200_csr();
     memset(m, 0, sizeof(*m));
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
+    m->cr_start = 0; m->cr_len = cols;
     int r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8 + 16);           // row_ptr + the max-value scalar
     if (r == B200_OK) m->d_maxval = (ull *)(m->d_rp + rows + 1);
     if (r == B200_OK && alloc_arrays) r = alloc_entries(ctx, m);
@@ -321,8 +326,8 @@ static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_ro
     }
     if (m->nnz) {
         int g = grid_for(m->nnz, 256, ctx->num_sms * 8);
-        if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag);
-        else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag);
+        if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 5);
+        else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 5);
         LAUNCH_CHECK(ctx);
     }
     if (check) {
@@ -331,6 +336,13 @@ static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_ro
         if (ctx->h_flag[0] & 2u) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone from 0 to nnz");
         if (ctx->h_flag[0]) return set_err(B200_ERR_FORMAT, "CSR holds an explicit zero value or a column index >= cols");
         if (device_rowptr) m->max_row_len = ctx->h_flag[4];
+        if (m->nnz && m->cols) {                                            // circular column range (see k_value_stats)
+            const long long n = (long long)m->cols, half = n / 2;
+            const long long omin = (long long)(~ctx->h_flag[5]), omax = (long long)ctx->h_flag[6], ref = (long long)ctx->h_flag[7];
+            long long start = ref + omin - half;
+            start %= n; if (start < 0) start += n;
+            m->cr_start = (u32)start; m->cr_len = (u64)(omax - omin + 1);
+        }
     }
     return B200_OK;
 }
@@ -509,6 +521,22 @@ static int ensure_cspan(b200_ctx *ctx, const b200_csr *B) {
     return B200_OK;
 }
 
+// operand-wide circular column offsets of a square right operand (k_cspan_bounds): one reduction, read back and cached
+static int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B) {
+    if (B->cs_state) return B200_OK;
+    b200_csr *Bm = const_cast<b200_csr *>(B);
+    if (B->rows != B->cols || B->nnz == 0) { Bm->cs_state = 2; return B200_OK; }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 12, 0, 12, ctx->stream));
+    k_cspan_bounds<<<grid_for(B->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(B->rows, B->d_rp, B->d_col, ctx->d_flag + 12);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 12, ctx->d_flag + 12, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const long long half = (long long)(B->cols / 2);
+    Bm->cs_lo = (long long)(~ctx->h_flag[12]) - half; Bm->cs_hi = (long long)ctx->h_flag[13] - half;
+    Bm->cs_state = ctx->h_flag[14] == 0 && Bm->cs_lo <= Bm->cs_hi ? 1 : 2;   // rows too long to scan: no bound
+    return B200_OK;
+}
+
 // sector-packed records for low-degree right operands (mean row length <= 4)
 static bool want_pack(const b200_csr *B) {
     const int forced = env_int("B200_PACK", -1);
@@ -629,7 +657,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     };
     // one-pass bins are cut on the product count P <= cap: expand the products into shared memory once and run every
     // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
-    const u32 nw4_full = (nwords + 3) / 4;
+    const u32 nw4_full = caps.full;
     auto launch_expand = [&](int bin, int nb, u32 cap, u32 nw4, u64 n, cudaStream_t bs) -> bool {
         if (nw4 == 0) return false;
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
@@ -757,7 +785,7 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
 // kernels mirror launch_numeric's: tiny / window bitmap / hash, heavy), so that C can be allocated at its exact size.
 static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const SymArgs &sa, u64 rows, u64 p_bound, bool packed, int lg,
                          Fan &fan, const WinCaps &caps) {
-    const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = (nwords + 3) / 4;
+    const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = caps.full;
     const u32 bstride = (u32)ctx->cap_rows;
     const size_t smem_max = ctx->smem_optin - 1024;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
@@ -860,14 +888,36 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // 100^3 torus wider windows lost to hash + sort (the per-row prefix over a mostly empty bitmap dominates).
     // Rows beyond the window take the hash + sort kernels.
     WinCaps caps;
+    // The arc of the index circle this multiply can touch: (column range of A, known on the host for every handle) +
+    // (offsets c - k of B's entries, a per-operand constant for a square B).  When the arc is short -- a GPU's row block of
+    // a torus or banded matrix, whatever the size of the whole matrix -- ONE window serves every row: the pre-pass needs
+    // no per-row window (WMODE 0), every row fits the bitmap, and the product's own column range is the arc.
+    u32 all_groups = (nwords + 3) / 4, all_rot = 0;
+    u64 arc_start = 0, arc_len = ncols;
+    if (B->rows == B->cols && A->cr_len < ncols && env_int("B200_ARC", 1)) {
+        r = ensure_cs_bounds(ctx, B);
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        if (B->cs_state == 1) {
+            const long long n = (long long)ncols;
+            const unsigned __int128 len = (unsigned __int128)A->cr_len + (unsigned __int128)(B->cs_hi - B->cs_lo);
+            if (len < (unsigned __int128)ncols) {
+                long long st = ((long long)A->cr_start + B->cs_lo) % n; if (st < 0) st += n;
+                arc_start = (u64)st; arc_len = (u64)len;
+            }
+        }
+    }
+    const bool use_arc = arc_len < ncols && (arc_len + 127) / 128 + 1 < (u64)all_groups && (arc_len + 127) / 128 <= 1024;
+    if (use_arc) { all_groups = (u32)((arc_len + 127) / 128); all_rot = (u32)arc_start; }
+    C->cr_start = (u32)arc_start; C->cr_len = arc_len;                     // a product's columns stay inside the arc
     {
-        const u32 nw4_full = (nwords + 3) / 4;
+        const u32 nw4_full = all_groups;
         const size_t accb1 = mode1 == 0 ? 4 : 8, pvb1 = (mode1 == 0 || sizeof(VT) == 4) ? 4 : 8;
         const int forced = env_int("B200_WINCAP", -1);                    // testing hook: force a small window (0: hash only)
         for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
             const u64 pcap = b200_hash_cap(hb == 0 ? 1 : hb), ncap = std::min<u64>(pcap, ncols);
             const size_t fixed = pcap * (4 + pvb1) + ncap * (4 + accb1);
-            u64 want = std::min<u64>(nw4_full, std::max<u64>(256, std::min<u64>(4096, (u64)env_int("B200_WINMUL", 3) * pcap)));
+            // (with a common arc of at most 512 groups every bin takes the whole arc: one window, no wide lists)
+            u64 want = std::min<u64>(nw4_full, std::max<u64>(use_arc ? 512 : 256, std::min<u64>(4096, (u64)env_int("B200_WINMUL", 3) * pcap)));
             if (forced >= 0) want = std::min<u64>(want, (u64)forced);
             const size_t avail = smem_max - (packed ? 0 : sizeof(EnumSmem));    // the balanced expansion keeps its tile in static shared memory
             const u64 fit = fixed + 24 * 32 <= avail ? (avail - fixed) / 24 : 0;
@@ -883,13 +933,18 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         CUDA_TRY(reset_scan(ctx, tiles_pre));
         // column windows only matter when some bin's bitmap is narrower than B; square operands get circular windows
         bool windows = false;
-        for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < (nwords + 3) / 4;
+        for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < all_groups;
+        if (windows && use_arc) { all_groups = (nwords + 3) / 4; all_rot = 0; }   // a bin cannot hold the arc: per-row windows over the plain column space
+        caps.full = all_groups;
+        if (ctx->trace) fprintf(stderr, "[b200 trace] arc: A.cr=(%u,%llu) B.cs=[%lld,%lld] state %d arc=(%llu,%llu) use_arc=%d windows=%d groups=%u caps=%u %u %u %u %u %u %u %u\n",
+                                A->cr_start, (ull)A->cr_len, B->cs_lo, B->cs_hi, B->cs_state, (ull)arc_start, (ull)arc_len, (int)use_arc, (int)windows, all_groups,
+                                caps.cap[0], caps.cap[1], caps.cap[2], caps.cap[3], caps.cap[4], caps.cap[5], caps.cap[6], caps.cap[7]);
         const bool circular = windows && B->rows == B->cols && env_int("B200_CIRCULAR", 1);
         if (circular) { r = ensure_cspan(ctx, B); if (r != B200_OK) { b200_csr_free(ctx, C); return r; } }
         const int wmode = !windows ? 0 : circular ? 2 : 1;
 #define PREPASS1(GG, WW) k_prepass<GG, WW><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, WW == 2 ? B->d_cspan : B->d_span, B->d_desc, ncols,   \
                                                                              ctx->d_prod, ctx->d_nnz_row, ctx->d_tmp_ptr, ctx->d_tile_pre, ctx->d_ctrl,   \
-                                                                             ctx->d_bin_rows, bstride, ctx->d_win, caps)
+                                                                             ctx->d_bin_rows, bstride, ctx->d_win, caps, all_groups, all_rot)
 #define PREPASS(GG) do { if (wmode == 2) PREPASS1(GG, 2); else if (wmode == 1) PREPASS1(GG, 1); else PREPASS1(GG, 0); } while (0)
         if (G == 1) PREPASS(1); else if (G == 4) PREPASS(4); else if (G == 8) PREPASS(8); else PREPASS(32);
 #undef PREPASS1

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(256) k_build_cspan(u64 n, const u64 *__restric
 }
 
 // per hash bin: how many 128-column groups the bin's shared-memory bitmap holds (0: the bin has no bitmap kernel)
-struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; };
+// `full`: groups that hold any row of this multiply (bins with cap >= full have no wide list)
+struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; u32 full; };
 
 // Walk the intermediate products of one A row.  `ngrp` groups of G lanes each take A entries
 // grp, grp+ngrp, ...; the G lanes of a group stride over that entry's B row.  Two A entries are
@@ -133,8 +134,9 @@ __global__ void __launch_bounds__(256) k_row_products(u64 rows, const u64 *__res
 // One-pass pre-pass, one launch: product count P_i per row, totals, the bin lists (block-wise reservation in every
 // bin's own list, so a CTA's rows stay consecutive) and -- through a decoupled look-back over the CTAs in ticket
 // order -- the scratch offsets prefix(min(P_i, cols)) that the numeric kernels write their rows at.
-// WMODE 0 (the whole column space fits every bin's bitmap): lengths come from the 8-byte descriptors and every row gets
-// the full window -- half the gather bytes, no min/max reductions.  WMODE 1: plain window [cmin, cmax] from the sorted B
+// WMODE 0 (one window fits every row of this multiply -- the whole column space, or the arc of the index circle the host
+// derived from the operands' column ranges): lengths come from the 8-byte descriptors and every row gets the window
+// {0, all_groups, all_rot} -- half the gather bytes, no min/max reductions.  WMODE 1: plain window [cmin, cmax] from the sorted B
 // rows' first/last columns.  WMODE 2 (square B, `bspan` holds circular spans): columns are measured from a per-row
 // reference ref = the row's first A column, d(c) = (c - ref + n/2) mod n, so rows that wrap around the index space keep
 // a narrow window; win = {window base in d (multiple of 128), 128-column groups, rot = (ref - n/2) mod n, 0}.
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
                                                  const uint4 *__restrict__ bspan, const uint2 *__restrict__ bdesc, u64 ncols, u64 *__restrict__ prod,
                                                  u32 *__restrict__ nnz_row, u64 *__restrict__ tmp_ptr, u64 *tile_status,
                                                  B200Ctrl *ctrl, u32 *__restrict__ bin_rows, u32 bin_stride,
-                                                 uint4 *__restrict__ win, WinCaps caps) {
+                                                 uint4 *__restrict__ win, WinCaps caps, u32 all_groups, u32 all_rot) {
     // G lanes per row, 256/G rows per step, enough (unrolled) steps for >= 32 rows per CTA (16, 64 and 128 measured slower): ncu showed half of this
     // kernel's stall samples at the barrier behind the look-back when every CTA was a tile of 8 rows (3375 tiles for
     // the 30^3 torus); fewer, larger tiles shorten that chain and the unrolled steps keep several rows' gathers in flight.
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
                 cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, m));
             }
         }
-        if (!WINDOWS) { cmin = 0; cmax = ncols ? (u32)(ncols - 1) : 0u; }
+        if (!WINDOWS) { cmin = 0; cmax = all_groups * 128u - 1u; rot = all_rot; }   // one window for every row, chosen by the host
         if (sub == 0) {
             u64 bound = 0; u32 binloc = (u32)B200_BIN_NONE << 24;
             if (row < rows) {
@@ -1507,17 +1509,57 @@ __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__res
 // =======================================================================================
 // 8. small utilities: value max / zero check on upload, index narrowing, add, pattern compare
 // =======================================================================================
+// Largest value, format check, and the circular column range of the matrix: offsets o = (c - col[0] + cols/2) mod cols of
+// all its columns, reduced to range[0] = max(~o) (i.e. the minimum, kept as a maximum so that a zeroed word is its
+// identity), range[1] = max(o), range[2] = col[0].  A row block of a banded / torus matrix covers a short arc of the
+// index circle even when it wraps around its end; the host turns the arc into one bitmap window for the whole multiply.
 template <typename VT>
 __global__ void __launch_bounds__(256) k_value_stats(u64 nnz, const VT *__restrict__ val, const u32 *__restrict__ col, u64 cols,
-                                                     ull *maxval, u32 *bad) {
-    u64 m = 0; u32 z = 0;
+                                                     ull *maxval, u32 *bad, u32 *range) {
+    u64 m = 0; u32 z = 0, ninv = 0, omax = 0;
+    const u32 ref = col[0], half = (u32)(cols / 2);
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
         const u64 v = val[i];
-        m = v > m ? v : m; z |= (v == 0) | ((u64)col[i] >= cols);
+        const u32 c = col[i];
+        m = v > m ? v : m; z |= (v == 0) | ((u64)c >= cols);
+        long long t = (long long)c - (long long)ref + (long long)half;
+        if (t < 0) t += (long long)cols; else if (t >= (long long)cols) t -= (long long)cols;
+        ninv = max(ninv, ~(u32)t); omax = max(omax, (u32)t);
     }
     m = warp_max_u64(m);
     z = __any_sync(0xFFFFFFFFu, z);
-    if ((threadIdx.x & 31) == 0) { if (m) atomicMax(maxval, (ull)m); if (z) atomicOr(bad, 1u); }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) { ninv = max(ninv, __shfl_xor_sync(0xFFFFFFFFu, ninv, k)); omax = max(omax, __shfl_xor_sync(0xFFFFFFFFu, omax, k)); }
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicMax(maxval, (ull)m);
+        if (z) atomicOr(bad, 1u);
+        atomicMax(&range[0], ninv); atomicMax(&range[1], omax);
+        if (blockIdx.x == 0 && threadIdx.x == 0) range[2] = ref;
+    }
+}
+
+// Operand-wide circular column offsets of a square right operand: u = (c - k + n/2) mod n over the entries of every row k
+// with at most B200_CSPAN_MAXLEN entries, reduced to out[0] = max(~u), out[1] = max(u); out[2] counts the longer rows
+// (not scanned: with any of them present the operand has no useful bound).
+#define B200_CSPAN_MAXLEN 64
+__global__ void __launch_bounds__(256) k_cspan_bounds(u64 n, const u64 *__restrict__ rp, const u32 *__restrict__ col, u32 *out) {
+    const u32 half = (u32)(n / 2);
+    u32 ninv = 0, umax = 0, skipped = 0;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        const u64 s = rp[k], e = rp[k + 1];
+        if (e - s > B200_CSPAN_MAXLEN) { skipped++; continue; }
+        for (u64 j = s; j < e; j++) {
+            long long t = (long long)col[j] - (long long)k + (long long)half;
+            if (t < 0) t += (long long)n; else if (t >= (long long)n) t -= (long long)n;
+            ninv = max(ninv, ~(u32)t); umax = max(umax, (u32)t);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        ninv = max(ninv, __shfl_xor_sync(0xFFFFFFFFu, ninv, m)); umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, m));
+        skipped += __shfl_xor_sync(0xFFFFFFFFu, skipped, m);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], ninv); atomicMax(&out[1], umax); if (skipped) atomicAdd(&out[2], skipped); }
 }
 
 // longest row + row_ptr sanity for handles adopted from device arrays (the host never sees their row_ptr)

@@ -448,3 +448,37 @@ def test_circular_window_exact_mode(gpu_ctx, oracle, monkeypatch):
         p = p.matmul(a)
         p_o = oracle.matmul(p_o, a_o)
         assert_same(p.to_host(), p_o, f"A^{k}")
+
+
+# ------------------------------------------------------------------ operand-level arc windows (row blocks of a long torus: one window for all rows)
+@pytest.mark.parametrize("arc", ["1", "0"])
+@pytest.mark.parametrize("block", [(0, 500), (1800, 2400), (3600, 4096)])
+def test_arc_window_of_a_row_block(gpu_ctx, oracle, monkeypatch, arc, block):
+    """A GPU's row block of a 64 x 8 x 8 torus touches a short circular arc of the 4096 columns, and each multiply by A widens
+    the arc by A's column span.  With B200_ARC=1 the engine uses that arc as the one bitmap window of every row (blocks at
+    the ends of the index space wrap around it); with 0 it falls back to per-row windows.  Both must give the reference bytes."""
+    monkeypatch.setenv("B200_ARC", arc)
+    full = hostgen.lattice([64, 8, 8], True, 64)
+    a_h = hostgen.thin(full, 0.15, bytes([11] * 32))
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p = B200Matrix(gpu_ctx.row_block(a.device, block[0], block[1]))
+    p_o = to_o(oracle, a_h.row_block(block[0], block[1]))
+    for k in range(2, 7):
+        p = p.matmul(a, want_stats=True)
+        p_o = oracle.matmul(p_o, a_o)
+        assert_same(p.to_host(), p_o, f"A^{k} block={block} arc={arc}")
+
+
+def test_arc_window_exact_mode_and_add(gpu_ctx, oracle, monkeypatch):
+    """Arc windows with the exact-memory (count first) path, and a product handle that went through add() keeps a valid arc."""
+    monkeypatch.setenv("B200_EXACT", "1")
+    full = hostgen.lattice([64, 8, 8], True, 32)
+    a_h = hostgen.thin(full, 0.15, bytes([12] * 32))
+    a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
+    p = B200Matrix(gpu_ctx.row_block(a.device, 3900, 4096))
+    p_o = to_o(oracle, a_h.row_block(3900, 4096))
+    for k in range(2, 5):
+        q, q_o = p.matmul(a), oracle.matmul(p_o, a_o)
+        assert_same(q.to_host(), q_o, f"A^{k}")
+        p, p_o = q.add(q), oracle.add(q_o, q_o)
+        assert_same(p.to_host(), p_o, f"sum {k}")
