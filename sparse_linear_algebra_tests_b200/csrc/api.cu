@@ -191,10 +191,10 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_num_cta<VT, 0>, optin); allow_big_smem(k_num_cta<VT, 1>, optin);
     allow_big_smem(k_num_rank<VT, 0>, optin); allow_big_smem(k_num_rank<VT, 1>, optin);
     allow_big_smem(k_num_warp<VT, 0>, optin); allow_big_smem(k_num_warp<VT, 1>, optin);
-    allow_big_smem(k_num_expand<VT, 0, false, false>, optin); allow_big_smem(k_num_expand<VT, 0, false, true>, optin);
-    allow_big_smem(k_num_expand<VT, 0, true, false>, optin); allow_big_smem(k_num_expand<VT, 0, true, true>, optin);
-    allow_big_smem(k_num_expand<VT, 1, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, false, true>, optin);
-    allow_big_smem(k_num_expand<VT, 1, true, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, true>, optin);
+    allow_big_smem(k_num_expand<VT, 0, false, false, false>, optin); allow_big_smem(k_num_expand<VT, 0, false, false, true>, optin); allow_big_smem(k_num_expand<VT, 0, false, true, false>, optin); allow_big_smem(k_num_expand<VT, 0, false, true, true>, optin);
+    allow_big_smem(k_num_expand<VT, 0, true, false, false>, optin); allow_big_smem(k_num_expand<VT, 0, true, false, true>, optin); allow_big_smem(k_num_expand<VT, 0, true, true, false>, optin); allow_big_smem(k_num_expand<VT, 0, true, true, true>, optin);
+    allow_big_smem(k_num_expand<VT, 1, false, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, false, false, true>, optin); allow_big_smem(k_num_expand<VT, 1, false, true, false>, optin); allow_big_smem(k_num_expand<VT, 1, false, true, true>, optin);
+    allow_big_smem(k_num_expand<VT, 1, true, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, false, true>, optin); allow_big_smem(k_num_expand<VT, 1, true, true, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, true, true>, optin);
 }
 
 static int env_int_early(const char *name) { const char *v = getenv(name); return v && *v ? atoi(v) : 0; }
@@ -225,8 +225,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     static_assert(sizeof(B200Ctrl) <= B200_CTRL_BYTES, "control block outgrew its slot");
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));   // + the epoch word the final scan publishes
     memset(ctx->h_ctrl, 0, sizeof(B200Ctrl) + 64);
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 64));
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 64));
+    CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 128));
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 128));
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     for (int i = 0; i < B200_NAUX; i++) { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -242,8 +242,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     allow_big_smem(k_num_cta<u64, 2>, ctx->smem_optin); allow_big_smem(k_num_rank<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_num_warp<u64, 2>, ctx->smem_optin);
     allow_big_smem(k_sym_expand<false>, ctx->smem_optin); allow_big_smem(k_sym_expand<true>, ctx->smem_optin);
-    allow_big_smem(k_num_expand<u64, 2, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true>, ctx->smem_optin);
-    allow_big_smem(k_num_expand<u64, 2, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true>, ctx->smem_optin);
+    allow_big_smem(k_num_expand<u64, 2, false, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, false, true>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, false, true, true>, ctx->smem_optin);
+    allow_big_smem(k_num_expand<u64, 2, true, false, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, false, true>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true, false>, ctx->smem_optin); allow_big_smem(k_num_expand<u64, 2, true, true, true>, ctx->smem_optin);
     cudaGetLastError();
     *out = ctx;
     return B200_OK;
@@ -320,28 +320,33 @@ static int grid_for(u64 n, int threads, int cap) { u64 g = (n + threads - 1) / t
 static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr = false) {
     CUDA_TRY(cudaMemsetAsync(m->d_maxval, 0, 16, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 32, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 16, 0, 36, ctx->stream));
     if (device_rowptr && m->rows) {
         k_rowptr_stats<<<grid_for(m->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(m->rows, m->nnz, m->d_rp, ctx->d_flag + 4, ctx->d_flag);
         LAUNCH_CHECK(ctx);
     }
     if (m->nnz) {
         int g = grid_for(m->nnz, 256, ctx->num_sms * 8);
-        if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 5);
-        else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 5);
+        if (m->val_bits == 32) k_value_stats<u32><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u32 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 16);
+        else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 16);
         LAUNCH_CHECK(ctx);
     }
     if (check) {
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 128, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_flag[0] & 2u) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone from 0 to nnz");
         if (ctx->h_flag[0]) return set_err(B200_ERR_FORMAT, "CSR holds an explicit zero value or a column index >= cols");
         if (device_rowptr) m->max_row_len = ctx->h_flag[4];
         if (m->nnz && m->cols) {                                            // circular column range (see k_value_stats)
-            const long long n = (long long)m->cols, half = n / 2;
-            const long long omin = (long long)(~ctx->h_flag[5]), omax = (long long)ctx->h_flag[6], ref = (long long)ctx->h_flag[7];
-            long long start = ref + omin - half;
-            start %= n; if (start < 0) start += n;
-            m->cr_start = (u32)start; m->cr_len = (u64)(omax - omin + 1);
+            const long long n = (long long)m->cols, half = n / 2, quarter = n / 4, ref = (long long)ctx->h_flag[24];
+            m->cr_start = 0; m->cr_len = m->cols;
+            for (int f = 0; f < 4; f++) {                                   // shortest arc over the four cuts
+                const long long omin = (long long)(~ctx->h_flag[16 + 2 * f]), omax = (long long)ctx->h_flag[17 + 2 * f];
+                if (omax < omin || (u64)(omax - omin + 1) >= m->cr_len) continue;
+                long long start = ref + omin - half + (long long)f * quarter;
+                start %= n; if (start < 0) start += n;
+                m->cr_start = (u32)start; m->cr_len = (u64)(omax - omin + 1);
+            }
         }
     }
     return B200_OK;
@@ -597,6 +602,14 @@ static int wait_for_report(b200_ctx *ctx, u32 epoch) {
     return B200_OK;
 }
 
+// row_ptr scan: 8192-row tiles (1024 threads) while that still fills the GPU's latency budget, 2048-row tiles beyond
+static void launch_scan_rowptr(b200_ctx *ctx, u64 rows, u64 *rp, cudaStream_t s, B200Ctrl *host_mirror, u32 epoch) {
+    if (rows <= (1ull << 19))
+        k_scan_rowptr<1024><<<(unsigned)((rows + 1024 * SCAN_ITEMS - 1) / (1024 * SCAN_ITEMS)), 1024, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
+    else
+        k_scan_rowptr<SCAN_THREADS><<<(unsigned)((rows + SCAN_TILE - 1) / SCAN_TILE), SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
+}
+
 // Independent per-bin kernels are spread over the main stream and a few auxiliary streams.
 struct Fan {
     b200_ctx *ctx; int next; bool used[B200_NAUX]; bool forked;
@@ -637,6 +650,25 @@ static int pick_mode(u64 max_row_products, u64 maxA, u64 maxB) {
     return mode;
 }
 
+// k_num_expand's compile-time switches (packed B records, pattern-only B, touched-span tracking) from run-time flags
+template <typename VT, int MODE>
+static void expand_dispatch(bool packed, bool bpat, bool span, int eg, int et, size_t smem, cudaStream_t bs, const NumArgs<VT> &na,
+                            const uint4 *pack, const u32 *bin_rows, B200Ctrl *ctrl, int bin, int nb, u32 pcap, u32 ncap, u32 nw4,
+                            const uint4 *win, u32 ncols, const OutArgs<VT> &o) {
+#define K(P, Q, S) k_num_expand<VT, MODE, P, Q, S><<<eg, et, smem, bs>>>(na, P ? pack : nullptr, bin_rows, ctrl, bin, nb, pcap, ncap, nw4, win, ncols, o)
+    switch ((packed ? 4 : 0) | (bpat ? 2 : 0) | (span ? 1 : 0)) {
+        case 0: K(false, false, false); break;
+        case 1: K(false, false, true); break;
+        case 2: K(false, true, false); break;
+        case 3: K(false, true, true); break;
+        case 4: K(true, false, false); break;
+        case 5: K(true, false, true); break;
+        case 6: K(true, true, false); break;
+        default: K(true, true, true); break;
+    }
+#undef K
+}
+
 // Launch the numeric kernels of every list the pre-pass filled.  The list sizes live on the device only, so grids are
 // sized from `rows` and bins that no row can reach (p_bound) are skipped.
 template <typename VT>
@@ -670,11 +702,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         const u64 gdiv = (u64)std::max(1, env_int("B200_GDIV", 8)), gmul = (u64)std::max(1, env_int("B200_GMUL", 4));
         const int eg = (int)std::max<u64>(1, std::min<u64>((n + gdiv - 1) / gdiv, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * gmul));
         if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
+        const bool span = (int)nw4 > et && env_int("B200_SPAN", 1);       // more bitmap groups than threads: walk only the groups a row touches
 #define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
-        do { if (packed) { if (bpat) k_num_expand<VTT, MODE, true, true><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); \
-                           else k_num_expand<VTT, MODE, true, false><<<eg, et, ex_smem, bs>>>(NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); }   \
-             else { if (bpat) k_num_expand<VTT, MODE, false, true><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO);         \
-                    else k_num_expand<VTT, MODE, false, false><<<eg, et, ex_smem, bs>>>(NA, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO); } } while (0)
+        expand_dispatch<VTT, MODE>(packed, bpat, span, eg, et, ex_smem, bs, NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO)
         if (mode == 0) EXPAND(0, VT, na, o);
         else if (mode == 1) EXPAND(1, VT, na, o);
         else EXPAND(2, u64, na64, o64);
@@ -977,7 +1007,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
-            k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, ctx->h_ctrl, epoch);
+            launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_ctrl, epoch);
             LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(ctx->ev[1], s);
             r = wait_for_report(ctx, epoch);
@@ -1027,7 +1057,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         fan.join();
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
-        k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl, ctx->h_ctrl, epoch);
+        launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_ctrl, epoch);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
         r = wait_for_report(ctx, epoch);
@@ -1147,7 +1177,7 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);
     LAUNCH_CHECK(ctx);
-    k_scan_rowptr<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, C->d_rp, ctx->d_tile_status, ctx->d_ctrl);
+    launch_scan_rowptr(ctx, rows, C->d_rp, s, nullptr, 0);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

@@ -1012,7 +1012,7 @@ __device__ __forceinline__ BRowRef load_brow(const uint4 *__restrict__ pack, con
 #define B200_EXPAND_REC_EARLY 1   // 1: next row's B records are fetched right after the rank phase (live across accumulate + emit)
 #define B200_EXPAND_ILP 2   // products each thread keeps in flight in the mark / accumulate loops
 
-template <typename VT, int MODE, bool PACK, bool BPAT>
+template <typename VT, int MODE, bool PACK, bool BPAT, bool SPAN>
 __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *__restrict__ pack, const u32 *__restrict__ bin_rows,
                                                     B200Ctrl *ctrl, int bin, int nbins, u32 pcap, u32 ncap, u32 nw4,
                                                     const uint4 *__restrict__ win, u32 ncols, OutArgs<VT> o) {
@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     constexpr int E = B200_EXPAND_PRE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
-    __shared__ u32 s_P;
+    __shared__ u32 s_P, s_wlo, s_whi;
     __shared__ EnumStore<!PACK> s_enum;                                     // only the non-packed expansion needs it
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += o.bin_cnt[bin + b];            // consecutive bins share one launch
@@ -1043,7 +1043,10 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     for (u32 t = tid; t < nw4; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
     for (u32 t = tid; t < ncap; t += nt) acc.clear(t);
-    if (tid == 0) s_P = 0;
+    if (tid == 0) { s_P = 0; s_wlo = 0xFFFFFFFFu; s_whi = 0; }
+    // SPAN (bitmaps with more groups than the CTA has threads): the products also track the bitmap words they touch, and
+    // the rank, emit and clear phases walk only the groups between the lowest and the highest of them.
+    u32 wlo = 0xFFFFFFFFu, whi = 0;
     // The row's column window.  Columns are first rotated, d = (c - rot) mod ncols (rot = 0 unless the pre-pass built
     // circular windows), then bitmap word 0 is d-word `wbase` (a multiple of four), `groups` 128-column groups long.
     u32 wbase = 0, groups = nw4, rot = 0;
@@ -1054,7 +1057,9 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         if (PAIR) pp[dst] = make_uint2(c, (u32)x);
         else { pc[dst] = c; pv[dst] = (u64)x; }
         const u32 d = dcol(c);
-        atomicOr(&bm[(d >> 5) - wbase], __funnelshift_l(0u, 1u, d));         // mark the column while it is in a register
+        const u32 w = (d >> 5) - wbase;
+        atomicOr(&bm[w], __funnelshift_l(0u, 1u, d));                        // mark the column while it is in a register
+        if (SPAN) { wlo = min(wlo, w); whi = max(whi, w); }
     };
     // products of one warp's 32 A entries -> a slice of the product buffer
     auto expand32 = [&](bool valid, VT av, const BRowRef &b) {
@@ -1130,9 +1135,16 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             if (PACK && has_next && t < lenA_n) { kn[e] = a.colA[rs_n + t]; avn[e] = a.valA[rs_n + t]; }
         }
         if (r + 2 < r_end) row_nn = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r + 2);
+        if (SPAN) {
+            wlo = __reduce_min_sync(0xFFFFFFFFu, wlo); whi = __reduce_max_sync(0xFFFFFFFFu, whi);
+            if (lane == 0 && wlo <= whi) { atomicMin(&s_wlo, wlo); atomicMax(&s_whi, whi); }
+            wlo = 0xFFFFFFFFu; whi = 0;
+        }
         __syncthreads();
         const u32 P = s_P;
-        const u32 nnz = rank_prefix_v4(bm4, wpre4, groups, s_warp);
+        u32 g0 = 0, gn = groups;                                             // groups that hold a product
+        if (SPAN) { const u32 lo = s_wlo, hi = s_whi; g0 = lo <= hi ? lo >> 2 : 0u; gn = lo <= hi ? (hi >> 2) - g0 + 1 : 0u; }
+        const u32 nnz = rank_prefix_v4(bm4 + g0, wpre4 + g0, gn, s_warp);
 #if B200_EXPAND_REC_EARLY
 #pragma unroll
         for (int e = 0; e < E; e++) {
@@ -1171,9 +1183,9 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         u32 r0 = nnz;
         if (rot) {
             const u32 split = ncols - rot;                                   // first d that maps to a column below rot
-            const u32 wlo = wbase << 5, whi = wlo + (groups << 7);
-            if (split <= wlo) r0 = 0;
-            else if (split < whi) { const u32 sw = (split >> 5) - wbase; r0 = (u32)wpre[sw] + __popc(bm[sw] & (__funnelshift_l(0u, 1u, split) - 1u)); }
+            const u32 slo = (wbase << 5) + (g0 << 7), shi = slo + (gn << 7);  // d range whose prefixes are valid (holds every entry)
+            if (split <= slo) r0 = 0;
+            else if (split < shi) { const u32 sw = (split >> 5) - wbase; r0 = (u32)wpre[sw] + __popc(bm[sw] & (__funnelshift_l(0u, 1u, split) - 1u)); }
         }
         const u32 shift_hi = nnz - r0;                                       // d-rank t -> t - r0 (t >= r0) or t + shift_hi
         for (u32 t0 = tid; t0 < nnz; t0 += 2 * nt) {
@@ -1199,8 +1211,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             av[e] = avn[e];
         }
 #endif
-        for (u32 t = tid; t < groups; t += nt) bm4[t] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { s_P = 0; if (o.nnz_out) o.nnz_out[row] = nnz; }
+        for (u32 t = tid; t < gn; t += nt) bm4[g0 + t] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) { s_P = 0; if (SPAN) { s_wlo = 0xFFFFFFFFu; s_whi = 0; } if (o.nnz_out) o.nnz_out[row] = nnz; }
         __syncthreads();
         row = row_n; rs = rs_n; lenA = lenA_n; wbase = wn.x >> 5; groups = wn.y; rot = wn.z;
         row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn; wn = wnn;
@@ -1395,20 +1407,22 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 }
 
 // =======================================================================================
-// 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64); its last CTA reports to the host
+// 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64); its last CTA reports to the host.
+//    Tiles of THREADS*8 rows: 1024-thread tiles keep the look-back chain of a small matrix a few tiles long.
 // =======================================================================================
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
                                                               u64 *tile_status, B200Ctrl *ctrl,
                                                               B200Ctrl *host_mirror = nullptr, u32 epoch = 0) {
     __shared__ u32 s_tile, s_last;
-    __shared__ u64 s_wsum[SCAN_THREADS / 32];
+    __shared__ u64 s_wsum[THREADS / 32];
     __shared__ u64 s_excl;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket[0], 1u);            // tiles start in ticket order
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 base = (u64)tile * SCAN_TILE + (u64)tid * SCAN_ITEMS;
+    const u64 base = (u64)tile * (THREADS * SCAN_ITEMS) + (u64)tid * SCAN_ITEMS;
     u32 item[SCAN_ITEMS]; u64 tsum = 0; u32 tmaxv = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
@@ -1422,7 +1436,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_rowptr(u64 rows, const u3
     __syncthreads();
     u64 wbase = 0, agg = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_THREADS / 32; i++) { if (i < w) wbase += s_wsum[i]; agg += s_wsum[i]; }
+    for (int i = 0; i < THREADS / 32; i++) { if (i < w) wbase += s_wsum[i]; agg += s_wsum[i]; }
     const u64 texcl = wbase + incl - tsum;                                   // exclusive within the tile
     // publish the tile aggregate, then look back over the predecessors
     if (w == 0) {
@@ -1511,30 +1525,41 @@ __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__res
 // =======================================================================================
 // Largest value, format check, and the circular column range of the matrix: offsets o = (c - col[0] + cols/2) mod cols of
 // all its columns, reduced to range[0] = max(~o) (i.e. the minimum, kept as a maximum so that a zeroed word is its
-// identity), range[1] = max(o), range[2] = col[0].  A row block of a banded / torus matrix covers a short arc of the
+// identity), range[1] = max(o), in four frames (range[2f], range[2f+1]: the circle cut at ref + n/2 + f*(n/4), so that any arc
+// of at most three quarters of the circle is seen unbroken by one of them), range[8] = col[0].  A row block of a banded / torus matrix covers a short arc of the
 // index circle even when it wraps around its end; the host turns the arc into one bitmap window for the whole multiply.
 template <typename VT>
 __global__ void __launch_bounds__(256) k_value_stats(u64 nnz, const VT *__restrict__ val, const u32 *__restrict__ col, u64 cols,
                                                      ull *maxval, u32 *bad, u32 *range) {
-    u64 m = 0; u32 z = 0, ninv = 0, omax = 0;
-    const u32 ref = col[0], half = (u32)(cols / 2);
+    u64 m = 0; u32 z = 0;
+    u32 ninv[4] = {0, 0, 0, 0}, omax[4] = {0, 0, 0, 0};
+    const u32 ref = col[0], half = (u32)(cols / 2), quarter = (u32)(cols / 4);
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (u64)gridDim.x * blockDim.x) {
         const u64 v = val[i];
         const u32 c = col[i];
         m = v > m ? v : m; z |= (v == 0) | ((u64)c >= cols);
         long long t = (long long)c - (long long)ref + (long long)half;
         if (t < 0) t += (long long)cols; else if (t >= (long long)cols) t -= (long long)cols;
-        ninv = max(ninv, ~(u32)t); omax = max(omax, (u32)t);
+#pragma unroll
+        for (int f = 0; f < 4; f++) {                                       // frame f: the circle cut f quarters further on
+            long long tf = t - (long long)f * quarter;
+            if (tf < 0) tf += (long long)cols;
+            ninv[f] = max(ninv[f], ~(u32)tf); omax[f] = max(omax[f], (u32)tf);
+        }
     }
     m = warp_max_u64(m);
     z = __any_sync(0xFFFFFFFFu, z);
 #pragma unroll
-    for (int k = 16; k > 0; k >>= 1) { ninv = max(ninv, __shfl_xor_sync(0xFFFFFFFFu, ninv, k)); omax = max(omax, __shfl_xor_sync(0xFFFFFFFFu, omax, k)); }
+    for (int f = 0; f < 4; f++) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) { ninv[f] = max(ninv[f], __shfl_xor_sync(0xFFFFFFFFu, ninv[f], k)); omax[f] = max(omax[f], __shfl_xor_sync(0xFFFFFFFFu, omax[f], k)); }
+    }
     if ((threadIdx.x & 31) == 0) {
         if (m) atomicMax(maxval, (ull)m);
         if (z) atomicOr(bad, 1u);
-        atomicMax(&range[0], ninv); atomicMax(&range[1], omax);
-        if (blockIdx.x == 0 && threadIdx.x == 0) range[2] = ref;
+#pragma unroll
+        for (int f = 0; f < 4; f++) { atomicMax(&range[2 * f], ninv[f]); atomicMax(&range[2 * f + 1], omax[f]); }
+        if (blockIdx.x == 0 && threadIdx.x == 0) range[8] = ref;
     }
 }
 
