@@ -68,6 +68,7 @@ struct b200_ctx {
     u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint4 *d_win;
     // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
     unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
+    size_t scan_clean_bytes;   // leading bytes of d_scan known to be zero on the stream (left so by k_compact_rows)
     // heavy-row scratch
     void *d_heavy; size_t cap_heavy;
     // one-pass scratch CSR (bound-offset rows), kept across multiplies so the steady state allocates nothing
@@ -82,8 +83,10 @@ struct b200_ctx {
     u64 launches;
     // developer timeline (B200_TRACE=1): an event after every launch, on the stream it went to
     bool trace; cudaStream_t cur_stream;
+    bool hosttime; double ht[8];   // B200_HOSTTIME=1: host clock at the phase boundaries of a multiply (dev tool)
     std::vector<std::pair<int, cudaEvent_t>> *marks;
 };
+static inline double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
 static void trace_mark(b200_ctx *ctx, int line) {
     cudaEvent_t e; cudaEventCreate(&e);
     cudaEventRecord(e, ctx->cur_stream ? ctx->cur_stream : ctx->stream);
@@ -137,7 +140,7 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     }
     const u64 tiles = (rows + SCAN_TILE - 1) / SCAN_TILE + 1, tiles_pre = rows / 8 + 2;  // pre-pass: >= 8 rows per CTA
     if (!ctx->d_scan || tiles > ctx->cap_tiles || tiles_pre > ctx->cap_tiles_pre) {
-        dfree(ctx, ctx->d_scan); ctx->d_scan = nullptr;
+        dfree(ctx, ctx->d_scan); ctx->d_scan = nullptr; ctx->scan_clean_bytes = 0;
         const u64 ct = tiles + 64, cp = tiles_pre + tiles_pre / 8 + 1024;
         TRY(dmalloc(ctx, (void **)&ctx->d_scan, B200_CTRL_BYTES + (ct + cp) * 8));
         ctx->d_ctrl = (B200Ctrl *)ctx->d_scan;
@@ -148,8 +151,12 @@ static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     return B200_OK;
 }
 // zero the control block and the scan status words a multiply over `rows` rows will use
+// (skipped when the previous multiply's compaction kernel already left them zeroed: scan_clean_bytes)
 static cudaError_t reset_scan(b200_ctx *ctx, u64 tiles_pre) {
-    return cudaMemsetAsync(ctx->d_scan, 0, B200_CTRL_BYTES + (ctx->cap_tiles + tiles_pre) * 8, ctx->stream);
+    const size_t need = B200_CTRL_BYTES + (ctx->cap_tiles + tiles_pre) * 8;
+    const bool clean = ctx->scan_clean_bytes >= need;
+    ctx->scan_clean_bytes = 0;                                             // whoever asked is about to use the area
+    return clean ? cudaSuccess : cudaMemsetAsync(ctx->d_scan, 0, need, ctx->stream);
 }
 static int ensure_tmp(b200_ctx *ctx, size_t col_bytes, size_t val_bytes) {
     if (col_bytes > ctx->cap_tmp_col) {
@@ -235,6 +242,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     // one auxiliary stream measured as good as three, with half the event calls
     { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : 1; }
     ctx->timing = true;
+    ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
     setup_kernels_vt<u32>(ctx->smem_optin);
     setup_kernels_vt<u64>(ctx->smem_optin);
@@ -484,7 +492,16 @@ extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_
 }
 
 // ---------------------------------------------------------------------------- SpGEMM
-static int env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
+// Developer switches (B200_*) are read per multiply so tests can flip them; a multiply looks at ~40 of them, so the
+// environment is scanned once per call and the lookups are skipped entirely when no B200_ variable is set.
+extern char **environ;
+static bool g_env_any = true;
+static void env_refresh() {
+    bool any = false;
+    for (char **e = environ; e && *e; e++) if (!strncmp(*e, "B200_", 5)) { any = true; break; }
+    g_env_any = any;
+}
+static int env_int(const char *name, int dflt) { if (!g_env_any) return dflt; const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
 // lanes cooperating on one A entry while walking its B row: largest power of two <= mean B row length / 2
 static int pick_lg(const b200_csr *B, int max_lg) {
@@ -908,10 +925,12 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool cheap_bound = hb128 * esz <= (unsigned __int128)(total_b / 16);
 
     if (timing) cudaEventRecord(ctx->ev[0], s);
+    if (ctx->hosttime) ctx->ht[0] = host_now_us();
     if (ctx->trace) trace_mark(ctx, __LINE__);
     const unsigned row_grid = (unsigned)((rows + 255) / 256);
     const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
     u64 tmp_entries = 0;
+    size_t scan_bytes = 0;                                                // control block + scan status words this multiply uses
     const int mode1 = pick_mode<VT>(p_bound, maxA, maxB);                 // one-pass accumulator width (host-side bound)
     // Per hash bin: the largest column window (in 128-column groups) its k_num_expand bitmap holds.  Narrow column
     // spaces fit whole; otherwise a bin with capacity P gets a window of 384*P columns (at most 512 K columns): on the
@@ -960,6 +979,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const int G = avgA <= 2.0 ? 1 : avgA <= 6.0 ? 4 : avgA <= 24.0 ? 8 : 32;
         const u64 tile_rows = std::max(256 / G, B200_PREPASS_MIN_ROWS);   // B200_PREPASS_ROWS(G)
         const u64 tiles_pre = (rows + tile_rows - 1) / tile_rows;
+        scan_bytes = B200_CTRL_BYTES + (ctx->cap_tiles + tiles_pre) * 8;
         CUDA_TRY(reset_scan(ctx, tiles_pre));
         // column windows only matter when some bin's bitmap is narrower than B; square operands get circular windows
         bool windows = false;
@@ -1053,14 +1073,18 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
         }
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride};
+        if (ctx->hosttime) ctx->ht[1] = host_now_us();                       // pre-pass enqueued
         if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
         fan.join();
+        if (ctx->hosttime) ctx->ht[2] = host_now_us();                       // numeric kernels enqueued
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
         launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_ctrl, epoch);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
+        if (ctx->hosttime) ctx->ht[3] = host_now_us();                       // scan enqueued
         r = wait_for_report(ctx, epoch);
+        if (ctx->hosttime) ctx->ht[4] = host_now_us();                       // report seen
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const B200Ctrl hc = *ctx->h_ctrl;
         C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
@@ -1073,8 +1097,10 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
             const u64 want = (rows << llg) / 256 + 1;
             k_compact_rows<VT><<<(unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64), 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg,
-                                                                                                      &ctx->d_ctrl->max_val_out, C->d_maxval);
+                                                                                                      &ctx->d_ctrl->max_val_out, C->d_maxval,
+                                                                                                      (u64 *)ctx->d_scan, B200_CTRL_BYTES / 8, scan_bytes / 8);
             LAUNCH_CHECK(ctx);
+            ctx->scan_clean_bytes = scan_bytes;
         }
         if (timing) cudaEventRecord(ctx->ev[3], s);
         if (st) {
@@ -1083,7 +1109,14 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
             for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
             if (timing) {
+                if (ctx->hosttime) ctx->ht[5] = host_now_us();               // compaction enqueued
                 CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+                if (ctx->hosttime) {
+                    float g1 = 0, g2 = 0, g3 = 0;
+                    cudaEventElapsedTime(&g1, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&g2, ctx->ev[0], ctx->ev[2]); cudaEventElapsedTime(&g3, ctx->ev[0], ctx->ev[3]);
+                    fprintf(stderr, "[b200 hosttime] host us: prepass queued %.1f, numeric queued %.1f, scan queued %.1f, report seen %.1f, compaction queued %.1f | gpu us: scan done %.1f, alloc point %.1f, compaction done %.1f\n",
+                            ctx->ht[1] - ctx->ht[0], ctx->ht[2] - ctx->ht[0], ctx->ht[3] - ctx->ht[0], ctx->ht[4] - ctx->ht[0], ctx->ht[5] - ctx->ht[0], g1 * 1e3, g2 * 1e3, g3 * 1e3);
+                }
                 cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[2], ctx->ev[3]);   // one-pass: compaction of the scratch rows
                 cudaEventElapsedTime(&st->ms_numeric, ctx->ev[0], ctx->ev[1]);    // counts + bins + numeric kernels + row_ptr scan
                 cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
@@ -1102,6 +1135,7 @@ extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, 
     if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch: A is %llux%llu, B is %llux%llu", (ull)A->rows, (ull)A->cols, (ull)B->rows, (ull)B->cols);
     if (A->val_bits != B->val_bits) return set_err(B200_ERR_SHAPE, "value width mismatch: A is u%d, B is u%d", A->val_bits, B->val_bits);
     CUDA_TRY(cudaSetDevice(ctx->device));
+    env_refresh();
     return A->val_bits == 32 ? spgemm_typed<u32>(ctx, A, B, C, stats) : spgemm_typed<u64>(ctx, A, B, C, stats);
 }
 

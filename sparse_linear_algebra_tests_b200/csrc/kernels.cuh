@@ -1047,17 +1047,18 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     // SPAN (bitmaps with more groups than the CTA has threads): the products also track the bitmap words they touch, and
     // the rank, emit and clear phases walk only the groups between the lowest and the highest of them.
     u32 wlo = 0xFFFFFFFFu, whi = 0;
-    // The row's column window.  Columns are first rotated, d = (c - rot) mod ncols (rot = 0 unless the pre-pass built
-    // circular windows), then bitmap word 0 is d-word `wbase` (a multiple of four), `groups` 128-column groups long.
-    u32 wbase = 0, groups = nw4, rot = 0;
-    auto dcol = [&](u32 c) -> u32 { return c >= rot ? c - rot : c - rot + ncols; };
+    // The row's column window: bit d of the bitmap is column (org + d) mod ncols, `groups` 128-column groups long.  The
+    // pre-pass hands out {first bit in the rotated column space, groups, rotation}; org folds the two offsets into one.
+    u32 groups = nw4, org = 0;
+    auto dcol = [&](u32 c) -> u32 { return c >= org ? c - org : c - org + ncols; };
+    auto origin = [&](const uint4 &wn) -> u32 { const u64 t = (u64)wn.x + wn.z; return (u32)(t >= ncols ? t - ncols : t); };
 
     auto put = [&](u32 dst, VT av, u32 c, u32 jb) {
         const PV x = BPAT ? (PV)av : product_value<MODE, VT>(av, a.valB[jb]);
         if (PAIR) pp[dst] = make_uint2(c, (u32)x);
         else { pc[dst] = c; pv[dst] = (u64)x; }
         const u32 d = dcol(c);
-        const u32 w = (d >> 5) - wbase;
+        const u32 w = d >> 5;
         atomicOr(&bm[w], __funnelshift_l(0u, 1u, d));                        // mark the column while it is in a register
         if (SPAN) { wlo = min(wlo, w); whi = max(whi, w); }
     };
@@ -1089,7 +1090,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
     u64 rs = a.rpA[row];
     u32 lenA = (u32)(a.rpA[row + 1] - rs);
     uint4 wn = win[row];
-    wbase = wn.x >> 5; groups = wn.y; rot = wn.z;
+    groups = wn.y; org = origin(wn);
     u32 row_n = 0, lenA_n = 0; u64 rs_n = 0;
     wn = make_uint4(0, 0, 0, 0);
     if (r_begin + 1 < r_end) { row_n = bin_row_at(bin_rows, o.bin_cnt, o.bin_stride, bin, nbins, r_begin + 1); rs_n = a.rpA[row_n]; lenA_n = (u32)(a.rpA[row_n + 1] - rs_n); wn = win[row_n]; }
@@ -1168,8 +1169,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             }
 #pragma unroll
             for (int j = 0; j < B200_EXPAND_ILP; j++) {
-                const u32 dd = c[j] != B200_EMPTY_KEY ? dcol(c[j]) : wbase << 5;   // padding lanes read word 0
-                const u32 w = (dd >> 5) - wbase;
+                const u32 dd = c[j] != B200_EMPTY_KEY ? dcol(c[j]) : 0u;          // padding lanes read word 0
+                const u32 w = dd >> 5;
                 pos[j] = (u32)wpre[w] + __popc(bm[w] & (__funnelshift_l(0u, 1u, dd) - 1u));
             }
 #pragma unroll
@@ -1177,15 +1178,15 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
                 if (c[j] != B200_EMPTY_KEY) { cols[pos[j]] = c[j]; acc.addv(pos[j], x[j]); }
         }
         __syncthreads();
-        // ---- emit (coalesced), leaving accumulators, bitmap and the product counter clean.  Ranks are in d order; with a
-        // rotated window the entries whose column is below `rot` (d >= ncols - rot) belong in FRONT of the others: the
-        // row is written rotated by r0 = number of entries with d < ncols - rot.
+        // ---- emit (coalesced), leaving accumulators, bitmap and the product counter clean.  Ranks are in d order; when the
+        // window starts at a column org > 0 the entries whose column is below org (d >= ncols - org) belong in FRONT of
+        // the others: the row is written rotated by r0 = number of entries with d < ncols - org.
         u32 r0 = nnz;
-        if (rot) {
-            const u32 split = ncols - rot;                                   // first d that maps to a column below rot
-            const u32 slo = (wbase << 5) + (g0 << 7), shi = slo + (gn << 7);  // d range whose prefixes are valid (holds every entry)
+        if (org) {
+            const u32 split = ncols - org;                                   // first d that maps to a column below org
+            const u32 slo = g0 << 7, shi = slo + (gn << 7);                  // d range whose prefixes are valid (holds every entry)
             if (split <= slo) r0 = 0;
-            else if (split < shi) { const u32 sw = (split >> 5) - wbase; r0 = (u32)wpre[sw] + __popc(bm[sw] & (__funnelshift_l(0u, 1u, split) - 1u)); }
+            else if (split < shi) { const u32 sw = split >> 5; r0 = (u32)wpre[sw] + __popc(bm[sw] & (__funnelshift_l(0u, 1u, split) - 1u)); }
         }
         const u32 shift_hi = nnz - r0;                                       // d-rank t -> t - r0 (t >= r0) or t + shift_hi
         for (u32 t0 = tid; t0 < nnz; t0 += 2 * nt) {
@@ -1214,7 +1215,7 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
         for (u32 t = tid; t < gn; t += nt) bm4[g0 + t] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { s_P = 0; if (SPAN) { s_wlo = 0xFFFFFFFFu; s_whi = 0; } if (o.nnz_out) o.nnz_out[row] = nnz; }
         __syncthreads();
-        row = row_n; rs = rs_n; lenA = lenA_n; wbase = wn.x >> 5; groups = wn.y; rot = wn.z;
+        row = row_n; rs = rs_n; lenA = lenA_n; groups = wn.y; org = origin(wn);
         row_n = row_nn; rs_n = rs_nn; lenA_n = lenA_nn; wn = wnn;
     }
     vmax = warp_max_u64(vmax);
@@ -1499,10 +1500,19 @@ template <typename VT>
 __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__restrict__ src_ptr, const u64 *__restrict__ rpC,
                                                       const u32 *__restrict__ src_col, const VT *__restrict__ src_val,
                                                       u32 *__restrict__ colC, VT *__restrict__ valC, int lanes_lg,
-                                                      const ull *max_val_src, ull *max_val_dst) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *max_val_dst = *max_val_src;    // the product's max-value scalar rides along
-    const u32 L = 1u << lanes_lg;                                           // lanes per row
+                                                      const ull *max_val_src, ull *max_val_dst,
+                                                      u64 *scan_area, u32 ctrl_words, u64 scan_words) {
     const u64 gthread = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    // The last kernel of a multiply: the product's max-value scalar rides along, and the control block and scan status
+    // words (scan_area[0..scan_words), the first ctrl_words of them the control block that holds the scalar) are left
+    // zeroed, so the next multiply starts without a memset.
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) *max_val_dst = *max_val_src;
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < ctrl_words; i += blockDim.x) scan_area[i] = 0;
+    }
+    for (u64 i = ctrl_words + gthread; i < scan_words; i += (u64)gridDim.x * blockDim.x) scan_area[i] = 0;
+    const u32 L = 1u << lanes_lg;                                           // lanes per row
     const u64 nsub = ((u64)gridDim.x * blockDim.x) >> lanes_lg;
     const u32 sub = threadIdx.x & (L - 1);
     for (u64 row = gthread >> lanes_lg; row < rows; row += nsub) {
