@@ -64,6 +64,7 @@ struct b200_ctx {
     size_t smem_optin, total_mem;
     cudaStream_t stream; bool own_stream;
     B200Ctrl *d_ctrl, *h_ctrl;
+    u64 *h_report;          // pinned: the final scan's report, one {word, epoch} chunk per 32-bit word of the control block
     // per-row scratch, grown on demand
     u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint4 *d_win;
     // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
@@ -230,8 +231,10 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     uint64_t thresh = UINT64_MAX;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     static_assert(sizeof(B200Ctrl) <= B200_CTRL_BYTES, "control block outgrew its slot");
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));   // + the epoch word the final scan publishes
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));
     memset(ctx->h_ctrl, 0, sizeof(B200Ctrl) + 64);
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_report, sizeof(B200Ctrl) * 2));
+    memset(ctx->h_report, 0, sizeof(B200Ctrl) * 2);
     CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 128));
     CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 128));
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -264,7 +267,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
     cudaStreamSynchronize(ctx->stream);
-    cudaFreeHost(ctx->h_ctrl); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
+    cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
@@ -598,29 +601,37 @@ static int launch_row_products(b200_ctx *ctx, const b200_csr *A, const b200_csr 
     return B200_OK;
 }
 
-// The final scan's last CTA writes the control block and then the epoch word into pinned host memory; polling that word
-// costs a PCIe write latency instead of a memcpy + stream synchronise.  A stream query every so often catches a failed
-// launch (the word would never arrive).
+// The final scan's last CTA writes the control block into pinned host memory as {word, epoch} chunks; the host waits until
+// every chunk carries this multiply's epoch and reassembles the block into ctx->h_ctrl.  This costs one PCIe write latency
+// instead of a memcpy + stream synchronise.  A stream query every so often catches a failed launch (the chunks would
+// never arrive).
 static int wait_for_report(b200_ctx *ctx, u32 epoch) {
-    volatile u32 *word = reinterpret_cast<volatile u32 *>(ctx->h_ctrl) + sizeof(B200Ctrl) / 4;
-    for (u64 spins = 1; *word != epoch; spins++) {
-        if ((spins & 0xFFF) == 0) {
-            const cudaError_t q = cudaStreamQuery(ctx->stream);
-            if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
-            if (q != cudaSuccess) return set_err(B200_ERR_CUDA, "multiply failed on the device: %s", cudaGetErrorString(q));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));                  // finished: the report must be there now
-            if (*word != epoch) return set_err(B200_ERR_CUDA, "the row_ptr scan finished without reporting (epoch %u)", epoch);
-        }
+    volatile u64 *chunk = ctx->h_report;
+    u32 *out = reinterpret_cast<u32 *>(ctx->h_ctrl);
+    const u32 n = sizeof(B200Ctrl) / 4;
+    u64 spins = 0;
+    for (u32 i = 0; i < n; i++) {
+        u64 c;
+        while ((u32)((c = chunk[i]) >> 32) != epoch) {
+            if ((++spins & 0xFFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+                if (q != cudaSuccess) return set_err(B200_ERR_CUDA, "multiply failed on the device: %s", cudaGetErrorString(q));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));              // finished: the report must be there now
+                if ((u32)(chunk[i] >> 32) != epoch) return set_err(B200_ERR_CUDA, "the row_ptr scan finished without reporting (epoch %u)", epoch);
+            }
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+            __builtin_ia32_pause();
 #endif
+        }
+        out[i] = (u32)c;
     }
     __sync_synchronize();
     return B200_OK;
 }
 
 // row_ptr scan: 8192-row tiles (1024 threads) while that still fills the GPU's latency budget, 2048-row tiles beyond
-static void launch_scan_rowptr(b200_ctx *ctx, u64 rows, u64 *rp, cudaStream_t s, B200Ctrl *host_mirror, u32 epoch) {
+static void launch_scan_rowptr(b200_ctx *ctx, u64 rows, u64 *rp, cudaStream_t s, u64 *host_mirror, u32 epoch) {
     if (rows <= (1ull << 19))
         k_scan_rowptr<1024><<<(unsigned)((rows + 1024 * SCAN_ITEMS - 1) / (1024 * SCAN_ITEMS)), 1024, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
     else
@@ -1027,7 +1038,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
-            launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_ctrl, epoch);
+            launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, epoch);
             LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(ctx->ev[1], s);
             r = wait_for_report(ctx, epoch);
@@ -1079,7 +1090,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (ctx->hosttime) ctx->ht[2] = host_now_us();                       // numeric kernels enqueued
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
-        launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_ctrl, epoch);
+        launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, epoch);
         LAUNCH_CHECK(ctx);
         if (timing) cudaEventRecord(ctx->ev[1], s);
         if (ctx->hosttime) ctx->ht[3] = host_now_us();                       // scan enqueued
@@ -1090,6 +1101,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
         r = alloc_entries(ctx, C);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        if (ctx->hosttime) ctx->ht[6] = host_now_us();                       // C allocated
         if (timing) cudaEventRecord(ctx->ev[2], s);
         if (ctx->trace) trace_mark(ctx, __LINE__);
         {
@@ -1114,8 +1126,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 if (ctx->hosttime) {
                     float g1 = 0, g2 = 0, g3 = 0;
                     cudaEventElapsedTime(&g1, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&g2, ctx->ev[0], ctx->ev[2]); cudaEventElapsedTime(&g3, ctx->ev[0], ctx->ev[3]);
-                    fprintf(stderr, "[b200 hosttime] host us: prepass queued %.1f, numeric queued %.1f, scan queued %.1f, report seen %.1f, compaction queued %.1f | gpu us: scan done %.1f, alloc point %.1f, compaction done %.1f\n",
-                            ctx->ht[1] - ctx->ht[0], ctx->ht[2] - ctx->ht[0], ctx->ht[3] - ctx->ht[0], ctx->ht[4] - ctx->ht[0], ctx->ht[5] - ctx->ht[0], g1 * 1e3, g2 * 1e3, g3 * 1e3);
+                    fprintf(stderr, "[b200 hosttime] host us: prepass queued %.1f, numeric queued %.1f, scan queued %.1f, report seen %.1f, C allocated %.1f, compaction queued %.1f | gpu us: scan done %.1f, alloc point %.1f, compaction done %.1f\n",
+                            ctx->ht[1] - ctx->ht[0], ctx->ht[2] - ctx->ht[0], ctx->ht[3] - ctx->ht[0], ctx->ht[4] - ctx->ht[0], ctx->ht[6] - ctx->ht[0], ctx->ht[5] - ctx->ht[0], g1 * 1e3, g2 * 1e3, g3 * 1e3);
                 }
                 cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[2], ctx->ev[3]);   // one-pass: compaction of the scratch rows
                 cudaEventElapsedTime(&st->ms_numeric, ctx->ev[0], ctx->ev[1]);    // counts + bins + numeric kernels + row_ptr scan

@@ -75,6 +75,7 @@ __device__ __forceinline__ u32 b200_hash(u32 c, int shift) { return (c * 0x9E377
 
 __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) { return *reinterpret_cast<const volatile u32 *>(p); }
 __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) { return *reinterpret_cast<const volatile u64 *>(p); }
+__device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) { *reinterpret_cast<volatile u64 *>(p) = v; }
 
 // saturating arithmetic (reference: src/graph_csr.rs:30-37, src/graph_sprs.rs:29-51)
 __device__ __forceinline__ u32 sat_add(u32 a, u32 b) { u32 s = a + b; return s < a ? 0xFFFFFFFFu : s; }

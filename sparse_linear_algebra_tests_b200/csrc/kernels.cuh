@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
                                                               u64 *tile_status, B200Ctrl *ctrl,
-                                                              B200Ctrl *host_mirror = nullptr, u32 epoch = 0) {
+                                                              u64 *host_mirror = nullptr, u32 epoch = 0) {
     __shared__ u32 s_tile, s_last;
     __shared__ u64 s_wsum[THREADS / 32];
     __shared__ u64 s_excl;
@@ -1477,8 +1477,10 @@ __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
     if (lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
-    // Report to the host without a stream synchronise: the last CTA to finish copies the control block into pinned
-    // host memory and then publishes the epoch word the host is polling.
+    // Report to the host without a stream synchronise: the last CTA to finish copies the control block into pinned host
+    // memory as self-validating 8-byte chunks {word, epoch}.  An aligned 8-byte store reaches the host whole, so the
+    // host simply waits until every chunk carries this multiply's epoch: no system-scope fence, no second "ready" word
+    // (two fences over PCIe cost ~10 us of the ~17 us this kernel took with them).
     if (host_mirror) {
         __syncthreads();
         if (tid == 0) { __threadfence(); s_last = atomicAdd(&ctrl->scan_done, 1u) == gridDim.x - 1 ? 1u : 0u; }
@@ -1486,11 +1488,7 @@ __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__
         if (s_last) {
             __threadfence();
             const volatile u32 *src = reinterpret_cast<const volatile u32 *>(ctrl);
-            volatile u32 *dst = reinterpret_cast<volatile u32 *>(host_mirror);
-            for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) dst[i] = src[i];
-            __threadfence_system();
-            __syncthreads();
-            if (tid == 0) { dst[sizeof(B200Ctrl) / 4] = epoch; __threadfence_system(); }
+            for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) st_volatile_u64(host_mirror + i, ((u64)epoch << 32) | (u64)src[i]);
         }
     }
 }
