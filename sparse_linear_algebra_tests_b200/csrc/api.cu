@@ -706,7 +706,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     const size_t smem_max = ctx->smem_optin - 1024;
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
-    OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt, o.bin_stride};
+    OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt, o.bin_stride, o.narrow};
     const size_t accb = mode == 0 ? 4 : 8;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto do_tiny = [&]() -> int {
@@ -1083,7 +1083,9 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
             fan.join();
         }
-        OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride};
+        // u64 values that provably stay below 2^32 (mode 0) cross the scratch as u32: 8 instead of 12 bytes per entry, twice
+        const bool narrow = sizeof(VT) == 8 && mode == 0 && env_int("B200_NARROW", 1);
+        OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride, narrow ? 1u : 0u};
         if (ctx->hosttime) ctx->ht[1] = host_now_us();                       // pre-pass enqueued
         if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
         fan.join();
@@ -1108,9 +1110,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const double avg = (double)C->nnz / (double)rows;
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
             const u64 want = (rows << llg) / 256 + 1;
-            k_compact_rows<VT><<<(unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64), 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg,
-                                                                                                      &ctx->d_ctrl->max_val_out, C->d_maxval,
-                                                                                                      (u64 *)ctx->d_scan, B200_CTRL_BYTES / 8, scan_bytes / 8);
+            const unsigned cg = (unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64);
+            if (narrow) k_compact_rows<VT, u32><<<cg, 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const u32 *)tmp_val, C->d_col, (VT *)C->d_val, llg,
+                                                                  &ctx->d_ctrl->max_val_out, C->d_maxval, (u64 *)ctx->d_scan, B200_CTRL_BYTES / 8, scan_bytes / 8);
+            else k_compact_rows<VT, VT><<<cg, 256, 0, s>>>(rows, ctx->d_tmp_ptr, C->d_rp, (const u32 *)tmp_col, (const VT *)tmp_val, C->d_col, (VT *)C->d_val, llg,
+                                                          &ctx->d_ctrl->max_val_out, C->d_maxval, (u64 *)ctx->d_scan, B200_CTRL_BYTES / 8, scan_bytes / 8);
             LAUNCH_CHECK(ctx);
             ctx->scan_clean_bytes = scan_bytes;
         }

@@ -44,7 +44,14 @@ struct OutArgs {
     u32 *nnz_out;                // may be null (exact mode)
     const u32 *bin_cnt;          // list sizes (ctrl->sym_bin_count)
     u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
+    u32 narrow;                  // scratch mode, u64 values proven < 2^32 (accumulator mode 0): the scratch holds them as
+                                 // u32 (val is then a u32 array); the compaction kernel widens them on the way into C
 };
+template <typename VT>
+__device__ __forceinline__ void put_val(const OutArgs<VT> &o, u64 idx, VT v) {
+    if (sizeof(VT) == 8 && o.narrow) reinterpret_cast<u32 *>(o.val)[idx] = (u32)v;
+    else o.val[idx] = v;
+}
 
 // desc = {first entry, length}; span = {length, first column, last column, -} (what the one-pass pre-pass gathers: the
 // product count and the column window of a row of C follow from these alone because B's rows are sorted)
@@ -611,7 +618,7 @@ __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__re
         const u32 tails = __ballot_sync(0xFFFFFFFFu, tail);
         if (tail) {
             const u64 pos = cur.base + __popc(tails & ((1u << lane) - 1u));
-            o.col[pos] = key; o.val[pos] = val;
+            o.col[pos] = key; put_val(o, pos, val);
             vmax = vmax > (u64)val ? vmax : (u64)val;
         }
         if (lane == 0 && o.nnz_out) o.nnz_out[cur.row] = __popc(tails);
@@ -795,7 +802,7 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
         for (u32 t = lane; t < total; t += 32) {
             const u64 wd = words[t];
             const VT v = emit_val<VT>(acc.get((u32)wd));
-            o.col[obase + t] = (u32)(wd >> 32); o.val[obase + t] = v;
+            o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         if (lane == 0 && o.nnz_out) o.nnz_out[row] = total;
@@ -855,7 +862,7 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
         for (u32 t = tid; t < total; t += nt) {
             const u64 wd = words[t];
             const VT v = emit_val<VT>(acc.get((u32)wd));
-            o.col[obase + t] = (u32)(wd >> 32); o.val[obase + t] = v;
+            o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         if (tid == 0 && o.nnz_out) o.nnz_out[row] = total;
@@ -928,7 +935,7 @@ __global__ void __launch_bounds__(1024) k_num_rank(NumArgs<VT> a, const u32 *__r
         const u64 obase = o.base[row];
         for (u32 t = tid; t < nnz; t += nt) {
             const VT v = emit_val<VT>(acc.get(t));
-            o.col[obase + t] = cols[t]; o.val[obase + t] = v;
+            o.col[obase + t] = cols[t]; put_val(o, obase + t, v);
             vmax = vmax > (u64)v ? vmax : (u64)v;
         }
         if (tid == 0 && o.nnz_out) o.nnz_out[row] = nnz;
@@ -1196,8 +1203,8 @@ __global__ void __launch_bounds__(512) k_num_expand(NumArgs<VT> a, const uint4 *
             const VT v0 = emit_val<VT>(acc.get(t0)), v1 = h1 ? emit_val<VT>(acc.get(t1)) : (VT)0;
             const u32 q0 = t0 >= r0 ? t0 - r0 : t0 + shift_hi, q1 = t1 >= r0 ? t1 - r0 : t1 + shift_hi;
             acc.clear(t0);
-            o.col[obase + q0] = c0; o.val[obase + q0] = v0;
-            if (h1) { acc.clear(t1); o.col[obase + q1] = c1; o.val[obase + q1] = v1; }
+            o.col[obase + q0] = c0; put_val(o, obase + q0, v0);
+            if (h1) { acc.clear(t1); o.col[obase + q1] = c1; put_val(o, obase + q1, v1); }
             const u64 m = (u64)(v0 > v1 ? v0 : v1);
             vmax = vmax > m ? vmax : m;
         }
@@ -1397,7 +1404,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                 const u64 pos = obase + __ldcg(&wpre[c >> 5]) + __popc(wd & ((1u << (c & 31)) - 1u));
                 ull v = __ldcg(&vals[t]);
                 if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
-                o.col[pos] = c; o.val[pos] = (VT)v;
+                o.col[pos] = c; put_val(o, pos, (VT)v);
                 vmax = vmax > v ? vmax : v;
             }
         }
@@ -1494,9 +1501,9 @@ __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__
 }
 
 // one-pass mode: move every row from the scratch CSR (bound offsets) to its exact place
-template <typename VT>
+template <typename VT, typename SV>
 __global__ void __launch_bounds__(256) k_compact_rows(u64 rows, const u64 *__restrict__ src_ptr, const u64 *__restrict__ rpC,
-                                                      const u32 *__restrict__ src_col, const VT *__restrict__ src_val,
+                                                      const u32 *__restrict__ src_col, const SV *__restrict__ src_val,
                                                       u32 *__restrict__ colC, VT *__restrict__ valC, int lanes_lg,
                                                       const ull *max_val_src, ull *max_val_dst,
                                                       u64 *scan_area, u32 ctrl_words, u64 scan_words) {
