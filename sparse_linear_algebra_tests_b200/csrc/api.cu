@@ -630,12 +630,13 @@ static int wait_for_report(b200_ctx *ctx, u32 epoch) {
     return B200_OK;
 }
 
-// row_ptr scan: 8192-row tiles (1024 threads) while that still fills the GPU's latency budget, 2048-row tiles beyond
+// row_ptr scan: 2048-row tiles either way; up to 512 K rows as 1024 threads x 2 rows (coalesced stores, all tiles
+// co-resident), beyond that as 256 threads x 8 rows
 static void launch_scan_rowptr(b200_ctx *ctx, u64 rows, u64 *rp, cudaStream_t s, u64 *host_mirror, u32 epoch) {
-    if (rows <= (1ull << 19))
-        k_scan_rowptr<1024><<<(unsigned)((rows + 1024 * SCAN_ITEMS - 1) / (1024 * SCAN_ITEMS)), 1024, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
-    else
-        k_scan_rowptr<SCAN_THREADS><<<(unsigned)((rows + SCAN_TILE - 1) / SCAN_TILE), SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
+    const unsigned tiles = (unsigned)((rows + SCAN_TILE - 1) / SCAN_TILE);
+    static_assert(SCAN_TILE == 1024 * 2, "both variants cut the rows into SCAN_TILE pieces");
+    if (rows <= (1ull << 19)) k_scan_rowptr<1024, 2><<<tiles, 1024, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
+    else k_scan_rowptr<SCAN_THREADS, SCAN_ITEMS><<<tiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
 }
 
 // Independent per-bin kernels are spread over the main stream and a few auxiliary streams.

@@ -1416,10 +1416,11 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
 
 // =======================================================================================
 // 7. row_ptr: single-pass decoupled look-back exclusive scan of nnz_row (u32 -> u64); its last CTA reports to the host.
-//    Tiles of THREADS*8 rows: 1024-thread tiles keep the look-back chain of a small matrix a few tiles long.
+//    Tiles of THREADS*ITEMS rows.  Small matrices use 1024 threads x 2 rows: a thread's two row_ptr words are one 16-byte
+//    piece of a contiguous 512-byte warp store (eight rows per thread made every store a sector of its own).
 // =======================================================================================
 
-template <int THREADS>
+template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__restrict__ nnz_row, u64 *__restrict__ rpC,
                                                               u64 *tile_status, B200Ctrl *ctrl,
                                                               u64 *host_mirror = nullptr, u32 epoch = 0) {
@@ -1430,10 +1431,10 @@ __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__
     if (tid == 0) s_tile = atomicAdd(&ctrl->scan_ticket[0], 1u);            // tiles start in ticket order
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 base = (u64)tile * (THREADS * SCAN_ITEMS) + (u64)tid * SCAN_ITEMS;
-    u32 item[SCAN_ITEMS]; u64 tsum = 0; u32 tmaxv = 0;
+    const u64 base = (u64)tile * (THREADS * ITEMS) + (u64)tid * ITEMS;
+    u32 item[ITEMS]; u64 tsum = 0; u32 tmaxv = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         item[i] = base + i < rows ? nnz_row[base + i] : 0u;
         tsum += item[i]; tmaxv = item[i] > tmaxv ? item[i] : tmaxv;
     }
@@ -1476,11 +1477,11 @@ __global__ void __launch_bounds__(THREADS) k_scan_rowptr(u64 rows, const u32 *__
     u64 run = s_excl + texcl;
     if (tile == 0 && tid == 0) rpC[0] = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         run += item[i];
         if (base + i < rows) rpC[base + i + 1] = run;
     }
-    if (base < rows && base + SCAN_ITEMS >= rows) ctrl->total_nnz = run;      // thread holding the last row
+    if (base < rows && base + ITEMS >= rows) ctrl->total_nnz = run;      // thread holding the last row
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) tmaxv = max(tmaxv, __shfl_xor_sync(0xFFFFFFFFu, tmaxv, m));
     if (lane == 0 && tmaxv) atomicMax(&ctrl->max_row_nnz, (ull)tmaxv);
