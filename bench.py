@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--epn", type=float, default=3.0)
     ap.add_argument("--bits", type=int, default=64, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # the large configurations of BASELINE.json (not the driver's default line): a fixed-size torus cut over the ranks
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the torus stays side^3 whatever --gpus is (e.g. --side 200 --max-power 5)")
+    ap.add_argument("--max-power", type=int, default=7)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (its pinned staging is 12 B per result entry)")
     return ap.parse_args()
 
 
@@ -58,7 +62,7 @@ def dist_env():
 
 
 def workload_config(args, world):
-    dims = [args.side * world, args.side, args.side]
+    dims = [args.side * (1 if args.strong else world), args.side, args.side]
     return {"workload": f"repeated exponentiation A^2..A^{MAX_POWER} on the {dims[0]}x{dims[1]}x{dims[2]} Moore torus, "
                         f"~{args.epn:g} e/n, StdRng([42;32]) thinning (graph_magnus.rs:699-788)",
             "dims": dims, "val_bits": args.bits, "left": "A^(k-1) (resident row block per GPU)", "right": "A (replicated)",
@@ -68,7 +72,7 @@ def workload_config(args, world):
 
 def build_operand(args, world):
     from sparse_linear_algebra_tests_b200 import hostgen
-    full = hostgen.lattice([args.side * world, args.side, args.side], True, args.bits)
+    full = hostgen.lattice([args.side * (1 if args.strong else world), args.side, args.side], True, args.bits)
     density = args.epn / (full.nnz() / full.rows)
     return hostgen.thin(full, density, bytes([42] * 32))
 
@@ -302,6 +306,18 @@ def run_b200(args):
 
     # ---- end to end through the public API with host buffers (pinned H2D of A, pinned D2H of every power)
     e2e = None
+    if args.no_e2e:
+        if rank == 0:
+            cfg = workload_config(args, world)
+            cfg.update({"nodes": n_rows, "nnz_A": n_nnz, "products_per_step": int(total_products), "nnz_per_power_rank0": nnzs,
+                        "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                              "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+                              "dtype": f"u{args.bits}", "data": "synthetic", "config": cfg, "per_power": per_power, "gpu_launches": total_launches,
+                              "wall_s_timed_region": wall, "clocks": clocks, "e2e": None, "roofline": roofline}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     a_loc = hostgen.HostCsr(n_rows, n_cols, d_rp.cpu().numpy().view(np.uint64), d_ci.cpu().numpy().view(np.uint32),
                             d_vv.cpu().numpy().view(np.uint32 if args.bits == 32 else np.uint64))
     blk = a_loc.row_block(r0, r1)
@@ -353,7 +369,7 @@ def run_b200(args):
     cfg.update({"nodes": n_rows, "nnz_A": n_nnz, "products_per_step": int(total_products), "nnz_per_power_rank0": nnzs,
                 "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
            "data": "synthetic", "config": cfg, "per_power": per_power, "gpu_launches": total_launches, "wall_s_timed_region": wall,
            "clocks": clocks, "e2e": e2e, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
@@ -367,7 +383,9 @@ def run_b200(args):
 
 
 def main():
+    global MAX_POWER
     args = parse_args()
+    MAX_POWER = args.max_power
     if args.impl == "reference":
         run_reference(args)
     else:

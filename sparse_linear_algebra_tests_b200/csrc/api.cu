@@ -1029,10 +1029,13 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             tmp_entries = ctx->h_ctrl->total_bound;
-            size_t free_b = 0, tot_b = 0;
-            CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
-            const size_t reusable = ctx->cap_tmp_col + ctx->cap_tmp_val;      // scratch the context already owns
-            exact = (unsigned __int128)tmp_entries * esz > (unsigned __int128)((free_b + reusable) / 3);
+            // scratch the context already owns decides first (steady state of a loop: no driver query at all)
+            if ((size_t)tmp_entries * 4 > ctx->cap_tmp_col || (size_t)tmp_entries * sizeof(VT) > ctx->cap_tmp_val) {
+                size_t free_b = 0, tot_b = 0;
+                CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+                const size_t reusable = ctx->cap_tmp_col + ctx->cap_tmp_val;
+                exact = (unsigned __int128)tmp_entries * esz > (unsigned __int128)((free_b + reusable) / 3);
+            }
         }
         if (exact) {
             r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps);
