@@ -917,7 +917,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const u32 nwords = (u32)((ncols + 31) / 32);
     const int lg = pick_lg(B, 5);
     const u64 p_bound = A->max_row_len * B->max_row_len;                 // host-known bound of the largest P_i
-    const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
     const size_t smem_max = ctx->smem_optin - 1024;
     const u64 maxA = A->h_maxval, maxB = B->h_maxval;
     const bool bpat = maxB == 1;
@@ -939,7 +938,6 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     if (timing) cudaEventRecord(ctx->ev[0], s);
     if (ctx->hosttime) ctx->ht[0] = host_now_us();
     if (ctx->trace) trace_mark(ctx, __LINE__);
-    const unsigned row_grid = (unsigned)((rows + 255) / 256);
     const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
     u64 tmp_entries = 0;
     size_t scan_bytes = 0;                                                // control block + scan status words this multiply uses
@@ -1226,7 +1224,6 @@ static int add_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_c
     if (rows == 0) { TRY(alloc_entries(ctx, C)); CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, 8, s)); *out = C; return B200_OK; }
     int r = ensure_row_scratch(ctx, rows);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-    const u64 ntiles = (rows + SCAN_TILE - 1) / SCAN_TILE;
     CUDA_TRY(reset_scan(ctx, 0));
     const unsigned g = (unsigned)((rows + 255) / 256);
     k_add_rows<VT, false><<<g, 256, 0, s>>>(view<VT>(A), view<VT>(B), ctx->d_nnz_row, nullptr, nullptr, nullptr, ctx->d_ctrl);

@@ -5,11 +5,14 @@
 //   k_prepass           product count P_i and column window per row, bin lists, scratch offsets (look-back scan)
 //   k_sym_*             exact mode only: distinct output columns per row (count-only twins of the numeric kernels)
 //   k_num_*             values: saturating accumulate, in-row column order, write col/val
-//   k_scan_rowptr       decoupled look-back scan of the exact row lengths -> row_ptr_C (u64); reports to the host
-//   k_compact_rows      scratch mode only: rows from their bound offsets to their exact places
+//   k_scan_rowptr       decoupled look-back scan of the exact row lengths -> row_ptr_C (u64); its last CTA reports the
+//                       control block to pinned host memory as {word, epoch} chunks (the host never synchronises)
+//   k_compact_rows      scratch mode only: rows from their bound offsets to their exact places (widening the scratch's
+//                       32-bit values when mode 0 let them travel narrow); leaves the scan area zeroed for the next multiply
 // Row classes: tiny (warp register merge), window-bitmap rank (k_num_expand: CTA per row, no sort), hash + bitonic sort
 // (warp or CTA per row, any column space), heavy (global-memory table).  All inner loops use 32-bit offsets; 64-bit only
-// for row bases.
+// for row bases.  Column windows of the bitmap kernel: whole column space, one operand-level arc of the index circle
+// (row blocks of a torus / banded matrix), or per-row plain / circular windows from the pre-pass (api.cu decides).
 #pragma once
 #include "common.cuh"
 
