@@ -128,6 +128,22 @@ int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *
  * power_until_stable, src/graph_csr.rs:567-570). */
 int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same);
 
+/* ---- fixture generators on the device: large inputs without a host build ---------------------------
+ * N-d Moore lattice / torus, CsrMatrix::lattice (src/graph_csr.rs:177-222; MagnusMatrix::lattice, src/graph_magnus.rs:146):
+ * node ids row-major with the last dimension fastest, offsets enumerated with dimension 0 as the least-significant
+ * digit, torus wrap via rem_euclid, the all-zero offset skipped, duplicate neighbours (side-2 torus) summed.
+ * ndims <= 4, at most 2^32-1 nodes. */
+int b200_lattice(b200_ctx *ctx, const uint64_t *dims, int ndims, int torus, int val_bits, b200_csr **out);
+/* Symmetric Bernoulli thinning, CsrMatrix::thin (src/graph_csr.rs:225-247) with StdRng::from_seed(seed32) (rand 0.9:
+ * ChaCha12): entries visited row-major, one draw per stored entry with r <= c, a kept (r,c) also keeps its stored mirror.
+ * `skip_draws` = next_u64 outputs already taken from the same generator (bench_matmul_magnus shares one StdRng over its
+ * grid, src/graph_magnus.rs:800-821); `draws_consumed` (may be NULL) receives the number this call took. */
+int b200_thin(b200_ctx *ctx, const b200_csr *A, double density, const uint8_t *seed32, uint64_t skip_draws, b200_csr **out,
+              uint64_t *draws_consumed);
+/* Host twin of the generator the device kernels use (runs without a GPU): StdRng::from_seed(seed32).next_u64() outputs
+ * number first .. first+n-1. */
+int b200_stdrng_u64(const uint8_t *seed32, uint64_t first, uint64_t n, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ EXPORTS = [
     "b200_csr_from_device", "b200_csr_free", "b200_csr_info", "b200_csr_device_ptrs", "b200_csr_max_value",
     "b200_csr_download", "b200_csr_download_idx64", "b200_csr_download_async", "b200_spgemm", "b200_row_products",
     "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
+    "b200_lattice", "b200_thin", "b200_stdrng_u64",
 ]
 
 _lib = None
@@ -86,6 +87,9 @@ def load():
         "b200_csr_row_block": [vp, vp, u64, u64, C.POINTER(vp)],
         "b200_csr_add": [vp, vp, vp, C.POINTER(vp)],
         "b200_csr_same_pattern": [vp, vp, vp, C.POINTER(i32)],
+        "b200_lattice": [vp, vp, i32, i32, i32, C.POINTER(vp)],
+        "b200_thin": [vp, vp, C.c_double, vp, u64, C.POINTER(vp), C.POINTER(u64)],
+        "b200_stdrng_u64": [vp, u64, u64, vp],
     }
     for name, args in sigs.items():
         f = getattr(L, name)
@@ -99,6 +103,15 @@ def check(code: int):
     if code != B200_OK:
         msg = load().b200_last_error().decode("utf-8", "replace")
         raise (ShapeMismatch if code == B200_ERR_SHAPE else B200Error)(code, msg)
+
+
+def stdrng_u64(seed: bytes, first: int, n: int) -> np.ndarray:
+    """StdRng::from_seed(seed).next_u64() outputs first..first+n-1 from the engine's own ChaCha12 (host side, no GPU)."""
+    assert len(seed) == 32
+    out = np.zeros(n, dtype=np.uint64)
+    sb = (C.c_ubyte * 32).from_buffer_copy(seed)
+    check(load().b200_stdrng_u64(sb, int(first), int(n), out.ctypes.data))
+    return out
 
 
 def _vdtype(bits: int):
@@ -174,6 +187,21 @@ class Context:
         s = C.c_int()
         check(load().b200_csr_same_pattern(self._h, a._h, b._h, C.byref(s)))
         return bool(s.value)
+
+    def lattice(self, dims, torus: bool, val_bits: int = 32) -> "DeviceCsr":
+        """Moore lattice / torus built on the device (src/graph_csr.rs:177-222)."""
+        d = np.asarray(list(dims), dtype=np.uint64)
+        h = C.c_void_p()
+        check(load().b200_lattice(self._h, d.ctypes.data, int(d.size), int(bool(torus)), val_bits, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def thin(self, a: "DeviceCsr", density: float, seed: bytes = bytes([42] * 32), skip: int = 0):
+        """Symmetric thinning on the device (src/graph_csr.rs:225-247, StdRng::from_seed(seed)); returns (matrix, draws taken)."""
+        assert len(seed) == 32
+        sb = (C.c_ubyte * 32).from_buffer_copy(seed)
+        h, n = C.c_void_p(), C.c_uint64()
+        check(load().b200_thin(self._h, a._h, float(density), sb, int(skip), C.byref(h), C.byref(n)))
+        return DeviceCsr(self, h), int(n.value)
 
     def row_products(self, a: "DeviceCsr", b: "DeviceCsr") -> np.ndarray:
         out = np.zeros(a.rows, dtype=np.uint64)

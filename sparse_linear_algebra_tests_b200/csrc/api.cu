@@ -10,6 +10,7 @@
 
 #include "../../include/b200_spgemm.h"
 #include "kernels.cuh"
+#include "gen.cuh"
 
 #define B200_NAUX 3
 
@@ -1261,5 +1262,109 @@ extern "C" int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b20
     CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *same = ctx->h_flag[0] == 0;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------- fixture generators on the device (gen.cuh)
+// exclusive u64 prefix of ctx->d_nnz_row[0..rows) into `out` (rows + 1 words); returns total and the longest row
+static int scan_row_counts(b200_ctx *ctx, u64 rows, u64 *out, u64 *total, u64 *max_len) {
+    CUDA_TRY(reset_scan(ctx, 0));
+    launch_scan_rowptr(ctx, rows, out, ctx->stream, nullptr, 0);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *total = ctx->h_ctrl->total_nnz; *max_len = ctx->h_ctrl->max_row_nnz;
+    return B200_OK;
+}
+
+extern "C" int b200_lattice(b200_ctx *ctx, const uint64_t *dims, int ndims, int torus, int val_bits, b200_csr **out) {
+    if (!ctx || !out || (ndims > 0 && !dims)) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (ndims < 0 || ndims > B200_LATTICE_MAXD) return set_err(B200_ERR_BADARG, "lattice: 0..%d dimensions supported, got %d", B200_LATTICE_MAXD, ndims);
+    if (val_bits != 32 && val_bits != 64) return set_err(B200_ERR_BADARG, "val_bits must be 32 or 64");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    LatticeDims L; memset(&L, 0, sizeof(L)); L.nd = ndims; L.torus = torus ? 1 : 0;
+    unsigned __int128 total128 = 1;
+    for (int d = 0; d < ndims; d++) { if (!dims[d]) return set_err(B200_ERR_BADARG, "lattice: dimension %d is 0", d); L.dim[d] = dims[d]; total128 *= dims[d]; }
+    if (total128 > 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "lattice: more than 2^32-1 nodes (NodeId is u32)");
+    const u64 total = (u64)total128;
+    for (int d = ndims - 1; d >= 0; d--) L.stride[d] = d == ndims - 1 ? 1 : L.stride[d + 1] * L.dim[d + 1];   // last dimension fastest
+    b200_csr *C = nullptr;
+    TRY(csr_alloc(ctx, total, total, 0, val_bits, false, &C));
+    int r = ensure_row_scratch(ctx, total);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    const unsigned g = (unsigned)((total + 127) / 128);
+    cudaStream_t s = ctx->stream;
+    if (val_bits == 32) k_lattice<u32, false><<<g, 128, 0, s>>>(total, L, ctx->d_nnz_row, nullptr, nullptr, nullptr);
+    else k_lattice<u64, false><<<g, 128, 0, s>>>(total, L, ctx->d_nnz_row, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK(ctx);
+    u64 nnz = 0, maxlen = 0;
+    r = scan_row_counts(ctx, total, C->d_rp, &nnz, &maxlen);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    C->nnz = nnz; C->max_row_len = maxlen;
+    r = alloc_entries(ctx, C);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    if (nnz) {
+        if (val_bits == 32) k_lattice<u32, true><<<g, 128, 0, s>>>(total, L, nullptr, C->d_rp, C->d_col, (u32 *)C->d_val);
+        else k_lattice<u64, true><<<g, 128, 0, s>>>(total, L, nullptr, C->d_rp, C->d_col, (u64 *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    }
+    r = finish_new_csr(ctx, C, true, false);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    *out = C;
+    return B200_OK;
+}
+
+template <typename VT>
+static int thin_typed(b200_ctx *ctx, const b200_csr *A, double density, const ChaChaKey &key, u64 skip, b200_csr **out, u64 *draws) {
+    const u64 rows = A->rows;
+    cudaStream_t s = ctx->stream;
+    b200_csr *C = nullptr;
+    TRY(csr_alloc(ctx, rows, A->cols, 0, A->val_bits, false, &C));
+    int r = ensure_row_scratch(ctx, rows);
+    u64 *base_u = nullptr;
+    if (r == B200_OK) r = dmalloc(ctx, (void **)&base_u, (rows + 1) * 8);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    const unsigned g = (unsigned)((rows + 255) / 256);
+    u64 nu = 0, nnz = 0, maxlen = 0;
+    k_thin_upper_count<<<g, 256, 0, s>>>(rows, A->d_rp, A->d_col, ctx->d_nnz_row);
+    LAUNCH_CHECK(ctx);
+    r = scan_row_counts(ctx, rows, base_u, &nu, &maxlen);                  // draw number of every row's first upper entry
+    if (r == B200_OK) {
+        k_thin_rows<VT, false><<<g, 256, 0, s>>>(rows, A->d_rp, A->d_col, (const VT *)A->d_val, base_u, key, skip, density, ctx->d_nnz_row, nullptr, nullptr, nullptr);
+        LAUNCH_CHECK(ctx);
+        r = scan_row_counts(ctx, rows, C->d_rp, &nnz, &maxlen);
+    }
+    if (r == B200_OK) { C->nnz = nnz; C->max_row_len = maxlen; r = alloc_entries(ctx, C); }
+    if (r == B200_OK && nnz) {
+        k_thin_rows<VT, true><<<g, 256, 0, s>>>(rows, A->d_rp, A->d_col, (const VT *)A->d_val, base_u, key, skip, density, nullptr, C->d_rp, C->d_col, (VT *)C->d_val);
+        LAUNCH_CHECK(ctx);
+    }
+    dfree(ctx, base_u);
+    if (r == B200_OK) r = finish_new_csr(ctx, C, true, false);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    if (draws) *draws = nu;
+    *out = C;
+    return B200_OK;
+}
+
+extern "C" int b200_thin(b200_ctx *ctx, const b200_csr *A, double density, const uint8_t *seed32, uint64_t skip_draws, b200_csr **out,
+                         uint64_t *draws_consumed) {
+    if (!ctx || !A || !seed32 || !out) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->rows != A->cols) return set_err(B200_ERR_SHAPE, "thin: the matrix must be square (%llux%llu)", (ull)A->rows, (ull)A->cols);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ChaChaKey key;
+    for (int i = 0; i < 8; i++) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
+    if (A->rows == 0) { TRY(csr_alloc(ctx, 0, 0, 0, A->val_bits, true, out)); CUDA_TRY(cudaMemsetAsync((*out)->d_rp, 0, 8 + 16, ctx->stream)); if (draws_consumed) *draws_consumed = 0; return B200_OK; }
+    return A->val_bits == 32 ? thin_typed<u32>(ctx, A, density, key, skip_draws, out, draws_consumed)
+                             : thin_typed<u64>(ctx, A, density, key, skip_draws, out, draws_consumed);
+}
+
+// Host twin of the generator the device kernels use (no GPU needed): StdRng::from_seed(seed).next_u64() numbers
+// first .. first+n-1.  Lets a CPU-only test pin the device algorithm's ChaCha12 against the oracle.
+extern "C" int b200_stdrng_u64(const uint8_t *seed32, uint64_t first, uint64_t n, uint64_t *out) {
+    if (!seed32 || (n && !out)) return set_err(B200_ERR_BADARG, "NULL argument");
+    ChaChaKey key;
+    for (int i = 0; i < 8; i++) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
+    for (u64 i = 0; i < n; i++) out[i] = stdrng_u64_at(key, first + i);
     return B200_OK;
 }

@@ -140,12 +140,24 @@ class B200Matrix:
         return cls.from_host(hostgen.from_coo(n, n, r, c, np.ones(m, hostgen.vdtype(val_bits)), val_bits), ctx)
 
     @classmethod
-    def lattice(cls, dims, torus: bool, val_bits: int = 64, ctx=None) -> "B200Matrix":
+    def lattice(cls, dims, torus: bool, val_bits: int = 64, ctx=None, device: bool = True) -> "B200Matrix":
+        """N-d Moore lattice / torus (src/graph_csr.rs:177-222).  Built by the engine's device generator (up to 4
+        dimensions); `device=False`, or more dimensions, builds it with the host generator and uploads."""
+        if device and len(list(dims)) <= 4:
+            return cls((ctx or default_context()).lattice(dims, torus, val_bits))
         return cls.from_host(hostgen.lattice(dims, torus, val_bits), ctx)
 
-    def thin(self, density: float, seed: bytes = bytes([42] * 32)) -> "B200Matrix":
-        """Symmetric Bernoulli thinning driven by StdRng::from_seed(seed) (src/graph_csr.rs:225-247)."""
-        return B200Matrix.from_host(hostgen.thin(self.to_host(), density, seed), self._dev.ctx)
+    def thin(self, density: float, seed: bytes = bytes([42] * 32), skip: int = 0, device: bool = True) -> "B200Matrix":
+        """Symmetric Bernoulli thinning driven by StdRng::from_seed(seed) (src/graph_csr.rs:225-247); `skip` = draws
+        already taken from the same generator.  `last_draws` on the result = draws this call consumed."""
+        if device:
+            dev, n = self._dev.ctx.thin(self._dev, density, seed, skip)
+            out = B200Matrix(dev)
+        else:
+            h = self.to_host()
+            out, n = B200Matrix.from_host(hostgen.thin(h, density, seed, skip), self._dev.ctx), hostgen.draws_of_thin(h)
+        out.last_draws = n
+        return out
 
     # ------------------------------------------------------------------ queries
     def get(self, r: int, c: int) -> int:

@@ -482,3 +482,49 @@ def test_arc_window_exact_mode_and_add(gpu_ctx, oracle, monkeypatch):
         assert_same(q.to_host(), q_o, f"A^{k}")
         p, p_o = q.add(q), oracle.add(q_o, q_o)
         assert_same(p.to_host(), p_o, f"sum {k}")
+
+
+# ------------------------------------------------------------------ fixture generators on the device
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("dims,torus", [([5], False), ([5], True), ([1], True), ([3, 3], True), ([2, 2, 2], False), ([2, 2, 2], True),
+                                        ([4, 3], False), ([6, 5, 4], True), ([3, 1, 4], True), ([3, 2, 2, 3], True), ([7, 6, 5], False), ([], True)])
+def test_device_lattice_equals_host_builder(gpu_ctx, dims, torus, bits):
+    """CsrMatrix::lattice on the device (src/graph_csr.rs:177-222) against the host builder that the oracle pins:
+    1-D 5 -> 8 entries, torus 10; 3x3 torus 72; 2x2x2 -> 56 (the reference's own counts, src/graph_csr.rs:1011-1093),
+    side-1 and side-2 torus dimensions (self loops and summed duplicates), four dimensions, the empty shape."""
+    got = B200Matrix.lattice(dims, torus, bits, gpu_ctx).to_host()
+    want = hostgen.lattice(dims, torus, bits)
+    assert_same(got, want, f"lattice {dims} torus={torus}")
+    counts = {((5,), False): 8, ((5,), True): 10, ((3, 3), True): 72, ((2, 2, 2), False): 56}
+    if (tuple(dims), torus) in counts:
+        assert got.nnz() == counts[(tuple(dims), torus)]
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_device_thin_equals_host_builder_and_shares_a_generator(gpu_ctx, bits):
+    """CsrMatrix::thin on the device (src/graph_csr.rs:225-247) with StdRng([42;32]) and other seeds; a second thinning that
+    continues the same generator (the sweep of bench_matmul_magnus, src/graph_magnus.rs:800-821) must skip the first one's
+    draws; side-2 torus values (2) and self loops ride through."""
+    taken = 0
+    for dims, dens, seed in (([6, 6, 6], 3.0 / 26.0, bytes([42] * 32)), ([9, 7], 0.4, bytes(range(32))), ([2, 3, 4], 0.5, bytes([7] * 32)),
+                             ([12], 0.9, bytes([1] * 32)), ([5, 5, 5], 0.0, bytes([3] * 32)), ([5, 5, 5], 1.0, bytes([3] * 32))):
+        full_h = hostgen.lattice(dims, True, bits)
+        full = B200Matrix.lattice(dims, True, bits, gpu_ctx)
+        got = full.thin(dens, seed)
+        assert_same(got.to_host(), hostgen.thin(full_h, dens, seed), f"thin {dims} {dens}")
+        assert got.last_draws == hostgen.draws_of_thin(full_h)
+    shared = bytes([42] * 32)
+    for side, epn in ((5, 2.0), (5, 8.0), (6, 3.0)):                 # three instances from one generator, as the sweep does
+        full_h = hostgen.lattice([side] * 3, True, bits)
+        got = B200Matrix.lattice([side] * 3, True, bits, gpu_ctx).thin(epn / 26.0, shared, skip=taken)
+        assert_same(got.to_host(), hostgen.thin(full_h, epn / 26.0, shared, taken), f"shared generator side={side}")
+        taken += got.last_draws
+
+
+def test_device_built_reference_instance_multiplies_like_the_host_built_one(gpu_ctx, oracle):
+    """The 30^3 bench instance built entirely on the device: same matrix (README nnz 81 434) and the same A^2."""
+    a = B200Matrix.lattice([30, 30, 30], True, 64, gpu_ctx).thin(3.0 / 26.0, bytes([42] * 32))
+    a_h = hostgen.reference_bench_instance(30, 3.0, 64)
+    assert_same(a.to_host(), a_h, "device-built bench instance")
+    assert a.nnz() == 81434
+    assert_same(a.matmul(a).to_host(), oracle.matmul(to_o(oracle, a_h), to_o(oracle, a_h)), "A^2 of the device-built instance")

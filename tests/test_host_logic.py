@@ -126,3 +126,17 @@ def test_thin_with_a_shared_generator_consumes_the_stream_in_order():
         have = set(zip(got.row_of_entry().tolist(), got.col_idx.tolist()))
         assert have == want
     assert not same(first, second)
+
+
+def test_engine_chacha12_host_twin_matches_the_pinned_generator():
+    """gen.cuh's ChaCha12 is one __host__ __device__ function; its host side is exported (b200_stdrng_u64) so that the
+    generator the device thinning kernels run can be pinned without a GPU: StdRng::from_seed next_u64 outputs must equal
+    hostgen's (which reproduce the README's nnz column through the oracle), from any starting draw."""
+    from sparse_linear_algebra_tests_b200 import _native
+    for seed in (bytes([42] * 32), bytes(range(32)), bytes([0] * 32)):
+        want = hostgen.stdrng_u64(seed, 5000)
+        assert np.array_equal(_native.stdrng_u64(seed, 0, 5000), want)
+        assert np.array_equal(_native.stdrng_u64(seed, 4093, 907), want[4093:])
+    # counters beyond 2^32 blocks use the high counter word
+    far = (1 << 35) + 5
+    assert np.array_equal(_native.stdrng_u64(bytes([42] * 32), far, 16)[8:], _native.stdrng_u64(bytes([42] * 32), far + 8, 8))
