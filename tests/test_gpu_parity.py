@@ -528,3 +528,19 @@ def test_device_built_reference_instance_multiplies_like_the_host_built_one(gpu_
     assert_same(a.to_host(), a_h, "device-built bench instance")
     assert a.nnz() == 81434
     assert_same(a.matmul(a).to_host(), oracle.matmul(to_o(oracle, a_h), to_o(oracle, a_h)), "A^2 of the device-built instance")
+
+
+def test_device_thin_of_a_non_symmetric_matrix(gpu_ctx):
+    """thin() looks the mirror up with get(c, r) (src/graph_csr.rs:238): on a matrix that is not symmetric a kept upper entry
+    whose mirror is absent stays alone, and a lower entry whose mirror is absent can never be kept.  Random directed graph with
+    self loops added, values > 1."""
+    rng = np.random.default_rng(5)
+    n = 300
+    r = rng.integers(0, n, 4000); c = rng.integers(0, n, 4000); v = rng.integers(1, 9, 4000)
+    a_h = hostgen.from_coo(n, n, np.concatenate([r, np.arange(0, n, 7)]), np.concatenate([c, np.arange(0, n, 7)]),
+                           np.concatenate([v, np.full(len(range(0, n, 7)), 3)]), 64)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    for dens, seed in ((0.5, bytes([42] * 32)), (0.9, bytes([9] * 32))):
+        got = a.thin(dens, seed)
+        assert_same(got.to_host(), hostgen.thin(a_h, dens, seed), f"non-symmetric thin {dens}")
+        assert got.last_draws == hostgen.draws_of_thin(a_h)
