@@ -17,22 +17,30 @@ ap.add_argument("--side", type=int, default=200); ap.add_argument("--epn", type=
 ap.add_argument("--scale", type=int, default=20); ap.add_argument("--ef", type=int, default=16)
 ap.add_argument("--abc", type=float, nargs=3, default=[0.45, 0.15, 0.15])
 ap.add_argument("--bits", type=int, default=64); ap.add_argument("--check", type=int, default=1); ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--device-build", type=int, default=0, help="torus: build the instance with the engine's device generators (b200_lattice + b200_thin) instead of hostgen")
 args = ap.parse_args()
 
 peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
 
 t0 = time.time()
-if args.kind == "torus":
+ctx = Context(0); set_default_context(ctx)
+a = None
+if args.kind == "torus" and args.device_build:
+    a = B200Matrix.lattice([args.side] * 3, True, args.bits, ctx).thin(args.epn / 26.0, bytes([42] * 32))
+    ctx.synchronize()
+    a_h = a.to_host() if args.check else None
+    steps = list(range(2, args.power + 1))
+    print(f"torus (device-built): n={a.n} nnz={a.nnz()} built in {time.time() - t0:.2f}s", flush=True)
+elif args.kind == "torus":
     a_h = hostgen.thinned_torus([args.side] * 3, args.epn / 26.0, bytes([42] * 32), args.bits)
     steps = list(range(2, args.power + 1))
 else:
     a_h = hostgen.rmat(args.scale, args.ef, args.abc[0], args.abc[1], args.abc[2], 42, args.bits)
     steps = [2]
-print(f"{args.kind}: n={a_h.rows} nnz={a_h.nnz()} built in {time.time() - t0:.1f}s", flush=True)
-
-ctx = Context(0); set_default_context(ctx)
-a = B200Matrix.from_host(a_h)
+if a is None:
+    print(f"{args.kind}: n={a_h.rows} nnz={a_h.nnz()} built in {time.time() - t0:.1f}s", flush=True)
+    a = B200Matrix.from_host(a_h)
 if args.check:
     from oracle import oracle as O
     a_o = O.Csr(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values); p_o = a_o
