@@ -77,6 +77,26 @@ def build_operand(args, world):
     return hostgen.thin(full, density, bytes([42] * 32))
 
 
+def host_threads():
+    """Every host core this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which made
+    round 1's CPU arm single-threaded at N > 1.  The oracle's parallel regions take the thread count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def source_sha():
+    """Hash of the kernel sources: stamps profiles/r2_traffic.json so that a stale ncu figure is never reported."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "sparse_linear_algebra_tests_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def algorithmic_bytes(nnz_a, nnz_b, nnz_c, rows_a, rows_b, vbytes):
     return (nnz_a + nnz_b + nnz_c) * (4 + vbytes) + (rows_a + rows_b + rows_a + 3) * 8
 
@@ -123,19 +143,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU (reference arm / baseline)
-def cpu_chain(a_h, iters=3):
+def cpu_chain(a_h, iters=3, keep=False):
     """Reference protocol on the CPU restatement of CsrMatrix::matmul_par: per power 1 warm-up (kept as the next
-    left operand) + `iters` timed multiplies with the result dropped.  Returns per-power seconds and products."""
+    left operand) + `iters` timed multiplies with the result dropped.  Returns per-power seconds and products (and,
+    with `keep`, every power -- the checker of the GPU chain)."""
     from oracle import oracle as O
-    nt = O.max_threads()
+    nt = host_threads()
     a = O.Csr(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values)
-    p, secs, prods = a, [], []
+    p, secs, prods, kept = a, [], [], []
     for _k in range(2, MAX_POWER + 1):
         prods.append(int(O.row_products(p, a).sum()))
         nxt = O.matmul_par(p, a, nt)
         secs.append(O.time_matmul(p, a, True, nt, iters))
         p = nxt
-    return secs, prods, nt
+        if keep:
+            kept.append(p)
+    return (secs, prods, nt, kept) if keep else (secs, prods, nt)
 
 
 def run_reference(args):
@@ -264,6 +287,15 @@ def run_b200(args):
     ctx.set_timing(True)
 
     my_ms = float(np.mean(step_ms))
+    # per-rank step time and product count, so that jitter (spread of one rank's steps) and imbalance (spread over ranks)
+    # can be told apart in the line
+    mine = torch.tensor([my_ms, float(np.min(step_ms)), float(np.max(step_ms)), float(sum(prods))], dtype=torch.float64, device=dev)
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": i, "ms_mean": float(t[0]), "ms_min": float(t[1]), "ms_max": float(t[2]), "products": int(t[3])} for i, t in enumerate(allr)]
     t_ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(sum(prods)), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -289,14 +321,17 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     top = max(best, key=lambda s: s["bytes_algorithmic"])
     achieved = top["bytes_algorithmic"] / (top["ms_total"] * 1e-3) / 1e9
-    # DRAM bytes of that multiply from the committed ncu capture (profiles/r1_traffic.json: dram__bytes_read.sum +
-    # dram__bytes_write.sum over its kernels); only valid for the single-GPU 30^3 u64 workload it was taken on
+    # DRAM bytes of that multiply from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum over its
+    # kernels); reported only when the capture was taken on this workload AND on these kernel sources (hash stamp)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if world == 1 and args.side == 30 and args.bits == 64 and os.path.exists(tpath):
-        traffic = float(json.load(open(tpath))["traffic"])
-    roofline = {"bound": "hbm", "kernel": f"all kernels of the largest multiply A^{MAX_POWER} = A^{MAX_POWER - 1} x A "
-                                           "(pre-pass, per-bin numeric k_num_expand/k_num_tiny, row_ptr scan, host report, compaction)",
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if world == 1 and args.side == 30 and args.bits == 64 and MAX_POWER == 7 and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("source_sha") == source_sha():
+            traffic = float(tj["traffic"])
+    kernels = "k_fz_prepass + k_fz_numeric (pre-pass; fused numeric + placement, C written once)" if top.get("pipeline") == 1 else \
+              "binned pipeline (pre-pass, per-bin numeric, row_ptr scan, host report, compaction)"
+    roofline = {"bound": "hbm", "kernel": f"all kernels of the largest multiply A^{MAX_POWER} = A^{MAX_POWER - 1} x A: " + kernels,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes": top["bytes_algorithmic"], "ms": top["ms_total"], "traffic": traffic,
                 "numeric_only_frac": top["bytes_algorithmic"] / (top["ms_numeric"] * 1e-3) / 1e9 / peak if top["ms_numeric"] else None}
@@ -313,7 +348,7 @@ def run_b200(args):
                         "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-                              "dtype": f"u{args.bits}", "data": "synthetic", "config": cfg, "per_power": per_power, "gpu_launches": total_launches,
+                              "dtype": f"u{args.bits}", "data": "synthetic", "config": cfg, "per_power": per_power, "per_rank": per_rank, "gpu_launches": total_launches,
                               "wall_s_timed_region": wall, "clocks": clocks, "e2e": None, "roofline": roofline}), flush=True)
         if world > 1:
             dist.destroy_process_group()
@@ -370,10 +405,18 @@ def run_b200(args):
                 "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
-           "data": "synthetic", "config": cfg, "per_power": per_power, "gpu_launches": total_launches, "wall_s_timed_region": wall,
+           "data": "synthetic", "config": cfg, "per_power": per_power, "per_rank": per_rank, "gpu_launches": total_launches, "wall_s_timed_region": wall,
            "clocks": clocks, "e2e": e2e, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
-        secs, cprods, nt = cpu_chain(a_loc, 3)
+        secs, cprods, nt, cpu_powers = cpu_chain(a_loc, 3, keep=True)
+        # the GPU chain of this run against the CPU chain it is timed beside: every power, every array, bit for bit
+        gpu_powers, _ = chain()
+        for k, (g, c) in zip(range(2, MAX_POWER + 1), zip(gpu_powers, cpu_powers)):
+            rp, ci, vv = g.download()
+            if not (np.array_equal(rp, c.row_ptr) and np.array_equal(ci, c.col_idx) and np.array_equal(vv, c.values)):
+                raise SystemExit(f"bench.py: A^{k} from the GPU differs from the CPU restatement -- the timed result is wrong")
+        del gpu_powers
+        out["parity"] = f"A^2..A^{MAX_POWER} of this run bit-identical to the CPU chain (row_ptr, col_idx, values)"
         out["cpu_baseline"] = {"value": sum(cprods) / sum(secs), "unit": UNIT, "cores": nt, "kind": "port",
                                "sample": f"full A^2..A^{MAX_POWER} chain, reference protocol (1 warm-up + 3 timed multiplies per power)",
                                "ms_per_power": [s * 1e3 for s in secs], "ms_per_step": sum(secs) * 1e3}

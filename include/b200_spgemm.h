@@ -37,7 +37,8 @@ extern "C" {
 #define B200_ERR_SHAPE   2   /* operand shapes / value widths do not agree            */
 #define B200_ERR_ALLOC   3   /* device or pinned-host allocation failed               */
 #define B200_ERR_CUDA    4   /* no device, launch failure, or any other CUDA error    */
-#define B200_ERR_FORMAT  5   /* CSR invariant violated (explicit zero, col >= cols)   */
+#define B200_ERR_FORMAT  5   /* CSR invariant violated (explicit zero, col >= cols, unsorted or repeated column in a row) */
+#define B200_ERR_NCCL    6   /* NCCL missing or a collective failed                   */
 
 typedef struct b200_ctx b200_ctx;
 typedef struct b200_csr b200_csr;
@@ -56,10 +57,43 @@ typedef struct b200_stats {
     float    ms_total;          /* first kernel to last kernel, incl. the host's read of nnz in the middle      */
     int32_t  acc_mode;          /* 0: 32-bit accumulators proved safe, 1: 64-bit, 2: saturating                 */
     int32_t  kernel_launches;   /* kernels launched by this multiply                                            */
-    uint32_t sym_bin_rows[16];  /* rows per pre-pass list: [0] tiny, [1..8] bitmap bins (P <= 64<<hb; 1 and 2
-                                   share list 2), [9] heavy, [10..15] hash lists of bins 0..5 (window too wide)  */
-    uint32_t num_bin_rows[16];  /* same lists (kept for layout compatibility)                                   */
+    uint32_t sym_bin_rows[16];  /* binned pipeline: rows per pre-pass list: [0] tiny, [1..8] bitmap bins (P <= 64<<hb; 1
+                                   and 2 share list 2), [9] heavy, [10..15] hash lists of bins 0..5 (window too wide).
+                                   fused pipeline: [0] tiny, [1] dense, [2] other (counted beforehand), [3] empty rows,
+                                   [9] heavy and [10..15] hash lists of the "other" rows                          */
+    uint32_t pipeline;          /* 1 fused, 2 binned                                                             */
+    uint32_t reserved[15];
 } b200_stats;
+
+/* Tuning switches of a context: the analogue of MagnusConfig::default() (src/graph_magnus.rs:227,237), passed through
+ * the ABI instead of being read from the environment.  b200_config_default fills every field; b200_ctx_configure
+ * installs a copy (between multiplies).  -1 / 0 mean "engine decides" where noted. */
+typedef struct b200_config {
+    uint32_t struct_bytes;       /* sizeof(b200_config) as the caller compiled it (checked)                               */
+    int32_t pipeline;            /* 0 auto; 1 fused (pre-pass + one persistent numeric/placement kernel); 2 binned (a
+                                    kernel per row bin, scratch or exact placement)                                        */
+    int32_t placement;           /* binned pipeline: -1 auto, 0 scratch CSR + compaction, 1 exact (count pass first)       */
+    int32_t exact_limit_mb;      /* binned, auto placement: scratch bound above which the exact placement runs; -1 auto    */
+    int32_t force_acc_mode;      /* -1 auto (proved from the operands); 1 / 2 force the 64-bit / saturating accumulators   */
+    int32_t window_cap_groups;   /* binned: clamp of a bin's bitmap window in 128-column groups (0: hash kernels only); -1 */
+    int32_t window_mul;          /* binned: window of a bin = window_mul * 128 * capacity columns (default 3)              */
+    int32_t circular_windows;    /* per-row windows measured on the index circle for square right operands (default 1)     */
+    int32_t arc_window;          /* operand-level arc windows (default 1)                                                  */
+    int32_t touched_span;        /* binned: walk only the touched part of wide bitmaps (default 1)                         */
+    int32_t narrow_scratch;      /* binned: u64 values cross the scratch CSR as u32 when 32-bit sums are proved (1)        */
+    int32_t expand_kernel;       /* binned: 0 sends every medium row through hash + sort (default 1)                       */
+    int32_t pack_b;              /* sector-packed right operand: -1 auto (mean row <= 4), 0 off, 1 on                      */
+    int32_t lanes_per_entry_lg;  /* lanes cooperating on one A entry, log2; -1 auto                                        */
+    int32_t expand_div, hash_div, grid_div, grid_mul;   /* binned: thread / grid sizing divisors (8, 32, 8, 4)            */
+    int32_t aux_streams;         /* auxiliary streams the per-bin kernels fan out over (default 1, at most 3)              */
+    int32_t fused_threads;       /* fused: threads per CTA of the numeric kernel (0 auto = 256; multiple of 32, <= 256)    */
+    int32_t fused_window_cols;   /* fused: preferred cap of the dense accumulator window in columns (0 auto)               */
+    int32_t fused_dense_pmax;    /* fused: rows with more intermediate products go to the heavy kernel (0 auto = 65536)    */
+    int32_t heavy_chunk_cols;    /* heavy rows: columns per chunk of the chunked kernel (0 auto, from shared memory)       */
+    int32_t heavy_kernel;        /* heavy rows: 1 chunked TMA kernel (default), 0 single-CTA global-memory table          */
+    int32_t reserved[8];
+} b200_config;
+int b200_config_default(b200_config *cfg);
 
 const char *b200_last_error(void);
 /* Number of CUDA devices visible (0 when there is none or no driver). */
@@ -74,6 +108,8 @@ int b200_ctx_synchronize(b200_ctx *ctx);
 int b200_ctx_kernel_launches(b200_ctx *ctx, uint64_t *out);
 /* Per-phase CUDA-event timing in b200_stats costs a few event records; on by default. */
 int b200_ctx_set_timing(b200_ctx *ctx, int enabled);
+int b200_ctx_configure(b200_ctx *ctx, const b200_config *cfg);
+int b200_ctx_get_config(b200_ctx *ctx, b200_config *cfg);
 
 /* Host CSR -> device handle.  Replaces constructing a CsrMatrix / MagnusMatrix from its three
  * arrays (src/graph_csr.rs:42-53; SparseMatrixCSR::new at src/graph_magnus.rs:74).
@@ -109,8 +145,14 @@ int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr,
  * Csr<I,V>::matmul / matmul_par (linalg/src/csr.rs:308-356, 361-466) and
  * MagnusMatrix::matmul / matmul_seq (src/graph_magnus.rs:225-242).  Result: ascending unique
  * columns per row, saturating sums of saturating products, zeros dropped, row_ptr[0] = 0 --
- * bit-identical to the reference's CSR output.  `stats` may be NULL. */
+ * bit-identical to the reference's CSR output.  `stats` may be NULL.
+ * The call is asynchronous when `stats` is NULL: the product handle is returned while its kernels are still queued and its
+ * size (nnz) reaches the host later through a pinned report; any call that needs the size (b200_csr_info with an nnz
+ * pointer, downloads, using the handle as an operand) waits for that report by itself.  With `stats` the call returns
+ * after the multiply has finished on the device.  b200_csr_product_stats returns the same numbers later. */
 int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **C, b200_stats *stats);
+/* Measurements of the multiply that produced C (waits for that multiply); B200_ERR_BADARG for handles that are not products. */
+int b200_csr_product_stats(b200_ctx *ctx, const b200_csr *C, b200_stats *stats);
 
 /* Per-row intermediate-product counts of A x B (host array of A.rows u64); the quantity the
  * multi-GPU row split is balanced on. */

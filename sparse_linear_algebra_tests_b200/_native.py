@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200spgemm.so")
 
-B200_OK, B200_ERR_BADARG, B200_ERR_SHAPE, B200_ERR_ALLOC, B200_ERR_CUDA, B200_ERR_FORMAT = range(6)
+B200_OK, B200_ERR_BADARG, B200_ERR_SHAPE, B200_ERR_ALLOC, B200_ERR_CUDA, B200_ERR_FORMAT, B200_ERR_NCCL = range(7)
 
 
 class B200Error(RuntimeError):
@@ -32,18 +32,28 @@ class Stats(C.Structure):
                 ("nnz_c", C.c_uint64), ("products", C.c_uint64), ("max_row_products", C.c_uint64),
                 ("max_row_nnz", C.c_uint64), ("bytes_algorithmic", C.c_uint64), ("ms_symbolic", C.c_float),
                 ("ms_numeric", C.c_float), ("ms_total", C.c_float), ("acc_mode", C.c_int32),
-                ("kernel_launches", C.c_int32), ("sym_bin_rows", C.c_uint32 * 16), ("num_bin_rows", C.c_uint32 * 16)]
+                ("kernel_launches", C.c_int32), ("sym_bin_rows", C.c_uint32 * 16), ("pipeline", C.c_uint32),
+                ("reserved", C.c_uint32 * 15)]
 
     def as_dict(self) -> dict:
-        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.endswith("_rows")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("sym_bin_rows", "reserved")}
         d["sym_bin_rows"] = list(self.sym_bin_rows)
-        d["num_bin_rows"] = list(self.num_bin_rows)
         return d
+
+
+class Config(C.Structure):
+    """b200_config (include/b200_spgemm.h): the tuning switches of a context, the MagnusConfig analogue."""
+    _fields_ = [("struct_bytes", C.c_uint32)] + [(n, C.c_int32) for n in (
+        "pipeline", "placement", "exact_limit_mb", "force_acc_mode", "window_cap_groups", "window_mul", "circular_windows",
+        "arc_window", "touched_span", "narrow_scratch", "expand_kernel", "pack_b", "lanes_per_entry_lg", "expand_div", "hash_div",
+        "grid_div", "grid_mul", "aux_streams", "fused_threads", "fused_window_cols", "fused_dense_pmax", "heavy_chunk_cols",
+        "heavy_kernel")] + [("reserved", C.c_int32 * 8)]
 
 
 EXPORTS = [
     "b200_last_error", "b200_device_count", "b200_ctx_create", "b200_ctx_destroy", "b200_ctx_synchronize",
-    "b200_ctx_kernel_launches", "b200_ctx_set_timing", "b200_csr_upload", "b200_csr_upload_idx64",
+    "b200_ctx_kernel_launches", "b200_ctx_set_timing", "b200_config_default", "b200_ctx_configure", "b200_ctx_get_config",
+    "b200_csr_product_stats", "b200_csr_upload", "b200_csr_upload_idx64",
     "b200_csr_from_device", "b200_csr_free", "b200_csr_info", "b200_csr_device_ptrs", "b200_csr_max_value",
     "b200_csr_download", "b200_csr_download_idx64", "b200_csr_download_async", "b200_spgemm", "b200_row_products",
     "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
@@ -71,6 +81,10 @@ def load():
         "b200_ctx_synchronize": [vp],
         "b200_ctx_kernel_launches": [vp, C.POINTER(u64)],
         "b200_ctx_set_timing": [vp, i32],
+        "b200_config_default": [C.POINTER(Config)],
+        "b200_ctx_configure": [vp, C.POINTER(Config)],
+        "b200_ctx_get_config": [vp, C.POINTER(Config)],
+        "b200_csr_product_stats": [vp, vp, C.POINTER(Stats)],
         "b200_csr_upload": [vp, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
         "b200_csr_upload_idx64": [vp, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
         "b200_csr_from_device": [vp, u64, u64, u64, vp, vp, vp, i32, C.POINTER(vp)],
@@ -145,6 +159,24 @@ class Context:
     def set_timing(self, enabled: bool):
         check(load().b200_ctx_set_timing(self._h, int(enabled)))
 
+    def config(self) -> Config:
+        c = Config()
+        check(load().b200_ctx_get_config(self._h, C.byref(c)))
+        return c
+
+    def configure(self, **fields) -> Config:
+        """Change tuning switches (b200_ctx_configure); returns the configuration that was in force before."""
+        old, new = self.config(), self.config()
+        for k, v in fields.items():
+            if not hasattr(new, k) or k in ("struct_bytes", "reserved"):
+                raise B200Error(B200_ERR_BADARG, f"unknown configuration field {k!r}")
+            setattr(new, k, int(v))
+        check(load().b200_ctx_configure(self._h, C.byref(new)))
+        return old
+
+    def restore(self, cfg: Config):
+        check(load().b200_ctx_configure(self._h, C.byref(cfg)))
+
     def kernel_launches(self) -> int:
         v = C.c_uint64()
         check(load().b200_ctx_kernel_launches(self._h, C.byref(v)))
@@ -158,6 +190,16 @@ class Context:
             raise B200Error(B200_ERR_BADARG, f"values must be uint32 or uint64, got {vv.dtype}")
         bits = 32 if vv.dtype == np.uint32 else 64
         ci = np.ascontiguousarray(col_idx)
+        if rp.ndim != 1 or rp.size != rows + 1:
+            raise B200Error(B200_ERR_BADARG, f"row_ptr must hold rows + 1 = {rows + 1} entries, got {rp.size}")
+        if ci.ndim != 1 or vv.ndim != 1 or ci.size != int(rp[-1]) or vv.size != int(rp[-1]):
+            raise B200Error(B200_ERR_BADARG, f"col_idx / values must hold row_ptr[-1] = {int(rp[-1])} entries, got {ci.size} / {vv.size}")
+        if ci.dtype.kind not in "ui":
+            raise B200Error(B200_ERR_BADARG, f"col_idx must be an integer array, got {ci.dtype}")
+        if ci.dtype.kind == "i" and ci.size and int(ci.min()) < 0:
+            raise B200Error(B200_ERR_FORMAT, "negative column index")
+        if ci.dtype.itemsize == 8:   # 64-bit columns take the path that range-checks them on the device
+            ci = np.ascontiguousarray(ci, dtype=np.uint64)
         h = C.c_void_p()
         if ci.dtype == np.uint64:   # MAGNUS usize columns
             check(load().b200_csr_upload_idx64(self._h, rows, cols, rp.ctypes.data, ci.ctypes.data, vv.ctypes.data, bits, C.byref(h)))
@@ -172,6 +214,8 @@ class Context:
         return DeviceCsr(self, h)
 
     def spgemm(self, a: "DeviceCsr", b: "DeviceCsr", want_stats: bool = False):
+        """C = A x B.  Without `want_stats` the call returns while the kernels are still queued (the product's nnz is
+        fetched from the device report the first time it is asked for)."""
         h = C.c_void_p()
         st = Stats() if want_stats else None
         check(load().b200_spgemm(self._h, a._h, b._h, C.byref(h), C.byref(st) if want_stats else None))
@@ -225,9 +269,24 @@ class DeviceCsr:
     def __init__(self, ctx: Context, handle):
         self.ctx = ctx
         self._h = handle
-        r, c, n, b = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
-        check(load().b200_csr_info(self._h, C.byref(r), C.byref(c), C.byref(n), C.byref(b)))
-        self.rows, self.cols, self.nnz, self.val_bits = int(r.value), int(c.value), int(n.value), int(b.value)
+        r, c, b = C.c_uint64(), C.c_uint64(), C.c_int()
+        check(load().b200_csr_info(self._h, C.byref(r), C.byref(c), None, C.byref(b)))
+        self.rows, self.cols, self.val_bits = int(r.value), int(c.value), int(b.value)
+        self._nnz = None
+
+    @property
+    def nnz(self) -> int:
+        """Stored entries; for a product still in flight this waits for its device report."""
+        if self._nnz is None:
+            n = C.c_uint64()
+            check(load().b200_csr_info(self._h, None, None, C.byref(n), None))
+            self._nnz = int(n.value)
+        return self._nnz
+
+    def product_stats(self) -> Stats:
+        st = Stats()
+        check(load().b200_csr_product_stats(self.ctx._h, self._h, C.byref(st)))
+        return st
 
     def free(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):

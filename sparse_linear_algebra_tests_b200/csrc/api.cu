@@ -1,35 +1,17 @@
 // api.cu -- extern "C" entry points (include/b200_spgemm.h) and host orchestration of the kernels.
 // No CPU fallback anywhere in this file: every compute entry point runs CUDA kernels or fails.
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <cstdarg>
-#include <string>
-#include <vector>
-#include <algorithm>
-
-#include "../../include/b200_spgemm.h"
+#include "engine.cuh"
 #include "kernels.cuh"
 #include "gen.cuh"
 
-#define B200_NAUX 3
-
 // ---------------------------------------------------------------------------- error plumbing
 static thread_local std::string g_last_error;
-static int set_err(int code, const char *fmt, ...) {
+int set_err(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
     g_last_error = buf;
     return code;
 }
-#define CUDA_TRY(expr)                                                                             \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess)                                                                     \
-            return set_err(_e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA,       \
-                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
-#define TRY(expr) do { int _r = (expr); if (_r != B200_OK) return _r; } while (0)
 
 extern "C" const char *b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -39,63 +21,13 @@ extern "C" int b200_device_count(void) {
     return n;
 }
 
-// ---------------------------------------------------------------------------- handles
-struct b200_csr {
-    u64 rows, cols, nnz;
-    int val_bits;
-    u64 *d_rp; u32 *d_col; void *d_val;
-    ull *d_maxval;          // device scalar: largest stored value (lives behind row_ptr, same allocation)
-    bool val_shares_col;    // values live in the col_idx allocation (products: one allocation per multiply)
-    u64 max_row_len;        // host-known upper bound of the longest row
-    uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
-    uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (pre-pass: plain column windows)
-    uint4 *d_cspan;         // square operands: {len, min, max} of (col - row + n/2) mod n (pre-pass: circular windows)
-    uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
-    u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
-    // circular column range: every stored column is (cr_start + o) mod cols for some o < cr_len (cr_len = cols: unknown / everything)
-    u32 cr_start; u64 cr_len;
-    // square operands used on the right: signed offsets (c - k) of all entries lie in [cs_lo, cs_hi]; cs_state 0 unknown, 1 known, 2 none
-    long long cs_lo, cs_hi; int cs_state;
-    cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
-    b200_ctx *ctx;
-};
-
-struct b200_ctx {
-    int device, num_sms;
-    size_t smem_optin, total_mem;
-    cudaStream_t stream; bool own_stream;
-    B200Ctrl *d_ctrl, *h_ctrl;
-    u64 *h_report;          // pinned: the final scan's report, one {word, epoch} chunk per 32-bit word of the control block
-    // per-row scratch, grown on demand
-    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint4 *d_win;
-    // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
-    unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
-    size_t scan_clean_bytes;   // leading bytes of d_scan known to be zero on the stream (left so by k_compact_rows)
-    // heavy-row scratch
-    void *d_heavy; size_t cap_heavy;
-    // one-pass scratch CSR (bound-offset rows), kept across multiplies so the steady state allocates nothing
-    void *d_tmp_col, *d_tmp_val; size_t cap_tmp_col, cap_tmp_val;
-    u32 *d_flag;            // small device flag word (+ pinned mirror)
-    u32 *h_flag;
-    cudaEvent_t ev[4];
-    cudaStream_t aux[B200_NAUX]; cudaEvent_t ev_fork, ev_join[B200_NAUX]; int naux_enabled;
-    cudaStream_t copy; cudaEvent_t ev_ready;   // D2H stream: downloads overlap the next multiply
-    bool timing;
-    u32 epoch;              // multiplies reported through the pinned mirror so far
-    u64 launches;
-    // developer timeline (B200_TRACE=1): an event after every launch, on the stream it went to
-    bool trace; cudaStream_t cur_stream;
-    bool hosttime; double ht[8];   // B200_HOSTTIME=1: host clock at the phase boundaries of a multiply (dev tool)
-    std::vector<std::pair<int, cudaEvent_t>> *marks;
-};
-static inline double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
-static void trace_mark(b200_ctx *ctx, int line) {
+void trace_mark(b200_ctx *ctx, int line) {
     cudaEvent_t e; cudaEventCreate(&e);
     cudaEventRecord(e, ctx->cur_stream ? ctx->cur_stream : ctx->stream);
     ctx->marks->push_back(std::make_pair(line, e));
     ctx->cur_stream = nullptr;
 }
-static void trace_dump(b200_ctx *ctx, const char *what) {
+void trace_dump(b200_ctx *ctx, const char *what) {
     if (!ctx->trace || ctx->marks->empty()) return;
     cudaDeviceSynchronize();
     fprintf(stderr, "[b200 trace] %s\n", what);
@@ -107,7 +39,6 @@ static void trace_dump(b200_ctx *ctx, const char *what) {
     ctx->marks->clear();
 }
 
-static int host_maxval(b200_ctx *ctx, const b200_csr *m);
 
 template <typename VT>
 static CsrView<VT> view(const b200_csr *m) {
@@ -115,20 +46,17 @@ static CsrView<VT> view(const b200_csr *m) {
     return v;
 }
 
-#define LAUNCH_CHECK(ctx)                                                                          \
-    do { (ctx)->launches++; if ((ctx)->trace) trace_mark(ctx, __LINE__); cudaError_t _e = cudaGetLastError(); \
-         if (_e != cudaSuccess) return set_err(B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
-static int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
+int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
     if (e != cudaSuccess) { cudaGetLastError(); return set_err(B200_ERR_ALLOC, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
     return B200_OK;
 }
-static void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+void dfree(b200_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
 #define B200_CTRL_BYTES 512
-static int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
+int ensure_row_scratch(b200_ctx *ctx, u64 rows) {
     if (rows > ctx->cap_rows) {
         dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_win);
         ctx->d_prod = nullptr; ctx->d_nnz_row = nullptr; ctx->d_bin_rows = nullptr; ctx->d_tmp_ptr = nullptr; ctx->d_win = nullptr; ctx->cap_rows = 0;
@@ -206,6 +134,45 @@ static void setup_kernels_vt(size_t optin) {
     allow_big_smem(k_num_expand<VT, 1, true, false, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, false, true>, optin); allow_big_smem(k_num_expand<VT, 1, true, true, false>, optin); allow_big_smem(k_num_expand<VT, 1, true, true, true>, optin);
 }
 
+// ---------------------------------------------------------------------------- configuration
+// Tuning switches live in a plain struct passed through the ABI (b200_config, the MagnusConfig::default() analogue of
+// /root/reference/src/graph_magnus.rs:227): b200_config_default fills the defaults, b200_ctx_configure installs a copy.
+// The B200_* environment variables of round 1 are read ONCE, when a context is created, as developer overrides of the
+// defaults; nothing on the multiply path touches the environment.
+extern "C" int b200_config_default(b200_config *c) {
+    if (!c) return set_err(B200_ERR_BADARG, "config is NULL");
+    memset(c, 0, sizeof(*c));
+    c->struct_bytes = (uint32_t)sizeof(b200_config);
+    c->pipeline = 0; c->placement = -1; c->exact_limit_mb = -1; c->force_acc_mode = -1; c->window_cap_groups = -1; c->window_mul = 3;
+    c->circular_windows = 1; c->arc_window = 1; c->touched_span = 1; c->narrow_scratch = 1; c->expand_kernel = 1; c->pack_b = -1;
+    c->lanes_per_entry_lg = -1; c->expand_div = 8; c->hash_div = 32; c->grid_div = 8; c->grid_mul = 4; c->aux_streams = 1;
+    c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1;
+    return B200_OK;
+}
+static void config_from_env(b200_config *c) {
+    struct { const char *name; int32_t *field; } tab[] = {
+        {"B200_PIPELINE", &c->pipeline}, {"B200_EXACT", &c->placement}, {"B200_EXACT_MB", &c->exact_limit_mb}, {"B200_FORCE_MODE", &c->force_acc_mode},
+        {"B200_WINCAP", &c->window_cap_groups}, {"B200_WINMUL", &c->window_mul}, {"B200_CIRCULAR", &c->circular_windows}, {"B200_ARC", &c->arc_window},
+        {"B200_SPAN", &c->touched_span}, {"B200_NARROW", &c->narrow_scratch}, {"B200_EXPAND", &c->expand_kernel}, {"B200_PACK", &c->pack_b},
+        {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
+        {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
+        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel},
+    };
+    for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
+}
+extern "C" int b200_ctx_configure(b200_ctx *ctx, const b200_config *c) {
+    if (!ctx || !c) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (c->struct_bytes != sizeof(b200_config)) return set_err(B200_ERR_BADARG, "b200_config.struct_bytes is %u, this library expects %zu (call b200_config_default first)", c->struct_bytes, sizeof(b200_config));
+    ctx->cfg = *c;
+    ctx->naux_enabled = std::max(0, std::min(B200_NAUX, (int)c->aux_streams));
+    return B200_OK;
+}
+extern "C" int b200_ctx_get_config(b200_ctx *ctx, b200_config *c) {
+    if (!ctx || !c) return set_err(B200_ERR_BADARG, "NULL argument");
+    *c = ctx->cfg;
+    return B200_OK;
+}
+
 static int env_int_early(const char *name) { const char *v = getenv(name); return v && *v ? atoi(v) : 0; }
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     if (!out) return set_err(B200_ERR_BADARG, "b200_ctx_create: out is NULL");
@@ -244,7 +211,14 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     // one auxiliary stream measured as good as three, with half the event calls
-    { const char *v = getenv("B200_NAUX"); ctx->naux_enabled = v && *v ? std::max(0, std::min(B200_NAUX, atoi(v))) : 1; }
+    b200_config_default(&ctx->cfg);
+    config_from_env(&ctx->cfg);
+    ctx->naux_enabled = std::max(0, std::min(B200_NAUX, (int)ctx->cfg.aux_streams));
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_freport, (size_t)B200_REPORT_SLOTS * sizeof(B200Ctrl) * 2));
+    memset(ctx->h_freport, 0, (size_t)B200_REPORT_SLOTS * sizeof(B200Ctrl) * 2);
+    for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) CUDA_TRY(cudaEventCreate(&ctx->f_ev[i][j]));
+    ctx->f_dirty = true;
+    fz_setup(ctx);
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
@@ -267,7 +241,10 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
+    dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_roworg); dfree(ctx, ctx->d_rowclass);
     cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(ctx->h_freport);
+    for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->f_ev[i][j]);
     cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
@@ -295,18 +272,21 @@ extern "C" int b200_ctx_set_timing(b200_ctx *ctx, int enabled) {
 
 // ---------------------------------------------------------------------------- CSR handles
 // col_idx and values of m->nnz entries in ONE allocation (values behind the columns, 256-byte aligned)
-static int alloc_entries(b200_ctx *ctx, b200_csr *m) {
-    const size_t col_bytes = ((size_t)m->nnz * 4 + 255) & ~(size_t)255;
-    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)m->nnz * (size_t)(m->val_bits / 8)));
+int alloc_entries(b200_ctx *ctx, b200_csr *m) {
+    const u64 cap = std::max(m->nnz, m->cap_entries);                     // products of the fused path are allocated from a bound
+    m->cap_entries = cap;
+    const size_t col_bytes = ((size_t)cap * 4 + 255) & ~(size_t)255;
+    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)cap * (size_t)(m->val_bits / 8)));
     m->d_val = (unsigned char *)m->d_col + col_bytes;
     m->val_shares_col = true;
     return B200_OK;
 }
-static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out) {
+int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out) {
     b200_csr *m = new b200_csr();
     memset(m, 0, sizeof(*m));
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
     m->cr_start = 0; m->cr_len = cols;
+    m->pending_slot = -1; m->max_row_span = cols;
     int r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8 + 16);           // row_ptr + the max-value scalar
     if (r == B200_OK) m->d_maxval = (ull *)(m->d_rp + rows + 1);
     if (r == B200_OK && alloc_arrays) r = alloc_entries(ctx, m);
@@ -318,6 +298,8 @@ static int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, b
 extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (!m) return B200_OK;
     if (!ctx) ctx = m->ctx;
+    if (m->pending_slot >= 0 && ctx->slot_owner[m->pending_slot] == m) ctx->slot_owner[m->pending_slot] = nullptr;   // its report is simply never read
+    delete m->stats;
     if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
     dfree(ctx, m->d_rp); dfree(ctx, m->d_col); if (!m->val_shares_col) dfree(ctx, m->d_val);
     dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_cspan); dfree(ctx, m->d_pack);
@@ -332,7 +314,7 @@ static int grid_for(u64 n, int threads, int cap) { u64 g = (n + threads - 1) / t
 static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr = false) {
     CUDA_TRY(cudaMemsetAsync(m->d_maxval, 0, 16, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 32, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 16, 0, 36, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 16, 0, 48, ctx->stream));
     if (device_rowptr && m->rows) {
         k_rowptr_stats<<<grid_for(m->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(m->rows, m->nnz, m->d_rp, ctx->d_flag + 4, ctx->d_flag);
         LAUNCH_CHECK(ctx);
@@ -343,11 +325,20 @@ static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_ro
         else k_value_stats<u64><<<g, 256, 0, ctx->stream>>>(m->nnz, (const u64 *)m->d_val, m->d_col, m->cols, m->d_maxval, ctx->d_flag, ctx->d_flag + 16);
         LAUNCH_CHECK(ctx);
     }
+    if (m->rows && m->nnz) {
+        // columns strictly ascending inside every row (the kernels take a row's first / last column as its min / max and
+        // merge or binary-search sorted rows); flag bit 4
+        k_rows_sorted<<<grid_for(m->rows, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(m->rows, m->d_rp, m->d_col, m->nnz, ctx->d_flag);
+        LAUNCH_CHECK(ctx);
+        TRY(fz_row_span(ctx, m));
+    }
     if (check) {
         CUDA_TRY(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 128, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_flag[0] & 2u) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone from 0 to nnz");
+        if (ctx->h_flag[0] & 4u) return set_err(B200_ERR_FORMAT, "column indices are not strictly ascending inside every row");
         if (ctx->h_flag[0]) return set_err(B200_ERR_FORMAT, "CSR holds an explicit zero value or a column index >= cols");
+        m->max_row_span = m->nnz ? (u64)ctx->h_flag[26] : 0;
         if (device_rowptr) m->max_row_len = ctx->h_flag[4];
         if (m->nnz && m->cols) {                                            // circular column range (see k_value_stats)
             const long long n = (long long)m->cols, half = n / 2, quarter = n / 4, ref = (long long)ctx->h_flag[24];
@@ -443,6 +434,7 @@ extern "C" int b200_csr_from_device(b200_ctx *ctx, uint64_t rows, uint64_t cols,
 
 extern "C" int b200_csr_info(const b200_csr *m, uint64_t *rows, uint64_t *cols, uint64_t *nnz, int *val_bits) {
     if (!m) return set_err(B200_ERR_BADARG, "matrix is NULL");
+    if (nnz) RESOLVE((b200_ctx *)nullptr, m);                                            // a fused product learns its size from the device report
     if (rows) *rows = m->rows; if (cols) *cols = m->cols; if (nnz) *nnz = m->nnz; if (val_bits) *val_bits = m->val_bits;
     return B200_OK;
 }
@@ -462,6 +454,7 @@ extern "C" int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *ou
 extern "C" int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
     if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, m);
     // the copies run on the context's copy stream, after everything queued on the compute stream so far
     b200_csr *mm = const_cast<b200_csr *>(m);
     if (!mm->ev_copy) CUDA_TRY(cudaEventCreateWithFlags(&mm->ev_copy, cudaEventDisableTiming));
@@ -481,6 +474,7 @@ extern "C" int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row
 extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values) {
     if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, m);
     u64 *tmp = nullptr;
     if (col_idx && m->nnz) {
         TRY(dmalloc(ctx, (void **)&tmp, m->nnz * 8));
@@ -496,20 +490,10 @@ extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_
 }
 
 // ---------------------------------------------------------------------------- SpGEMM
-// Developer switches (B200_*) are read per multiply so tests can flip them; a multiply looks at ~40 of them, so the
-// environment is scanned once per call and the lookups are skipped entirely when no B200_ variable is set.
-extern char **environ;
-static bool g_env_any = true;
-static void env_refresh() {
-    bool any = false;
-    for (char **e = environ; e && *e; e++) if (!strncmp(*e, "B200_", 5)) { any = true; break; }
-    g_env_any = any;
-}
-static int env_int(const char *name, int dflt) { if (!g_env_any) return dflt; const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
 // lanes cooperating on one A entry while walking its B row: largest power of two <= mean B row length / 2
-static int pick_lg(const b200_csr *B, int max_lg) {
-    const int forced = env_int("B200_LG", -1);
+int pick_lg(const b200_ctx *ctx, const b200_csr *B, int max_lg) {
+    const int forced = ctx->cfg.lanes_per_entry_lg;
     if (forced >= 0) return std::min(forced, max_lg);
     const double avg = B->rows ? (double)B->nnz / (double)B->rows : 1.0;
     int lg = 0;
@@ -517,8 +501,8 @@ static int pick_lg(const b200_csr *B, int max_lg) {
     return lg;
 }
 // threads that own one row of hash bin hb: ~one group per 4 A entries, assuming deg_A ~ cap/2
-static int bin_threads(int hb, int lg) {
-    const int div = std::max(1, env_int("B200_TDIV", 32));
+static int bin_threads(const b200_ctx *ctx, int hb, int lg) {
+    const int div = std::max(1, (int)ctx->cfg.hash_div);
     long t = ((long)b200_hash_cap(hb) << lg) / div;
     t = std::max(32L, std::min(1024L, t));
     long need = (long)b200_hash_slots(hb) / 16;                           // sort path keeps <= 16 slots per thread
@@ -526,7 +510,7 @@ static int bin_threads(int hb, int lg) {
 }
 
 // B row descriptors {start,len}: built once per right operand and cached in the handle
-static int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
+int ensure_desc(b200_ctx *ctx, const b200_csr *B) {
     if (B->d_desc) return B200_OK;
     if (B->nnz >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "right operand with >= 2^32 stored entries is not supported");
     b200_csr *Bm = const_cast<b200_csr *>(B);
@@ -548,7 +532,7 @@ static int ensure_cspan(b200_ctx *ctx, const b200_csr *B) {
 }
 
 // operand-wide circular column offsets of a square right operand (k_cspan_bounds): one reduction, read back and cached
-static int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B) {
+int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B) {
     if (B->cs_state) return B200_OK;
     b200_csr *Bm = const_cast<b200_csr *>(B);
     if (B->rows != B->cols || B->nnz == 0) { Bm->cs_state = 2; return B200_OK; }
@@ -564,12 +548,12 @@ static int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B) {
 }
 
 // sector-packed records for low-degree right operands (mean row length <= 4)
-static bool want_pack(const b200_csr *B) {
-    const int forced = env_int("B200_PACK", -1);
+bool want_pack(const b200_ctx *ctx, const b200_csr *B) {
+    const int forced = ctx->cfg.pack_b;
     if (forced >= 0) return forced != 0;
     return B->rows && (double)B->nnz / (double)B->rows <= 4.0;
 }
-static int ensure_pack(b200_ctx *ctx, const b200_csr *B) {
+int ensure_pack(b200_ctx *ctx, const b200_csr *B) {
     if (B->d_pack) return B200_OK;
     b200_csr *Bm = const_cast<b200_csr *>(B);
     TRY(dmalloc(ctx, (void **)&Bm->d_pack, (B->rows + 1) * 2 * sizeof(uint4)));
@@ -579,7 +563,8 @@ static int ensure_pack(b200_ctx *ctx, const b200_csr *B) {
 }
 
 // host copy of a handle's largest value (read back once; products get it from their own final read-back)
-static int host_maxval(b200_ctx *ctx, const b200_csr *m) {
+int host_maxval(b200_ctx *ctx, const b200_csr *m) {
+    RESOLVE(ctx, m);
     if (m->h_maxval_known) return B200_OK;
     b200_csr *mm = const_cast<b200_csr *>(m);
     CUDA_TRY(cudaMemcpyAsync(ctx->h_flag + 2, m->d_maxval, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -640,43 +625,21 @@ static void launch_scan_rowptr(b200_ctx *ctx, u64 rows, u64 *rp, cudaStream_t s,
     else k_scan_rowptr<SCAN_THREADS, SCAN_ITEMS><<<tiles, SCAN_THREADS, 0, s>>>(rows, ctx->d_nnz_row, rp, ctx->d_tile_status, ctx->d_ctrl, host_mirror, epoch);
 }
 
-// Independent per-bin kernels are spread over the main stream and a few auxiliary streams.
-struct Fan {
-    b200_ctx *ctx; int next; bool used[B200_NAUX]; bool forked;
-    explicit Fan(b200_ctx *c) : ctx(c), next(0), forked(false) { for (int i = 0; i < B200_NAUX; i++) used[i] = false; }
-    cudaStream_t pick() {
-        const int n = ctx->naux_enabled;
-        if (n == 0) return ctx->stream;
-        const int slot = next++ % (n + 1);
-        if (slot == n) return ctx->stream;
-        ctx->cur_stream = ctx->aux[slot];
-        if (!forked) { cudaEventRecord(ctx->ev_fork, ctx->stream); forked = true; }
-        if (!used[slot]) { cudaStreamWaitEvent(ctx->aux[slot], ctx->ev_fork, 0); used[slot] = true; }
-        return ctx->aux[slot];
-    }
-    void join() {
-        for (int i = 0; i < B200_NAUX; i++)
-            if (used[i]) { cudaEventRecord(ctx->ev_join[i], ctx->aux[i]); cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0); used[i] = false; }
-        forked = false; next = 0;
-    }
-};
-
 static int ctas_per_sm(const b200_ctx *ctx, int threads, size_t smem) {
     return std::max(1, std::min(32, std::min(2048 / threads, (int)(ctx->smem_optin / (smem + 1024)))));
 }
 
 // accumulator width from a proof that no row sum can overflow: rows_bound * max(A) * max(B)
-template <typename VT>
-static int pick_mode(u64 max_row_products, u64 maxA, u64 maxB) {
+int pick_mode_bits(const b200_ctx *ctx, int val_bits, u64 max_row_products, u64 maxA, u64 maxB) {
     unsigned __int128 bound = (unsigned __int128)max_row_products * maxA;
     bool over64 = (bound >> 64) != 0;
     if (!over64) { bound *= maxB; over64 = (bound >> 64) != 0; }
     int mode;
     if (!over64 && (u64)bound < (1ull << 32)) mode = 0;
-    else if (sizeof(VT) == 4) mode = 1;                                   // clamped 32-bit products, < 2^32 of them per row
+    else if (val_bits == 32) mode = 1;                                    // clamped 32-bit products, < 2^32 of them per row
     else mode = over64 ? 2 : 1;
-    const int forced = env_int("B200_FORCE_MODE", -1);                    // testing hook: a wider mode is always valid
-    if (forced > mode && forced <= (sizeof(VT) == 8 ? 2 : 1)) mode = forced;
+    const int forced = ctx->cfg.force_acc_mode;                           // testing hook: a wider mode is always valid
+    if (forced > mode && forced <= (val_bits == 64 ? 2 : 1)) mode = forced;
     return mode;
 }
 
@@ -703,7 +666,9 @@ static void expand_dispatch(bool packed, bool bpat, bool span, int eg, int et, s
 // sized from `rows` and bins that no row can reach (p_bound) are skipped.
 template <typename VT>
 static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u64 rows, u64 p_bound, u64 heavy_cap,
-                          int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps) {
+                          int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps,
+                          B200Ctrl *ctrl = nullptr, bool wide_only = false) {
+    if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32);
     const size_t smem_max = ctx->smem_optin - 1024;
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
@@ -712,8 +677,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     const size_t accb = mode == 0 ? 4 : 8;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto do_tiny = [&]() -> int {
+        if (wide_only) return B200_OK;
         const int g = (int)std::min<u64>((rows + 31) / 32, (u64)ctx->num_sms * 32);   // >= 4 rows per warp: the software pipeline needs a row stream
-        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctx->d_ctrl, o, bpat, B->cols <= (1ull << 27), mode == 0);
+        k_num_tiny<VT><<<g, 256, 0, fan.pick()>>>(na, ctx->d_bin_rows, ctrl, o, bpat, B->cols < (1ull << 27), mode == 0);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
@@ -721,20 +687,20 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
     const u32 nw4_full = caps.full;
     auto launch_expand = [&](int bin, int nb, u32 cap, u32 nw4, u64 n, cudaStream_t bs) -> bool {
-        if (nw4 == 0) return false;
+        if (nw4 == 0 || wide_only) return false;
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
         const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
         const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
         if (ex_smem + (packed ? 0 : sizeof(EnumSmem)) > smem_max) return false;
         // threads: ~8 products or ~8 bitmap groups each, whichever asks for more
-        const int et = std::max(32, std::min(512, (int)std::max<u32>(pcap, nw4) / std::max(1, env_int("B200_EDIV", 8)) / 32 * 32));
+        const int et = std::max(32, std::min(512, (int)std::max<u32>(pcap, nw4) / std::max(1, (int)ctx->cfg.expand_div) / 32 * 32));
         // a CTA should see several rows (one bitmap/accumulator clear and one pipeline fill per CTA): at most rows/8 CTAs
-        const u64 gdiv = (u64)std::max(1, env_int("B200_GDIV", 8)), gmul = (u64)std::max(1, env_int("B200_GMUL", 4));
+        const u64 gdiv = (u64)std::max(1, (int)ctx->cfg.grid_div), gmul = (u64)std::max(1, (int)ctx->cfg.grid_mul);
         const int eg = (int)std::max<u64>(1, std::min<u64>((n + gdiv - 1) / gdiv, (u64)ctx->num_sms * ctas_per_sm(ctx, et, ex_smem) * gmul));
         if (ctx->trace) { cudaStream_t keep = ctx->cur_stream; trace_mark(ctx, -(int)pcap); ctx->cur_stream = keep; }
-        const bool span = (int)nw4 > et && env_int("B200_SPAN", 1);       // more bitmap groups than threads: walk only the groups a row touches
+        const bool span = (int)nw4 > et && ctx->cfg.touched_span;       // more bitmap groups than threads: walk only the groups a row touches
 #define EXPAND(MODE, VTT, NA, OO)                                                                                                     \
-        expand_dispatch<VTT, MODE>(packed, bpat, span, eg, et, ex_smem, bs, NA, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO)
+        expand_dispatch<VTT, MODE>(packed, bpat, span, eg, et, ex_smem, bs, NA, B->d_pack, ctx->d_bin_rows, ctrl, bin, nb, pcap, ncap, nw4, ctx->d_win, (u32)B->cols, OO)
         if (mode == 0) EXPAND(0, VT, na, o);
         else if (mode == 1) EXPAND(1, VT, na, o);
         else EXPAND(2, u64, na64, o64);
@@ -746,21 +712,21 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4);
         const int g = (int)std::min<u64>((n + 7) / 8, (u64)ctx->num_sms * 16);
         const int wlg = std::min(lg, 5);
-        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o);
-        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o);
-        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, first_bin, nb, wlg, o64);
+        if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctrl, first_bin, nb, wlg, o);
+        else if (mode == 1) k_num_warp<VT, 1><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctrl, first_bin, nb, wlg, o);
+        else k_num_warp<u64, 2><<<g, 256, smem, bs>>>(na64, ctx->d_bin_rows, ctrl, first_bin, nb, wlg, o64);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
     auto launch_cta_hash = [&](int bin, int hb, u64 n, cudaStream_t bs) -> int {
         const u32 slots = b200_hash_slots(hb);
-        const int threads = bin_threads(hb, lg);
+        const int threads = bin_threads(ctx, hb, lg);
         const size_t smem = (size_t)slots * (4 + accb);
         if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
         const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
-        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
-        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o);
-        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, bin, slots, lg, o64);
+        if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctrl, bin, slots, lg, o);
+        else if (mode == 1) k_num_cta<VT, 1><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctrl, bin, slots, lg, o);
+        else k_num_cta<u64, 2><<<g, threads, smem, bs>>>(na64, ctx->d_bin_rows, ctrl, bin, slots, lg, o64);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
@@ -790,9 +756,9 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
             const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * 2);
             cudaStream_t bs = fan.pick();
             const u32 cap = (u32)heavy_cap;
-            if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
-            else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
-            else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, cap, nwords, 5, o64);
+            if (mode == 0) k_num_rank<VT, 0><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
+            else if (mode == 1) k_num_rank<VT, 1><<<g, 1024, heavy_rank_smem, bs>>>(na, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, cap, nwords, 5, o);
+            else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, cap, nwords, 5, o64);
             LAUNCH_CHECK(ctx);
         } else {
             u64 max_slots = 1; while (max_slots < 2 * heavy_cap) max_slots <<= 1;
@@ -805,8 +771,8 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
             u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
             u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
             u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
-            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64);
-            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o);
+            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64);
+            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o);
             LAUNCH_CHECK(ctx);
         }
     }
@@ -827,15 +793,16 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     return B200_OK;
 }
 
-static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwords, Fan &fan) {
+static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwords, Fan &fan, B200Ctrl *ctrl = nullptr) {
+    if (!ctrl) ctrl = ctx->d_ctrl;
     const size_t smem_max = ctx->smem_optin - 1024;
     if ((size_t)nwords * 4 <= smem_max) {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows);
+        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows);
     } else {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
         TRY(ensure_heavy_scratch(ctx, (size_t)g * nwords * 4));
-        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row, (u32)ctx->cap_rows);
+        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row, (u32)ctx->cap_rows);
     }
     LAUNCH_CHECK(ctx);
     return B200_OK;
@@ -844,33 +811,34 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
 // Exact mode, first half: distinct-column counts for every list the one-pass pre-pass produced (the lists and the
 // kernels mirror launch_numeric's: tiny / window bitmap / hash, heavy), so that C can be allocated at its exact size.
 static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const SymArgs &sa, u64 rows, u64 p_bound, bool packed, int lg,
-                         Fan &fan, const WinCaps &caps) {
+                         Fan &fan, const WinCaps &caps, B200Ctrl *ctrl = nullptr, bool wide_only = false) {
+    if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = caps.full;
     const u32 bstride = (u32)ctx->cap_rows;
     const size_t smem_max = ctx->smem_optin - 1024;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto count_expand = [&](int bin, int nb, u32 pcap, u32 nw4) -> int {
-        if (nw4 == 0) return B200_OK;
+        if (nw4 == 0 || wide_only) return B200_OK;
         const size_t smem = (size_t)nw4 * 16;
         const int t = std::max(32, std::min(512, (int)std::max<u32>(pcap / 2, nw4) / 8 / 32 * 32));
         const int g = (int)std::max<u64>(1, std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4));
         cudaStream_t bs = fan.pick();
-        if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
-        else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctx->d_ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
+        if (packed) k_sym_expand<true><<<g, t, smem, bs>>>(sa, B->d_pack, ctx->d_bin_rows, ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
+        else k_sym_expand<false><<<g, t, smem, bs>>>(sa, nullptr, ctx->d_bin_rows, ctrl, bin, nb, nw4, ctx->d_win, (u32)B->cols, ctx->d_nnz_row, bstride);
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
-    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan));
+    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan, ctrl));
     for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) {
         if (!reachable(hb)) continue;
         TRY(count_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb]));
         if (caps.cap[hb] < nw4_full) {
             const u32 slots = b200_hash_slots(hb);
-            const int threads = bin_threads(hb, lg);
+            const int threads = bin_threads(ctx, hb, lg);
             const size_t smem = (size_t)slots * 4;
             if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
-            k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
+            k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
             LAUNCH_CHECK(ctx);
         }
     }
@@ -878,16 +846,36 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         TRY(count_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1]));
         if (caps.cap[1] < nw4_full) {
             const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
-            k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, B200_BIN_WIDE0 + 1, 1, std::min(lg, 5), ctx->d_nnz_row, bstride);
+            k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + 1, 1, std::min(lg, 5), ctx->d_nnz_row, bstride);
             LAUNCH_CHECK(ctx);
         }
     }
-    {
+    if (!wide_only) {
         const int g = (int)std::min<u64>((rows + 31) / 32, (u64)ctx->num_sms * 32);   // >= 4 rows per warp: the software pipeline needs a row stream
-        k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctx->d_ctrl, ctx->d_nnz_row);
+        k_sym_tiny<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, ctx->d_nnz_row);
         LAUNCH_CHECK(ctx);
     }
     return B200_OK;
+}
+
+// The same kernels for the fused pipeline's "other" rows (hash and heavy lists only; fused.cu places the rows in between)
+int legacy_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, u64 p_bound, int lg, Fan &fan) {
+    SymArgs sa{A->d_rp, A->d_col, B->d_desc, B->d_col};
+    WinCaps caps; for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) caps.cap[hb] = 0;
+    caps.full = 1;                                                         // every bin has a hash ("wide") list, none a bitmap list
+    return launch_counts(ctx, A, B, sa, A->rows, p_bound, false, lg, fan, caps, ctrl, true);
+}
+int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, b200_csr *C, u64 p_bound, u64 heavy_cap, int mode,
+                   bool packed, bool bpat, int lg, Fan &fan) {
+    WinCaps caps; for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) caps.cap[hb] = 0;
+    caps.full = 1;
+    const u32 bstride = (u32)ctx->cap_rows;
+    if (A->val_bits == 32) {
+        OutArgs<u32> o{C->d_rp, C->d_col, (u32 *)C->d_val, nullptr, ctrl->sym_bin_count, bstride, 0u};
+        return launch_numeric<u32>(ctx, A, B, A->rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps, ctrl, true);
+    }
+    OutArgs<u64> o{C->d_rp, C->d_col, (u64 *)C->d_val, nullptr, ctrl->sym_bin_count, bstride, 0u};
+    return launch_numeric<u64>(ctx, A, B, A->rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps, ctrl, true);
 }
 
 template <typename VT>
@@ -909,14 +897,14 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
     int r = ensure_row_scratch(ctx, rows);
     if (r == B200_OK) r = ensure_desc(ctx, B);
-    const bool packed = want_pack(B);
+    const bool packed = want_pack(ctx, B);
     if (r == B200_OK && packed) r = ensure_pack(ctx, B);
     if (r == B200_OK) r = host_maxval(ctx, A);
     if (r == B200_OK) r = host_maxval(ctx, B);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     SymArgs sa{A->d_rp, A->d_col, B->d_desc, B->d_col};
     const u32 nwords = (u32)((ncols + 31) / 32);
-    const int lg = pick_lg(B, 5);
+    const int lg = pick_lg(ctx, B, 5);
     const u64 p_bound = A->max_row_len * B->max_row_len;                 // host-known bound of the largest P_i
     const size_t smem_max = ctx->smem_optin - 1024;
     const u64 maxA = A->h_maxval, maxB = B->h_maxval;
@@ -942,7 +930,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
     u64 tmp_entries = 0;
     size_t scan_bytes = 0;                                                // control block + scan status words this multiply uses
-    const int mode1 = pick_mode<VT>(p_bound, maxA, maxB);                 // one-pass accumulator width (host-side bound)
+    const int mode1 = pick_mode_bits(ctx, (int)sizeof(VT) * 8, p_bound, maxA, maxB);                 // one-pass accumulator width (host-side bound)
     // Per hash bin: the largest column window (in 128-column groups) its k_num_expand bitmap holds.  Narrow column
     // spaces fit whole; otherwise a bin with capacity P gets a window of 384*P columns (at most 512 K columns): on the
     // 100^3 torus wider windows lost to hash + sort (the per-row prefix over a mostly empty bitmap dominates).
@@ -954,7 +942,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // no per-row window (WMODE 0), every row fits the bitmap, and the product's own column range is the arc.
     u32 all_groups = (nwords + 3) / 4, all_rot = 0;
     u64 arc_start = 0, arc_len = ncols;
-    if (B->rows == B->cols && A->cr_len < ncols && env_int("B200_ARC", 1)) {
+    if (B->rows == B->cols && A->cr_len < ncols && ctx->cfg.arc_window) {
         r = ensure_cs_bounds(ctx, B);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         if (B->cs_state == 1) {
@@ -969,19 +957,23 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool use_arc = arc_len < ncols && (arc_len + 127) / 128 + 1 < (u64)all_groups && (arc_len + 127) / 128 <= 1024;
     if (use_arc) { all_groups = (u32)((arc_len + 127) / 128); all_rot = (u32)arc_start; }
     C->cr_start = (u32)arc_start; C->cr_len = arc_len;                     // a product's columns stay inside the arc
+    if (B->rows == B->cols && B->cs_state == 1 && A->max_row_span < ncols) {
+        const u64 sb = A->max_row_span + (u64)(B->cs_hi - B->cs_lo);       // a row's arc grows by B's offset range
+        C->max_row_span = sb <= ncols / 2 ? sb : ncols;
+    }
     {
         const u32 nw4_full = all_groups;
         const size_t accb1 = mode1 == 0 ? 4 : 8, pvb1 = (mode1 == 0 || sizeof(VT) == 4) ? 4 : 8;
-        const int forced = env_int("B200_WINCAP", -1);                    // testing hook: force a small window (0: hash only)
+        const int forced = ctx->cfg.window_cap_groups;                    // testing hook: force a small window (0: hash only)
         for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) {
             const u64 pcap = b200_hash_cap(hb == 0 ? 1 : hb), ncap = std::min<u64>(pcap, ncols);
             const size_t fixed = pcap * (4 + pvb1) + ncap * (4 + accb1);
             // (with a common arc of at most 512 groups every bin takes the whole arc: one window, no wide lists)
-            u64 want = std::min<u64>(nw4_full, std::max<u64>(use_arc ? 512 : 256, std::min<u64>(4096, (u64)env_int("B200_WINMUL", 3) * pcap)));
+            u64 want = std::min<u64>(nw4_full, std::max<u64>(use_arc ? 512 : 256, std::min<u64>(4096, (u64)ctx->cfg.window_mul * pcap)));
             if (forced >= 0) want = std::min<u64>(want, (u64)forced);
             const size_t avail = smem_max - (packed ? 0 : sizeof(EnumSmem));    // the balanced expansion keeps its tile in static shared memory
             const u64 fit = fixed + 24 * 32 <= avail ? (avail - fixed) / 24 : 0;
-            caps.cap[hb] = env_int("B200_EXPAND", 1) ? (u32)std::min<u64>(want, fit) : 0u;
+            caps.cap[hb] = ctx->cfg.expand_kernel ? (u32)std::min<u64>(want, fit) : 0u;
         }
     }
     {
@@ -1000,7 +992,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (ctx->trace) fprintf(stderr, "[b200 trace] arc: A.cr=(%u,%llu) B.cs=[%lld,%lld] state %d arc=(%llu,%llu) use_arc=%d windows=%d groups=%u caps=%u %u %u %u %u %u %u %u\n",
                                 A->cr_start, (ull)A->cr_len, B->cs_lo, B->cs_hi, B->cs_state, (ull)arc_start, (ull)arc_len, (int)use_arc, (int)windows, all_groups,
                                 caps.cap[0], caps.cap[1], caps.cap[2], caps.cap[3], caps.cap[4], caps.cap[5], caps.cap[6], caps.cap[7]);
-        const bool circular = windows && B->rows == B->cols && env_int("B200_CIRCULAR", 1);
+        const bool circular = windows && B->rows == B->cols && ctx->cfg.circular_windows;
         if (circular) { r = ensure_cspan(ctx, B); if (r != B200_OK) { b200_csr_free(ctx, C); return r; } }
         const int wmode = !windows ? 0 : circular ? 2 : 1;
 #define PREPASS1(GG, WW) k_prepass<GG, WW><<<(unsigned)tiles_pre, 256, 0, s>>>(rows, A->d_rp, A->d_col, WW == 2 ? B->d_cspan : B->d_span, B->d_desc, ncols,   \
@@ -1017,8 +1009,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         // A^5: 135 vs 101 ms) the scratch path is faster, so it stays the default while the scratch fits: decided from the
         // host-known bound nnz(A) * maxlen(B) when that is small (1/16 of device memory), else from the pre-pass's exact
         // figure.  B200_EXACT / B200_EXACT_MB override.
-        const int exact_env = env_int("B200_TWOPASS", 0) ? 1 : env_int("B200_EXACT", -1);   // B200_TWOPASS: older name of the switch
-        const int exact_mb = env_int("B200_EXACT_MB", -1);
+        const int exact_env = ctx->cfg.placement;
+        const int exact_mb = ctx->cfg.exact_limit_mb;
         bool exact = exact_env >= 0 ? exact_env != 0 : (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20));
         tmp_entries = (u64)hb128;
         if (exact_env < 0 && !exact && !cheap_bound) {
@@ -1062,7 +1054,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
                 st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
                 st->acc_mode = mode1; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-                for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
+                for (int i = 0; i < B200_STAT_BINS; i++) st->sym_bin_rows[i] = hc.sym_bin_count[i];
+                st->pipeline = 2;
                 if (timing) {
                     CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
                     cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan
@@ -1087,7 +1080,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             fan.join();
         }
         // u64 values that provably stay below 2^32 (mode 0) cross the scratch as u32: 8 instead of 12 bytes per entry, twice
-        const bool narrow = sizeof(VT) == 8 && mode == 0 && env_int("B200_NARROW", 1);
+        const bool narrow = sizeof(VT) == 8 && mode == 0 && ctx->cfg.narrow_scratch;
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride, narrow ? 1u : 0u};
         if (ctx->hosttime) ctx->ht[1] = host_now_us();                       // pre-pass enqueued
         if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
@@ -1126,7 +1119,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
             st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
             st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-            for (int i = 0; i < B200_STAT_BINS; i++) { st->sym_bin_rows[i] = hc.sym_bin_count[i]; st->num_bin_rows[i] = hc.sym_bin_count[i]; }
+            for (int i = 0; i < B200_STAT_BINS; i++) st->sym_bin_rows[i] = hc.sym_bin_count[i];
+                st->pipeline = 2;
             if (timing) {
                 if (ctx->hosttime) ctx->ht[5] = host_now_us();               // compaction enqueued
                 CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
@@ -1153,9 +1147,21 @@ extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, 
     if (!ctx || !A || !B || !C) return set_err(B200_ERR_BADARG, "NULL argument");
     if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch: A is %llux%llu, B is %llux%llu", (ull)A->rows, (ull)A->cols, (ull)B->rows, (ull)B->cols);
     if (A->val_bits != B->val_bits) return set_err(B200_ERR_SHAPE, "value width mismatch: A is u%d, B is u%d", A->val_bits, B->val_bits);
+    if (A->ctx != ctx || B->ctx != ctx) return set_err(B200_ERR_BADARG, "operand handles belong to another context");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    env_refresh();
+    RESOLVE(ctx, A); RESOLVE(ctx, B);
+    bool handled = false;
+    TRY(A->val_bits == 32 ? spgemm_fused<u32>(ctx, A, B, C, stats, &handled) : spgemm_fused<u64>(ctx, A, B, C, stats, &handled));
+    if (handled) return B200_OK;
     return A->val_bits == 32 ? spgemm_typed<u32>(ctx, A, B, C, stats) : spgemm_typed<u64>(ctx, A, B, C, stats);
+}
+
+extern "C" int b200_csr_product_stats(b200_ctx *ctx, const b200_csr *C, b200_stats *stats) {
+    if (!ctx || !C || !stats) return set_err(B200_ERR_BADARG, "NULL argument");
+    RESOLVE(ctx, C);
+    if (!C->stats) return set_err(B200_ERR_BADARG, "the handle is not the product of a multiply (or its multiply kept no statistics)");
+    *stats = *C->stats;
+    return B200_OK;
 }
 
 // ---------------------------------------------------------------------------- sharding helpers
@@ -1163,6 +1169,7 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     if (!ctx || !A || !B || !host_out) return set_err(B200_ERR_BADARG, "NULL argument");
     if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A); RESOLVE(ctx, B);
     if (A->rows == 0) return B200_OK;
     TRY(ensure_row_scratch(ctx, A->rows));
     TRY(ensure_desc(ctx, B));
@@ -1194,6 +1201,7 @@ extern "C" int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t r0,
     if (!ctx || !A || !out) return set_err(B200_ERR_BADARG, "NULL argument");
     if (r0 > r1 || r1 > A->rows) return set_err(B200_ERR_BADARG, "row range [%llu,%llu) outside 0..%llu", (ull)r0, (ull)r1, (ull)A->rows);
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A);
     u64 ends[2];
     CUDA_TRY(cudaMemcpyAsync(&ends[0], A->d_rp + r0, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(&ends[1], A->d_rp + r1, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1247,12 +1255,15 @@ extern "C" int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B,
     if (!ctx || !A || !B || !C) return set_err(B200_ERR_BADARG, "NULL argument");
     if (A->rows != B->rows || A->cols != B->cols) return set_err(B200_ERR_SHAPE, "add: shape mismatch");
     if (A->val_bits != B->val_bits) return set_err(B200_ERR_SHAPE, "add: value width mismatch");
+    if (A->ctx != ctx || B->ctx != ctx) return set_err(B200_ERR_BADARG, "operand handles belong to another context");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A); RESOLVE(ctx, B);
     return A->val_bits == 32 ? add_typed<u32>(ctx, A, B, C) : add_typed<u64>(ctx, A, B, C);
 }
 
 extern "C" int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same) {
     if (!ctx || !A || !B || !same) return set_err(B200_ERR_BADARG, "NULL argument");
+    RESOLVE(ctx, A); RESOLVE(ctx, B);
     if (A->rows != B->rows || A->cols != B->cols || A->nnz != B->nnz) { *same = 0; return B200_OK; }
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 64, ctx->stream));
@@ -1352,6 +1363,7 @@ extern "C" int b200_thin(b200_ctx *ctx, const b200_csr *A, double density, const
     if (!ctx || !A || !seed32 || !out) return set_err(B200_ERR_BADARG, "NULL argument");
     if (A->rows != A->cols) return set_err(B200_ERR_SHAPE, "thin: the matrix must be square (%llux%llu)", (ull)A->rows, (ull)A->cols);
     CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A);
     ChaChaKey key;
     for (int i = 0; i < 8; i++) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
     if (A->rows == 0) { TRY(csr_alloc(ctx, 0, 0, 0, A->val_bits, true, out)); CUDA_TRY(cudaMemsetAsync((*out)->d_rp, 0, 8 + 16, ctx->stream)); if (draws_consumed) *draws_consumed = 0; return B200_OK; }

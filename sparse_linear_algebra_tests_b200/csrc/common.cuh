@@ -60,6 +60,12 @@ struct B200Ctrl {
     u32 scan_ticket[2];
     u32 error_flag;           // set by kernels on impossible states (table overflow)
     u32 scan_done;            // CTAs of the final row_ptr scan that have finished (the last one reports to the host)
+    // fused path (fused.cu)
+    u32 num_units;            // work units the pre-pass cut the rows into
+    u32 unit_ticket;          // next unit to hand out (persistent numeric kernel)
+    u32 fused_done, pre_done; // CTAs that have finished (the last one reports / cleans up)
+    u32 class_count[4];       // rows per class: empty, tiny, dense, other
+    u32 pad_[2];
 };
 
 // Read-only view of a device CSR.

@@ -1,0 +1,153 @@
+// engine.cuh -- host-side state shared by the engine's translation units (api.cu, fused.cu, heavy.cu, coo.cu, comm.cu):
+// the two handle types behind the C ABI, error plumbing, allocation helpers and the per-operand caches.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b200_spgemm.h"
+#include "common.cuh"
+
+#define B200_NAUX 3
+#define B200_REPORT_SLOTS 16      // multiplies whose device report may be outstanding at once (fused path)
+
+// ---------------------------------------------------------------------------- error plumbing (api.cu)
+int set_err(int code, const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return set_err(_e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA,       \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr) do { int _r = (expr); if (_r != B200_OK) return _r; } while (0)
+// ---------------------------------------------------------------------------- handles
+struct b200_csr {
+    u64 rows, cols, nnz;
+    int val_bits;
+    u64 *d_rp; u32 *d_col; void *d_val;
+    ull *d_maxval;          // device scalar: largest stored value (lives behind row_ptr, same allocation)
+    bool val_shares_col;    // values live in the col_idx allocation (products: one allocation per multiply)
+    u64 max_row_len;        // host-known upper bound of the longest row
+    uint2 *d_desc;          // {start,len} per row, built lazily when used as a right operand
+    uint4 *d_span;          // {len, first col, last col, -} per row, built with d_desc (pre-pass: plain column windows)
+    uint4 *d_cspan;         // square operands: {len, min, max} of (col - row + n/2) mod n (pre-pass: circular windows)
+    uint4 *d_pack;          // sector-packed rows (low-degree right operands), built lazily
+    u64 h_maxval; bool h_maxval_known;   // host copy of *d_maxval once it has been read back
+    // circular column range: every stored column is (cr_start + o) mod cols for some o < cr_len (cr_len = cols: unknown / everything)
+    u32 cr_start; u64 cr_len;
+    // square operands used on the right: signed offsets (c - k) of all entries lie in [cs_lo, cs_hi]; cs_state 0 unknown, 1 known, 2 none
+    long long cs_lo, cs_hi; int cs_state;
+    cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
+    b200_ctx *ctx;
+    // ---- fused path (fused.cu): a product is returned before the host knows its size
+    u64 cap_entries;        // entries the col/val allocation holds (>= nnz; products are allocated from a bound)
+    u64 max_row_span;       // every row's columns lie on an arc of the index circle of at most this many + 1 columns (cols: unknown)
+    int pending_slot;       // >= 0: nnz / max_row_len / h_maxval arrive with report slot `pending_slot` (see resolve_pending)
+    u32 pending_epoch;
+    u64 est_nnz;            // while pending: host-side estimate of nnz (heuristics of a multiply queued behind this one)
+    b200_stats *stats;      // measurements of the multiply that produced this handle (filled when the report is read)
+    bool stats_timed;       // the report slot's events were recorded for it
+};
+
+struct b200_ctx {
+    int device, num_sms;
+    size_t smem_optin, total_mem;
+    cudaStream_t stream; bool own_stream;
+    B200Ctrl *d_ctrl, *h_ctrl;
+    u64 *h_report;          // pinned: the final scan's report, one {word, epoch} chunk per 32-bit word of the control block
+    // per-row scratch, grown on demand
+    u64 cap_rows; u64 *d_prod; u64 *d_tmp_ptr; u32 *d_nnz_row; u32 *d_bin_rows; uint4 *d_win;
+    // one buffer, one memset per multiply: control block | status of the row_ptr scan | status of the pre-pass scan
+    unsigned char *d_scan; u64 *d_tile_status, *d_tile_pre; u64 cap_tiles, cap_tiles_pre;
+    size_t scan_clean_bytes;   // leading bytes of d_scan known to be zero on the stream (left so by k_compact_rows)
+    // heavy-row scratch
+    void *d_heavy; size_t cap_heavy;
+    // one-pass scratch CSR (bound-offset rows), kept across multiplies so the steady state allocates nothing
+    void *d_tmp_col, *d_tmp_val; size_t cap_tmp_col, cap_tmp_val;
+    u32 *d_flag;            // small device flag word (+ pinned mirror)
+    u32 *h_flag;
+    cudaEvent_t ev[4];
+    cudaStream_t aux[B200_NAUX]; cudaEvent_t ev_fork, ev_join[B200_NAUX]; int naux_enabled;
+    cudaStream_t copy; cudaEvent_t ev_ready;   // D2H stream: downloads overlap the next multiply
+    bool timing;
+    u32 epoch;              // multiplies reported through the pinned mirror so far
+    u64 launches;
+    // developer timeline (B200_TRACE=1): an event after every launch, on the stream it went to
+    bool trace; cudaStream_t cur_stream;
+    bool hosttime; double ht[8];   // B200_HOSTTIME=1: host clock at the phase boundaries of a multiply (dev tool)
+    std::vector<std::pair<int, cudaEvent_t>> *marks;
+    // ---- fused path (fused.cu): pre-pass -> one persistent numeric kernel that also places the rows of C
+    unsigned char *d_fz;    // one self-cleaning buffer: control block | pre-pass tile status | unit status
+    B200Ctrl *d_fctrl; u64 *d_ftile, *d_fustat; u64 cap_ftile, cap_fustat;
+    u32 *d_units, *d_roworg; unsigned char *d_rowclass; u64 cap_frows;
+    bool f_dirty;           // the self-cleaning buffer must be zeroed before its next use (first use, failed multiply)
+    u64 *h_freport;         // pinned ring of B200_REPORT_SLOTS reports, {word, epoch} chunks
+    b200_csr *slot_owner[B200_REPORT_SLOTS];
+    cudaEvent_t f_ev[B200_REPORT_SLOTS][3];
+    u32 fepoch;
+    b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
+};
+
+// resolve a handle whose size is still on its way from the device (no-op for every other handle)
+int resolve_pending(b200_ctx *ctx, const b200_csr *m);
+static inline int resolve_if_pending(b200_ctx *c, const b200_csr *m) { return m && m->pending_slot >= 0 ? resolve_pending(c ? c : m->ctx, m) : B200_OK; }
+#define RESOLVE(c_, m_) TRY(resolve_if_pending((c_), (m_)))
+
+static inline double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
+void trace_mark(b200_ctx *ctx, int line);
+void trace_dump(b200_ctx *ctx, const char *what);
+
+#define LAUNCH_CHECK(ctx)                                                                          \
+    do { (ctx)->launches++; if ((ctx)->trace) trace_mark(ctx, __LINE__); cudaError_t _e = cudaGetLastError(); \
+         if (_e != cudaSuccess) return set_err(B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+int dmalloc(b200_ctx *ctx, void **p, size_t bytes);
+void dfree(b200_ctx *ctx, void *p);
+
+// Independent per-bin kernels are spread over the main stream and a few auxiliary streams.
+struct Fan {
+    b200_ctx *ctx; int next; bool used[B200_NAUX]; bool forked;
+    explicit Fan(b200_ctx *c) : ctx(c), next(0), forked(false) { for (int i = 0; i < B200_NAUX; i++) used[i] = false; }
+    cudaStream_t pick() {
+        const int n = ctx->naux_enabled;
+        if (n == 0) return ctx->stream;
+        const int slot = next++ % (n + 1);
+        if (slot == n) return ctx->stream;
+        ctx->cur_stream = ctx->aux[slot];
+        if (!forked) { cudaEventRecord(ctx->ev_fork, ctx->stream); forked = true; }
+        if (!used[slot]) { cudaStreamWaitEvent(ctx->aux[slot], ctx->ev_fork, 0); used[slot] = true; }
+        return ctx->aux[slot];
+    }
+    void join() {
+        for (int i = 0; i < B200_NAUX; i++)
+            if (used[i]) { cudaEventRecord(ctx->ev_join[i], ctx->aux[i]); cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0); used[i] = false; }
+        forked = false; next = 0;
+    }
+};
+
+
+// ---- helpers of api.cu that the other translation units use
+int ensure_row_scratch(b200_ctx *ctx, u64 rows);
+int ensure_desc(b200_ctx *ctx, const b200_csr *B);
+int ensure_pack(b200_ctx *ctx, const b200_csr *B);
+int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B);
+bool want_pack(const b200_ctx *ctx, const b200_csr *B);
+int pick_lg(const b200_ctx *ctx, const b200_csr *B, int max_lg);
+int pick_mode_bits(const b200_ctx *ctx, int val_bits, u64 max_row_products, u64 maxA, u64 maxB);
+int host_maxval(b200_ctx *ctx, const b200_csr *m);
+int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out);
+int alloc_entries(b200_ctx *ctx, b200_csr *m);
+// count / numeric kernels of the binned pipeline over the hash ("wide") and heavy lists only, writing C at its final offsets
+int legacy_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, u64 p_bound, int lg, Fan &fan);
+int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, b200_csr *C, u64 p_bound, u64 heavy_cap, int mode,
+                   bool packed, bool bpat, int lg, Fan &fan);
+// ---- fused.cu
+template <typename VT>
+int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);
+int fz_row_span(b200_ctx *ctx, b200_csr *m);
+void fz_setup(b200_ctx *ctx);

@@ -28,3 +28,15 @@ def gpu_ctx():
     pkg.set_default_context(ctx)
     yield ctx
     pkg.set_default_context(None)
+
+
+@pytest.fixture
+def cfg(gpu_ctx):
+    """Change tuning switches of the engine context (b200_ctx_configure) for one test; restored afterwards."""
+    saved = gpu_ctx.config()
+
+    def set_(**fields):
+        gpu_ctx.configure(**fields)
+
+    yield set_
+    gpu_ctx.restore(saved)

@@ -197,7 +197,7 @@ def test_ragged_rows_hit_every_hash_bin(gpu_ctx, oracle, bits):
     a_h = hostgen.from_coo(n, n, r, c, rng.integers(1, 4, size=r.size, dtype=np.uint64).astype(hostgen.vdtype(bits)), bits)
     b_h = rand_csr(rng, n, n, 5 * n, bits)
     c = check_product(oracle, gpu_ctx, a_h, b_h)
-    assert c.last_stats.num_bin_rows[9] > 0, "heavy numeric bin not exercised"
+    assert c.last_stats.sym_bin_rows[9] > 0, "heavy numeric bin not exercised"
 
 
 def test_wide_column_space_sort_emission_and_global_heavy(gpu_ctx, oracle):
@@ -210,7 +210,7 @@ def test_wide_column_space_sort_emission_and_global_heavy(gpu_ctx, oracle):
     a_h = hostgen.from_coo(n, n, r, c, np.ones(r.size, np.uint64), 64)
     b_h = rand_csr(rng, n, n, 4 * n, 64)
     c = check_product(oracle, gpu_ctx, a_h, b_h)
-    assert c.last_stats.num_bin_rows[9] > 0
+    assert c.last_stats.sym_bin_rows[9] > 0
 
 
 def test_rectangular_row_block_matches_rows_of_full_product(gpu_ctx, oracle):
@@ -316,13 +316,13 @@ def test_engine_reproduces_golden_fixture(gpu_ctx, path):
             assert_same(p.to_host(), m[f"M{k}"], f"squaring {k}")
 
 
-def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, monkeypatch):
-    """B200_TWOPASS=1 (older name of B200_EXACT=1) forces the exact-allocation path (counts -> row_ptr -> numeric) used
+def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, cfg):
+    """placement=1 (b200_config) forces the exact-allocation path (counts -> row_ptr -> numeric) used
     when the scratch CSR would not fit; both must give the same bytes."""
     a_h = hostgen.reference_bench_instance(12, 3.0, 64)
     a = B200Matrix.from_host(a_h, gpu_ctx)
     one = a.matmul(a).matmul(a).to_host()
-    monkeypatch.setenv("B200_TWOPASS", "1")
+    cfg(pipeline=2, placement=1)
     two = a.matmul(a).matmul(a).to_host()
     assert_same(one, two)
     assert_same(one, oracle.matmul(oracle.matmul(to_o(oracle, a_h), to_o(oracle, a_h)), to_o(oracle, a_h)))
@@ -331,11 +331,11 @@ def test_two_pass_fallback_path_is_bit_identical(gpu_ctx, oracle, monkeypatch):
 # ------------------------------------------------------------------ column windows: bitmap path vs hash path of the one-pass numeric
 @pytest.mark.parametrize("wincap", ["0", "1", "3", "16"])
 @pytest.mark.parametrize("bits", [32, 64])
-def test_column_window_split_is_bit_identical(gpu_ctx, oracle, monkeypatch, wincap, bits):
+def test_column_window_split_is_bit_identical(gpu_ctx, oracle, cfg, wincap, bits):
     """Rows whose column window exceeds their bin's shared-memory bitmap leave k_num_expand for the hash + sort kernels.
-    B200_WINCAP shrinks the window (in 128-column groups; 0 = hash only) so that both lists are populated on a small
+    window_cap_groups shrinks the window (in 128-column groups; 0 = hash only) so that both lists are populated on a small
     torus; every split must give the reference's bytes."""
-    monkeypatch.setenv("B200_WINCAP", wincap)
+    cfg(pipeline=2, window_cap_groups=int(wincap))
     a_h = hostgen.reference_bench_instance(12, 3.0, bits)
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
     p, p_o = a, a_o
@@ -360,11 +360,11 @@ def test_window_of_a_banded_matrix_far_from_column_zero(gpu_ctx, oracle):
 # ------------------------------------------------------------------ exact mode (count pass, C written once) vs one-pass scratch + compaction
 @pytest.mark.parametrize("exact", ["0", "1"])
 @pytest.mark.parametrize("bits", [32, 64])
-def test_exact_and_scratch_modes_give_the_same_bytes(gpu_ctx, oracle, monkeypatch, exact, bits):
-    """B200_EXACT=1: every list gets a count kernel first and the numeric kernels write C at its final offsets;
-    B200_EXACT=0: rows go to a scratch CSR at bound offsets and are compacted.  The engine picks by size; both are
+def test_exact_and_scratch_modes_give_the_same_bytes(gpu_ctx, oracle, cfg, exact, bits):
+    """placement=1: every list gets a count kernel first and the numeric kernels write C at its final offsets;
+    placement=0: rows go to a scratch CSR at bound offsets and are compacted.  The engine picks by size; both are
     forced here over the torus chain, ragged rows through every bin including the heavy one, and a wide column space."""
-    monkeypatch.setenv("B200_EXACT", exact)
+    cfg(pipeline=2, placement=int(exact))
     a_h = hostgen.reference_bench_instance(12, 3.0, bits)
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
     p, p_o = a, a_o
@@ -387,8 +387,8 @@ def test_exact_and_scratch_modes_give_the_same_bytes(gpu_ctx, oracle, monkeypatc
     check_product(oracle, gpu_ctx, wide, rand_csr(rng, wide_n, wide_n, 3 * wide_n, bits), f"wide exact={exact}")
 
 
-def test_exact_mode_saturating_values(gpu_ctx, oracle, monkeypatch):
-    monkeypatch.setenv("B200_EXACT", "1")
+def test_exact_mode_saturating_values(gpu_ctx, oracle, cfg):
+    cfg(pipeline=2, placement=1)
     rng = np.random.default_rng(9)
     a_h = rand_csr(rng, 500, 500, 6000, 64, 3)
     a_h.values[:] = rng.integers(1 << 61, 1 << 63, size=a_h.nnz(), dtype=np.uint64)
@@ -416,12 +416,11 @@ def test_einsum_ab_bc_ac_equals_matmul(gpu_ctx, oracle):
 # ------------------------------------------------------------------ circular column windows (torus rows that wrap around the index space)
 @pytest.mark.parametrize("circular", ["1", "0"])
 @pytest.mark.parametrize("wincap", ["2", "8", "64"])
-def test_circular_windows_on_a_long_torus(gpu_ctx, oracle, monkeypatch, circular, wincap):
+def test_circular_windows_on_a_long_torus(gpu_ctx, oracle, cfg, circular, wincap):
     """48 x 6 x 6 torus (1728 columns = 14 groups of 128): with a window of a few groups only rows away from the ends of
     the index space fit a plain window; measured from the row's own reference column every row does.  The rows that wrap
     come out of the kernel rotated and must land in ascending column order; both settings must give the reference bytes."""
-    monkeypatch.setenv("B200_WINCAP", wincap)
-    monkeypatch.setenv("B200_CIRCULAR", circular)
+    cfg(pipeline=2, window_cap_groups=int(wincap), circular_windows=int(circular))
     full = hostgen.lattice([48, 6, 6], True, 64)
     a_h = hostgen.thin(full, 0.2, bytes([7] * 32))
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
@@ -437,9 +436,8 @@ def test_circular_windows_on_a_long_torus(gpu_ctx, oracle, monkeypatch, circular
     assert_same(got, want, "row block")
 
 
-def test_circular_window_exact_mode(gpu_ctx, oracle, monkeypatch):
-    monkeypatch.setenv("B200_WINCAP", "4")
-    monkeypatch.setenv("B200_EXACT", "1")
+def test_circular_window_exact_mode(gpu_ctx, oracle, cfg):
+    cfg(pipeline=2, window_cap_groups=4, placement=1)
     full = hostgen.lattice([40, 5, 5], True, 32)
     a_h = hostgen.thin(full, 0.25, bytes([9] * 32))
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
@@ -453,11 +451,11 @@ def test_circular_window_exact_mode(gpu_ctx, oracle, monkeypatch):
 # ------------------------------------------------------------------ operand-level arc windows (row blocks of a long torus: one window for all rows)
 @pytest.mark.parametrize("arc", ["1", "0"])
 @pytest.mark.parametrize("block", [(0, 500), (1800, 2400), (3600, 4096)])
-def test_arc_window_of_a_row_block(gpu_ctx, oracle, monkeypatch, arc, block):
+def test_arc_window_of_a_row_block(gpu_ctx, oracle, cfg, arc, block):
     """A GPU's row block of a 64 x 8 x 8 torus touches a short circular arc of the 4096 columns, and each multiply by A widens
-    the arc by A's column span.  With B200_ARC=1 the engine uses that arc as the one bitmap window of every row (blocks at
+    the arc by A's column span.  With arc_window=1 the engine uses that arc as the one bitmap window of every row (blocks at
     the ends of the index space wrap around it); with 0 it falls back to per-row windows.  Both must give the reference bytes."""
-    monkeypatch.setenv("B200_ARC", arc)
+    cfg(pipeline=2, arc_window=int(arc))
     full = hostgen.lattice([64, 8, 8], True, 64)
     a_h = hostgen.thin(full, 0.15, bytes([11] * 32))
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)
@@ -469,9 +467,9 @@ def test_arc_window_of_a_row_block(gpu_ctx, oracle, monkeypatch, arc, block):
         assert_same(p.to_host(), p_o, f"A^{k} block={block} arc={arc}")
 
 
-def test_arc_window_exact_mode_and_add(gpu_ctx, oracle, monkeypatch):
+def test_arc_window_exact_mode_and_add(gpu_ctx, oracle, cfg):
     """Arc windows with the exact-memory (count first) path, and a product handle that went through add() keeps a valid arc."""
-    monkeypatch.setenv("B200_EXACT", "1")
+    cfg(pipeline=2, placement=1)
     full = hostgen.lattice([64, 8, 8], True, 32)
     a_h = hostgen.thin(full, 0.15, bytes([12] * 32))
     a, a_o = B200Matrix.from_host(a_h, gpu_ctx), to_o(oracle, a_h)

@@ -22,16 +22,16 @@ def test_reference_bench_instance_matches_readme_nnz(oracle):
     """bench_repeated_exponentiation (src/graph_magnus.rs:699-788) rebuilt with rand 0.9.2's StdRng (ChaCha12, seed
     [42;32]) must reproduce the nnz column of the reference README.md:42-47 (252k, 655k, 1.57M, 3.38M, 6.59M, 11.7M).
     A different random stream gives 249k/646k/1.54M/..., so all six matching pins the generator, the
-    thinning, from_coo and the multiply at once.  A^6, A^7 are covered by the GPU property test (CPU time)."""
+    thinning, from_coo and the multiply at once."""
     a = oracle.reference_bench_instance(30, 3.0, 32)
     assert a.rows == 27000 and a.nnz() == 81434
     p, got = a, []
-    for _k in range(2, 6):
+    for _k in range(2, 8):
         p = oracle.matmul_par(p, a)
         got.append(p.nnz())
-    assert got == [251590, 655391, 1574848, 3383207]
+    assert got == [251590, 655391, 1574848, 3383207, 6590100, 11736555]
     fmt = lambda n: f"{n / 1e3:.0f}k" if n < 1e6 else f"{n / 1e6:.3g}M"
-    assert [fmt(n) for n in got] == ["252k", "655k", "1.57M", "3.38M"]
+    assert [fmt(n) for n in got] == ["252k", "655k", "1.57M", "3.38M", "6.59M", "11.7M"]
 
 
 def test_chacha12_stream_is_deterministic_and_blockwise(oracle):

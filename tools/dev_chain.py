@@ -9,9 +9,12 @@ ap.add_argument("--side", type=int, default=30); ap.add_argument("--epn", type=f
 ap.add_argument("--steps", type=int, default=7); ap.add_argument("--bits", type=int, default=64)
 ap.add_argument("--check", type=int, default=1); ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--block", type=int, default=0, help="with --xmul N: multiply only rank 0's row block (the per-GPU work of the N-GPU run)")
+ap.add_argument("--cfg", default="", help="b200_config fields, e.g. pipeline=1,fused_threads=128")
 ap.add_argument("--xmul", type=int, default=1, help="torus is (side*xmul) x side x side: the weak-scaling workload of bench.py --gpus xmul, on one GPU")
 args = ap.parse_args()
 ctx = Context(0); set_default_context(ctx)
+if args.cfg:
+    ctx.configure(**{k: int(v) for k, v in (kv.split("=") for kv in args.cfg.split(","))})
 if args.xmul == 1:
     a_h = hostgen.reference_bench_instance(args.side, args.epn, args.bits)
 else:
@@ -40,5 +43,5 @@ for k in range(2, args.steps + 1):
     gbs = d["bytes_algorithmic"] / (d["ms_total"] * 1e-3) / 1e9
     print(f"A^{k}: nnz={d['nnz_c']} prod={d['products']} sym={d['ms_symbolic']:.3f}ms num={d['ms_numeric']:.3f}ms total={d['ms_total']:.3f}ms "
           f"launches={d['kernel_launches']} mode={d['acc_mode']} {gbs:.0f}GB/s Mprod/s={d['products']/d['ms_total']/1e3:.0f} {ok}")
-    print("    sym bins", d["sym_bin_rows"][:10], "num bins", d["num_bin_rows"][:10])
+    print("    pipeline", d["pipeline"], "rows per list / class", d["sym_bin_rows"])
     p = c

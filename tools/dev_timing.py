@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sparse_linear_algebra_tests_b200 import Context, hostgen
 dev = torch.device("cuda", 0); stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
 ctx = Context(0, stream.cuda_stream)
+if len(sys.argv) > 1:
+    ctx.configure(**{k: int(v) for k, v in (kv.split("=") for kv in sys.argv[1].split(","))})
 a_h = hostgen.reference_bench_instance(30, 3.0, 64)
 A = ctx.upload(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values)
 def chain(stats):
