@@ -91,7 +91,9 @@ typedef struct b200_config {
     int32_t fused_dense_pmax;    /* fused: rows with more intermediate products go to the heavy kernel (0 auto = 65536)    */
     int32_t heavy_chunk_cols;    /* heavy rows: columns per chunk of the chunked kernel (0 auto, from shared memory)       */
     int32_t heavy_kernel;        /* heavy rows: 1 chunked TMA kernel (default), 0 single-CTA global-memory table          */
-    int32_t reserved[8];
+    int32_t fused_ring_slots;    /* fused: accumulator slots per CTA holding finished rows until they are placed (0 auto)  */
+    int32_t fused_product_slots; /* fused: product buffer entries per CTA (rows with more generate their products twice)   */
+    int32_t reserved[6];
 } b200_config;
 int b200_config_default(b200_config *cfg);
 

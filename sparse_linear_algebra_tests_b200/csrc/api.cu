@@ -156,7 +156,7 @@ static void config_from_env(b200_config *c) {
         {"B200_SPAN", &c->touched_span}, {"B200_NARROW", &c->narrow_scratch}, {"B200_EXPAND", &c->expand_kernel}, {"B200_PACK", &c->pack_b},
         {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
         {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
-        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel},
+        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel},
     };
     for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
 }
@@ -241,7 +241,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
-    dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_roworg); dfree(ctx, ctx->d_rowclass);
+    dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_rowwin); dfree(ctx, ctx->d_rowclass); dfree(ctx, ctx->d_spill_acc); dfree(ctx, ctx->d_spill_col);
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->h_freport);
     for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->f_ev[i][j]);

@@ -84,7 +84,8 @@ struct b200_ctx {
     // ---- fused path (fused.cu): pre-pass -> one persistent numeric kernel that also places the rows of C
     unsigned char *d_fz;    // one self-cleaning buffer: control block | pre-pass tile status | unit status
     B200Ctrl *d_fctrl; u64 *d_ftile, *d_fustat; u64 cap_ftile, cap_fustat;
-    u32 *d_units, *d_roworg; unsigned char *d_rowclass; u64 cap_frows;
+    u32 *d_units; uint4 *d_rowwin; unsigned char *d_rowclass; u64 cap_frows;
+    u64 *d_spill_acc; u32 *d_spill_col; u64 cap_spill;   // per-CTA global slots for the upper ranks of rows longer than the shared-memory slots
     bool f_dirty;           // the self-cleaning buffer must be zeroed before its next use (first use, failed multiply)
     u64 *h_freport;         // pinned ring of B200_REPORT_SLOTS reports, {word, epoch} chunks
     b200_csr *slot_owner[B200_REPORT_SLOTS];

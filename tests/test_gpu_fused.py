@@ -40,17 +40,21 @@ def chain_check(O, ctx, a_h, powers, left_h=None, what=""):
 
 
 # ------------------------------------------------------------------ the headline instance, every power, both value widths
+@pytest.mark.parametrize("pipeline", [0, 1, 2], ids=["default", "fused", "binned"])
 @pytest.mark.parametrize("bits", [64, 32])
-def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, bits):
+def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, cfg, bits, pipeline):
     """BASELINE configs[1]: the reference's exact operand (StdRng([42;32]) thinning of the 30^3 Moore torus, 81 434 nnz),
-    A^2..A^7, row_ptr / col_idx / values byte for byte; nnz per power = the README column (README.md:42-47)."""
+    A^2..A^7, row_ptr / col_idx / values byte for byte, through both pipelines; nnz per power = the README column
+    (README.md:42-47)."""
+    cfg(pipeline=pipeline)
     a_h = hostgen.reference_bench_instance(30, 3.0, bits)
     assert a_h.nnz() == 81434
-    gpu = chain_check(oracle, gpu_ctx, a_h, 7, what=f"u{bits}")
+    gpu = chain_check(oracle, gpu_ctx, a_h, 7, what=f"u{bits} pipeline {pipeline}")
     assert [g.nnz() for g in gpu] == [251590, 655391, 1574848, 3383207, 6590100, 11736555]
     st = gpu[-1].device.product_stats()
-    assert st.pipeline == 1 and st.nnz_c == 11736555                          # the fused pipeline ran the headline multiply
-    assert st.sym_bin_rows[2] == 0, "a row of the headline multiply left the fused kernel for the counted lists"
+    assert st.nnz_c == 11736555 and st.pipeline == (1 if pipeline == 1 else 2)
+    if pipeline == 1:
+        assert st.sym_bin_rows[2] == 0, "a row of the headline multiply left the fused kernel for the counted lists"
 
 
 @pytest.mark.parametrize("fields", [
@@ -89,6 +93,15 @@ def test_fused_windows_that_wrap_around_the_index_space(gpu_ctx, oracle, cfg, fi
         chain_check(oracle, gpu_ctx, a_h, 5, left_h=a_h.row_block(r0, r1), what=f"block {r0}:{r1}")
 
 
+def test_fused_rows_longer_than_ring_and_product_buffer(gpu_ctx, oracle, cfg):
+    """Tiny ring and product buffer: rows that spill to the per-CTA global slots (longer than the ring) and rows that
+    generate their products twice (more products than the buffer), interleaved with rows that fit."""
+    a_h = hostgen.reference_bench_instance(12, 4.0, 64)
+    for fields in (dict(fused_ring_slots=256, fused_product_slots=64), dict(fused_ring_slots=256, fused_product_slots=4096), dict(fused_ring_slots=8192, fused_product_slots=64)):
+        cfg(pipeline=1, **fields)
+        chain_check(oracle, gpu_ctx, a_h, 6, what=str(fields))
+
+
 def test_fused_mixed_classes_and_empty_rows(gpu_ctx, oracle, cfg):
     """Tiny, dense, heavy and empty rows interleaved in one left operand (unit boundaries at every class change), random
     columns (no arc structure: the window is the whole column space)."""
@@ -96,7 +109,7 @@ def test_fused_mixed_classes_and_empty_rows(gpu_ctx, oracle, cfg):
     rng = np.random.default_rng(17)
     n = 20000
     lens = rng.choice([0, 0, 1, 2, 3, 5, 9, 40, 120, 700, 3000], size=1500)
-    lens[7] = 15000
+    lens[7] = 19000                                         # ~76 k products: beyond the dense class, a heavy row
     rows = rng.choice(n, size=lens.size, replace=False)
     r = np.concatenate([np.full(l, i) for i, l in zip(rows, lens)])
     c = np.concatenate([rng.choice(n, size=l, replace=False) for l in lens])
