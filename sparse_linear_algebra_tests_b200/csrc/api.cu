@@ -924,7 +924,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     if (dense128 < hb128) hb128 = dense128;
     const bool cheap_bound = hb128 * esz <= (unsigned __int128)(total_b / 16);
 
-    if (timing) cudaEventRecord(ctx->ev[0], s);
+    // this multiply's slot in the pinned report ring (a slot still owned by an unread product is read first)
+    u32 epoch = 0; int slot = 0; u64 *mirror = nullptr;
+    r = claim_report_slot(ctx, &epoch, &slot, &mirror);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    if (timing) { cudaEventRecord(ctx->ev[0], s); cudaEventRecord(ctx->f_ev[slot][0], s); }
     if (ctx->hosttime) ctx->ht[0] = host_now_us();
     if (ctx->trace) trace_mark(ctx, __LINE__);
     const u32 bstride = (u32)ctx->cap_rows;                               // every bin's row list has room for all rows
@@ -1032,11 +1036,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-            const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
-            launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, epoch);
+            const u32 xepoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
+            launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, xepoch);
             LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(ctx->ev[1], s);
-            r = wait_for_report(ctx, epoch);
+            r = wait_for_report(ctx, xepoch);
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             const B200Ctrl hc = *ctx->h_ctrl;
             C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz;
@@ -1050,18 +1054,24 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
             if (timing) cudaEventRecord(ctx->ev[3], s);
-            if (st) {
-                st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
-                st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
-                st->acc_mode = mode1; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-                for (int i = 0; i < B200_STAT_BINS; i++) st->sym_bin_rows[i] = hc.sym_bin_count[i];
-                st->pipeline = 2;
-                if (timing) {
+            {
+                // the exact placement has waited for the device anyway: its statistics are complete here
+                b200_stats *xs = new b200_stats();
+                memset(xs, 0, sizeof(*xs));
+                xs->rows = rows; xs->cols = ncols; xs->nnz_a = A->nnz; xs->nnz_b = B->nnz;
+                xs->nnz_c = C->nnz; xs->products = hc.total_products; xs->max_row_products = hc.max_row_products; xs->max_row_nnz = hc.max_row_nnz;
+                xs->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
+                xs->acc_mode = mode1; xs->kernel_launches = (int32_t)(ctx->launches - launches0);
+                for (int i = 0; i < B200_STAT_BINS; i++) xs->sym_bin_rows[i] = hc.sym_bin_count[i];
+                xs->pipeline = 2;
+                if (timing && st) {
                     CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
-                    cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan
-                    cudaEventElapsedTime(&st->ms_numeric, ctx->ev[2], ctx->ev[3]);    // numeric kernels into the final arrays
-                    cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
+                    cudaEventElapsedTime(&xs->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan
+                    cudaEventElapsedTime(&xs->ms_numeric, ctx->ev[2], ctx->ev[3]);    // numeric kernels into the final arrays
+                    cudaEventElapsedTime(&xs->ms_total, ctx->ev[0], ctx->ev[3]);
                 }
+                C->stats = xs;
+                if (st) *st = *xs;
             }
             trace_dump(ctx, "exact multiply");
             *out = C;
@@ -1087,23 +1097,21 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         fan.join();
         if (ctx->hosttime) ctx->ht[2] = host_now_us();                       // numeric kernels enqueued
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-        const u32 epoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;         // never 0
-        launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, epoch);
-        LAUNCH_CHECK(ctx);
-        if (timing) cudaEventRecord(ctx->ev[1], s);
-        if (ctx->hosttime) ctx->ht[3] = host_now_us();                       // scan enqueued
-        r = wait_for_report(ctx, epoch);
-        if (ctx->hosttime) ctx->ht[4] = host_now_us();                       // report seen
-        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-        const B200Ctrl hc = *ctx->h_ctrl;
-        C->nnz = hc.total_nnz; C->max_row_len = hc.max_row_nnz; C->h_maxval = hc.max_val_out; C->h_maxval_known = true;
+        // ---- C is allocated from the scratch bound BEFORE its size is known, so nothing below waits for the device: the row_ptr
+        //      scan's last CTA reports the control block (nnz, longest row, largest value, product count) into this multiply's
+        //      slot of the pinned report ring, and the handle is handed out "pending": whoever needs those numbers first
+        //      (b200_csr_info, a download, the next multiply taking C as an operand) reads the slot (resolve_pending).
+        C->cap_entries = std::max<u64>(tmp_entries, 1);
         r = alloc_entries(ctx, C);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-        if (ctx->hosttime) ctx->ht[6] = host_now_us();                       // C allocated
-        if (timing) cudaEventRecord(ctx->ev[2], s);
+        launch_scan_rowptr(ctx, rows, C->d_rp, s, mirror, epoch);
+        LAUNCH_CHECK(ctx);
+        if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
         if (ctx->trace) trace_mark(ctx, __LINE__);
         {
-            const double avg = (double)C->nnz / (double)rows;
+            // lanes per row of the compaction from an estimate of the mean row (products / ~1.5); any value is correct
+            const double meanP = ((double)A->nnz / (double)rows) * (B->rows ? (double)B->nnz / (double)B->rows : 0.0);
+            const double avg = std::min((double)ncols, meanP / 1.5);
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
             const u64 want = (rows << llg) / 256 + 1;
             const unsigned cg = (unsigned)std::min<u64>(want, (u64)ctx->num_sms * 64);
@@ -1114,29 +1122,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             LAUNCH_CHECK(ctx);
             ctx->scan_clean_bytes = scan_bytes;
         }
-        if (timing) cudaEventRecord(ctx->ev[3], s);
-        if (st) {
-            st->nnz_c = C->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
-            st->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
-            st->acc_mode = mode; st->kernel_launches = (int32_t)(ctx->launches - launches0);
-            for (int i = 0; i < B200_STAT_BINS; i++) st->sym_bin_rows[i] = hc.sym_bin_count[i];
-                st->pipeline = 2;
-            if (timing) {
-                if (ctx->hosttime) ctx->ht[5] = host_now_us();               // compaction enqueued
-                CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
-                if (ctx->hosttime) {
-                    float g1 = 0, g2 = 0, g3 = 0;
-                    cudaEventElapsedTime(&g1, ctx->ev[0], ctx->ev[1]); cudaEventElapsedTime(&g2, ctx->ev[0], ctx->ev[2]); cudaEventElapsedTime(&g3, ctx->ev[0], ctx->ev[3]);
-                    fprintf(stderr, "[b200 hosttime] host us: prepass queued %.1f, numeric queued %.1f, scan queued %.1f, report seen %.1f, C allocated %.1f, compaction queued %.1f | gpu us: scan done %.1f, alloc point %.1f, compaction done %.1f\n",
-                            ctx->ht[1] - ctx->ht[0], ctx->ht[2] - ctx->ht[0], ctx->ht[3] - ctx->ht[0], ctx->ht[4] - ctx->ht[0], ctx->ht[6] - ctx->ht[0], ctx->ht[5] - ctx->ht[0], g1 * 1e3, g2 * 1e3, g3 * 1e3);
-                }
-                cudaEventElapsedTime(&st->ms_symbolic, ctx->ev[2], ctx->ev[3]);   // one-pass: compaction of the scratch rows
-                cudaEventElapsedTime(&st->ms_numeric, ctx->ev[0], ctx->ev[1]);    // counts + bins + numeric kernels + row_ptr scan
-                cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
-            }
-        }
+        if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
         trace_dump(ctx, "one-pass multiply");
+        mark_pending(ctx, C, slot, epoch, A, B, mode, 2, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
         *out = C;
+        if (st) { TRY(resolve_pending(ctx, C)); *st = *C->stats; }
         return B200_OK;
     }
 

@@ -151,4 +151,7 @@ int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);
 int fz_row_span(b200_ctx *ctx, b200_csr *m);
+int claim_report_slot(b200_ctx *ctx, u32 *epoch, int *slot, u64 **mirror);
+void mark_pending(b200_ctx *ctx, b200_csr *C, int slot, u32 epoch, const b200_csr *A, const b200_csr *B, int mode, int pipeline,
+                  int32_t launches, bool timed, u64 max_row_len_bound);
 void fz_setup(b200_ctx *ctx);

@@ -974,6 +974,28 @@ static int fz_wait_report(b200_ctx *ctx, int slot, u32 epoch, B200Ctrl *out) {
     return B200_OK;
 }
 
+// this multiply's slot in the pinned report ring; a slot still owned by an unread product is read first
+int claim_report_slot(b200_ctx *ctx, u32 *epoch, int *slot, u64 **mirror) {
+    const u32 e = ++ctx->fepoch ? ctx->fepoch : ++ctx->fepoch;              // never 0: a zeroed chunk is "no report"
+    const int sl = (int)(e % B200_REPORT_SLOTS);
+    if (ctx->slot_owner[sl]) TRY(resolve_pending(ctx, ctx->slot_owner[sl]));
+    *epoch = e; *slot = sl; *mirror = ctx->h_freport + (size_t)sl * (sizeof(B200Ctrl) / 4);
+    return B200_OK;
+}
+// hand a product out before its size is known: what the report will fill in, and what is known now
+void mark_pending(b200_ctx *ctx, b200_csr *C, int slot, u32 epoch, const b200_csr *A, const b200_csr *B, int mode, int pipeline,
+                  int32_t launches, bool timed, u64 max_row_len_bound) {
+    C->pending_slot = slot; C->pending_epoch = epoch; ctx->slot_owner[slot] = C;
+    C->nnz = 0; C->max_row_len = max_row_len_bound; C->h_maxval_known = false;
+    b200_stats *st = new b200_stats();
+    memset(st, 0, sizeof(*st));
+    st->rows = A->rows; st->cols = B->cols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; st->acc_mode = mode; st->pipeline = (uint32_t)pipeline;
+    st->kernel_launches = launches;
+    st->bytes_algorithmic = (A->nnz + B->nnz) * (u64)(4 + A->val_bits / 8) + (A->rows + B->rows + A->rows + 3) * 8;   // + nnz(C) entries at resolve
+    delete C->stats;
+    C->stats = st; C->stats_timed = timed;
+}
+
 int resolve_pending(b200_ctx *ctx, const b200_csr *cm) {
     b200_csr *m = const_cast<b200_csr *>(cm);
     if (m->pending_slot < 0) return B200_OK;
@@ -989,14 +1011,21 @@ int resolve_pending(b200_ctx *ctx, const b200_csr *cm) {
         b200_stats *st = m->stats;
         st->nnz_c = m->nnz; st->products = hc.total_products; st->max_row_products = hc.max_row_products; st->max_row_nnz = hc.max_row_nnz;
         st->bytes_algorithmic += m->nnz * (u64)(4 + m->val_bits / 8);        // operands and row pointers were counted at launch
-        st->sym_bin_rows[0] = hc.class_count[FZ_TINY]; st->sym_bin_rows[1] = hc.class_count[FZ_DENSE];
-        st->sym_bin_rows[2] = hc.class_count[FZ_OTHER]; st->sym_bin_rows[3] = hc.class_count[FZ_EMPTY];
-        for (int i = 0; i < 6; i++) st->sym_bin_rows[10 + i] = hc.sym_bin_count[B200_BIN_WIDE0 + i];
-        st->sym_bin_rows[9] = hc.sym_bin_count[B200_BIN_HEAVY];
+        if (st->pipeline == 1) {
+            st->sym_bin_rows[0] = hc.class_count[FZ_TINY]; st->sym_bin_rows[1] = hc.class_count[FZ_DENSE];
+            st->sym_bin_rows[2] = hc.class_count[FZ_OTHER]; st->sym_bin_rows[3] = hc.class_count[FZ_EMPTY];
+            for (int i = 0; i < 6; i++) st->sym_bin_rows[10 + i] = hc.sym_bin_count[B200_BIN_WIDE0 + i];
+            st->sym_bin_rows[9] = hc.sym_bin_count[B200_BIN_HEAVY];
+        } else {
+            for (int i = 0; i < B200_STAT_BINS; i++) st->sym_bin_rows[i] = hc.sym_bin_count[i];
+        }
         if (ctx->timing && m->stats_timed) {
             if (cudaEventSynchronize(ctx->f_ev[slot][2]) == cudaSuccess) {
-                cudaEventElapsedTime(&st->ms_symbolic, ctx->f_ev[slot][0], ctx->f_ev[slot][1]);
-                cudaEventElapsedTime(&st->ms_numeric, ctx->f_ev[slot][1], ctx->f_ev[slot][2]);
+                // fused: pre-pass | numeric + placement.  binned: pre-pass + numeric kernels + row_ptr scan | compaction
+                float first = 0, second = 0;
+                cudaEventElapsedTime(&first, ctx->f_ev[slot][0], ctx->f_ev[slot][1]);
+                cudaEventElapsedTime(&second, ctx->f_ev[slot][1], ctx->f_ev[slot][2]);
+                if (st->pipeline == 1) { st->ms_symbolic = first; st->ms_numeric = second; } else { st->ms_numeric = first; st->ms_symbolic = second; }
                 cudaEventElapsedTime(&st->ms_total, ctx->f_ev[slot][0], ctx->f_ev[slot][2]);
             } else cudaGetLastError();
         }
@@ -1095,11 +1124,8 @@ int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *
 
     TRY(ensure_row_scratch(ctx, rows));
     TRY(fz_ensure_scratch(ctx, rows));
-    // report slot of this multiply; a slot still owned by an unread product is read first
-    const u32 epoch = ++ctx->fepoch ? ctx->fepoch : ++ctx->fepoch;
-    const int slot = (int)(epoch % B200_REPORT_SLOTS);
-    if (ctx->slot_owner[slot]) TRY(resolve_pending(ctx, ctx->slot_owner[slot]));
-    u64 *mirror = ctx->h_freport + (size_t)slot * (sizeof(B200Ctrl) / 4);
+    u32 epoch = 0; int slot = 0; u64 *mirror = nullptr;
+    TRY(claim_report_slot(ctx, &epoch, &slot, &mirror));
     const bool timing = ctx->timing;
     if (timing) cudaEventRecord(ctx->f_ev[slot][0], s);
 
@@ -1199,15 +1225,8 @@ int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *
         ctx->f_dirty = false;                                                 // the kernels queued above leave the buffers clean
         if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
         // ---- hand the product out; its size follows through the report
-        C->pending_slot = slot; C->pending_epoch = final_epoch; ctx->slot_owner[slot] = C;
+        mark_pending(ctx, C, slot, final_epoch, A, B, mode, 1, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
         C->est_nnz = std::max<u64>(1, (u64)(meanP * (double)rows / 1.6));
-        C->nnz = 0; C->max_row_len = std::min<u64>(p_bound, ncols);
-        b200_stats *st = new b200_stats();
-        memset(st, 0, sizeof(*st));
-        st->rows = rows; st->cols = ncols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; st->acc_mode = mode; st->pipeline = 1;
-        st->kernel_launches = (int32_t)(ctx->launches - launches0);
-        st->bytes_algorithmic = (A->nnz + B->nnz) * (u64)esz + (A->rows + B->rows + rows + 3) * 8;
-        C->stats = st; C->stats_timed = timing;
         *out = C; *handled = true;
         if (st_out) { TRY(resolve_pending(ctx, C)); *st_out = *C->stats; }
     }
