@@ -70,8 +70,9 @@ typedef struct b200_stats {
  * installs a copy (between multiplies).  -1 / 0 mean "engine decides" where noted. */
 typedef struct b200_config {
     uint32_t struct_bytes;       /* sizeof(b200_config) as the caller compiled it (checked)                               */
-    int32_t pipeline;            /* 0 auto; 1 fused (pre-pass + one persistent numeric/placement kernel); 2 binned (a
-                                    kernel per row bin, scratch or exact placement)                                        */
+    int32_t pipeline;            /* 0 auto (= 3); 1 fused (pre-pass + one persistent numeric/placement kernel); 2 binned (a
+                                    kernel per row bin, scratch or exact placement); 3 exact placement with the
+                                    row-per-warp count / numeric kernels, C written once, no host wait                     */
     int32_t placement;           /* binned pipeline: -1 auto, 0 scratch CSR + compaction, 1 exact (count pass first)       */
     int32_t exact_limit_mb;      /* binned, auto placement: scratch bound above which the exact placement runs; -1 auto    */
     int32_t force_acc_mode;      /* -1 auto (proved from the operands); 1 / 2 force the 64-bit / saturating accumulators   */
@@ -93,7 +94,9 @@ typedef struct b200_config {
     int32_t heavy_kernel;        /* heavy rows: 1 chunked TMA kernel (default), 0 single-CTA global-memory table          */
     int32_t fused_ring_slots;    /* fused: accumulator slots per CTA holding finished rows until they are placed (0 auto)  */
     int32_t fused_product_slots; /* fused: product buffer entries per CTA (rows with more generate their products twice)   */
-    int32_t reserved[6];
+    int32_t rw_cap_percent;      /* row-per-warp kernels: accumulator slots per warp as a percentage of the mean row's
+                                    intermediate products (0 auto = 140); longer rows are produced in several passes       */
+    int32_t reserved[5];
 } b200_config;
 int b200_config_default(b200_config *cfg);
 

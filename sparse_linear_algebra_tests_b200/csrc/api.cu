@@ -157,6 +157,7 @@ static void config_from_env(b200_config *c) {
         {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
         {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
         {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel},
+        {"B200_RW_CAP", &c->rw_cap_percent},
     };
     for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
 }
@@ -219,6 +220,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) CUDA_TRY(cudaEventCreate(&ctx->f_ev[i][j]));
     ctx->f_dirty = true;
     fz_setup(ctx);
+    rw_setup(ctx);
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
@@ -662,12 +664,31 @@ static void expand_dispatch(bool packed, bool bpat, bool span, int eg, int et, s
 #undef K
 }
 
+// Rows the row-per-warp kernels (rowwarp.cu) take in the exact placement: bitmap lists of hash bins 0..hb_max.
+struct RwPlan { int hb_max; u32 nw, cap; bool all_fit; };                   // hb_max < 0: none; all_fit: no row can land on a hash list of bins <= hb_max
+static const RwPlan kNoRw = {-1, 0u, 0u, false};
+
+// Last kernel of an exact-placement multiply whose result was handed out before its size was known: the control block
+// goes to the pinned report ring, the product's largest value to its handle, and the control block and scan status words
+// are left zeroed for the next multiply.
+__global__ void __launch_bounds__(256) k_finish_exact(B200Ctrl *ctrl, u64 *host_mirror, u32 epoch, ull *maxval_dst, u64 *scan_area,
+                                                      u32 ctrl_words, u64 scan_words) {
+    if (blockIdx.x == 0) {
+        const volatile u32 *src = reinterpret_cast<const volatile u32 *>(ctrl);
+        for (u32 i = threadIdx.x; i < sizeof(B200Ctrl) / 4; i += blockDim.x) st_volatile_u64(host_mirror + i, ((u64)epoch << 32) | (u64)src[i]);
+        if (threadIdx.x == 0) *maxval_dst = *reinterpret_cast<volatile ull *>(&ctrl->max_val_out);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < ctrl_words; i += blockDim.x) scan_area[i] = 0;
+    }
+    for (u64 i = ctrl_words + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < scan_words; i += (u64)gridDim.x * blockDim.x) scan_area[i] = 0;
+}
+
 // Launch the numeric kernels of every list the pre-pass filled.  The list sizes live on the device only, so grids are
 // sized from `rows` and bins that no row can reach (p_bound) are skipped.
 template <typename VT>
 static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u64 rows, u64 p_bound, u64 heavy_cap,
                           int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps,
-                          B200Ctrl *ctrl = nullptr, bool wide_only = false) {
+                          B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw, b200_csr *C = nullptr) {
     if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32);
     const size_t smem_max = ctx->smem_optin - 1024;
@@ -687,7 +708,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     // later phase one product per thread (k_num_expand).  Returns false when the bin's buffers do not fit shared memory.
     const u32 nw4_full = caps.full;
     auto launch_expand = [&](int bin, int nb, u32 cap, u32 nw4, u64 n, cudaStream_t bs) -> bool {
-        if (nw4 == 0 || wide_only) return false;
+        if (nw4 == 0 || wide_only || bin - B200_BIN_HASH0 <= rw.hb_max) return false;   // (rows of bins <= rw.hb_max: row-per-warp kernel)
         const u32 pcap = cap, ncap = (u32)std::min<u64>(cap, B->cols);
         const size_t pvb = (mode == 0 || sizeof(VT) == 4) ? 4 : 8;
         const size_t ex_smem = (size_t)nw4 * 24 + (size_t)pcap * (4 + pvb) + (size_t)ncap * (4 + accb);
@@ -734,7 +755,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         if (!(reachable(0) || reachable(1))) return B200_OK;
         // bins 0 and 1 share list HASH0+1; rows whose column window exceeds the bitmap are on the wide list
         if (launch_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1], rows, fan.pick())) LAUNCH_CHECK(ctx);
-        if (caps.cap[1] < nw4_full) TRY(launch_warp_hash(B200_BIN_WIDE0 + 1, 1, rows, fan.pick()));
+        if (caps.cap[1] < nw4_full && !(rw.hb_max >= 1 && rw.all_fit)) TRY(launch_warp_hash(B200_BIN_WIDE0 + 1, 1, rows, fan.pick()));
         return B200_OK;
     };
     auto do_bin = [&](int hb) -> int {
@@ -743,11 +764,13 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
         cudaStream_t bs = fan.pick();
         bool used = false;
         if (launch_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb], rows, bs)) { LAUNCH_CHECK(ctx); used = true; }
-        if (caps.cap[hb] < nw4_full) TRY(launch_cta_hash(B200_BIN_WIDE0 + hb, hb, rows, used ? fan.pick() : bs));
+        if (caps.cap[hb] < nw4_full && !(hb <= rw.hb_max && rw.all_fit)) TRY(launch_cta_hash(B200_BIN_WIDE0 + hb, hb, rows, used ? fan.pick() : bs));
         return B200_OK;
     };
     // the longest rows first: the big kernels start while the host is still queueing the small ones
     const bool heavy = p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1);
+    if (rw.hb_max >= 1 && (reachable(0) || reachable(1)) && !wide_only)
+        TRY(rw_launch(ctx, A, B, ctrl, B200_BIN_HASH0 + 1, rw.hb_max, false, mode, packed, bpat, rw.nw, rw.cap, C, fan.pick()));
     if (heavy) {
         const u64 n = rows;
         const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)heavy_cap * (4 + accb);
@@ -811,14 +834,14 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
 // Exact mode, first half: distinct-column counts for every list the one-pass pre-pass produced (the lists and the
 // kernels mirror launch_numeric's: tiny / window bitmap / hash, heavy), so that C can be allocated at its exact size.
 static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const SymArgs &sa, u64 rows, u64 p_bound, bool packed, int lg,
-                         Fan &fan, const WinCaps &caps, B200Ctrl *ctrl = nullptr, bool wide_only = false) {
+                         Fan &fan, const WinCaps &caps, B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw) {
     if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = caps.full;
     const u32 bstride = (u32)ctx->cap_rows;
     const size_t smem_max = ctx->smem_optin - 1024;
     auto reachable = [&](int hb) { return hb == 0 ? (p_bound > 32 || A->max_row_len > 32) : p_bound > (u64)b200_hash_cap(hb - 1); };
     auto count_expand = [&](int bin, int nb, u32 pcap, u32 nw4) -> int {
-        if (nw4 == 0 || wide_only) return B200_OK;
+        if (nw4 == 0 || wide_only || bin - B200_BIN_HASH0 <= rw.hb_max) return B200_OK;
         const size_t smem = (size_t)nw4 * 16;
         const int t = std::max(32, std::min(512, (int)std::max<u32>(pcap / 2, nw4) / 8 / 32 * 32));
         const int g = (int)std::max<u64>(1, std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * ctas_per_sm(ctx, t, smem) * 4));
@@ -828,11 +851,13 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         LAUNCH_CHECK(ctx);
         return B200_OK;
     };
+    if (rw.hb_max >= 1 && (reachable(0) || reachable(1)) && !wide_only)
+        TRY(rw_launch(ctx, A, B, ctrl, B200_BIN_HASH0 + 1, rw.hb_max, true, 0, packed, true, rw.nw, rw.cap, nullptr, fan.pick()));
     if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan, ctrl));
     for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) {
         if (!reachable(hb)) continue;
         TRY(count_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb]));
-        if (caps.cap[hb] < nw4_full) {
+        if (caps.cap[hb] < nw4_full && !(hb <= rw.hb_max && rw.all_fit)) {
             const u32 slots = b200_hash_slots(hb);
             const int threads = bin_threads(ctx, hb, lg);
             const size_t smem = (size_t)slots * 4;
@@ -844,7 +869,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
     }
     if (reachable(0) || reachable(1)) {
         TRY(count_expand(B200_BIN_HASH0, 2, b200_hash_cap(1), caps.cap[1]));
-        if (caps.cap[1] < nw4_full) {
+        if (caps.cap[1] < nw4_full && !(rw.hb_max >= 1 && rw.all_fit)) {
             const int g = (int)std::min<u64>((rows + 7) / 8, (u64)ctx->num_sms * 16);
             k_sym_warp<<<g, 256, 0, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + 1, 1, std::min(lg, 5), ctx->d_nnz_row, bstride);
             LAUNCH_CHECK(ctx);
@@ -946,7 +971,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // no per-row window (WMODE 0), every row fits the bitmap, and the product's own column range is the arc.
     u32 all_groups = (nwords + 3) / 4, all_rot = 0;
     u64 arc_start = 0, arc_len = ncols;
-    if (B->rows == B->cols && A->cr_len < ncols && ctx->cfg.arc_window) {
+    const bool want_rw = ctx->cfg.pipeline == 3 || ctx->cfg.pipeline == 0;
+    if (B->rows == B->cols && ((A->cr_len < ncols && ctx->cfg.arc_window) || (want_rw && ctx->cfg.circular_windows))) {
         r = ensure_cs_bounds(ctx, B);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
         if (B->cs_state == 1) {
@@ -965,6 +991,26 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const u64 sb = A->max_row_span + (u64)(B->cs_hi - B->cs_lo);       // a row's arc grows by B's offset range
         C->max_row_span = sb <= ncols / 2 ? sb : ncols;
     }
+    // Row-per-warp kernels (pipeline 3, the default): rows of 33..4096 products whose window fits a warp's bitmap.  The
+    // bitmap is sized from what the host knows about the operands: the longest arc a row of A covers plus the offset range of
+    // B's entries (square B), the operand-level arc, or the whole column space -- at most B200_RW_MAX_GROUPS groups.
+    RwPlan rw = kNoRw;
+    if (want_rw) {
+        u64 groups = all_groups;
+        bool all_fit = true;                                               // no row's window can exceed the bitmap: no hash lists
+        if (B->rows == B->cols && ctx->cfg.circular_windows && B->cs_state == 1 && A->max_row_span < ncols) {
+            const u64 width = A->max_row_span + (u64)(B->cs_hi - B->cs_lo) + 1;
+            if (width + 2 < ncols / 2) groups = std::min<u64>(groups, (width + 127 + 127) / 128);
+        }
+        if (groups > B200_RW_MAX_GROUPS) { groups = B200_RW_MAX_GROUPS; all_fit = false; }
+        if (ctx->cfg.window_cap_groups >= 0 && (u64)ctx->cfg.window_cap_groups < groups) { groups = std::max<u64>(1, (u64)ctx->cfg.window_cap_groups); all_fit = false; }
+        const double meanP = ((double)A->nnz / (double)rows) * ((double)B->nnz / (double)B->rows);
+        const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.4;
+        u64 cap = (u64)(factor * meanP) + 32;
+        cap = std::min<u64>(cap, std::min<u64>(std::min<u64>(p_bound, 8192), groups * 128));
+        cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
+        rw.hb_max = B200_RW_MAX_HB; rw.nw = (u32)groups * 4u; rw.cap = (u32)cap; rw.all_fit = all_fit;
+    }
     {
         const u32 nw4_full = all_groups;
         const size_t accb1 = mode1 == 0 ? 4 : 8, pvb1 = (mode1 == 0 || sizeof(VT) == 4) ? 4 : 8;
@@ -978,6 +1024,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const size_t avail = smem_max - (packed ? 0 : sizeof(EnumSmem));    // the balanced expansion keeps its tile in static shared memory
             const u64 fit = fixed + 24 * 32 <= avail ? (avail - fixed) / 24 : 0;
             caps.cap[hb] = ctx->cfg.expand_kernel ? (u32)std::min<u64>(want, fit) : 0u;
+            if (hb <= rw.hb_max) caps.cap[hb] = rw.nw / 4;
         }
     }
     {
@@ -1016,6 +1063,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const int exact_env = ctx->cfg.placement;
         const int exact_mb = ctx->cfg.exact_limit_mb;
         bool exact = exact_env >= 0 ? exact_env != 0 : (exact_mb >= 0 && hb128 * esz > (unsigned __int128)((u64)exact_mb << 20));
+        if (rw.hb_max >= 0) exact = true;                                  // the row-per-warp kernels write C once, at its final offsets
         tmp_entries = (u64)hb128;
         if (exact_env < 0 && !exact && !cheap_bound) {
             // the host-side bound is too loose to decide: read the pre-pass's exact scratch size sum(min(P_i, cols)) (one
@@ -1033,9 +1081,35 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             }
         }
         if (exact) {
-            r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps);
+            r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps, nullptr, false, rw);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            if (rw.hb_max >= 0 && cheap_bound) {
+                // ---- nothing waits for the device: C is allocated from the host-known bound nnz(A) * maxlen(B), the scan writes
+                //      row_ptr, the numeric kernels write every row once at its final offset, and the last kernel reports the
+                //      control block (nnz, longest row, largest value) into this multiply's slot of the pinned report ring.  The
+                //      handle is handed out "pending" (resolve_pending reads the slot when somebody needs the numbers).
+                launch_scan_rowptr(ctx, rows, C->d_rp, s, nullptr, 0);
+                LAUNCH_CHECK(ctx);
+                if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
+                C->cap_entries = std::max<u64>(tmp_entries, 1);
+                r = alloc_entries(ctx, C);
+                if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+                OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
+                r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, std::min<u64>(p_bound, ncols)), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C);
+                fan.join();
+                if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+                const unsigned fg = (unsigned)std::max<u64>(1, std::min<u64>(64, scan_bytes / 8 / 1024));
+                k_finish_exact<<<fg, 256, 0, s>>>(ctx->d_ctrl, mirror, epoch, C->d_maxval, (u64 *)ctx->d_scan, B200_CTRL_BYTES / 8, scan_bytes / 8);
+                LAUNCH_CHECK(ctx);
+                ctx->scan_clean_bytes = scan_bytes;
+                if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
+                trace_dump(ctx, "exact multiply (asynchronous)");
+                mark_pending(ctx, C, slot, epoch, A, B, mode1, 3, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
+                *out = C;
+                if (st) { TRY(resolve_pending(ctx, C)); *st = *C->stats; }
+                return B200_OK;
+            }
             const u32 xepoch = ++ctx->epoch ? ctx->epoch : ++ctx->epoch;
             launch_scan_rowptr(ctx, rows, C->d_rp, s, ctx->h_report, xepoch);
             LAUNCH_CHECK(ctx);
@@ -1049,7 +1123,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             if (timing) cudaEventRecord(ctx->ev[2], s);
             if (ctx->trace) trace_mark(ctx, __LINE__);
             OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
-            r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps);
+            r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
@@ -1063,7 +1137,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 xs->bytes_algorithmic = (A->nnz + B->nnz + C->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
                 xs->acc_mode = mode1; xs->kernel_launches = (int32_t)(ctx->launches - launches0);
                 for (int i = 0; i < B200_STAT_BINS; i++) xs->sym_bin_rows[i] = hc.sym_bin_count[i];
-                xs->pipeline = 2;
+                xs->pipeline = rw.hb_max >= 0 ? 3 : 2;
                 if (timing && st) {
                     CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
                     cudaEventElapsedTime(&xs->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan

@@ -147,6 +147,13 @@ int alloc_entries(b200_ctx *ctx, b200_csr *m);
 int legacy_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, u64 p_bound, int lg, Fan &fan);
 int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, b200_csr *C, u64 p_bound, u64 heavy_cap, int mode,
                    bool packed, bool bpat, int lg, Fan &fan);
+// ---- rowwarp.cu: row-per-warp count / numeric kernels of the exact placement
+#define B200_RW_MAX_HB 7          // hash bins 0..7 (33..8192 intermediate products) are rows a single warp produces
+#define B200_RW_MAX_GROUPS 256    // largest window bitmap of a warp, in 128-column groups
+void rw_setup(b200_ctx *ctx);
+size_t rw_smem_per_warp(bool count, int mode, u32 nw, u32 cap);
+int rw_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, int first_bin, int nbins, bool count, int mode,
+              bool packed, bool bpat, u32 nw, u32 cap, b200_csr *C, cudaStream_t s);
 // ---- fused.cu
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);

@@ -1025,7 +1025,7 @@ int resolve_pending(b200_ctx *ctx, const b200_csr *cm) {
                 float first = 0, second = 0;
                 cudaEventElapsedTime(&first, ctx->f_ev[slot][0], ctx->f_ev[slot][1]);
                 cudaEventElapsedTime(&second, ctx->f_ev[slot][1], ctx->f_ev[slot][2]);
-                if (st->pipeline == 1) { st->ms_symbolic = first; st->ms_numeric = second; } else { st->ms_numeric = first; st->ms_symbolic = second; }
+                if (st->pipeline != 2) { st->ms_symbolic = first; st->ms_numeric = second; } else { st->ms_numeric = first; st->ms_symbolic = second; }
                 cudaEventElapsedTime(&st->ms_total, ctx->f_ev[slot][0], ctx->f_ev[slot][2]);
             } else cudaGetLastError();
         }

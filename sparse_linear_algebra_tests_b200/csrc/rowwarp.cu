@@ -1,0 +1,312 @@
+// rowwarp.cu -- the row-per-warp kernels of the exact placement: one warp owns one row of C from its first product to its
+// last stored entry, nothing waits for another row, no CTA barrier anywhere.
+//
+//   k_rw<.., COUNT = true>    distinct output columns of a row: every intermediate product sets its column's bit in the warp's
+//                             window bitmap (shared memory), the row's length is the popcount.  Feeds the row_ptr scan.
+//   k_rw<.., COUNT = false>   values.  mark (as above) -> rank (exclusive prefix popcount per bitmap word, kept beside the
+//                             word) -> accumulate (each product is added into acc[rank(column)]: compact accumulators of
+//                             the row's LENGTH, not of its window, so a warp needs ~8 bytes per output entry and a bit per
+//                             window column) -> emit (lane per output entry, coalesced stores at row_ptr_C[row]; the rank
+//                             is the column's place in the sorted row, so there is no sort).
+// Rows come from the pre-pass's bin lists (largest bin first, dealt round-robin over the resident warps); a row's column
+// window {origin, groups} comes from the pre-pass too (whole column space, an operand-level arc, or a per-row plain /
+// circular window).  Rows with more entries than the warp has accumulator slots are produced in several passes over
+// their products (rank ranges), so the slot count is a tuning figure, not a limit.
+//
+// This is the MAGNUS "dense accumulation" category cut for a GPU: the accumulator is dense in RANK space,
+// the bitmap is the only thing that scales with the window.  It replaces, for rows of 33..4096 intermediate products,
+// the symbolic and numeric passes of CsrMatrix::matmul_par (/root/reference/src/graph_csr.rs:362-403, :430-476).
+#include "engine.cuh"
+#include "devutil.cuh"
+
+#define RW_WARPS 4
+#define RW_THREADS (RW_WARPS * 32)
+
+template <typename VT>
+struct RwArgs {
+    NumArgs<VT> a;
+    const uint4 *pack;
+    const u32 *bin_rows; const u32 *bin_cnt; u32 bin_stride;
+    int first_bin, nbins;        // lists first_bin .. first_bin + nbins - 1, walked from the last (longest rows) to the first
+    const uint4 *win; u32 ncols;
+    u32 nw;                      // bitmap words per warp (multiple of 4); no listed row's window has more
+    u32 cap;                     // accumulator slots per warp
+    u32 *nnz_row;                // COUNT: the row's length goes here
+    const u64 *rpC; u32 *colC; VT *valC;
+    B200Ctrl *ctrl;
+};
+
+__device__ __forceinline__ PackRec rw_load_pack(const uint4 *__restrict__ pack, u32 k) {
+    PackRec r;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+        : "l"(pack + 2 * (u64)k));
+    return r;
+}
+
+template <int MODE, typename VT>
+__device__ __forceinline__ u64 rw_product(VT a, VT b) {
+    if (MODE == 0) return (u64)((u32)a * (u32)b);
+    if (MODE == 2) return sat_mul((u64)a, (u64)b);
+    u64 x = (u64)a * (u64)b;
+    if (sizeof(VT) == 4) x = x > 0xFFFFFFFFull ? 0xFFFFFFFFull : x;
+    return x;
+}
+
+// All intermediate products of one A row, by one warp.
+// PACK (low-degree B, one 32-byte record per B row): lane per A entry; f6(columns[6], n, first index into B's arrays, a_ik)
+// gets the record's inline columns at once (so that its shared-memory reads overlap), f1(column, index, a_ik) the rest of
+// a longer row.  The loads run two entries ahead (A column, value) and one ahead (record): an iteration waits for neither.
+// Otherwise: lane per A entry for short B rows, the whole warp striding over the long ones (coalesced), all through f1.
+template <typename VT, bool PACK, bool NEEDV, typename F6, typename F1>
+__device__ __forceinline__ void rw_enumerate(const NumArgs<VT> &a, const uint4 *__restrict__ pack, u64 rs, u32 lenA, int lane, F6 f6, F1 f1) {
+    const u32 *__restrict__ Ac = a.colA + rs;
+    const VT *__restrict__ Av = a.valA + rs;
+    if constexpr (PACK) {
+        u32 t = (u32)lane;
+        bool v0 = t < lenA, v1 = t + 32 < lenA;
+        u32 k0 = 0, k1 = 0; VT x0 = 0, x1 = 0;
+        if (v0) { k0 = Ac[t]; if (NEEDV) x0 = Av[t]; }
+        if (v1) { k1 = Ac[t + 32]; if (NEEDV) x1 = Av[t + 32]; }
+        PackRec rec; rec.a = make_uint4(0, 0, 0, 0); rec.b = rec.a;
+        if (v0) rec = rw_load_pack(pack, k0);
+        for (u32 base = 0; base < lenA; base += 32) {
+            PackRec recn; recn.a = make_uint4(0, 0, 0, 0); recn.b = recn.a;
+            if (v1) recn = rw_load_pack(pack, k1);
+            const bool v2 = base + 64 + (u32)lane < lenA;
+            u32 k2 = 0; VT x2 = 0;
+            if (v2) { k2 = Ac[base + 64 + lane]; if (NEEDV) x2 = Av[base + 64 + lane]; }
+            const u32 len = v0 ? rec.a.y : 0u, st = rec.a.x;
+            const u32 c[B200_PACK_INLINE] = {rec.a.z, rec.a.w, rec.b.x, rec.b.y, rec.b.z, rec.b.w};
+            f6(c, len < B200_PACK_INLINE ? len : (u32)B200_PACK_INLINE, st, x0);
+            for (u32 j = B200_PACK_INLINE; j < len; j++) f1(a.colB[st + j], st + j, x0);
+            rec = recn; v0 = v1; x0 = x1; k1 = k2; x1 = x2; v1 = v2;
+        }
+    } else {
+        for (u32 base = 0; base < lenA; base += 32) {
+            const u32 t = base + lane;
+            const bool valid = t < lenA;
+            u32 st = 0, len = 0; VT x = 0;
+            if (valid) { const uint2 d = a.bdesc[Ac[t]]; st = d.x; len = d.y; if (NEEDV) x = Av[t]; }
+            u32 longm = __ballot_sync(0xFFFFFFFFu, len >= 16);
+            while (longm) {
+                const int src = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const u32 s = __shfl_sync(0xFFFFFFFFu, st, src), l = __shfl_sync(0xFFFFFFFFu, len, src);
+                const VT xs = shfl_any(x, src);
+                for (u32 j = lane; j < l; j += 32) f1(a.colB[s + j], s + j, xs);
+            }
+            if (len < 16) for (u32 j = 0; j < len; j++) f1(a.colB[st + j], st + j, x);
+        }
+    }
+}
+
+// r-th row of the lists, longest rows first
+template <typename VT>
+__device__ __forceinline__ u32 rw_row_at(const RwArgs<VT> &p, u32 r) {
+    int b = p.first_bin + p.nbins - 1;
+    while (b > p.first_bin && r >= p.bin_cnt[b]) { r -= p.bin_cnt[b]; b--; }
+    return p.bin_rows[(u64)b * p.bin_stride + r];
+}
+
+template <typename VT, int MODE, bool PACK, bool BPAT, bool COUNT>
+__global__ void __launch_bounds__(RW_THREADS) k_rw(RwArgs<VT> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 count = 0;
+    for (int b = 0; b < p.nbins; b++) count += p.bin_cnt[p.first_bin + b];
+    const u32 nwarps = gridDim.x * RW_WARPS;
+    u32 r = blockIdx.x * RW_WARPS + wid;
+    if (r >= count) return;
+    // per warp: COUNT: u32 bitmap[nw].  Numeric: {bits, prefix} uint2[nw] | acc[cap] | window offsets u16[cap]
+    const size_t per_warp = COUNT ? (size_t)p.nw * 4 : (size_t)p.nw * 8 + Acc<MODE>::bytes(p.cap) + (size_t)p.cap * 2;
+    unsigned char *base = smem_raw + (size_t)wid * per_warp;
+    u32 *bm = reinterpret_cast<u32 *>(base);                                 // COUNT
+    uint2 *bw = reinterpret_cast<uint2 *>(base);                             // numeric
+    Acc<MODE> acc; unsigned short *offs = nullptr;
+    if (!COUNT) { acc.bind(base + (size_t)p.nw * 8, p.cap); offs = reinterpret_cast<unsigned short *>(base + (size_t)p.nw * 8 + Acc<MODE>::bytes(p.cap)); }
+    if (COUNT) { for (u32 t = lane; t < p.nw; t += 32) bm[t] = 0; }
+    else {
+        for (u32 t = lane; t < p.nw; t += 32) bw[t] = make_uint2(0u, 0u);
+        for (u32 t = lane; t < p.cap; t += 32) acc.clear(t);
+    }
+    __syncwarp();
+    const u32 ncols = p.ncols;
+    u64 vmax = 0;
+    // row header one row ahead: id, A row extent, window, output base
+    u32 row = rw_row_at(p, r);
+    u64 rs = p.a.rpA[row];
+    u32 lenA = (u32)(p.a.rpA[row + 1] - rs);
+    uint4 wn = p.win[row];
+    u64 obase = COUNT ? 0ull : p.rpC[row];
+    for (; r < count; r += nwarps) {
+        const bool has_next = r + nwarps < count;
+        u32 row_n = 0;
+        if (has_next) row_n = rw_row_at(p, r + nwarps);
+        // bit d of the window is column (org + d) mod ncols
+        u32 org; { const u64 t = (u64)wn.x + wn.z; org = (u32)(t >= ncols ? t - ncols : t); }
+        const u32 words = wn.y * 4u;
+        auto dcol = [&](u32 c) -> u32 { return c >= org ? c - org : c - org + ncols; };
+        // ---- mark
+        auto mark1 = [&](u32 c, u32, VT) {
+            const u32 d = dcol(c);
+            if (COUNT) atomicOr(&bm[d >> 5], __funnelshift_l(0u, 1u, d));
+            else atomicOr(&bw[d >> 5].x, __funnelshift_l(0u, 1u, d));
+        };
+        rw_enumerate<VT, PACK, false>(p.a, p.pack, rs, lenA, lane,
+            [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32, VT) {
+#pragma unroll
+                for (int j = 0; j < B200_PACK_INLINE; j++) if ((u32)j < n) mark1(c[j], 0u, (VT)0);
+            }, mark1);
+        // next row's header (its id has arrived by now)
+        u64 rs_n = 0; u32 lenA_n = 0; uint4 wn_n = make_uint4(0, 0, 0, 0); u64 obase_n = 0;
+        if (has_next) {
+            rs_n = p.a.rpA[row_n]; lenA_n = (u32)(p.a.rpA[row_n + 1] - rs_n); wn_n = p.win[row_n];
+            if (!COUNT) obase_n = p.rpC[row_n];
+        }
+        __syncwarp();
+        // ---- rank: consecutive words per lane, warp scan of the lanes' popcounts
+        const u32 wpl = (words + 31) >> 5, w0 = (u32)lane * wpl;
+        u32 mine = 0;
+        for (u32 i = 0; i < wpl; i++) {
+            if (w0 + i < words) {
+                if (COUNT) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
+                else mine += __popc(bw[w0 + i].x);
+            }
+        }
+        u32 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        const u32 nnz = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if constexpr (COUNT) {
+            if (lane == 0) p.nnz_row[row] = nnz;
+            __syncwarp();
+        } else {
+            u32 run = incl - mine;
+            for (u32 i = 0; i < wpl; i++) {
+                if (w0 + i < words) { bw[w0 + i].y = run; run += __popc(bw[w0 + i].x); }
+            }
+            __syncwarp();
+            // Ranks are in d order; when the window starts at a column org > 0 the entries whose column lies below org
+            // (d >= ncols - org) belong in FRONT of the others: the row is written rotated by r0 = entries with d < ncols - org.
+            u32 r0 = nnz;
+            if (org) {
+                const u32 split = ncols - org;
+                if (split < words * 32u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
+            }
+            const u32 shift_hi = nnz - r0;
+            for (u32 pass = 0; pass < nnz; pass += p.cap) {
+                // ---- accumulate at the column's rank (ranks pass .. pass + cap - 1 in this pass)
+                auto acc1 = [&](u32 c, u32 jb, VT av) {
+                    const u32 d = dcol(c);
+                    const uint2 s = bw[d >> 5];
+                    const u32 pos = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, d) - 1u)) - pass;
+                    if (pos < p.cap) {
+                        offs[pos] = (unsigned short)d;
+                        acc.addv(pos, BPAT ? (u64)av : rw_product<MODE, VT>(av, p.a.valB[jb]));
+                    }
+                };
+                rw_enumerate<VT, PACK, true>(p.a, p.pack, rs, lenA, lane,
+                    [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32 st, VT av) {
+                        // all six bitmap words first, then the six accumulations: the reads do not wait for the writes
+                        u32 d[B200_PACK_INLINE], pos[B200_PACK_INLINE]; uint2 s[B200_PACK_INLINE]; u64 x[B200_PACK_INLINE];
+#pragma unroll
+                        for (int j = 0; j < B200_PACK_INLINE; j++) {
+                            d[j] = 0; s[j] = make_uint2(0u, 0u); x[j] = (u64)av;
+                            if ((u32)j < n) { d[j] = dcol(c[j]); s[j] = bw[d[j] >> 5]; if (!BPAT) x[j] = rw_product<MODE, VT>(av, p.a.valB[st + j]); }
+                        }
+#pragma unroll
+                        for (int j = 0; j < B200_PACK_INLINE; j++) pos[j] = s[j].y + __popc(s[j].x & (__funnelshift_l(0u, 1u, d[j]) - 1u)) - pass;
+#pragma unroll
+                        for (int j = 0; j < B200_PACK_INLINE; j++)
+                            if ((u32)j < n && pos[j] < p.cap) { offs[pos[j]] = (unsigned short)d[j]; acc.addv(pos[j], x[j]); }
+                    }, acc1);
+                __syncwarp();
+                // ---- emit: lane per entry, coalesced; the accumulators are left clean
+                const u32 m = min(p.cap, nnz - pass);
+                for (u32 t = lane; t < m; t += 32) {
+                    u32 c = org + (u32)offs[t]; if (c >= ncols) c -= ncols;
+                    const VT v = emit_val<VT>(acc.get(t));
+                    acc.clear(t);
+                    const u32 g = pass + t;
+                    const u32 q = g >= r0 ? g - r0 : g + shift_hi;
+                    p.colC[obase + q] = c; p.valC[obase + q] = v;
+                    vmax = vmax > (u64)v ? vmax : (u64)v;
+                }
+                __syncwarp();
+            }
+            for (u32 i = 0; i < wpl; i++) if (w0 + i < words) bw[w0 + i] = make_uint2(0u, 0u);
+            __syncwarp();
+        }
+        row = row_n; rs = rs_n; lenA = lenA_n; wn = wn_n; obase = obase_n;
+    }
+    if (!COUNT) {
+        vmax = warp_max_u64(vmax);
+        if (lane == 0 && vmax) atomicMax(&p.ctrl->max_val_out, (ull)vmax);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+struct RwKernel { const void *fn; int regs; size_t static_smem; };
+// [value width][mode][packed][pattern-only B][count]
+static RwKernel g_rw[2][3][2][2][2];
+template <typename VT, int MODE, bool PACK, bool BPAT, bool COUNT>
+static void rw_register(size_t optin) {
+    RwKernel &k = g_rw[sizeof(VT) == 8][MODE][PACK][BPAT][COUNT];
+    k.fn = (const void *)k_rw<VT, MODE, PACK, BPAT, COUNT>;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k.fn) == cudaSuccess) { k.regs = fa.numRegs; k.static_smem = fa.sharedSizeBytes; } else { cudaGetLastError(); k.regs = 64; k.static_smem = 0; }
+    if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - k.static_smem)) != cudaSuccess) cudaGetLastError();
+}
+template <typename VT, int MODE>
+static void rw_register_mode(size_t o) {
+    rw_register<VT, MODE, false, false, false>(o); rw_register<VT, MODE, false, true, false>(o);
+    rw_register<VT, MODE, true, false, false>(o); rw_register<VT, MODE, true, true, false>(o);
+}
+void rw_setup(b200_ctx *ctx) {
+    const size_t o = ctx->smem_optin;
+    rw_register_mode<u32, 0>(o); rw_register_mode<u32, 1>(o);
+    rw_register_mode<u64, 0>(o); rw_register_mode<u64, 1>(o); rw_register_mode<u64, 2>(o);
+    // the count kernels touch no values: one pair (packed or not) serves every width and mode
+    rw_register<u32, 0, false, true, true>(o); rw_register<u32, 0, true, true, true>(o);
+}
+
+size_t rw_smem_per_warp(bool count, int mode, u32 nw, u32 cap) {
+    return count ? (size_t)nw * 4 : (size_t)nw * 8 + (size_t)cap * ((mode == 0 ? 4 : 8) + 2);
+}
+
+template <typename VT>
+static cudaError_t rw_go(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, int first_bin, int nbins, u32 nw, u32 cap,
+                         b200_csr *C, const void *fn, int grid, size_t smem, cudaStream_t s) {
+    RwArgs<VT> p;
+    p.a = NumArgs<VT>{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
+    p.pack = B->d_pack; p.bin_rows = ctx->d_bin_rows; p.bin_cnt = ctrl->sym_bin_count; p.bin_stride = (u32)ctx->cap_rows;
+    p.first_bin = first_bin; p.nbins = nbins; p.win = ctx->d_win; p.ncols = (u32)B->cols; p.nw = nw; p.cap = cap;
+    p.nnz_row = ctx->d_nnz_row; p.rpC = C ? C->d_rp : nullptr; p.colC = C ? C->d_col : nullptr; p.valC = C ? (VT *)C->d_val : nullptr; p.ctrl = ctrl;
+    void *kargs[] = {(void *)&p};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(RW_THREADS), kargs, smem, s);
+}
+
+// Launch the row-per-warp kernel over the pre-pass lists first_bin .. first_bin + nbins - 1.  count: lengths into
+// ctx->d_nnz_row; else values into C at C->d_rp.
+int rw_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, int first_bin, int nbins, bool count, int mode,
+              bool packed, bool bpat, u32 nw, u32 cap, b200_csr *C, cudaStream_t s) {
+    const bool v64 = A->val_bits == 64;
+    const RwKernel &k = count ? g_rw[0][0][packed ? 1 : 0][1][1] : g_rw[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][packed ? 1 : 0][bpat ? 1 : 0][0];
+    if (!k.fn) return set_err(B200_ERR_CUDA, "row-per-warp kernel variant is not registered");
+    const size_t smem = rw_smem_per_warp(count, mode, nw, cap) * RW_WARPS;
+    if (smem + k.static_smem > ctx->smem_optin) return set_err(B200_ERR_CUDA, "row-per-warp kernel needs %zu B of shared memory", smem);
+    const int by_smem = (int)((size_t)(228 * 1024) / (smem + k.static_smem + 1024));
+    const int regs_per_cta = ((k.regs * 32 + 511) / 512 * 512) * RW_WARPS;
+    const int by_regs = regs_per_cta ? 65536 / regs_per_cta : 32;
+    const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), std::min(2048 / RW_THREADS, 32)));
+    const u64 want = (A->rows + RW_WARPS - 1) / RW_WARPS;
+    const int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
+    // (the count variant is instantiated for u32 values only and never reads one)
+    const cudaError_t le = v64 && !count ? rw_go<u64>(ctx, A, B, ctrl, first_bin, nbins, nw, cap, C, k.fn, grid, smem, s)
+                                         : rw_go<u32>(ctx, A, B, ctrl, first_bin, nbins, nw, cap, C, k.fn, grid, smem, s);
+    ctx->launches++;
+    if (ctx->trace) trace_mark(ctx, __LINE__);
+    if (le != cudaSuccess) return set_err(B200_ERR_CUDA, "row-per-warp kernel launch failed: %s", cudaGetErrorString(le));
+    return B200_OK;
+}
