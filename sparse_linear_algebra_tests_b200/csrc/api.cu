@@ -1009,7 +1009,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         u64 cap = (u64)(factor * meanP) + 32;
         cap = std::min<u64>(cap, std::min<u64>(std::min<u64>(p_bound, 8192), groups * 128));
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
-        rw.hb_max = B200_RW_MAX_HB; rw.nw = (u32)groups * 4u; rw.cap = (u32)cap; rw.all_fit = all_fit;
+        rw.hb_max = B200_RW_MAX_HB; rw.nw = ((u32)groups * 4u + 31u) & ~31u; rw.cap = (u32)cap; rw.all_fit = all_fit;   // (a lane owns nw / 32 consecutive words)
     }
     {
         const u32 nw4_full = all_groups;
@@ -1024,7 +1024,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const size_t avail = smem_max - (packed ? 0 : sizeof(EnumSmem));    // the balanced expansion keeps its tile in static shared memory
             const u64 fit = fixed + 24 * 32 <= avail ? (avail - fixed) / 24 : 0;
             caps.cap[hb] = ctx->cfg.expand_kernel ? (u32)std::min<u64>(want, fit) : 0u;
-            if (hb <= rw.hb_max) caps.cap[hb] = rw.nw / 4;
+            if (hb <= rw.hb_max) caps.cap[hb] = std::min<u32>(rw.nw / 4, all_groups);
         }
     }
     {
@@ -1040,6 +1040,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < all_groups;
         if (windows && use_arc) { all_groups = (nwords + 3) / 4; all_rot = 0; }   // a bin cannot hold the arc: per-row windows over the plain column space
         caps.full = all_groups;
+        if (ctx->trace) fprintf(stderr, "[b200 trace] rw: hb_max %d nw %u cap %u all_fit %d A.max_row_span %llu p_bound %llu\n", rw.hb_max, rw.nw, rw.cap, (int)rw.all_fit, (ull)A->max_row_span, (ull)p_bound);
         if (ctx->trace) fprintf(stderr, "[b200 trace] arc: A.cr=(%u,%llu) B.cs=[%lld,%lld] state %d arc=(%llu,%llu) use_arc=%d windows=%d groups=%u caps=%u %u %u %u %u %u %u %u\n",
                                 A->cr_start, (ull)A->cr_len, B->cs_lo, B->cs_hi, B->cs_state, (ull)arc_start, (ull)arc_len, (int)use_arc, (int)windows, all_groups,
                                 caps.cap[0], caps.cap[1], caps.cap[2], caps.cap[3], caps.cap[4], caps.cap[5], caps.cap[6], caps.cap[7]);

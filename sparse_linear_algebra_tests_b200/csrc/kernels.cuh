@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) k_build_pack(u64 rows, const u64 *__restr
         const u32 len = (u32)(rp[i + 1] - s);
         u32 c[B200_PACK_INLINE];
 #pragma unroll
-        for (int j = 0; j < B200_PACK_INLINE; j++) c[j] = j < (int)len ? col[s + j] : B200_EMPTY_KEY;
+        for (int j = 0; j < B200_PACK_INLINE; j++) c[j] = len ? col[s + (j < (int)len ? j : (int)len - 1)] : 0u;   // unused slots repeat the last column (rowwarp.cu runs them unpredicated)
         pack[2 * i] = make_uint4((u32)s, len, c[0], c[1]);
         pack[2 * i + 1] = make_uint4(c[2], c[3], c[4], c[5]);
     }

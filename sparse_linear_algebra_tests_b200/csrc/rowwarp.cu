@@ -16,11 +16,15 @@
 // This is the MAGNUS "dense accumulation" category cut for a GPU: the accumulator is dense in RANK space,
 // the bitmap is the only thing that scales with the window.  It replaces, for rows of 33..4096 intermediate products,
 // the symbolic and numeric passes of CsrMatrix::matmul_par (/root/reference/src/graph_csr.rs:362-403, :430-476).
+#include <type_traits>
 #include "engine.cuh"
 #include "devutil.cuh"
 
 #define RW_WARPS 4
 #define RW_THREADS (RW_WARPS * 32)
+#ifndef RW_MIN_CTAS
+#define RW_MIN_CTAS 8
+#endif
 
 template <typename VT>
 struct RwArgs {
@@ -31,6 +35,7 @@ struct RwArgs {
     const uint4 *win; u32 ncols;
     u32 nw;                      // bitmap words per warp (multiple of 4); no listed row's window has more
     u32 cap;                     // accumulator slots per warp
+    u32 nsm;                     // SMs of the device (CTA -> slice mapping)
     u32 *nnz_row;                // COUNT: the row's length goes here
     const u64 *rpC; u32 *colC; VT *valC;
     B200Ctrl *ctrl;
@@ -55,45 +60,61 @@ __device__ __forceinline__ u64 rw_product(VT a, VT b) {
 
 // All intermediate products of one A row, by one warp.
 // PACK (low-degree B, one 32-byte record per B row): lane per A entry; f6(columns[6], n, first index into B's arrays, a_ik)
-// gets the record's inline columns at once (so that its shared-memory reads overlap), f1(column, index, a_ik) the rest of
-// a longer row.  The loads run two entries ahead (A column, value) and one ahead (record): an iteration waits for neither.
+// gets the record's inline columns at once (its slots are straight-line predicated code whose shared-memory reads overlap),
+// f1(column, index, a_ik) the rest of a longer row.  Two entry streams (even / odd blocks of 32 entries) are kept in
+// flight, each with its A column and value two blocks ahead and its record one block ahead, so a step waits for neither
+// and no register is moved between the stages.
 // Otherwise: lane per A entry for short B rows, the whole warp striding over the long ones (coalesced), all through f1.
-template <typename VT, bool PACK, bool NEEDV, typename F6, typename F1>
+// XT: what is kept of a_ik (u32 when 32-bit sums are proven, else the value type).
+template <typename VT, typename XT, bool PACK, bool NEEDV, typename F6, typename F1>
 __device__ __forceinline__ void rw_enumerate(const NumArgs<VT> &a, const uint4 *__restrict__ pack, u64 rs, u32 lenA, int lane, F6 f6, F1 f1) {
     const u32 *__restrict__ Ac = a.colA + rs;
     const VT *__restrict__ Av = a.valA + rs;
     if constexpr (PACK) {
-        u32 t = (u32)lane;
-        bool v0 = t < lenA, v1 = t + 32 < lenA;
-        u32 k0 = 0, k1 = 0; VT x0 = 0, x1 = 0;
-        if (v0) { k0 = Ac[t]; if (NEEDV) x0 = Av[t]; }
-        if (v1) { k1 = Ac[t + 32]; if (NEEDV) x1 = Av[t + 32]; }
-        PackRec rec; rec.a = make_uint4(0, 0, 0, 0); rec.b = rec.a;
-        if (v0) rec = rw_load_pack(pack, k0);
-        for (u32 base = 0; base < lenA; base += 32) {
-            PackRec recn; recn.a = make_uint4(0, 0, 0, 0); recn.b = recn.a;
-            if (v1) recn = rw_load_pack(pack, k1);
-            const bool v2 = base + 64 + (u32)lane < lenA;
-            u32 k2 = 0; VT x2 = 0;
-            if (v2) { k2 = Ac[base + 64 + lane]; if (NEEDV) x2 = Av[base + 64 + lane]; }
-            const u32 len = v0 ? rec.a.y : 0u, st = rec.a.x;
+        u32 kA = 0, kB = 0; XT xA = 0, xB = 0, xAn = 0, xBn = 0;
+        PackRec rA, rB; rA.a.y = 0; rB.a.y = 0;
+        {
+            const u32 t0 = (u32)lane, t1 = t0 + 32, t2 = t0 + 64, t3 = t0 + 96;
+            u32 k0 = 0, k1 = 0;
+            if (t0 < lenA) { k0 = Ac[t0]; if (NEEDV) xA = (XT)Av[t0]; }
+            if (t1 < lenA) { k1 = Ac[t1]; if (NEEDV) xB = (XT)Av[t1]; }
+            if (t2 < lenA) { kA = Ac[t2]; if (NEEDV) xAn = (XT)Av[t2]; }
+            if (t3 < lenA) { kB = Ac[t3]; if (NEEDV) xBn = (XT)Av[t3]; }
+            if (t0 < lenA) rA = rw_load_pack(pack, k0);
+            if (t1 < lenA) rB = rw_load_pack(pack, k1);
+        }
+        auto step = [&](PackRec &rec, XT &x, XT &xn, u32 &kn, u32 t) {
+            // t: this lane's entry of the block being consumed; its stream's next entry is t + 64, the one after t + 128
+            const u32 len = rec.a.y, st = rec.a.x;
             const u32 c[B200_PACK_INLINE] = {rec.a.z, rec.a.w, rec.b.x, rec.b.y, rec.b.z, rec.b.w};
-            f6(c, len < B200_PACK_INLINE ? len : (u32)B200_PACK_INLINE, st, x0);
-            for (u32 j = B200_PACK_INLINE; j < len; j++) f1(a.colB[st + j], st + j, x0);
-            rec = recn; v0 = v1; x0 = x1; k1 = k2; x1 = x2; v1 = v2;
+            const XT xc = x;
+            rec.a.y = 0;
+            if (t + 64 < lenA) rec = rw_load_pack(pack, kn);
+            x = xn;
+            if (t + 128 < lenA) { kn = Ac[t + 128]; if (NEEDV) xn = (XT)Av[t + 128]; }
+            if (len) {
+                // a record's unused inline slots repeat its last column (k_build_pack), so all six slots run unpredicated:
+                // marking a column twice is harmless, and f6 adds zero for the slots >= n
+                f6(c, len < B200_PACK_INLINE ? len : (u32)B200_PACK_INLINE, st, xc);
+                for (u32 j = B200_PACK_INLINE; j < len; j++) f1(a.colB[st + j], st + j, xc);
+            }
+        };
+        for (u32 base = 0; base < lenA; base += 64) {
+            step(rA, xA, xAn, kA, base + lane);
+            if (base + 32 < lenA) step(rB, xB, xBn, kB, base + 32 + lane);
         }
     } else {
         for (u32 base = 0; base < lenA; base += 32) {
             const u32 t = base + lane;
             const bool valid = t < lenA;
-            u32 st = 0, len = 0; VT x = 0;
-            if (valid) { const uint2 d = a.bdesc[Ac[t]]; st = d.x; len = d.y; if (NEEDV) x = Av[t]; }
+            u32 st = 0, len = 0; XT x = 0;
+            if (valid) { const uint2 d = a.bdesc[Ac[t]]; st = d.x; len = d.y; if (NEEDV) x = (XT)Av[t]; }
             u32 longm = __ballot_sync(0xFFFFFFFFu, len >= 16);
             while (longm) {
                 const int src = __ffs(longm) - 1;
                 longm &= longm - 1;
                 const u32 s = __shfl_sync(0xFFFFFFFFu, st, src), l = __shfl_sync(0xFFFFFFFFu, len, src);
-                const VT xs = shfl_any(x, src);
+                const XT xs = shfl_any(x, src);
                 for (u32 j = lane; j < l; j += 32) f1(a.colB[s + j], s + j, xs);
             }
             if (len < 16) for (u32 j = 0; j < len; j++) f1(a.colB[st + j], st + j, x);
@@ -101,24 +122,52 @@ __device__ __forceinline__ void rw_enumerate(const NumArgs<VT> &a, const uint4 *
     }
 }
 
-// r-th row of the lists, longest rows first
+// The rows a warp takes: every list (longest rows first) is cut into one slice per CTA, CTAs resident on the same SM
+// take adjacent slices, and the warps of a CTA interleave inside their slice -- so the rows in flight on an SM are
+// neighbours and share most of their B records (lattice-like operands), which then come from L1 instead of L2.
+struct RwCursor { int b; u32 r, hi; };
 template <typename VT>
-__device__ __forceinline__ u32 rw_row_at(const RwArgs<VT> &p, u32 r) {
-    int b = p.first_bin + p.nbins - 1;
-    while (b > p.first_bin && r >= p.bin_cnt[b]) { r -= p.bin_cnt[b]; b--; }
-    return p.bin_rows[(u64)b * p.bin_stride + r];
+__device__ __forceinline__ bool rw_next(const RwArgs<VT> &p, RwCursor &cur, u32 slice, u32 nslices, u32 wid, u32 &row) {
+    while (true) {
+        if (cur.r < cur.hi) { row = p.bin_rows[(u64)cur.b * p.bin_stride + cur.r]; cur.r += RW_WARPS; return true; }
+        if (--cur.b < p.first_bin) return false;
+        const u64 cnt = p.bin_cnt[cur.b];
+        cur.r = (u32)(cnt * slice / nslices) + wid; cur.hi = (u32)(cnt * (slice + 1) / nslices);
+    }
+}
+
+// shared-memory accesses by 32-bit shared address (one register, immediate offsets; no generic-address arithmetic)
+__device__ __forceinline__ void sm_red_or(u32 addr, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sm_red_add(u32 addr, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sm_st_u16(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ uint2 sm_ld_v2(u32 addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+
+// WRAP: the window's origin is not column 0 (bit d is column (org + d) mod ncols); else d = c.
+template <bool WRAP>
+__device__ __forceinline__ u32 rw_dcol(u32 c, u32 org, u32 ncols) {
+    if (!WRAP) return c;
+    const u32 d = c - org;
+    return c >= org ? d : d + ncols;
 }
 
 template <typename VT, int MODE, bool PACK, bool BPAT, bool COUNT>
-__global__ void __launch_bounds__(RW_THREADS) k_rw(RwArgs<VT> p) {
+__global__ void __launch_bounds__(RW_THREADS, COUNT ? 10 : RW_MIN_CTAS) k_rw(RwArgs<VT> p) {
+    // a_ik as the accumulate phase keeps it: 32 bits when 32-bit sums are proven
+    typedef typename std::conditional<MODE == 0, u32, VT>::type XT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u32 count = 0;
-    for (int b = 0; b < p.nbins; b++) count += p.bin_cnt[p.first_bin + b];
-    const u32 nwarps = gridDim.x * RW_WARPS;
-    u32 r = blockIdx.x * RW_WARPS + wid;
-    if (r >= count) return;
-    // per warp: COUNT: u32 bitmap[nw].  Numeric: {bits, prefix} uint2[nw] | acc[cap] | window offsets u16[cap]
+    const u32 nslices = gridDim.x;
+    const u32 per_sm = p.nsm && gridDim.x % p.nsm == 0 ? gridDim.x / p.nsm : 0u;
+    const u32 slice = per_sm ? (blockIdx.x % p.nsm) * per_sm + blockIdx.x / p.nsm : blockIdx.x;
+    RwCursor cur; cur.b = p.first_bin + p.nbins; cur.r = 0; cur.hi = 0;
+    u32 row;
+    bool have = rw_next(p, cur, slice, nslices, (u32)wid, row);
+    if (!have) return;
+    // per warp: COUNT: u32 bitmap[nw].  Numeric: {bits, prefix} uint2[nw] | acc[cap] | window offsets u16[cap].  nw % 32 == 0.
     const size_t per_warp = COUNT ? (size_t)p.nw * 4 : (size_t)p.nw * 8 + Acc<MODE>::bytes(p.cap) + (size_t)p.cap * 2;
     unsigned char *base = smem_raw + (size_t)wid * per_warp;
     u32 *bm = reinterpret_cast<u32 *>(base);                                 // COUNT
@@ -131,33 +180,38 @@ __global__ void __launch_bounds__(RW_THREADS) k_rw(RwArgs<VT> p) {
         for (u32 t = lane; t < p.cap; t += 32) acc.clear(t);
     }
     __syncwarp();
-    const u32 ncols = p.ncols;
+    const u32 sm_bits = (u32)__cvta_generic_to_shared(base);                 // bitmap words: 4 (COUNT) or 8 bytes apart
+    const u32 sm_acc = sm_bits + p.nw * 8, sm_offs = sm_acc + (u32)Acc<MODE>::bytes(p.cap);
+    const u32 ncols = p.ncols, cap = p.cap;
     u64 vmax = 0;
     // row header one row ahead: id, A row extent, window, output base
-    u32 row = rw_row_at(p, r);
     u64 rs = p.a.rpA[row];
     u32 lenA = (u32)(p.a.rpA[row + 1] - rs);
     uint4 wn = p.win[row];
     u64 obase = COUNT ? 0ull : p.rpC[row];
-    for (; r < count; r += nwarps) {
-        const bool has_next = r + nwarps < count;
+    while (have) {
         u32 row_n = 0;
-        if (has_next) row_n = rw_row_at(p, r + nwarps);
+        const bool has_next = rw_next(p, cur, slice, nslices, (u32)wid, row_n);
         // bit d of the window is column (org + d) mod ncols
         u32 org; { const u64 t = (u64)wn.x + wn.z; org = (u32)(t >= ncols ? t - ncols : t); }
-        const u32 words = wn.y * 4u;
-        auto dcol = [&](u32 c) -> u32 { return c >= org ? c - org : c - org + ncols; };
+        const u32 wpl = (wn.y * 4u + 31u) >> 5, w0 = (u32)lane * wpl;         // bitmap words per lane (consecutive); wpl * 32 <= nw
         // ---- mark
-        auto mark1 = [&](u32 c, u32, VT) {
-            const u32 d = dcol(c);
-            if (COUNT) atomicOr(&bm[d >> 5], __funnelshift_l(0u, 1u, d));
-            else atomicOr(&bw[d >> 5].x, __funnelshift_l(0u, 1u, d));
-        };
-        rw_enumerate<VT, PACK, false>(p.a, p.pack, rs, lenA, lane,
-            [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32, VT) {
+        auto mark = [&](auto wrap) {
+            constexpr bool WRAP = decltype(wrap)::value;
+            rw_enumerate<VT, u32, PACK, false>(p.a, p.pack, rs, lenA, lane,
+                [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32, u32) {
 #pragma unroll
-                for (int j = 0; j < B200_PACK_INLINE; j++) if ((u32)j < n) mark1(c[j], 0u, (VT)0);
-            }, mark1);
+                    for (int j = 0; j < B200_PACK_INLINE; j++) {
+                        const u32 d = rw_dcol<WRAP>(c[j], org, ncols);
+                        sm_red_or(sm_bits + (d >> 5) * (COUNT ? 4u : 8u), __funnelshift_l(0u, 1u, d));
+                    }
+                },
+                [&](u32 c, u32, u32) {
+                    const u32 d = rw_dcol<WRAP>(c, org, ncols);
+                    sm_red_or(sm_bits + (d >> 5) * (COUNT ? 4u : 8u), __funnelshift_l(0u, 1u, d));
+                });
+        };
+        if (org) mark(std::true_type{}); else mark(std::false_type{});
         // next row's header (its id has arrived by now)
         u64 rs_n = 0; u32 lenA_n = 0; uint4 wn_n = make_uint4(0, 0, 0, 0); u64 obase_n = 0;
         if (has_next) {
@@ -166,13 +220,11 @@ __global__ void __launch_bounds__(RW_THREADS) k_rw(RwArgs<VT> p) {
         }
         __syncwarp();
         // ---- rank: consecutive words per lane, warp scan of the lanes' popcounts
-        const u32 wpl = (words + 31) >> 5, w0 = (u32)lane * wpl;
         u32 mine = 0;
-        for (u32 i = 0; i < wpl; i++) {
-            if (w0 + i < words) {
-                if (COUNT) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
-                else mine += __popc(bw[w0 + i].x);
-            }
+        if constexpr (COUNT) {
+            for (u32 i = 0; i < wpl; i++) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
+        } else {
+            for (u32 i = 0; i < wpl; i++) mine += __popc(bw[w0 + i].x);
         }
         u32 incl = mine;
 #pragma unroll
@@ -183,62 +235,81 @@ __global__ void __launch_bounds__(RW_THREADS) k_rw(RwArgs<VT> p) {
             __syncwarp();
         } else {
             u32 run = incl - mine;
-            for (u32 i = 0; i < wpl; i++) {
-                if (w0 + i < words) { bw[w0 + i].y = run; run += __popc(bw[w0 + i].x); }
-            }
+            for (u32 i = 0; i < wpl; i++) { const u32 b = bw[w0 + i].x; bw[w0 + i].y = run; run += __popc(b); }
             __syncwarp();
             // Ranks are in d order; when the window starts at a column org > 0 the entries whose column lies below org
             // (d >= ncols - org) belong in FRONT of the others: the row is written rotated by r0 = entries with d < ncols - org.
             u32 r0 = nnz;
             if (org) {
                 const u32 split = ncols - org;
-                if (split < words * 32u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
+                if (split < wpl * 1024u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
             }
             const u32 shift_hi = nnz - r0;
-            for (u32 pass = 0; pass < nnz; pass += p.cap) {
-                // ---- accumulate at the column's rank (ranks pass .. pass + cap - 1 in this pass)
-                auto acc1 = [&](u32 c, u32 jb, VT av) {
-                    const u32 d = dcol(c);
+            u32 *colp = p.colC + obase; VT *valp = p.valC + obase;
+            // ---- accumulate at the column's rank, then emit; rows longer than the accumulator take several passes over their
+            //      products (ranks pass .. pass + cap - 1 in each)
+            auto accumulate = [&](auto wrap, auto multi, u32 pass) {
+                constexpr bool WRAP = decltype(wrap)::value, MULTI = decltype(multi)::value;
+                auto acc1 = [&](u32 c, u32 jb, XT av) {
+                    const u32 d = rw_dcol<WRAP>(c, org, ncols);
                     const uint2 s = bw[d >> 5];
                     const u32 pos = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, d) - 1u)) - pass;
-                    if (pos < p.cap) {
+                    if (!MULTI || pos < cap) {
                         offs[pos] = (unsigned short)d;
-                        acc.addv(pos, BPAT ? (u64)av : rw_product<MODE, VT>(av, p.a.valB[jb]));
+                        acc.addv(pos, BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, p.a.valB[jb]));
                     }
                 };
-                rw_enumerate<VT, PACK, true>(p.a, p.pack, rs, lenA, lane,
-                    [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32 st, VT av) {
-                        // all six bitmap words first, then the six accumulations: the reads do not wait for the writes
-                        u32 d[B200_PACK_INLINE], pos[B200_PACK_INLINE]; uint2 s[B200_PACK_INLINE]; u64 x[B200_PACK_INLINE];
+                rw_enumerate<VT, XT, PACK, true>(p.a, p.pack, rs, lenA, lane,
+                    [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32 st, XT av) {
+                        // all six bitmap words first, then the six accumulations: the reads do not wait for the writes.  Slots >= n
+                        // repeat the record's last column: they add zero to its accumulator.
+                        u32 d[B200_PACK_INLINE], pos[B200_PACK_INLINE]; uint2 s[B200_PACK_INLINE];
 #pragma unroll
-                        for (int j = 0; j < B200_PACK_INLINE; j++) {
-                            d[j] = 0; s[j] = make_uint2(0u, 0u); x[j] = (u64)av;
-                            if ((u32)j < n) { d[j] = dcol(c[j]); s[j] = bw[d[j] >> 5]; if (!BPAT) x[j] = rw_product<MODE, VT>(av, p.a.valB[st + j]); }
-                        }
+                        for (int j = 0; j < B200_PACK_INLINE; j++) { d[j] = rw_dcol<WRAP>(c[j], org, ncols); s[j] = sm_ld_v2(sm_bits + (d[j] >> 5) * 8u); }
 #pragma unroll
                         for (int j = 0; j < B200_PACK_INLINE; j++) pos[j] = s[j].y + __popc(s[j].x & (__funnelshift_l(0u, 1u, d[j]) - 1u)) - pass;
 #pragma unroll
-                        for (int j = 0; j < B200_PACK_INLINE; j++)
-                            if ((u32)j < n && pos[j] < p.cap) { offs[pos[j]] = (unsigned short)d[j]; acc.addv(pos[j], x[j]); }
+                        for (int j = 0; j < B200_PACK_INLINE; j++) {
+                            const bool live = (u32)j < n;
+                            if (MODE == 0 && BPAT && !MULTI) {
+                                sm_st_u16(sm_offs + pos[j] * 2u, d[j]);
+                                sm_red_add(sm_acc + pos[j] * 4u, live ? (u32)av : 0u);
+                            } else if (live && (!MULTI || pos[j] < cap)) {
+                                offs[pos[j]] = (unsigned short)d[j];
+                                acc.addv(pos[j], BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, p.a.valB[st + j]));
+                            }
+                        }
                     }, acc1);
-                __syncwarp();
-                // ---- emit: lane per entry, coalesced; the accumulators are left clean
-                const u32 m = min(p.cap, nnz - pass);
+            };
+            auto emit = [&](u32 pass) {
+                const u32 m = min(cap, nnz - pass);
                 for (u32 t = lane; t < m; t += 32) {
                     u32 c = org + (u32)offs[t]; if (c >= ncols) c -= ncols;
                     const VT v = emit_val<VT>(acc.get(t));
                     acc.clear(t);
                     const u32 g = pass + t;
                     const u32 q = g >= r0 ? g - r0 : g + shift_hi;
-                    p.colC[obase + q] = c; p.valC[obase + q] = v;
+                    colp[q] = c; valp[q] = v;
                     vmax = vmax > (u64)v ? vmax : (u64)v;
                 }
+            };
+            if (nnz <= cap) {
+                if (org) accumulate(std::true_type{}, std::false_type{}, 0u); else accumulate(std::false_type{}, std::false_type{}, 0u);
                 __syncwarp();
+                emit(0u);
+                __syncwarp();
+            } else {
+                for (u32 pass = 0; pass < nnz; pass += cap) {
+                    accumulate(std::true_type{}, std::true_type{}, pass);
+                    __syncwarp();
+                    emit(pass);
+                    __syncwarp();
+                }
             }
-            for (u32 i = 0; i < wpl; i++) if (w0 + i < words) bw[w0 + i] = make_uint2(0u, 0u);
+            for (u32 i = 0; i < wpl; i++) bw[w0 + i] = make_uint2(0u, 0u);
             __syncwarp();
         }
-        row = row_n; rs = rs_n; lenA = lenA_n; wn = wn_n; obase = obase_n;
+        have = has_next; row = row_n; rs = rs_n; lenA = lenA_n; wn = wn_n; obase = obase_n;
     }
     if (!COUNT) {
         vmax = warp_max_u64(vmax);
@@ -281,7 +352,7 @@ static cudaError_t rw_go(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B2
     RwArgs<VT> p;
     p.a = NumArgs<VT>{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     p.pack = B->d_pack; p.bin_rows = ctx->d_bin_rows; p.bin_cnt = ctrl->sym_bin_count; p.bin_stride = (u32)ctx->cap_rows;
-    p.first_bin = first_bin; p.nbins = nbins; p.win = ctx->d_win; p.ncols = (u32)B->cols; p.nw = nw; p.cap = cap;
+    p.first_bin = first_bin; p.nbins = nbins; p.win = ctx->d_win; p.ncols = (u32)B->cols; p.nw = nw; p.cap = cap; p.nsm = (u32)ctx->num_sms;
     p.nnz_row = ctx->d_nnz_row; p.rpC = C ? C->d_rp : nullptr; p.colC = C ? C->d_col : nullptr; p.valC = C ? (VT *)C->d_val : nullptr; p.ctrl = ctrl;
     void *kargs[] = {(void *)&p};
     return cudaLaunchKernel(fn, dim3(grid), dim3(RW_THREADS), kargs, smem, s);
@@ -301,7 +372,8 @@ int rw_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctr
     const int by_regs = regs_per_cta ? 65536 / regs_per_cta : 32;
     const int per_sm = std::max(1, std::min(std::min(by_smem, by_regs), std::min(2048 / RW_THREADS, 32)));
     const u64 want = (A->rows + RW_WARPS - 1) / RW_WARPS;
-    const int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
+    int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
+    if (grid > ctx->num_sms) grid = grid / ctx->num_sms * ctx->num_sms;     // whole waves: the slice mapping keeps an SM's CTAs adjacent
     // (the count variant is instantiated for u32 values only and never reads one)
     const cudaError_t le = v64 && !count ? rw_go<u64>(ctx, A, B, ctrl, first_bin, nbins, nw, cap, C, k.fn, grid, smem, s)
                                          : rw_go<u32>(ctx, A, B, ctrl, first_bin, nbins, nw, cap, C, k.fn, grid, smem, s);
