@@ -221,6 +221,9 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     ctx->f_dirty = true;
     fz_setup(ctx);
     rw_setup(ctx);
+    rwf_setup(ctx);
+    ctx->cap_cta_tot = 8192;
+    CUDA_TRY(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
@@ -247,7 +250,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->h_freport);
     for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->f_ev[i][j]);
-    cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag);
+    cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag); cudaFree(ctx->d_cta_tot);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
@@ -1010,6 +1013,32 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         cap = std::min<u64>(cap, std::min<u64>(std::min<u64>(p_bound, 8192), groups * 128));
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
         rw.hb_max = B200_RW_MAX_HB; rw.nw = ((u32)groups * 4u + 31u) & ~31u; rw.cap = (u32)cap; rw.all_fit = all_fit;   // (a lane owns nw / 32 consecutive words)
+    }
+    // One cooperative launch for the whole multiply (pipeline 4, the default where it applies): every row shares one window
+    // (the whole column space or the operand-level arc) that fits a warp's bitmap, rows are short enough for a single warp,
+    // and C can be allocated from the host-known bound.  Otherwise the listed pipelines below.
+    if ((ctx->cfg.pipeline == 4 || ctx->cfg.pipeline == 0) && all_groups <= B200_RW_MAX_GROUPS && p_bound <= 16384 && cheap_bound &&
+        B->nnz < 0xFFFFFFFFull && ctx->cfg.window_cap_groups < 0 && ctx->cfg.placement < 0) {
+        const u32 nw = (all_groups * 4u + 31u) & ~31u;
+        const double meanP = ((double)A->nnz / (double)rows) * ((double)B->nnz / (double)B->rows);
+        const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.4;
+        u64 cap = (u64)(factor * meanP) + 32;
+        cap = std::min<u64>(cap, std::min<u64>(p_bound, (u64)all_groups * 128));
+        cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
+        if (rw_smem_per_warp(false, mode1, nw, (u32)cap) * 4 + 1024 <= ctx->smem_optin) {
+            if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
+            if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
+            C->cap_entries = std::max<u64>((u64)hb128, 1);
+            r = alloc_entries(ctx, C);
+            if (r == B200_OK) r = rw_fused_launch(ctx, A, B, C, ctx->d_ctrl, mode1, packed, bpat, all_rot, all_groups * 4u, nw, (u32)cap, mirror, epoch, s);
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
+            trace_dump(ctx, "one-launch multiply");
+            mark_pending(ctx, C, slot, epoch, A, B, mode1, 4, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
+            *out = C;
+            if (st) { TRY(resolve_pending(ctx, C)); *st = *C->stats; }
+            return B200_OK;
+        }
     }
     {
         const u32 nw4_full = all_groups;

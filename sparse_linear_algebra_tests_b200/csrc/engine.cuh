@@ -91,6 +91,7 @@ struct b200_ctx {
     b200_csr *slot_owner[B200_REPORT_SLOTS];
     cudaEvent_t f_ev[B200_REPORT_SLOTS][3];
     u32 fepoch;
+    u64 *d_cta_tot; u64 cap_cta_tot;   // per-CTA totals of the one-launch multiply (rowwarp.cu)
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
 };
 
@@ -149,11 +150,14 @@ int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl
                    bool packed, bool bpat, int lg, Fan &fan);
 // ---- rowwarp.cu: row-per-warp count / numeric kernels of the exact placement
 #define B200_RW_MAX_HB 7          // hash bins 0..7 (33..8192 intermediate products) are rows a single warp produces
-#define B200_RW_MAX_GROUPS 256    // largest window bitmap of a warp, in 128-column groups
+#define B200_RW_MAX_GROUPS 512    // largest window bitmap of a warp, in 128-column groups (window offsets are kept as u16)
 void rw_setup(b200_ctx *ctx);
 size_t rw_smem_per_warp(bool count, int mode, u32 nw, u32 cap);
 int rw_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, int first_bin, int nbins, bool count, int mode,
               bool packed, bool bpat, u32 nw, u32 cap, b200_csr *C, cudaStream_t s);
+void rwf_setup(b200_ctx *ctx);
+int rw_fused_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, int mode, bool packed, bool bpat,
+                    u32 org, u32 words, u32 nw, u32 cap, u64 *mirror, u32 epoch, cudaStream_t s);
 // ---- fused.cu
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);

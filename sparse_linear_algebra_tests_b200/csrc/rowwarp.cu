@@ -17,13 +17,14 @@
 // the bitmap is the only thing that scales with the window.  It replaces, for rows of 33..4096 intermediate products,
 // the symbolic and numeric passes of CsrMatrix::matmul_par (/root/reference/src/graph_csr.rs:362-403, :430-476).
 #include <type_traits>
+#include <cooperative_groups.h>
 #include "engine.cuh"
 #include "devutil.cuh"
 
 #define RW_WARPS 4
 #define RW_THREADS (RW_WARPS * 32)
 #ifndef RW_MIN_CTAS
-#define RW_MIN_CTAS 8
+#define RW_MIN_CTAS 4
 #endif
 
 template <typename VT>
@@ -154,10 +155,170 @@ __device__ __forceinline__ u32 rw_dcol(u32 c, u32 org, u32 ncols) {
     return c >= org ? d : d + ncols;
 }
 
+// One warp's share of shared memory and the per-row phases that work on it.
+//   count layout  : u32 bitmap[nw]
+//   numeric layout: {bits, prefix} uint2[nw] | acc[cap] | window offsets u16[cap]          (nw % 32 == 0)
+// Both start at the same address and both leave every word they touched zeroed, so one kernel may run count_row over its
+// rows first and numeric_row afterwards (k_rw_fused) on the same zero-initialised region.
+template <typename VT, int MODE, bool PACK, bool BPAT>
+struct RwWarp {
+    typedef typename std::conditional<MODE == 0, u32, VT>::type XT;          // a_ik as the accumulate phase keeps it
+    const NumArgs<VT> &a; const uint4 *pack;
+    u32 *bm; uint2 *bw; Acc<MODE> acc; unsigned short *offs;
+    u32 sm_bits, sm_acc, sm_offs, nw, cap, ncols; int lane;
+
+    __device__ __forceinline__ RwWarp(const NumArgs<VT> &a_, const uint4 *pack_, unsigned char *base, u32 nw_, u32 cap_, u32 ncols_, int lane_)
+        : a(a_), pack(pack_), nw(nw_), cap(cap_), ncols(ncols_), lane(lane_) {
+        bm = reinterpret_cast<u32 *>(base); bw = reinterpret_cast<uint2 *>(base);
+        acc.bind(base + (size_t)nw * 8, cap);
+        offs = reinterpret_cast<unsigned short *>(base + (size_t)nw * 8 + Acc<MODE>::bytes(cap));
+        sm_bits = (u32)__cvta_generic_to_shared(base); sm_acc = sm_bits + nw * 8; sm_offs = sm_acc + (u32)Acc<MODE>::bytes(cap);
+    }
+    static __host__ __device__ size_t bytes(bool count_only, u32 nw, u32 cap) {
+        return count_only ? (size_t)nw * 4 : (size_t)nw * 8 + Acc<MODE>::bytes(cap) + (size_t)cap * 2;
+    }
+    __device__ __forceinline__ void zero(bool count_only) {
+        if (count_only) { for (u32 t = lane; t < nw; t += 32) bm[t] = 0; }
+        else { for (u32 t = lane; t < nw; t += 32) bw[t] = make_uint2(0u, 0u); for (u32 t = lane; t < cap; t += 32) acc.clear(t); }
+        __syncwarp();
+    }
+
+    // every product sets its column's bit (bit d of the window is column (org + d) mod ncols); STRIDE: bytes between bitmap words
+    template <u32 STRIDE, bool SUMP>
+    __device__ __forceinline__ u32 mark(u64 rs, u32 lenA, u32 org) {
+        u32 psum = 0;
+        auto go = [&](auto wrap) {
+            constexpr bool WRAP = decltype(wrap)::value;
+            rw_enumerate<VT, u32, PACK, false>(a, pack, rs, lenA, lane,
+                [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32, u32) {
+                    if (SUMP) psum += n;
+#pragma unroll
+                    for (int j = 0; j < B200_PACK_INLINE; j++) {
+                        const u32 d = rw_dcol<WRAP>(c[j], org, ncols);
+                        sm_red_or(sm_bits + (d >> 5) * STRIDE, __funnelshift_l(0u, 1u, d));
+                    }
+                },
+                [&](u32 c, u32, u32) {
+                    if (SUMP) psum++;
+                    const u32 d = rw_dcol<WRAP>(c, org, ncols);
+                    sm_red_or(sm_bits + (d >> 5) * STRIDE, __funnelshift_l(0u, 1u, d));
+                });
+        };
+        if (org) go(std::true_type{}); else go(std::false_type{});
+        return psum;
+    }
+
+    // distinct columns of the row; `mid` runs between the mark and the popcount (the callers fetch their next row's header there).
+    // P (SUMP): intermediate products of the row, summed over the warp.
+    template <bool SUMP, typename MID>
+    __device__ __forceinline__ u32 count_row(u64 rs, u32 lenA, u32 org, u32 words, u32 &P, MID mid) {
+        const u32 wpl = (words + 31u) >> 5, w0 = (u32)lane * wpl;
+        const u32 psum = mark<4u, SUMP>(rs, lenA, org);
+        mid();
+        __syncwarp();
+        u32 mine = 0;
+        for (u32 i = 0; i < wpl; i++) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
+        if (SUMP) P = warp_sum_u32(psum);
+        const u32 nnz = warp_sum_u32(mine);
+        __syncwarp();
+        return nnz;
+    }
+
+    // values of the row into colp / valp (the row's place in C); returns its length
+    template <typename MID>
+    __device__ __forceinline__ u32 numeric_row(u64 rs, u32 lenA, u32 org, u32 words, u32 *colp, VT *valp, const VT *valB, u64 &vmax, MID mid) {
+        const u32 wpl = (words + 31u) >> 5, w0 = (u32)lane * wpl;
+        mark<8u, false>(rs, lenA, org);
+        mid();
+        __syncwarp();
+        // ---- rank: consecutive words per lane, warp scan of the lanes' popcounts
+        u32 mine = 0;
+        for (u32 i = 0; i < wpl; i++) mine += __popc(bw[w0 + i].x);
+        u32 incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        const u32 nnz = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        u32 run = incl - mine;
+        for (u32 i = 0; i < wpl; i++) { const u32 b = bw[w0 + i].x; bw[w0 + i].y = run; run += __popc(b); }
+        __syncwarp();
+        // Ranks are in d order; when the window starts at a column org > 0 the entries whose column lies below org
+        // (d >= ncols - org) belong in FRONT of the others: the row is written rotated by r0 = entries with d < ncols - org.
+        u32 r0 = nnz;
+        if (org) {
+            const u32 split = ncols - org;
+            if (split < wpl * 1024u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
+        }
+        const u32 shift_hi = nnz - r0;
+        // ---- accumulate at the column's rank, then emit; rows longer than the accumulator take several passes over their
+        //      products (ranks pass .. pass + cap - 1 in each)
+        auto accumulate = [&](auto wrap, auto multi, u32 pass) {
+            constexpr bool WRAP = decltype(wrap)::value, MULTI = decltype(multi)::value;
+            auto acc1 = [&](u32 c, u32 jb, XT av) {
+                const u32 d = rw_dcol<WRAP>(c, org, ncols);
+                const uint2 s = bw[d >> 5];
+                const u32 pos = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, d) - 1u)) - pass;
+                if (!MULTI || pos < cap) {
+                    offs[pos] = (unsigned short)d;
+                    acc.addv(pos, BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, valB[jb]));
+                }
+            };
+            rw_enumerate<VT, XT, PACK, true>(a, pack, rs, lenA, lane,
+                [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32 st, XT av) {
+                    // all six bitmap words first, then the six accumulations: the reads do not wait for the writes.  Slots >= n
+                    // repeat the record's last column: they add zero to its accumulator.
+                    u32 d[B200_PACK_INLINE], pos[B200_PACK_INLINE]; uint2 s[B200_PACK_INLINE];
+#pragma unroll
+                    for (int j = 0; j < B200_PACK_INLINE; j++) { d[j] = rw_dcol<WRAP>(c[j], org, ncols); s[j] = sm_ld_v2(sm_bits + (d[j] >> 5) * 8u); }
+#pragma unroll
+                    for (int j = 0; j < B200_PACK_INLINE; j++) pos[j] = s[j].y + __popc(s[j].x & (__funnelshift_l(0u, 1u, d[j]) - 1u)) - pass;
+#pragma unroll
+                    for (int j = 0; j < B200_PACK_INLINE; j++) {
+                        const bool live = (u32)j < n;
+                        if (MODE == 0 && BPAT && !MULTI) {
+                            sm_st_u16(sm_offs + pos[j] * 2u, d[j]);
+                            sm_red_add(sm_acc + pos[j] * 4u, live ? (u32)av : 0u);
+                        } else if (live && (!MULTI || pos[j] < cap)) {
+                            offs[pos[j]] = (unsigned short)d[j];
+                            acc.addv(pos[j], BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, valB[st + j]));
+                        }
+                    }
+                }, acc1);
+        };
+        auto emit = [&](u32 pass) {
+            const u32 m = min(cap, nnz - pass);
+            for (u32 t = lane; t < m; t += 32) {
+                u32 c = org + (u32)offs[t]; if (c >= ncols) c -= ncols;
+                const VT v = emit_val<VT>(acc.get(t));
+                acc.clear(t);
+                const u32 g = pass + t;
+                const u32 q = g >= r0 ? g - r0 : g + shift_hi;
+                colp[q] = c; valp[q] = v;
+                vmax = vmax > (u64)v ? vmax : (u64)v;
+            }
+        };
+        if (nnz <= cap) {
+            if (org) accumulate(std::true_type{}, std::false_type{}, 0u); else accumulate(std::false_type{}, std::false_type{}, 0u);
+            __syncwarp();
+            emit(0u);
+            __syncwarp();
+        } else {
+            for (u32 pass = 0; pass < nnz; pass += cap) {
+                accumulate(std::true_type{}, std::true_type{}, pass);
+                __syncwarp();
+                emit(pass);
+                __syncwarp();
+            }
+        }
+        for (u32 i = 0; i < wpl; i++) bw[w0 + i] = make_uint2(0u, 0u);
+        __syncwarp();
+        return nnz;
+    }
+};
+
+__device__ __forceinline__ u32 rw_origin(const uint4 &wn, u32 ncols) { const u64 t = (u64)wn.x + wn.z; return (u32)(t >= ncols ? t - ncols : t); }
+
 template <typename VT, int MODE, bool PACK, bool BPAT, bool COUNT>
 __global__ void __launch_bounds__(RW_THREADS, COUNT ? 10 : RW_MIN_CTAS) k_rw(RwArgs<VT> p) {
-    // a_ik as the accumulate phase keeps it: 32 bits when 32-bit sums are proven
-    typedef typename std::conditional<MODE == 0, u32, VT>::type XT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 nslices = gridDim.x;
@@ -167,22 +328,9 @@ __global__ void __launch_bounds__(RW_THREADS, COUNT ? 10 : RW_MIN_CTAS) k_rw(RwA
     u32 row;
     bool have = rw_next(p, cur, slice, nslices, (u32)wid, row);
     if (!have) return;
-    // per warp: COUNT: u32 bitmap[nw].  Numeric: {bits, prefix} uint2[nw] | acc[cap] | window offsets u16[cap].  nw % 32 == 0.
-    const size_t per_warp = COUNT ? (size_t)p.nw * 4 : (size_t)p.nw * 8 + Acc<MODE>::bytes(p.cap) + (size_t)p.cap * 2;
-    unsigned char *base = smem_raw + (size_t)wid * per_warp;
-    u32 *bm = reinterpret_cast<u32 *>(base);                                 // COUNT
-    uint2 *bw = reinterpret_cast<uint2 *>(base);                             // numeric
-    Acc<MODE> acc; unsigned short *offs = nullptr;
-    if (!COUNT) { acc.bind(base + (size_t)p.nw * 8, p.cap); offs = reinterpret_cast<unsigned short *>(base + (size_t)p.nw * 8 + Acc<MODE>::bytes(p.cap)); }
-    if (COUNT) { for (u32 t = lane; t < p.nw; t += 32) bm[t] = 0; }
-    else {
-        for (u32 t = lane; t < p.nw; t += 32) bw[t] = make_uint2(0u, 0u);
-        for (u32 t = lane; t < p.cap; t += 32) acc.clear(t);
-    }
-    __syncwarp();
-    const u32 sm_bits = (u32)__cvta_generic_to_shared(base);                 // bitmap words: 4 (COUNT) or 8 bytes apart
-    const u32 sm_acc = sm_bits + p.nw * 8, sm_offs = sm_acc + (u32)Acc<MODE>::bytes(p.cap);
-    const u32 ncols = p.ncols, cap = p.cap;
+    typedef RwWarp<VT, MODE, PACK, BPAT> W;
+    W w(p.a, p.pack, smem_raw + (size_t)wid * W::bytes(COUNT, p.nw, p.cap), p.nw, p.cap, p.ncols, lane);
+    w.zero(COUNT);
     u64 vmax = 0;
     // row header one row ahead: id, A row extent, window, output base
     u64 rs = p.a.rpA[row];
@@ -192,128 +340,152 @@ __global__ void __launch_bounds__(RW_THREADS, COUNT ? 10 : RW_MIN_CTAS) k_rw(RwA
     while (have) {
         u32 row_n = 0;
         const bool has_next = rw_next(p, cur, slice, nslices, (u32)wid, row_n);
-        // bit d of the window is column (org + d) mod ncols
-        u32 org; { const u64 t = (u64)wn.x + wn.z; org = (u32)(t >= ncols ? t - ncols : t); }
-        const u32 wpl = (wn.y * 4u + 31u) >> 5, w0 = (u32)lane * wpl;         // bitmap words per lane (consecutive); wpl * 32 <= nw
-        // ---- mark
-        auto mark = [&](auto wrap) {
-            constexpr bool WRAP = decltype(wrap)::value;
-            rw_enumerate<VT, u32, PACK, false>(p.a, p.pack, rs, lenA, lane,
-                [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32, u32) {
-#pragma unroll
-                    for (int j = 0; j < B200_PACK_INLINE; j++) {
-                        const u32 d = rw_dcol<WRAP>(c[j], org, ncols);
-                        sm_red_or(sm_bits + (d >> 5) * (COUNT ? 4u : 8u), __funnelshift_l(0u, 1u, d));
-                    }
-                },
-                [&](u32 c, u32, u32) {
-                    const u32 d = rw_dcol<WRAP>(c, org, ncols);
-                    sm_red_or(sm_bits + (d >> 5) * (COUNT ? 4u : 8u), __funnelshift_l(0u, 1u, d));
-                });
-        };
-        if (org) mark(std::true_type{}); else mark(std::false_type{});
-        // next row's header (its id has arrived by now)
         u64 rs_n = 0; u32 lenA_n = 0; uint4 wn_n = make_uint4(0, 0, 0, 0); u64 obase_n = 0;
-        if (has_next) {
-            rs_n = p.a.rpA[row_n]; lenA_n = (u32)(p.a.rpA[row_n + 1] - rs_n); wn_n = p.win[row_n];
-            if (!COUNT) obase_n = p.rpC[row_n];
-        }
-        __syncwarp();
-        // ---- rank: consecutive words per lane, warp scan of the lanes' popcounts
-        u32 mine = 0;
+        auto mid = [&]() {                                                   // next row's header (its id has arrived by now)
+            if (has_next) {
+                rs_n = p.a.rpA[row_n]; lenA_n = (u32)(p.a.rpA[row_n + 1] - rs_n); wn_n = p.win[row_n];
+                if (!COUNT) obase_n = p.rpC[row_n];
+            }
+        };
+        const u32 org = rw_origin(wn, p.ncols);
         if constexpr (COUNT) {
-            for (u32 i = 0; i < wpl; i++) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
-        } else {
-            for (u32 i = 0; i < wpl; i++) mine += __popc(bw[w0 + i].x);
-        }
-        u32 incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-        const u32 nnz = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if constexpr (COUNT) {
+            u32 P;
+            const u32 nnz = w.template count_row<false>(rs, lenA, org, wn.y * 4u, P, mid);
             if (lane == 0) p.nnz_row[row] = nnz;
-            __syncwarp();
         } else {
-            u32 run = incl - mine;
-            for (u32 i = 0; i < wpl; i++) { const u32 b = bw[w0 + i].x; bw[w0 + i].y = run; run += __popc(b); }
-            __syncwarp();
-            // Ranks are in d order; when the window starts at a column org > 0 the entries whose column lies below org
-            // (d >= ncols - org) belong in FRONT of the others: the row is written rotated by r0 = entries with d < ncols - org.
-            u32 r0 = nnz;
-            if (org) {
-                const u32 split = ncols - org;
-                if (split < wpl * 1024u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
-            }
-            const u32 shift_hi = nnz - r0;
-            u32 *colp = p.colC + obase; VT *valp = p.valC + obase;
-            // ---- accumulate at the column's rank, then emit; rows longer than the accumulator take several passes over their
-            //      products (ranks pass .. pass + cap - 1 in each)
-            auto accumulate = [&](auto wrap, auto multi, u32 pass) {
-                constexpr bool WRAP = decltype(wrap)::value, MULTI = decltype(multi)::value;
-                auto acc1 = [&](u32 c, u32 jb, XT av) {
-                    const u32 d = rw_dcol<WRAP>(c, org, ncols);
-                    const uint2 s = bw[d >> 5];
-                    const u32 pos = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, d) - 1u)) - pass;
-                    if (!MULTI || pos < cap) {
-                        offs[pos] = (unsigned short)d;
-                        acc.addv(pos, BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, p.a.valB[jb]));
-                    }
-                };
-                rw_enumerate<VT, XT, PACK, true>(p.a, p.pack, rs, lenA, lane,
-                    [&](const u32 (&c)[B200_PACK_INLINE], u32 n, u32 st, XT av) {
-                        // all six bitmap words first, then the six accumulations: the reads do not wait for the writes.  Slots >= n
-                        // repeat the record's last column: they add zero to its accumulator.
-                        u32 d[B200_PACK_INLINE], pos[B200_PACK_INLINE]; uint2 s[B200_PACK_INLINE];
-#pragma unroll
-                        for (int j = 0; j < B200_PACK_INLINE; j++) { d[j] = rw_dcol<WRAP>(c[j], org, ncols); s[j] = sm_ld_v2(sm_bits + (d[j] >> 5) * 8u); }
-#pragma unroll
-                        for (int j = 0; j < B200_PACK_INLINE; j++) pos[j] = s[j].y + __popc(s[j].x & (__funnelshift_l(0u, 1u, d[j]) - 1u)) - pass;
-#pragma unroll
-                        for (int j = 0; j < B200_PACK_INLINE; j++) {
-                            const bool live = (u32)j < n;
-                            if (MODE == 0 && BPAT && !MULTI) {
-                                sm_st_u16(sm_offs + pos[j] * 2u, d[j]);
-                                sm_red_add(sm_acc + pos[j] * 4u, live ? (u32)av : 0u);
-                            } else if (live && (!MULTI || pos[j] < cap)) {
-                                offs[pos[j]] = (unsigned short)d[j];
-                                acc.addv(pos[j], BPAT ? (u64)av : rw_product<MODE, VT>((VT)av, p.a.valB[st + j]));
-                            }
-                        }
-                    }, acc1);
-            };
-            auto emit = [&](u32 pass) {
-                const u32 m = min(cap, nnz - pass);
-                for (u32 t = lane; t < m; t += 32) {
-                    u32 c = org + (u32)offs[t]; if (c >= ncols) c -= ncols;
-                    const VT v = emit_val<VT>(acc.get(t));
-                    acc.clear(t);
-                    const u32 g = pass + t;
-                    const u32 q = g >= r0 ? g - r0 : g + shift_hi;
-                    colp[q] = c; valp[q] = v;
-                    vmax = vmax > (u64)v ? vmax : (u64)v;
-                }
-            };
-            if (nnz <= cap) {
-                if (org) accumulate(std::true_type{}, std::false_type{}, 0u); else accumulate(std::false_type{}, std::false_type{}, 0u);
-                __syncwarp();
-                emit(0u);
-                __syncwarp();
-            } else {
-                for (u32 pass = 0; pass < nnz; pass += cap) {
-                    accumulate(std::true_type{}, std::true_type{}, pass);
-                    __syncwarp();
-                    emit(pass);
-                    __syncwarp();
-                }
-            }
-            for (u32 i = 0; i < wpl; i++) bw[w0 + i] = make_uint2(0u, 0u);
-            __syncwarp();
+            w.numeric_row(rs, lenA, org, wn.y * 4u, p.colC + obase, p.valC + obase, p.a.valB, vmax, mid);
         }
         have = has_next; row = row_n; rs = rs_n; lenA = lenA_n; wn = wn_n; obase = obase_n;
     }
     if (!COUNT) {
         vmax = warp_max_u64(vmax);
         if (lane == 0 && vmax) atomicMax(&p.ctrl->max_val_out, (ull)vmax);
+    }
+}
+
+// =======================================================================================
+// The whole multiply as ONE cooperative kernel (pipeline 4): every row's window is the same (the whole column space or the
+// operand-level arc), so nothing has to be classified beforehand.
+//   phase A  every CTA owns a contiguous range of rows (CTAs of one SM own adjacent ranges), its warps interleave over
+//            them: count_row -> nnz_row[row], intermediate products; the CTA's total goes to cta_tot[slice]
+//   grid sync
+//   phase B  the CTA's base = sum of the totals of the slices before it (no look-back chain: everything is there);
+//            row_ptr of its rows by a block scan over nnz_row
+//   phase C  numeric_row for every row, at row_ptr
+//   the last CTA to finish reports the control block to the pinned ring, hands the largest value to the product's handle
+//   and leaves the control block zeroed.
+// Replaces pre-pass, count kernels, row_ptr scan, numeric kernels and the finishing kernel of the exact placement: one
+// launch per multiply, which is what the small powers of a chain are bound by.
+// =======================================================================================
+template <typename VT>
+struct RwFusedArgs {
+    NumArgs<VT> a; const uint4 *pack;
+    u64 rows; u32 ncols, org, words;  // one window for every row: bit d is column (org + d) mod ncols, `words` bitmap words
+    u32 nw, cap, nsm;
+    u32 *nnz_row; u64 *cta_tot;
+    u64 *rpC; u32 *colC; VT *valC;
+    B200Ctrl *ctrl; u64 *host_mirror; u32 epoch; ull *maxval_dst;
+};
+
+template <typename VT, int MODE, bool PACK, bool BPAT>
+__global__ void __launch_bounds__(RW_THREADS, RW_MIN_CTAS) k_rw_fused(RwFusedArgs<VT> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u64 s_base, s_tot; __shared__ ull s_P, s_maxP; __shared__ u32 s_maxN, s_last, s_scan[RW_WARPS + 1];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 nslices = gridDim.x;
+    const u32 per_sm = p.nsm && gridDim.x % p.nsm == 0 ? gridDim.x / p.nsm : 0u;
+    const u32 slice = per_sm ? (blockIdx.x % p.nsm) * per_sm + blockIdx.x / p.nsm : blockIdx.x;
+    const u64 r_lo = p.rows * slice / nslices, r_hi = p.rows * (slice + 1) / nslices;
+    typedef RwWarp<VT, MODE, PACK, BPAT> W;
+    W w(p.a, p.pack, smem_raw + (size_t)wid * W::bytes(false, p.nw, p.cap), p.nw, p.cap, p.ncols, lane);
+    w.zero(false);
+    if (tid == 0) { s_tot = 0; s_P = 0; s_maxP = 0; s_maxN = 0; }
+    __syncthreads();
+    // ---- phase A: lengths
+    {
+        u64 tot = 0, Psum = 0; u32 maxP = 0, maxN = 0;
+        u64 row = r_lo + wid;
+        u64 rs = 0; u32 lenA = 0;
+        if (row < r_hi) { rs = p.a.rpA[row]; lenA = (u32)(p.a.rpA[row + 1] - rs); }
+        for (; row < r_hi; row += RW_WARPS) {
+            const u64 row_n = row + RW_WARPS;
+            u64 rs_n = 0; u32 lenA_n = 0;
+            auto mid = [&]() { if (row_n < r_hi) { rs_n = p.a.rpA[row_n]; lenA_n = (u32)(p.a.rpA[row_n + 1] - rs_n); } };
+            u32 P = 0, nnz = 0;
+            if (lenA) nnz = w.template count_row<true>(rs, lenA, p.org, p.words, P, mid); else mid();
+            if (lane == 0) p.nnz_row[row] = nnz;
+            tot += nnz; Psum += P; maxP = max(maxP, P); maxN = max(maxN, nnz);
+            rs = rs_n; lenA = lenA_n;
+        }
+        if (lane == 0) { atomicAdd((ull *)&s_tot, (ull)tot); atomicAdd(&s_P, (ull)Psum); atomicMax(&s_maxP, (ull)maxP); atomicMax(&s_maxN, maxN); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        p.cta_tot[slice] = s_tot;
+        if (s_P) atomicAdd(&p.ctrl->total_products, s_P);
+        atomicMax(&p.ctrl->max_row_products, s_maxP);
+        atomicMax(&p.ctrl->max_row_nnz, (ull)s_maxN);
+        __threadfence();
+    }
+    grid.sync();
+    // ---- phase B: this CTA's first entry, row_ptr of its rows
+    if (wid == 0) {
+        u64 sum = 0;
+        for (u32 i = lane; i < slice; i += 32) sum += __ldcg(&p.cta_tot[i]);
+        sum = warp_sum_u64(sum);
+        if (lane == 0) s_base = sum;
+    }
+    __syncthreads();
+    {
+        u64 run = s_base;
+        for (u64 r0 = r_lo; r0 < r_hi; r0 += RW_THREADS) {
+            const u64 r = r0 + tid;
+            const u32 v = r < r_hi ? p.nnz_row[r] : 0u;
+            u32 incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+            if (lane == 31) s_scan[wid] = incl;
+            __syncthreads();
+            u32 wbase = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < RW_WARPS; i++) { if (i < wid) wbase += s_scan[i]; total += s_scan[i]; }
+            if (r < r_hi) p.rpC[r] = run + wbase + incl - v;
+            run += total;
+            __syncthreads();
+        }
+        if (slice == nslices - 1 && tid == 0) { p.rpC[p.rows] = run; p.ctrl->total_nnz = run; }
+    }
+    __syncthreads();
+    // ---- phase C: values
+    {
+        u64 vmax = 0;
+        u64 row = r_lo + wid;
+        u64 rs = 0, obase = 0; u32 lenA = 0;
+        if (row < r_hi) { rs = p.a.rpA[row]; lenA = (u32)(p.a.rpA[row + 1] - rs); obase = p.rpC[row]; }
+        for (; row < r_hi; row += RW_WARPS) {
+            const u64 row_n = row + RW_WARPS;
+            u64 rs_n = 0, obase_n = 0; u32 lenA_n = 0;
+            auto mid = [&]() { if (row_n < r_hi) { rs_n = p.a.rpA[row_n]; lenA_n = (u32)(p.a.rpA[row_n + 1] - rs_n); obase_n = p.rpC[row_n]; } };
+            if (lenA) w.numeric_row(rs, lenA, p.org, p.words, p.colC + obase, p.valC + obase, p.a.valB, vmax, mid); else mid();
+            rs = rs_n; lenA = lenA_n; obase = obase_n;
+        }
+        vmax = warp_max_u64(vmax);
+        if (lane == 0 && vmax) atomicMax(&p.ctrl->max_val_out, (ull)vmax);
+    }
+    // ---- report: the last CTA to get here
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = atomicAdd(&p.ctrl->fused_done, 1u) == gridDim.x - 1 ? 1u : 0u; }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const volatile u32 *src = reinterpret_cast<const volatile u32 *>(p.ctrl);
+        for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) st_volatile_u64(p.host_mirror + i, ((u64)p.epoch << 32) | (u64)src[i]);
+        if (tid == 0) *p.maxval_dst = *reinterpret_cast<volatile ull *>(&p.ctrl->max_val_out);
+        __syncthreads();
+        u32 *cw = reinterpret_cast<u32 *>(p.ctrl);
+        for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) cw[i] = 0;
     }
 }
 
@@ -340,6 +512,61 @@ void rw_setup(b200_ctx *ctx) {
     rw_register_mode<u64, 0>(o); rw_register_mode<u64, 1>(o); rw_register_mode<u64, 2>(o);
     // the count kernels touch no values: one pair (packed or not) serves every width and mode
     rw_register<u32, 0, false, true, true>(o); rw_register<u32, 0, true, true, true>(o);
+}
+
+size_t rw_smem_per_warp(bool count, int mode, u32 nw, u32 cap);
+// fused (cooperative) kernel variants: [value width][mode][packed][pattern-only B]
+static RwKernel g_rwf[2][3][2][2];
+template <typename VT, int MODE, bool PACK, bool BPAT>
+static void rwf_register(size_t optin) {
+    RwKernel &k = g_rwf[sizeof(VT) == 8][MODE][PACK][BPAT];
+    k.fn = (const void *)k_rw_fused<VT, MODE, PACK, BPAT>;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k.fn) == cudaSuccess) { k.regs = fa.numRegs; k.static_smem = fa.sharedSizeBytes; } else { cudaGetLastError(); k.regs = 64; k.static_smem = 0; }
+    if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - k.static_smem)) != cudaSuccess) cudaGetLastError();
+}
+template <typename VT, int MODE>
+static void rwf_register_mode(size_t o) {
+    rwf_register<VT, MODE, false, false>(o); rwf_register<VT, MODE, false, true>(o); rwf_register<VT, MODE, true, false>(o); rwf_register<VT, MODE, true, true>(o);
+}
+void rwf_setup(b200_ctx *ctx) {
+    const size_t o = ctx->smem_optin;
+    rwf_register_mode<u32, 0>(o); rwf_register_mode<u32, 1>(o);
+    rwf_register_mode<u64, 0>(o); rwf_register_mode<u64, 1>(o); rwf_register_mode<u64, 2>(o);
+}
+
+template <typename VT>
+static cudaError_t rwf_go(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, u32 org, u32 words, u32 nw, u32 cap,
+                          u64 *mirror, u32 epoch, const void *fn, int grid, size_t smem, cudaStream_t s) {
+    RwFusedArgs<VT> p;
+    p.a = NumArgs<VT>{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
+    p.pack = B->d_pack; p.rows = A->rows; p.ncols = (u32)B->cols; p.org = org; p.words = words; p.nw = nw; p.cap = cap; p.nsm = (u32)ctx->num_sms;
+    p.nnz_row = ctx->d_nnz_row; p.cta_tot = ctx->d_cta_tot; p.rpC = C->d_rp; p.colC = C->d_col; p.valC = (VT *)C->d_val;
+    p.ctrl = ctrl; p.host_mirror = mirror; p.epoch = epoch; p.maxval_dst = C->d_maxval;
+    void *kargs[] = {(void *)&p};
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RW_THREADS), kargs, smem, s);
+}
+
+// The whole multiply in one cooperative launch (every row shares the window {org, words}); C's arrays are already allocated.
+int rw_fused_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, int mode, bool packed, bool bpat,
+                    u32 org, u32 words, u32 nw, u32 cap, u64 *mirror, u32 epoch, cudaStream_t s) {
+    const bool v64 = A->val_bits == 64;
+    const RwKernel &k = g_rwf[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][packed ? 1 : 0][bpat ? 1 : 0];
+    if (!k.fn) return set_err(B200_ERR_CUDA, "fused row-per-warp kernel variant is not registered");
+    const size_t smem = rw_smem_per_warp(false, mode, nw, cap) * RW_WARPS;
+    if (smem + k.static_smem > ctx->smem_optin) return set_err(B200_ERR_CUDA, "fused row-per-warp kernel needs %zu B of shared memory", smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, RW_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return set_err(B200_ERR_CUDA, "fused row-per-warp kernel does not fit an SM"); }
+    const u64 want = (A->rows + RW_WARPS - 1) / RW_WARPS;
+    int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
+    if (grid > ctx->num_sms) grid = grid / ctx->num_sms * ctx->num_sms;
+    if ((u64)grid > ctx->cap_cta_tot) return set_err(B200_ERR_CUDA, "internal: %d CTAs exceed the per-CTA scratch", grid);
+    const cudaError_t le = v64 ? rwf_go<u64>(ctx, A, B, C, ctrl, org, words, nw, cap, mirror, epoch, k.fn, grid, smem, s)
+                               : rwf_go<u32>(ctx, A, B, C, ctrl, org, words, nw, cap, mirror, epoch, k.fn, grid, smem, s);
+    ctx->launches++;
+    if (ctx->trace) { fprintf(stderr, "[b200 trace] fused rw: grid %d (%d/SM) regs %d smem %zu nw %u cap %u org %u words %u\n", grid, per_sm, k.regs, smem, nw, cap, org, words); trace_mark(ctx, __LINE__); }
+    if (le != cudaSuccess) return set_err(B200_ERR_CUDA, "fused row-per-warp kernel launch failed: %s", cudaGetErrorString(le));
+    return B200_OK;
 }
 
 size_t rw_smem_per_warp(bool count, int mode, u32 nw, u32 cap) {
