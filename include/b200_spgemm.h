@@ -70,9 +70,11 @@ typedef struct b200_stats {
  * installs a copy (between multiplies).  -1 / 0 mean "engine decides" where noted. */
 typedef struct b200_config {
     uint32_t struct_bytes;       /* sizeof(b200_config) as the caller compiled it (checked)                               */
-    int32_t pipeline;            /* 0 auto (= 3); 1 fused (pre-pass + one persistent numeric/placement kernel); 2 binned (a
-                                    kernel per row bin, scratch or exact placement); 3 exact placement with the
-                                    row-per-warp count / numeric kernels, C written once, no host wait                     */
+    int32_t pipeline;            /* 0 auto (4 where it applies, else 2); 1 fused look-back pipeline (round-2 experiment, kept
+                                    selectable); 2 binned (a kernel per row bin, scratch or exact placement); 3 exact
+                                    placement with the row-per-warp count / numeric kernels over the bin lists; 4 the whole
+                                    multiply as ONE cooperative launch (count, placement, numeric; C written once, no
+                                    host wait) -- needs one window for all rows that fits a warp's bitmap                  */
     int32_t placement;           /* binned pipeline: -1 auto, 0 scratch CSR + compaction, 1 exact (count pass first)       */
     int32_t exact_limit_mb;      /* binned, auto placement: scratch bound above which the exact placement runs; -1 auto    */
     int32_t force_acc_mode;      /* -1 auto (proved from the operands); 1 / 2 force the 64-bit / saturating accumulators   */

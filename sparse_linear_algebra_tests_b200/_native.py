@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200spgemm.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "csrc", "libb200spgemm.so")   # (developer override: A/B builds)
 
 B200_OK, B200_ERR_BADARG, B200_ERR_SHAPE, B200_ERR_ALLOC, B200_ERR_CUDA, B200_ERR_FORMAT, B200_ERR_NCCL = range(7)
 

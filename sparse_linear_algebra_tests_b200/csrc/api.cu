@@ -974,7 +974,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // no per-row window (WMODE 0), every row fits the bitmap, and the product's own column range is the arc.
     u32 all_groups = (nwords + 3) / 4, all_rot = 0;
     u64 arc_start = 0, arc_len = ncols;
-    const bool want_rw = ctx->cfg.pipeline == 3 || ctx->cfg.pipeline == 0;
+    const bool want_rw = ctx->cfg.pipeline == 3;                          // (auto: one-launch pipeline 4 where it applies, else the binned kernels)
     if (B->rows == B->cols && ((A->cr_len < ncols && ctx->cfg.arc_window) || (want_rw && ctx->cfg.circular_windows))) {
         r = ensure_cs_bounds(ctx, B);
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
@@ -1025,7 +1025,10 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         u64 cap = (u64)(factor * meanP) + 32;
         cap = std::min<u64>(cap, std::min<u64>(p_bound, (u64)all_groups * 128));
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
-        if (rw_smem_per_warp(false, mode1, nw, (u32)cap) * 4 + 1024 <= ctx->smem_optin) {
+        // auto: only while a warp's share of shared memory leaves >= 16 warps per SM (wide arcs of an N-GPU row block do not:
+        // the binned kernels, whose bitmap is per bin, are faster there -- measured on rank 0's block of the 8-GPU torus)
+        const size_t per_warp = rw_smem_per_warp(false, mode1, nw, (u32)cap);
+        if (per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 4 || per_warp <= 14 * 1024)) {
             if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
             if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
             C->cap_entries = std::max<u64>((u64)hb128, 1);

@@ -183,10 +183,11 @@ struct RwWarp {
         __syncwarp();
     }
 
-    // every product sets its column's bit (bit d of the window is column (org + d) mod ncols); STRIDE: bytes between bitmap words
+    // every product sets its column's bit (bit d of the window is column (org + d) mod ncols); STRIDE: bytes between bitmap words.
+    // wlo / whi: lowest and highest bitmap word the warp touched (the later phases walk only those).
     template <u32 STRIDE, bool SUMP>
-    __device__ __forceinline__ u32 mark(u64 rs, u32 lenA, u32 org) {
-        u32 psum = 0;
+    __device__ __forceinline__ u32 mark(u64 rs, u32 lenA, u32 org, u32 &wlo, u32 &whi) {
+        u32 psum = 0, lo = 0xFFFFFFFFu, hi = 0;
         auto go = [&](auto wrap) {
             constexpr bool WRAP = decltype(wrap)::value;
             rw_enumerate<VT, u32, PACK, false>(a, pack, rs, lenA, lane,
@@ -196,15 +197,20 @@ struct RwWarp {
                     for (int j = 0; j < B200_PACK_INLINE; j++) {
                         const u32 d = rw_dcol<WRAP>(c[j], org, ncols);
                         sm_red_or(sm_bits + (d >> 5) * STRIDE, __funnelshift_l(0u, 1u, d));
+                        // a record's columns ascend: without a wrap the first and the last (repeated) slot bound them
+                        if (WRAP || j == 0) lo = min(lo, d);
+                        if (WRAP || j == B200_PACK_INLINE - 1) hi = max(hi, d);
                     }
                 },
                 [&](u32 c, u32, u32) {
                     if (SUMP) psum++;
                     const u32 d = rw_dcol<WRAP>(c, org, ncols);
                     sm_red_or(sm_bits + (d >> 5) * STRIDE, __funnelshift_l(0u, 1u, d));
+                    lo = min(lo, d); hi = max(hi, d);
                 });
         };
         if (org) go(std::true_type{}); else go(std::false_type{});
+        wlo = __reduce_min_sync(0xFFFFFFFFu, lo) >> 5; whi = __reduce_max_sync(0xFFFFFFFFu, hi) >> 5;
         return psum;
     }
 
@@ -212,12 +218,15 @@ struct RwWarp {
     // P (SUMP): intermediate products of the row, summed over the warp.
     template <bool SUMP, typename MID>
     __device__ __forceinline__ u32 count_row(u64 rs, u32 lenA, u32 org, u32 words, u32 &P, MID mid) {
-        const u32 wpl = (words + 31u) >> 5, w0 = (u32)lane * wpl;
-        const u32 psum = mark<4u, SUMP>(rs, lenA, org);
+        u32 wlo, whi;
+        const u32 psum = mark<4u, SUMP>(rs, lenA, org, wlo, whi);
         mid();
         __syncwarp();
         u32 mine = 0;
-        for (u32 i = 0; i < wpl; i++) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
+        if (wlo <= whi) {                                                    // (a row without products touches nothing)
+            const u32 wpl = (whi - wlo + 32u) >> 5, w0 = wlo + (u32)lane * wpl;
+            for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
+        }
         if (SUMP) P = warp_sum_u32(psum);
         const u32 nnz = warp_sum_u32(mine);
         __syncwarp();
@@ -227,26 +236,29 @@ struct RwWarp {
     // values of the row into colp / valp (the row's place in C); returns its length
     template <typename MID>
     __device__ __forceinline__ u32 numeric_row(u64 rs, u32 lenA, u32 org, u32 words, u32 *colp, VT *valp, const VT *valB, u64 &vmax, MID mid) {
-        const u32 wpl = (words + 31u) >> 5, w0 = (u32)lane * wpl;
-        mark<8u, false>(rs, lenA, org);
+        u32 wlo, whi;
+        mark<8u, false>(rs, lenA, org, wlo, whi);
         mid();
         __syncwarp();
-        // ---- rank: consecutive words per lane, warp scan of the lanes' popcounts
+        if (wlo > whi) return 0u;                                            // no products (uniform over the warp)
+        // ---- rank: consecutive words per lane over the touched span, warp scan of the lanes' popcounts
+        const u32 wpl = (whi - wlo + 32u) >> 5, w0 = wlo + (u32)lane * wpl;
         u32 mine = 0;
-        for (u32 i = 0; i < wpl; i++) mine += __popc(bw[w0 + i].x);
+        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) mine += __popc(bw[w0 + i].x);
         u32 incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
         const u32 nnz = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u32 run = incl - mine;
-        for (u32 i = 0; i < wpl; i++) { const u32 b = bw[w0 + i].x; bw[w0 + i].y = run; run += __popc(b); }
+        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { const u32 b = bw[w0 + i].x; bw[w0 + i].y = run; run += __popc(b); }
         __syncwarp();
         // Ranks are in d order; when the window starts at a column org > 0 the entries whose column lies below org
         // (d >= ncols - org) belong in FRONT of the others: the row is written rotated by r0 = entries with d < ncols - org.
         u32 r0 = nnz;
         if (org) {
-            const u32 split = ncols - org;
-            if (split < wpl * 1024u) { const uint2 s = bw[split >> 5]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
+            const u32 split = ncols - org, sw = split >> 5;
+            if (sw < wlo) r0 = 0;
+            else if (sw <= whi) { const uint2 s = bw[sw]; r0 = s.y + __popc(s.x & (__funnelshift_l(0u, 1u, split) - 1u)); }
         }
         const u32 shift_hi = nnz - r0;
         // ---- accumulate at the column's rank, then emit; rows longer than the accumulator take several passes over their
@@ -309,7 +321,7 @@ struct RwWarp {
                 __syncwarp();
             }
         }
-        for (u32 i = 0; i < wpl; i++) bw[w0 + i] = make_uint2(0u, 0u);
+        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) bw[w0 + i] = make_uint2(0u, 0u);
         __syncwarp();
         return nnz;
     }
