@@ -98,7 +98,11 @@ typedef struct b200_config {
     int32_t fused_product_slots; /* fused: product buffer entries per CTA (rows with more generate their products twice)   */
     int32_t rw_cap_percent;      /* row-per-warp kernels: accumulator slots per warp as a percentage of the mean row's
                                     intermediate products (0 auto = 140); longer rows are produced in several passes       */
-    int32_t reserved[5];
+    int32_t heavy_min_products;  /* heavy rows: rows with at least this many intermediate products take the chunked kernel
+                                    (0 auto: 1024 per column chunk, at least 8193)                                         */
+    int32_t heavy_unit_products; /* heavy rows: intermediate products per work unit of the chunked kernel -- rows with more are
+                                    cut into several units of consecutive chunks, one CTA each (0 auto = 2^20)              */
+    int32_t reserved[3];
 } b200_config;
 int b200_config_default(b200_config *cfg);
 

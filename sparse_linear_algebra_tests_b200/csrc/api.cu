@@ -146,7 +146,7 @@ extern "C" int b200_config_default(b200_config *c) {
     c->pipeline = 0; c->placement = -1; c->exact_limit_mb = -1; c->force_acc_mode = -1; c->window_cap_groups = -1; c->window_mul = 3;
     c->circular_windows = 1; c->arc_window = 1; c->touched_span = 1; c->narrow_scratch = 1; c->expand_kernel = 1; c->pack_b = -1;
     c->lanes_per_entry_lg = -1; c->expand_div = 8; c->hash_div = 32; c->grid_div = 8; c->grid_mul = 4; c->aux_streams = 1;
-    c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1;
+    c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1; c->heavy_min_products = 0; c->heavy_unit_products = 0;
     return B200_OK;
 }
 static void config_from_env(b200_config *c) {
@@ -156,7 +156,7 @@ static void config_from_env(b200_config *c) {
         {"B200_SPAN", &c->touched_span}, {"B200_NARROW", &c->narrow_scratch}, {"B200_EXPAND", &c->expand_kernel}, {"B200_PACK", &c->pack_b},
         {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
         {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
-        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel},
+        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel}, {"B200_HEAVY_PMIN", &c->heavy_min_products}, {"B200_HEAVY_UNIT", &c->heavy_unit_products},
         {"B200_RW_CAP", &c->rw_cap_percent},
     };
     for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
@@ -222,6 +222,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     fz_setup(ctx);
     rw_setup(ctx);
     rwf_setup(ctx);
+    hv_setup(ctx);
     ctx->cap_cta_tot = 8192;
     CUDA_TRY(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
@@ -245,7 +246,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val);
+    dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val); dfree(ctx, ctx->d_hv);
     dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_rowwin); dfree(ctx, ctx->d_rowclass); dfree(ctx, ctx->d_spill_acc); dfree(ctx, ctx->d_spill_col);
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->h_freport);
@@ -281,7 +282,8 @@ int alloc_entries(b200_ctx *ctx, b200_csr *m) {
     const u64 cap = std::max(m->nnz, m->cap_entries);                     // products of the fused path are allocated from a bound
     m->cap_entries = cap;
     const size_t col_bytes = ((size_t)cap * 4 + 255) & ~(size_t)255;
-    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)cap * (size_t)(m->val_bits / 8)));
+    // (+32: the chunked heavy-row kernel fetches B-row segments as 16-byte aligned bulk copies, which may run a few entries past nnz)
+    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)cap * (size_t)(m->val_bits / 8) + 32));
     m->d_val = (unsigned char *)m->d_col + col_bytes;
     m->val_shares_col = true;
     return B200_OK;
@@ -691,10 +693,13 @@ __global__ void __launch_bounds__(256) k_finish_exact(B200Ctrl *ctrl, u64 *host_
 template <typename VT>
 static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u64 rows, u64 p_bound, u64 heavy_cap,
                           int mode, bool packed, bool bpat, int lg, OutArgs<VT> o, Fan &fan, const WinCaps &caps,
-                          B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw, b200_csr *C = nullptr) {
+                          B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw, b200_csr *C = nullptr,
+                          const HvPlan *hv = nullptr) {
     if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32);
     const size_t smem_max = ctx->smem_optin - 1024;
+    const bool hv_on = hv && hv->on;
+    const HvSkip skip{ctx->d_prod, hv_on ? hv->pmin : ~0ull, hv_on ? hv->cap_li : 0u};
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     NumArgs<u64> na64{A->d_rp, A->d_col, (const u64 *)A->d_val, B->d_desc, B->d_col, (const u64 *)B->d_val};
     OutArgs<u64> o64{o.base, o.col, (u64 *)o.val, o.nnz_out, o.bin_cnt, o.bin_stride, o.narrow};
@@ -777,7 +782,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     if (heavy) {
         const u64 n = rows;
         const size_t heavy_rank_smem = (size_t)nwords * 6 + 16 + (size_t)heavy_cap * (4 + accb);
-        if (heavy_cap < 65536 && heavy_rank_smem <= smem_max) {
+        if (!hv_on && heavy_cap < 65536 && heavy_rank_smem <= smem_max) {
             // heavy rows over a small column space: the rank kernel with accumulators sized for the longest row
             const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * 2);
             cudaStream_t bs = fan.pick();
@@ -797,9 +802,11 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
             u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
             u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
             u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
-            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64);
-            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o);
+            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64, skip);
+            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o, skip);
             LAUNCH_CHECK(ctx);
+            // the rows with enough products per column chunk: dense accumulation chunk by chunk (heavy.cu)
+            if (hv_on) TRY(hv_numeric(ctx, A, B, ctrl, *hv, mode, bpat, o.base, o.col, (void *)o.val, o.narrow, ctx->stream));
         }
     }
     // launch order: the bin that holds the row of mean size first (it carries most of the work), then outwards from
@@ -819,25 +826,30 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     return B200_OK;
 }
 
-static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwords, Fan &fan, B200Ctrl *ctrl = nullptr) {
+static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwords, Fan &fan, B200Ctrl *ctrl = nullptr,
+                            const b200_csr *A = nullptr, const b200_csr *B = nullptr, const HvPlan *hv = nullptr) {
     if (!ctrl) ctrl = ctx->d_ctrl;
     const size_t smem_max = ctx->smem_optin - 1024;
+    const bool hv_on = hv && hv->on && A && B;
+    const HvSkip skip{ctx->d_prod, hv_on ? hv->pmin : ~0ull, hv_on ? hv->cap_li : 0u};
     if ((size_t)nwords * 4 <= smem_max) {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows);
+        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows, skip);
     } else {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
         TRY(ensure_heavy_scratch(ctx, (size_t)g * nwords * 4));
-        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row, (u32)ctx->cap_rows);
+        k_sym_heavy<<<g, 1024, 0, ctx->stream>>>(sa, ctx->d_bin_rows, ctrl, nwords, (u32 *)ctx->d_heavy, ctx->d_nnz_row, (u32)ctx->cap_rows, skip);
     }
     LAUNCH_CHECK(ctx);
+    if (hv_on) TRY(hv_count(ctx, A, B, ctrl, *hv, ctx->stream));
     return B200_OK;
 }
 
 // Exact mode, first half: distinct-column counts for every list the one-pass pre-pass produced (the lists and the
 // kernels mirror launch_numeric's: tiny / window bitmap / hash, heavy), so that C can be allocated at its exact size.
 static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, const SymArgs &sa, u64 rows, u64 p_bound, bool packed, int lg,
-                         Fan &fan, const WinCaps &caps, B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw) {
+                         Fan &fan, const WinCaps &caps, B200Ctrl *ctrl = nullptr, bool wide_only = false, const RwPlan &rw = kNoRw,
+                         const HvPlan *hv = nullptr) {
     if (!ctrl) ctrl = ctx->d_ctrl;
     const u32 nwords = (u32)((B->cols + 31) / 32), nw4_full = caps.full;
     const u32 bstride = (u32)ctx->cap_rows;
@@ -856,7 +868,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
     };
     if (rw.hb_max >= 1 && (reachable(0) || reachable(1)) && !wide_only)
         TRY(rw_launch(ctx, A, B, ctrl, B200_BIN_HASH0 + 1, rw.hb_max, true, 0, packed, true, rw.nw, rw.cap, nullptr, fan.pick()));
-    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan, ctrl));
+    if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1)) TRY(launch_sym_heavy(ctx, sa, rows, nwords, fan, ctrl, A, B, hv));
     for (int hb = B200_NUM_HASH_BINS - 1; hb >= 2; hb--) {
         if (!reachable(hb)) continue;
         TRY(count_expand(B200_BIN_HASH0 + hb, 1, b200_hash_cap(hb), caps.cap[hb]));
@@ -866,7 +878,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
             const size_t smem = (size_t)slots * 4;
             if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
-            k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride);
+            k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride, HvSkip{nullptr, ~0ull, 0u});
             LAUNCH_CHECK(ctx);
         }
     }
@@ -968,6 +980,9 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     // 100^3 torus wider windows lost to hash + sort (the per-row prefix over a mostly empty bitmap dominates).
     // Rows beyond the window take the hash + sort kernels.
     WinCaps caps;
+    HvPlan hv;                                                            // chunked kernels for the heaviest rows (heavy.cu), where they apply
+    r = hv_plan(ctx, A, B, mode1, p_bound, &hv);
+    if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     // The arc of the index circle this multiply can touch: (column range of A, known on the host for every handle) +
     // (offsets c - k of B's entries, a per-operand constant for a square B).  When the arc is short -- a GPU's row block of
     // a torus or banded matrix, whatever the size of the whole matrix -- ONE window serves every row: the pre-pass needs
@@ -1114,7 +1129,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             }
         }
         if (exact) {
-            r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps, nullptr, false, rw);
+            r = launch_counts(ctx, A, B, sa, rows, p_bound, packed, lg, fan, caps, nullptr, false, rw, &hv);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             if (rw.hb_max >= 0 && cheap_bound) {
@@ -1129,7 +1144,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 r = alloc_entries(ctx, C);
                 if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
                 OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
-                r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, std::min<u64>(p_bound, ncols)), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C);
+                r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, std::min<u64>(p_bound, ncols)), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C, &hv);
                 fan.join();
                 if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
                 const unsigned fg = (unsigned)std::max<u64>(1, std::min<u64>(64, scan_bytes / 8 / 1024));
@@ -1156,7 +1171,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             if (timing) cudaEventRecord(ctx->ev[2], s);
             if (ctx->trace) trace_mark(ctx, __LINE__);
             OutArgs<VT> o{C->d_rp, C->d_col, (VT *)C->d_val, nullptr, ctx->d_ctrl->sym_bin_count, bstride};
-            r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C);
+            r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C, &hv);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
             CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
@@ -1191,16 +1206,17 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         tmp_col = ctx->d_tmp_col; tmp_val = ctx->d_tmp_val;
         const int mode = mode1;
         const u64 heavy_cap = std::min<u64>(p_bound, ncols);
-        if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) && !(heavy_cap < 65536 && (size_t)nwords * 6 + 16 + heavy_cap * 12 <= smem_max)) {
-            // heavy rows that need the global table: size it from their exact nnz (bitmap count first)
-            r = launch_sym_heavy(ctx, sa, rows, nwords, fan);
+        if (p_bound > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) && (hv.on || !(heavy_cap < 65536 && (size_t)nwords * 6 + 16 + heavy_cap * 12 <= smem_max))) {
+            // heavy rows that need the global table: size it from their exact nnz (bitmap count first); the rows the chunked
+            // kernels take get their per-chunk lengths here
+            r = launch_sym_heavy(ctx, sa, rows, nwords, fan, nullptr, A, B, &hv);
             fan.join();
         }
         // u64 values that provably stay below 2^32 (mode 0) cross the scratch as u32: 8 instead of 12 bytes per entry, twice
         const bool narrow = sizeof(VT) == 8 && mode == 0 && ctx->cfg.narrow_scratch;
         OutArgs<VT> o{ctx->d_tmp_ptr, (u32 *)tmp_col, (VT *)tmp_val, ctx->d_nnz_row, ctx->d_ctrl->sym_bin_count, bstride, narrow ? 1u : 0u};
         if (ctx->hosttime) ctx->ht[1] = host_now_us();                       // pre-pass enqueued
-        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps);
+        if (r == B200_OK) r = launch_numeric<VT>(ctx, A, B, rows, p_bound, heavy_cap, mode, packed, bpat, lg, o, fan, caps, nullptr, false, kNoRw, nullptr, &hv);
         fan.join();
         if (ctx->hosttime) ctx->ht[2] = host_now_us();                       // numeric kernels enqueued
         if (r != B200_OK) { b200_csr_free(ctx, C); return r; }

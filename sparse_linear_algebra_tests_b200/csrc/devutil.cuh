@@ -26,6 +26,29 @@ struct NumArgs {
     const uint2 *bdesc; const u32 *colB; const VT *valB;
 };
 
+// Where a numeric kernel puts its rows.  Exact mode: base = row_ptr_C (from the count pass), nnz_out = null.
+// Scratch mode: base = offsets from the scan of the per-row bounds min(P_i, cols), rows land in a scratch CSR and their
+// exact lengths in nnz_out.  Either way the rows to process come from the pre-pass's per-bin lists.
+template <typename VT>
+struct OutArgs {
+    const u64 *base; u32 *col; VT *val;
+    u32 *nnz_out;                // may be null (exact mode)
+    const u32 *bin_cnt;          // list sizes (ctrl->sym_bin_count)
+    u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
+    u32 narrow;                  // scratch mode, u64 values proven < 2^32 (accumulator mode 0): the scratch holds them as
+                                 // u32 (val is then a u32 array); the compaction kernel widens them on the way into C
+};
+template <typename VT>
+__device__ __forceinline__ void put_val(const OutArgs<VT> &o, u64 idx, VT v) {
+    if (sizeof(VT) == 8 && o.narrow) reinterpret_cast<u32 *>(o.val)[idx] = (u32)v;
+    else o.val[idx] = v;
+}
+
+// Rows of the pre-pass's heavy list that the chunked kernels (heavy.cu) take; the other heavy-row kernels leave them alone.
+// pmin = ~0: nothing is taken.
+struct HvSkip { const u64 *prod; u64 pmin; u32 cap_li; };
+__device__ __forceinline__ bool hv_skipped(const HvSkip &h, u32 li, u32 row) { return h.pmin != ~0ull && li < h.cap_li && h.prod[row] >= h.pmin; }
+
 // Walk the intermediate products of one A row.  `ngrp` groups of G lanes each take A entries
 // grp, grp+ngrp, ...; the G lanes of a group stride over that entry's B row.  Two A entries are
 // in flight per iteration so their dependent loads (A.col -> desc -> B.col) overlap.

@@ -92,6 +92,7 @@ struct b200_ctx {
     cudaEvent_t f_ev[B200_REPORT_SLOTS][3];
     u32 fepoch;
     u64 *d_cta_tot; u64 cap_cta_tot;   // per-CTA totals of the one-launch multiply (rowwarp.cu)
+    void *d_hv; size_t cap_hv;         // chunked heavy-row kernels (heavy.cu): control words | per-(row, chunk) counters | unit lists
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
 };
 
@@ -158,6 +159,18 @@ int rw_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctr
 void rwf_setup(b200_ctx *ctx);
 int rw_fused_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, int mode, bool packed, bool bpat,
                     u32 org, u32 words, u32 nw, u32 cap, u64 *mirror, u32 epoch, cudaStream_t s);
+// ---- heavy.cu: column-chunked kernels for the heaviest rows (TMA-staged B-row segments, dense accumulator per chunk)
+struct HvPlan {
+    bool on;
+    u32 W, nchunks, sw, nchunks_c, cap_li;   // numeric chunk columns, chunks, numeric chunks per count chunk, count chunks, list rows covered
+    u64 pmin, psplit;                        // rows with at least pmin intermediate products are taken; products per numeric work unit
+    void *ctl, *cnt, *units_c, *units_n;     // device: control words, per-(row, chunk) counters, work-unit lists
+};
+void hv_setup(b200_ctx *ctx);
+int hv_plan(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int mode, u64 p_bound, HvPlan *plan);
+int hv_count(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, const HvPlan &p, cudaStream_t s);
+int hv_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, const HvPlan &p, int mode, bool bpat,
+               const u64 *base, u32 *col, void *val, u32 narrow, cudaStream_t s);
 // ---- fused.cu
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);

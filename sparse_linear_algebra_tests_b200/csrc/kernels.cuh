@@ -17,24 +17,6 @@
 #include "devutil.cuh"
 
 
-// Where a numeric kernel puts its rows.  Exact mode: base = row_ptr_C (from the count pass), nnz_out = null.
-// Scratch mode: base = offsets from the scan of the per-row bounds min(P_i, cols), rows land in a scratch CSR and their
-// exact lengths in nnz_out.  Either way the rows to process come from the pre-pass's per-bin lists.
-template <typename VT>
-struct OutArgs {
-    const u64 *base; u32 *col; VT *val;
-    u32 *nnz_out;                // may be null (exact mode)
-    const u32 *bin_cnt;          // list sizes (ctrl->sym_bin_count)
-    u32 bin_stride;              // bin b's row list starts at bin_rows + b * bin_stride
-    u32 narrow;                  // scratch mode, u64 values proven < 2^32 (accumulator mode 0): the scratch holds them as
-                                 // u32 (val is then a u32 array); the compaction kernel widens them on the way into C
-};
-template <typename VT>
-__device__ __forceinline__ void put_val(const OutArgs<VT> &o, u64 idx, VT v) {
-    if (sizeof(VT) == 8 && o.narrow) reinterpret_cast<u32 *>(o.val)[idx] = (u32)v;
-    else o.val[idx] = v;
-}
-
 // desc = {first entry, length}; span = {length, first column, last column, -} (what the one-pass pre-pass gathers: the
 // product count and the column window of a row of C follow from these alone because B's rows are sorted)
 __global__ void __launch_bounds__(256) k_build_desc(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col,
@@ -484,7 +466,7 @@ __global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restri
 // 4b. CTA per row: key table, or a column bitmap when the whole column space fits shared memory
 template <bool BITMAP>
 __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
-                                                  u32 nwords, int lg, u32 *__restrict__ nnz_row, u32 bin_stride) {
+                                                  u32 nwords, int lg, u32 *__restrict__ nnz_row, u32 bin_stride, HvSkip skip) {
     extern __shared__ u32 smem[];
     __shared__ u32 s_count, s_warp[33];
     __shared__ EnumSmem s_enum;
@@ -495,6 +477,7 @@ __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restri
     const int shift = 32 - (31 - __clz(slots));
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
+        if (hv_skipped(skip, r, row)) continue;
         for (u32 t = tid; t < tabn; t += nt) smem[t] = BITMAP ? 0u : B200_EMPTY_KEY;
         if (tid == 0) s_count = 0;
         __syncthreads();
@@ -1116,7 +1099,7 @@ __global__ void __launch_bounds__(512) k_sym_expand(SymArgs a, const uint4 *__re
 // 6. heavy rows: table, bitmap and rank array in global scratch (one CTA per row at a time)
 // =======================================================================================
 __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, u32 nwords,
-                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row, u32 bin_stride) {
+                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ nnz_row, u32 bin_stride, HvSkip skip) {
     __shared__ u32 s_count, s_warp[33];
     __shared__ EnumSmem s_enum;
     const u32 count = ctrl->sym_bin_count[B200_BIN_HEAVY];
@@ -1125,6 +1108,7 @@ __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__rest
     const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
+        if (hv_skipped(skip, r, row)) continue;
         for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
         if (tid == 0) s_count = 0;
         __syncthreads();
@@ -1150,7 +1134,7 @@ template <typename VT, int MODE>   // MODE 1: plain 64-bit global atomics (u32 p
 __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
                                                     const u32 *__restrict__ nnz_row, u32 nwords, u64 max_slots,
                                                     u32 *__restrict__ scratch_bm, u32 *__restrict__ scratch_pre,
-                                                    u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o) {
+                                                    u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o, HvSkip skip) {
     __shared__ u32 s_warp[33];
     __shared__ EnumSmem s_enum;
     const u32 count = o.bin_cnt[B200_BIN_HEAVY];
@@ -1163,6 +1147,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
     u64 vmax = 0;
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
+        if (hv_skipped(skip, r, row)) continue;
         const u32 nnz = nnz_row[row];
         u64 slots = 1; while (slots < 2ull * nnz) slots <<= 1;            // <= max_slots by host sizing
         const int shift = 64 - (63 - __clzll(slots));

@@ -1,0 +1,92 @@
+"""Parity of the chunked heavy-row kernels (csrc/heavy.cu): column-space chunks, TMA-staged B-row segments, a dense
+accumulator per chunk, rows cut into several work units.  The reference reaches the corresponding MAGNUS levels
+through MagnusMatrix::matmul (src/graph_magnus.rs:225-232); the checker is the CSR restatement (oracle.matmul_par,
+src/graph_csr.rs:350-484).  Everything goes through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from sparse_linear_algebra_tests_b200 import B200Matrix, hostgen
+
+pytestmark = pytest.mark.gpu
+
+
+def to_o(O, h):
+    return O.Csr(h.rows, h.cols, h.row_ptr, h.col_idx, h.values)
+
+
+def assert_same(got, want, what=""):
+    assert np.array_equal(got.row_ptr, want.row_ptr), f"row_ptr differs {what}"
+    assert np.array_equal(got.col_idx, want.col_idx), f"col_idx differs {what}"
+    assert got.values.dtype == want.values.dtype, what
+    assert np.array_equal(got.values, want.values), f"values differ {what}"
+
+
+def hub_graph(n, hubs, hub_fill, deg, links, bits, vmax, seed, frac=0.25):
+    """`hubs` dense rows (a fraction hub_fill of all columns each), every other row `deg` random columns plus `links`
+    columns among the hubs: rows that link to hubs are heavy (their B rows are the hubs' long rows -- the segments the
+    chunked kernel stages through shared memory)."""
+    rng = np.random.default_rng(seed)
+    r, c = [], []
+    for h in range(hubs):
+        cols = np.nonzero(rng.random(n) < hub_fill)[0]
+        r.append(np.full(cols.size, h)); c.append(cols)
+    rest = np.arange(hubs, n)
+    r.append(np.repeat(rest, deg)); c.append(rng.integers(0, n, rest.size * deg))
+    linked = rest[rng.random(rest.size) < frac]
+    r.append(np.repeat(linked, links)); c.append(rng.integers(0, hubs, linked.size * links))
+    r = np.concatenate(r); c = np.concatenate(c)
+    v = rng.integers(1, vmax + 1, r.size, dtype=np.uint64).astype(hostgen.vdtype(bits))
+    return hostgen.from_coo(n, n, r, c, v, bits, saturating=True)
+
+
+@pytest.mark.parametrize("placement", [-1, 0, 1], ids=["auto", "scratch", "exact"])
+@pytest.mark.parametrize("bits,vmax", [(64, 1), (64, 1 << 20), (32, 3000), (64, (1 << 64) - 1)], ids=["u64-pattern", "u64-wide", "u32", "u64-saturating"])
+def test_hub_rows_through_small_chunks(gpu_ctx, oracle, cfg, bits, vmax, placement):
+    """1024-column chunks, rows cut into work units of ~4096 products: many chunks per row, several CTAs per row, long
+    segments (hub rows hold ~300 entries per chunk) through the bulk-copy stages, short ones through the enumeration; all
+    three accumulator modes and both placements."""
+    a_h = hub_graph(6000, 12, 0.3, 6, 6, bits, vmax, 7)
+    cfg(pipeline=2, placement=placement, heavy_chunk_cols=1024, heavy_min_products=8193, heavy_unit_products=4096)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    c = a.matmul(a, want_stats=True)
+    assert c.last_stats.sym_bin_rows[9] > 0, "no heavy row"
+    assert_same(c.to_host(), oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, a_h)), f"hub graph u{bits} vmax {vmax} placement {placement}")
+
+
+def test_chunked_kernel_on_and_off_agree(gpu_ctx, oracle, cfg):
+    """The same multiply with the chunked kernels switched off (global-memory table for every heavy row)."""
+    a_h = hub_graph(70000, 6, 0.06, 5, 3, 64, 50, 11, frac=0.03)
+    want = oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, a_h))
+    for on in (1, 0):
+        cfg(pipeline=2, heavy_kernel=on)
+        a = B200Matrix.from_host(a_h, gpu_ctx)
+        assert_same(a.matmul(a).to_host(), want, f"heavy_kernel={on}")
+
+
+@pytest.mark.parametrize("scale,bits", [(16, 64), (17, 32)])
+def test_graph500_skew_default_plan(gpu_ctx, oracle, scale, bits):
+    """Graph500-skew R-MAT with the automatic plan (column chunks sized from shared memory): hub rows of > 10^5 products."""
+    a_h = hostgen.rmat(scale, 16, 0.57, 0.19, 0.19, 42, bits)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    a_o = to_o(oracle, a_h)
+    c = a.matmul(a, want_stats=True)
+    assert c.last_stats.sym_bin_rows[9] > 0
+    assert_same(c.to_host(), oracle.matmul_par(a_o, a_o), f"graph500 scale {scale} u{bits}")
+
+
+def test_rectangular_right_operand_and_empty_chunks(gpu_ctx, oracle, cfg):
+    """Columns only in the first and the last chunk of a wide rectangular B: empty chunks in between, a last chunk that is
+    not full."""
+    rng = np.random.default_rng(3)
+    m, k, n = 40, 3000, 100_000 + 37
+    ar = np.repeat(np.arange(m), 600); ac = rng.integers(0, k, ar.size)
+    a_h = hostgen.from_coo(m, k, ar, ac, rng.integers(1, 9, ar.size, dtype=np.uint64), 64, saturating=True)
+    br = np.repeat(np.arange(k), 40)
+    bc = np.where(rng.random(br.size) < 0.5, rng.integers(0, 900, br.size), n - 1 - rng.integers(0, 900, br.size))
+    b_h = hostgen.from_coo(k, n, br, bc, rng.integers(1, 9, br.size, dtype=np.uint64), 64, saturating=True)
+    cfg(pipeline=2, heavy_chunk_cols=2048, heavy_min_products=8193)
+    a, b = B200Matrix.from_host(a_h, gpu_ctx), B200Matrix.from_host(b_h, gpu_ctx)
+    c = a.matmul(b, want_stats=True)
+    assert c.last_stats.sym_bin_rows[9] > 0
+    assert_same(c.to_host(), oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, b_h)), "rectangular")
