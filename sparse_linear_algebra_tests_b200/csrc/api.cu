@@ -902,13 +902,13 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
 int legacy_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, u64 p_bound, int lg, Fan &fan) {
     SymArgs sa{A->d_rp, A->d_col, B->d_desc, B->d_col};
     WinCaps caps; for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) caps.cap[hb] = 0;
-    caps.full = 1;                                                         // every bin has a hash ("wide") list, none a bitmap list
+    caps.heavy_from = 0xFFFFFFFFu; caps.full = 1;                          // every bin has a hash ("wide") list, none a bitmap list
     return launch_counts(ctx, A, B, sa, A->rows, p_bound, false, lg, fan, caps, ctrl, true);
 }
 int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, b200_csr *C, u64 p_bound, u64 heavy_cap, int mode,
                    bool packed, bool bpat, int lg, Fan &fan) {
     WinCaps caps; for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) caps.cap[hb] = 0;
-    caps.full = 1;
+    caps.heavy_from = 0xFFFFFFFFu; caps.full = 1;
     const u32 bstride = (u32)ctx->cap_rows;
     if (A->val_bits == 32) {
         OutArgs<u32> o{C->d_rp, C->d_col, (u32 *)C->d_val, nullptr, ctrl->sym_bin_count, bstride, 0u};
@@ -983,6 +983,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     HvPlan hv;                                                            // chunked kernels for the heaviest rows (heavy.cu), where they apply
     r = hv_plan(ctx, A, B, mode1, p_bound, &hv);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+    caps.heavy_from = hv.on ? hv.heavy_from : 0xFFFFFFFFu;               // (over few column chunks the chunked kernels also beat hash + sort on the largest hash bins)
     // The arc of the index circle this multiply can touch: (column range of A, known on the host for every handle) +
     // (offsets c - k of B's entries, a per-operand constant for a square B).  When the arc is short -- a GPU's row block of
     // a torus or banded matrix, whatever the size of the whole matrix -- ONE window serves every row: the pre-pass needs

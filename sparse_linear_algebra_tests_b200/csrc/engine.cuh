@@ -163,6 +163,7 @@ int rw_fused_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_cs
 struct HvPlan {
     bool on;
     u32 W, nchunks, sw, nchunks_c, cap_li;   // numeric chunk columns, chunks, numeric chunks per count chunk, count chunks, list rows covered
+    u32 heavy_from;                          // the pre-pass puts rows with at least this many products on the heavy list
     u64 pmin, psplit;                        // rows with at least pmin intermediate products are taken; products per numeric work unit
     void *ctl, *cnt, *units_c, *units_n;     // device: control words, per-(row, chunk) counters, work-unit lists
 };

@@ -22,10 +22,22 @@
 #include "engine.cuh"
 #include "devutil.cuh"
 
+#ifndef HV_THREADS
 #define HV_THREADS 1024
+#endif
+#ifndef HV_CTAS
+#define HV_CTAS 1                 // CTAs per SM the shared-memory budget is cut for
+#endif
+#ifndef HV_STAGE_ELEMS
 #define HV_STAGE_ELEMS 2048u      // entries per staged piece: 8 KiB of columns (+ 16 KiB of u64 values)
+#endif
 #define HV_NSTAGE 2
+#ifndef HV_LONG_MIN
 #define HV_LONG_MIN 256u          // segments at least this long are staged through shared memory by bulk copies
+#endif
+#ifndef HV_TINY_MAX
+#define HV_TINY_MAX 0u            // segments at most this long are walked by the thread that found them
+#endif
 #define HV_QCAP 256               // long segments queued per tile of HV_THREADS A entries (the rest take the short path)
 #define HV_MAX_SW 64              // numeric chunks per count chunk, at most
 
@@ -79,11 +91,23 @@ static __device__ __forceinline__ u32 hv_block_scan(u32 v, u32 *s_warp /* 33 */,
     return r;
 }
 
-// first index in col[0..n) whose column is >= key
+// first index in col[0..n) whose column is >= key.  16-ary: every step reads up to 15 pivots with independent loads, so the
+// chain of dependent L2 round trips is log16(n) long instead of log2(n) -- the search is latency, not bandwidth (a row of
+// <= 16 entries takes one step, the longest hub rows four).
 __device__ __forceinline__ u32 hv_lower_bound(const u32 *__restrict__ col, u32 n, u32 key) {
-    u32 lo = 0, hi = n;
-    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (col[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
+    u32 base = 0, len = n;
+    while (len > 16) {
+        const u32 step = (len + 15) >> 4;
+        u32 cnt = 0;
+#pragma unroll
+        for (u32 j = 1; j < 16; j++) { const u32 i = j * step; if (i < len) cnt += col[base + i] < key ? 1u : 0u; }
+        base += cnt * step;
+        len = min(step, n - base);
+    }
+    u32 cnt = 0;
+#pragma unroll
+    for (u32 j = 0; j < 16; j++) if (j < len) cnt += col[base + j] < key ? 1u : 0u;
+    return base + cnt;
 }
 
 // ---- planning: one thread per row of the heavy list
@@ -138,20 +162,20 @@ struct HvPiece { u32 gbase, n, s0, s1; u64 av; };
 // One kernel, two roles.  COUNT: units are count chunks (bitmap only); the per-numeric-chunk popcounts go to cnt.
 // Otherwise: units are groups of numeric chunks; every chunk is accumulated densely and written at o.base[row] + cnt.
 template <typename VT, int MODE, bool COUNT, bool BPAT>
-__global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, OutArgs<VT> o, B200Ctrl *ctrl) {
+__global__ void __launch_bounds__(HV_THREADS, HV_CTAS) k_hv(HvDev h, NumArgs<VT> a, OutArgs<VT> o, B200Ctrl *ctrl) {
     constexpr bool NEEDV = !COUNT && !BPAT;
     extern __shared__ __align__(128) unsigned char hv_smem[];
     __shared__ __align__(8) u64 s_bar[HV_NSTAGE];
     __shared__ HvPiece s_pd[HV_NSTAGE];
-    __shared__ u32 s_warp[33], s_unit, s_qn, s_cnt[HV_MAX_SW];
+    __shared__ u32 s_warp[33], s_unit, s_qn[2], s_cnt[HV_MAX_SW];
     __shared__ u32 s_pre[HV_THREADS + 1], s_start[HV_THREADS];
     __shared__ u64 s_av[HV_THREADS];
     __shared__ HvSeg<VT> s_q[HV_QCAP];
     __shared__ u32 s_qpre[HV_QCAP + 1];
 
     const u32 tid = threadIdx.x, nt = HV_THREADS, lane = tid & 31;
-    const u32 Wb = COUNT ? h.W * h.sw : h.W;                         // columns this kernel's bitmap covers
-    const u32 bwords = Wb >> 5;
+    const u32 Wb = COUNT ? h.W * h.sw : h.W;                         // columns of one chunk of this kernel
+    const u32 bwords = COUNT ? Wb >> 5 : 0u;                         // (the numeric pass needs no bitmap: a touched accumulator is never zero)
     u32 *bm = reinterpret_cast<u32 *>(hv_smem);
     Acc<MODE> acc;
     unsigned char *after_bm = hv_smem + (size_t)bwords * 4;
@@ -169,6 +193,8 @@ __global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, Ou
     }
     __syncthreads();
     u32 phase_bits = 0;                                              // bit s: parity of the next completion of stage s
+    u32 tile_par = 0;
+    if (tid < 2) s_qn[tid] = 0;
     u64 vmax = 0;
     const u32 n_units = COUNT ? h.ctl->n_count_units : h.ctl->n_num_units;
     u32 *ticket = COUNT ? &h.ctl->t_count : &h.ctl->t_num;
@@ -189,50 +215,87 @@ __global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, Ou
         const VT *__restrict__ Av = a.valA + rs;
         const u64 obase = COUNT ? 0ull : o.base[row];
 
+        // A row of at most HV_THREADS entries (one tile) keeps its entries in registers over the unit's chunks: B row extent,
+        // first / last column, a_ik, and a cursor -- the chunks ascend, so a segment starts where the last one ended and a
+        // chunk costs one search per entry instead of the whole chain A.col -> span -> desc -> two searches.
+        const bool single = lenA <= nt;
+        u32 r_st = 0, r_len = 0, r_first = 0, r_last = 0, r_cur = 0; VT r_av = 0;
+        if (single && tid < lenA) {
+            const u32 k = Ac[tid];
+            const uint4 sp = h.bspan[k];
+            r_st = a.bdesc[k].x; r_len = sp.x; r_first = sp.y; r_last = sp.z;
+            if (!COUNT) r_av = Av[tid];
+            const u64 cs = (u64)cfirst * Wb;                                   // first column of the unit
+            if (r_len && (u64)r_first < cs) r_cur = (u64)r_last < cs ? r_len : hv_lower_bound(a.colB + r_st, r_len, (u32)cs);
+        }
+
         for (u32 ch = cfirst; ch < cfirst + cn; ch++) {
             const u64 c0 = (u64)ch * Wb;
             const u64 c1 = min((u64)h.ncols, c0 + Wb);
+            u32 chunk_nnz = 1;                                             // numeric: an empty chunk is skipped altogether
+            if (!COUNT) {
+                const u32 *cr = h.cnt + (u64)li * h.nchunks;
+                chunk_nnz = (ch + 1 < h.nchunks ? cr[ch + 1] : h.nnz_row[row]) - cr[ch];
+                if (chunk_nnz == 0) {
+                    // (the cursors of a register-resident row need not move: the chunk holds none of its entries)
+                    continue;
+                }
+            }
             if (COUNT && tid < HV_MAX_SW) s_cnt[tid] = 0;
             // ---- accumulate: tiles of HV_THREADS entries of the A row
             for (u32 base = 0; base < lenA; base += nt) {
-                if (tid == 0) s_qn = 0;
-                __syncthreads();
+                // (the queue counters alternate: this tile fills s_qn[par], which the last tile but one left at zero)
+                const u32 par = tile_par; tile_par ^= 1u;
                 const u32 t = base + tid;
                 u32 seg_start = 0, seg_len = 0; VT av = 0;
-                if (t < lenA) {
+                if (single) {
+                    if (r_cur < r_len && (u64)r_first < c1) {
+                        const u32 hi = (u64)r_last < c1 ? r_len : r_cur + hv_lower_bound(a.colB + r_st + r_cur, r_len - r_cur, (u32)c1);
+                        seg_start = r_st + r_cur; seg_len = hi - r_cur; av = r_av;
+                        r_cur = hi;
+                    }
+                } else if (t < lenA) {
                     const u32 k = Ac[t];
                     const uint4 sp = h.bspan[k];                         // {len, first column, last column}
+                    const u32 st = a.bdesc[k].x;
                     if (sp.x && (u64)sp.y < c1 && (u64)sp.z >= c0) {
-                        const u32 st = a.bdesc[k].x;
                         const u32 lo = (u64)sp.y >= c0 ? 0u : hv_lower_bound(a.colB + st, sp.x, (u32)c0);
                         const u32 hi = (u64)sp.z < c1 ? sp.x : lo + hv_lower_bound(a.colB + st + lo, sp.x - lo, (u32)c1);
                         seg_start = st + lo; seg_len = hi - lo;
                         if (!COUNT) av = Av[t];
                     }
                 }
-                if (seg_len >= HV_LONG_MIN) {
-                    const u32 slot = atomicAdd(&s_qn, 1u);
-                    if (slot < HV_QCAP) { s_q[slot].start = seg_start; s_q[slot].len = seg_len; s_q[slot].av = av; seg_len = 0; }
-                }
-                // short segments: balanced enumeration (thread q takes products q, q + nt, ...)
-                u32 total;
-                const u32 ex = hv_block_scan(seg_len, s_warp, total);
-                s_pre[tid] = ex; s_start[tid] = seg_start;
-                if (!COUNT) s_av[tid] = (u64)av;
-                __syncthreads();
-                for (u32 q = tid; q < total; q += nt) {
-                    u32 lo = 0, hi = nt;
-                    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_pre[mid] <= q) lo = mid; else hi = mid; }
-                    const u32 jb = s_start[lo] + (q - s_pre[lo]);
+                auto one = [&](u32 jb, u64 xav) {
                     const u32 idx = (u32)((u64)a.colB[jb] - c0);
-                    atomicOr(&bm[idx >> 5], 1u << (idx & 31));
-                    if (!COUNT) {
-                        if (BPAT) acc.addv(idx, s_av[lo]);
-                        else acc.add(idx, (VT)s_av[lo], a.valB[jb]);
+                    if (COUNT) atomicOr(&bm[idx >> 5], 1u << (idx & 31));
+                    else if (BPAT) acc.addv(idx, xav);
+                    else acc.add(idx, (VT)xav, a.valB[jb]);
+                };
+                // three ways by segment length: a few entries -- the thread that found them walks them (most segments of a
+                // power-law operand: no scan, no search); long -- queued for the bulk-copy stages; the rest -- balanced
+                // enumeration (thread q takes products q, q + nt, ... of the tile's line of medium segments)
+                if (seg_len >= HV_LONG_MIN) {
+                    const u32 slot = atomicAdd(&s_qn[par], 1u);
+                    if (slot < HV_QCAP) { s_q[slot].start = seg_start; s_q[slot].len = seg_len; s_q[slot].av = av; seg_len = 0; }
+                } else if (seg_len <= HV_TINY_MAX) {
+                    for (u32 j = 0; j < seg_len; j++) one(seg_start + j, (u64)av);
+                    seg_len = 0;
+                }
+                if (tid == 0) s_qn[par ^ 1u] = 0;
+                if (__syncthreads_or(seg_len != 0)) {
+                    u32 total;
+                    const u32 ex = hv_block_scan(seg_len, s_warp, total);
+                    s_pre[tid] = ex; s_start[tid] = seg_start;
+                    if (!COUNT) s_av[tid] = (u64)av;
+                    __syncthreads();
+                    for (u32 q = tid; q < total; q += nt) {
+                        u32 lo = 0, hi = nt;
+                        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_pre[mid] <= q) lo = mid; else hi = mid; }
+                        one(s_start[lo] + (q - s_pre[lo]), COUNT ? 0ull : s_av[lo]);
                     }
                 }
                 // long segments: pieces of <= HV_STAGE_ELEMS entries, 16-byte aligned in B's arrays, through the stages
-                const u32 qn = min(s_qn, (u32)HV_QCAP);                   // (s_qn is final: the scan's barriers are behind us)
+                const u32 qn = min(s_qn[par], (u32)HV_QCAP);              // (final: a barrier lies behind every push)
                 if (qn) {
                     u32 np = 0;
                     if (tid < qn) {
@@ -274,11 +337,9 @@ __global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, Ou
                             const u32 g = pd.gbase + e;
                             if (g >= pd.s0 && g < pd.s1) {
                                 const u32 idx = (u32)((u64)scol[e] - c0);
-                                atomicOr(&bm[idx >> 5], 1u << (idx & 31));
-                                if (!COUNT) {
-                                    if (BPAT) acc.addv(idx, pd.av);
-                                    else acc.add(idx, (VT)pd.av, sval[e]);
-                                }
+                                if (COUNT) atomicOr(&bm[idx >> 5], 1u << (idx & 31));
+                                else if (BPAT) acc.addv(idx, pd.av);
+                                else acc.add(idx, (VT)pd.av, sval[e]);
                             }
                         }
                         __syncthreads();                                   // the stage is free again
@@ -289,8 +350,8 @@ __global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, Ou
             }
             __syncthreads();
             // ---- emit
-            const u32 wpt = (bwords + nt - 1) / nt, w0 = tid * wpt;
             if (COUNT) {
+                const u32 wpt = (bwords + nt - 1) / nt, w0 = tid * wpt;
                 const u32 wpc = h.W >> 5;                                  // bitmap words per numeric chunk
                 u32 curj = 0xFFFFFFFFu, run = 0;
                 for (u32 i = 0; i < wpt && w0 + i < bwords; i++) {
@@ -303,22 +364,32 @@ __global__ void __launch_bounds__(HV_THREADS, 1) k_hv(HvDev h, NumArgs<VT> a, Ou
                 if (tid < h.sw) { const u32 nc = ch * h.sw + tid; if (nc < h.nchunks) h.cnt[(u64)li * h.nchunks + nc] = s_cnt[tid]; }
                 __syncthreads();
             } else {
-                u32 mine = 0;
-                for (u32 i = 0; i < wpt && w0 + i < bwords; i++) mine += __popc(bm[w0 + i]);
+                // Every warp owns W / 32 consecutive columns and reads them 32 at a time (lane = column, conflict-free).  The
+                // sums of stored values are never zero (no explicit zeros; 32-bit sums are proven, 64-bit ones cannot wrap,
+                // saturating ones stick), so "accumulator != 0" is the chunk's pattern: ballots rank the entries, and the
+                // lanes holding one write consecutive places of C.
+                const u32 cpw = h.W / (HV_THREADS / 32), wbase = (tid >> 5) * cpw;   // columns per warp (a multiple of 32, at most 1024)
+                u32 mine = 0, mybal = 0;                                   // lane i keeps the ballot of the warp's i-th group of 32 columns
+                for (u32 i = 0, it = 0; i < cpw; i += 32, it++) {
+                    const u32 b = __ballot_sync(0xFFFFFFFFu, acc.get(wbase + i + lane) != 0);
+                    if (lane == it) mybal = b;
+                    mine += __popc(b);
+                }
                 u32 total;
-                u64 pos = obase + h.cnt[(u64)li * h.nchunks + ch] + hv_block_scan(mine, s_warp, total);
-                for (u32 i = 0; i < wpt && w0 + i < bwords; i++) {
-                    u32 wd = bm[w0 + i];
-                    bm[w0 + i] = 0;
-                    while (wd) {
-                        const u32 b = __ffs(wd) - 1; wd &= wd - 1;
-                        const u32 idx = ((w0 + i) << 5) + b;
+                const u32 wex = hv_block_scan(lane == 0 ? mine : 0u, s_warp, total);
+                u64 pos = obase + h.cnt[(u64)li * h.nchunks + ch] + __shfl_sync(0xFFFFFFFFu, wex, 0);
+                for (u32 i = 0, it = 0; i < cpw; i += 32, it++) {
+                    const u32 b = __shfl_sync(0xFFFFFFFFu, mybal, it);
+                    if (b == 0) continue;
+                    if ((b >> lane) & 1u) {
+                        const u32 idx = wbase + i + lane;
+                        const u64 q = pos + __popc(b & ((1u << lane) - 1u));
                         const VT v = emit_val<VT>(acc.get(idx));
                         acc.clear(idx);
-                        o.col[pos] = (u32)(c0 + idx); put_val(o, pos, v);
+                        o.col[q] = (u32)(c0 + idx); put_val(o, q, v);
                         vmax = vmax > (u64)v ? vmax : (u64)v;
-                        pos++;
                     }
+                    pos += __popc(b);
                 }
                 __syncthreads();
             }
@@ -366,11 +437,12 @@ int hv_plan(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int mode, u64 p
         const u64 heavy_cap = std::min<u64>(p_bound, ncols);
         if (heavy_cap < 65536 && (size_t)((ncols + 31) / 32) * 6 + 16 + heavy_cap * (4 + accb) <= ctx->smem_optin - 1024 && ctx->cfg.heavy_chunk_cols <= 0) return B200_OK;
     }
-    const size_t budget = ctx->smem_optin - g_hv_static - 512;
+    const size_t budget = (HV_CTAS == 1 ? ctx->smem_optin : (size_t)(228 * 1024) / HV_CTAS - 1024) - g_hv_static - 512;
     const size_t stages = (size_t)HV_NSTAGE * HV_STAGE_ELEMS * (4 + A->val_bits / 8);
     if (budget <= stages + 8192) return B200_OK;
     u64 W = (u64)(((budget - stages) * 8) / (accb * 8 + 1));           // an accumulator and a bitmap bit per column
     if (ctx->cfg.heavy_chunk_cols > 0) W = std::min<u64>(W, (u64)ctx->cfg.heavy_chunk_cols);
+    W = std::min<u64>(W, (u64)32 * HV_THREADS);                       // (a warp emits at most 1024 columns of a chunk)
     u64 Wp = 1024; while (Wp * 2 <= W) Wp *= 2;                       // a power of two, at least 1024 columns
     W = Wp;
     if ((size_t)W * accb + W / 8 + stages > budget) return B200_OK;
@@ -379,10 +451,14 @@ int hv_plan(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int mode, u64 p
     u64 sw = std::min<u64>(std::min<u64>(HV_MAX_SW, nchunks), std::max<u64>(1, (1ull << 20) / W));
     while (sw > 1 && (size_t)(sw * W / 8) + (size_t)HV_NSTAGE * HV_STAGE_ELEMS * 4 > budget) sw--;
     plan->W = (u32)W; plan->nchunks = (u32)nchunks; plan->sw = (u32)sw; plan->nchunks_c = (u32)((nchunks + sw - 1) / sw);
-    // rows whose products average >= 1024 per chunk (a chunk costs a bitmap walk and a handful of barriers whatever it holds)
-    plan->pmin = ctx->cfg.heavy_min_products > 0 ? (u64)ctx->cfg.heavy_min_products
-                                                 : std::max<u64>((u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) + 1, nchunks * 1024);
-    plan->pmin = std::max<u64>(plan->pmin, (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) + 1);   // (only rows of the heavy list)
+    // Rows take the chunked kernels when their products average >= 1024 per chunk (a chunk costs a few barriers and a walk
+    // over its accumulators whatever it holds).  Over few chunks that is below the largest hash bins' capacity: those rows
+    // (>= 512 products per chunk) then join the heavy list in the pre-pass instead of going through hash + sort.
+    const u64 top = (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) + 1;
+    const u64 from = std::min<u64>(top, std::max<u64>(1025, nchunks * 512));
+    plan->heavy_from = (u32)from;
+    plan->pmin = from < top ? from : std::max<u64>(top, nchunks * 1024);
+    if (ctx->cfg.heavy_min_products > 0) { plan->pmin = std::max<u64>((u64)ctx->cfg.heavy_min_products, 33); plan->heavy_from = (u32)std::min<u64>(top, plan->pmin); }
     plan->psplit = ctx->cfg.heavy_unit_products > 0 ? (u64)ctx->cfg.heavy_unit_products : 1ull << 20;
     if (p_bound < plan->pmin) return B200_OK;                          // no row can qualify
     // per-(row, chunk) counters: at most 256 MiB; rows of the heavy list beyond that keep the global-table kernel
@@ -428,7 +504,7 @@ int hv_count(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl
     NumArgs<u32> na{A->d_rp, A->d_col, nullptr, B->d_desc, B->d_col, nullptr};
     OutArgs<u32> o{nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 0u};
     void *kargs[] = {(void *)&h, (void *)&na, (void *)&o, (void *)&ctrl};
-    CUDA_TRY(cudaLaunchKernel(g_hv_count.fn, dim3(ctx->num_sms), dim3(HV_THREADS), kargs, smem, s));
+    CUDA_TRY(cudaLaunchKernel(g_hv_count.fn, dim3(ctx->num_sms * HV_CTAS), dim3(HV_THREADS), kargs, smem, s));
     LAUNCH_CHECK(ctx);
     k_hv_scan<<<pg, 256, 0, s>>>(h);
     LAUNCH_CHECK(ctx);
@@ -447,7 +523,7 @@ static int hv_numeric_t(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B20
     NumArgs<VT> na{A->d_rp, A->d_col, (const VT *)A->d_val, B->d_desc, B->d_col, (const VT *)B->d_val};
     OutArgs<VT> o{base, col, (VT *)val, nullptr, nullptr, 0u, narrow};
     void *kargs[] = {(void *)&h, (void *)&na, (void *)&o, (void *)&ctrl};
-    CUDA_TRY(cudaLaunchKernel(k.fn, dim3(ctx->num_sms), dim3(HV_THREADS), kargs, smem, s));
+    CUDA_TRY(cudaLaunchKernel(k.fn, dim3(ctx->num_sms * HV_CTAS), dim3(HV_THREADS), kargs, smem, s));
     LAUNCH_CHECK(ctx);
     return B200_OK;
 }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_build_cspan(u64 n, const u64 *__restric
 
 // per hash bin: how many 128-column groups the bin's shared-memory bitmap holds (0: the bin has no bitmap kernel)
 // `full`: groups that hold any row of this multiply (bins with cap >= full have no wide list)
-struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; u32 full; };
+struct WinCaps { u32 cap[B200_NUM_HASH_BINS]; u32 full; u32 heavy_from; };   // heavy_from: rows with at least this many products join the heavy list (chunked kernels; default 8193)
 
 
 // =======================================================================================
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) k_prepass(u64 rows, const u64 *__restrict
                 prod[row] = p;
                 bound = p < ncols ? p : ncols;
                 int b = sym_bin_of(p, lenA);
+                if (p >= (u64)caps.heavy_from && b != B200_BIN_NONE) b = B200_BIN_HEAVY;
                 if (b == B200_BIN_HASH0) b = B200_BIN_HASH0 + 1;           // the two smallest hash bins share a list
                 if (b != B200_BIN_NONE) {
                     // column window of the row, in 128-column groups; rows too wide for their bin's bitmap go to the hash list
