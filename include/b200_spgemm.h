@@ -193,6 +193,18 @@ int b200_lattice(b200_ctx *ctx, const uint64_t *dims, int ndims, int torus, int 
  * grid, src/graph_magnus.rs:800-821); `draws_consumed` (may be NULL) receives the number this call took. */
 int b200_thin(b200_ctx *ctx, const b200_csr *A, double density, const uint8_t *seed32, uint64_t skip_draws, b200_csr **out,
               uint64_t *draws_consumed);
+/* COO triplets -> CSR on the device: CsrMatrix::from_coo (src/graph_csr.rs:83-129; MagnusMatrix::from_coo, src/graph_magnus.rs:34-76):
+ * triplets ordered by (row, column) with a radix sort, duplicates summed -- plain `+=` (wrapping, as the reference's release
+ * build) or, with `saturating`, the saturating sum of linalg's from_coo (linalg/src/csr.rs:158-195) -- zero sums dropped.
+ * n triplets in host arrays (`_device`: arrays already on this context's device); B200_ERR_BADARG for an index out of range. */
+int b200_csr_from_coo(b200_ctx *ctx, uint64_t rows, uint64_t cols, uint64_t n, const uint32_t *row_idx, const uint32_t *col_idx,
+                      const void *values, int val_bits, int saturating, b200_csr **out);
+int b200_csr_from_coo_device(b200_ctx *ctx, uint64_t rows, uint64_t cols, uint64_t n, const uint32_t *d_row_idx, const uint32_t *d_col_idx,
+                             const void *d_values, int val_bits, int saturating, b200_csr **out);
+/* R-MAT graph built on the device (BASELINE configs[3]; SURVEY.md App. C -- the reference has no such generator): 2^scale nodes,
+ * edge_factor * 2^scale edges; level l of edge e takes draw e * scale + l of a counter-based splitmix64(seed): u < a -> quadrant
+ * (0,0), < a+b -> (0,1), < a+b+c -> (1,0), else (1,1); duplicate edges are summed by from_coo (plain +=). */
+int b200_rmat(b200_ctx *ctx, int scale, uint64_t edge_factor, double a, double b, double c, uint64_t seed, int val_bits, b200_csr **out);
 /* Host twin of the generator the device kernels use (runs without a GPU): StdRng::from_seed(seed32).next_u64() outputs
  * number first .. first+n-1. */
 int b200_stdrng_u64(const uint8_t *seed32, uint64_t first, uint64_t n, uint64_t *out);

@@ -57,7 +57,7 @@ EXPORTS = [
     "b200_csr_from_device", "b200_csr_free", "b200_csr_info", "b200_csr_device_ptrs", "b200_csr_max_value",
     "b200_csr_download", "b200_csr_download_idx64", "b200_csr_download_async", "b200_spgemm", "b200_row_products",
     "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
-    "b200_lattice", "b200_thin", "b200_stdrng_u64",
+    "b200_lattice", "b200_thin", "b200_stdrng_u64", "b200_csr_from_coo", "b200_csr_from_coo_device", "b200_rmat",
 ]
 
 _lib = None
@@ -104,6 +104,9 @@ def load():
         "b200_lattice": [vp, vp, i32, i32, i32, C.POINTER(vp)],
         "b200_thin": [vp, vp, C.c_double, vp, u64, C.POINTER(vp), C.POINTER(u64)],
         "b200_stdrng_u64": [vp, u64, u64, vp],
+        "b200_csr_from_coo": [vp, u64, u64, u64, vp, vp, vp, i32, i32, C.POINTER(vp)],
+        "b200_csr_from_coo_device": [vp, u64, u64, u64, vp, vp, vp, i32, i32, C.POINTER(vp)],
+        "b200_rmat": [vp, i32, u64, C.c_double, C.c_double, C.c_double, u64, i32, C.POINTER(vp)],
     }
     for name, args in sigs.items():
         f = getattr(L, name)
@@ -237,6 +240,27 @@ class Context:
         d = np.asarray(list(dims), dtype=np.uint64)
         h = C.c_void_p()
         check(load().b200_lattice(self._h, d.ctypes.data, int(d.size), int(bool(torus)), val_bits, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def from_coo(self, rows: int, cols: int, r, c, v, val_bits: int = 64, saturating: bool = False) -> "DeviceCsr":
+        """COO triplets -> CSR on the device (src/graph_csr.rs:83-129): radix sort by (row, column), duplicate sum, zero drop."""
+        r = np.ascontiguousarray(np.asarray(r).ravel())
+        c = np.ascontiguousarray(np.asarray(c).ravel())
+        if r.size and (int(r.max()) > 0xFFFFFFFF or int(c.max()) > 0xFFFFFFFF or int(r.min()) < 0 or int(c.min()) < 0):
+            raise B200Error(B200_ERR_BADARG, "triplet index out of range")
+        r32, c32 = r.astype(np.uint32), c.astype(np.uint32)
+        vv = np.ascontiguousarray(np.asarray(v).ravel().astype(np.uint32 if val_bits == 32 else np.uint64))
+        if not (r32.size == c32.size == vv.size):
+            raise B200Error(B200_ERR_BADARG, "triplet arrays differ in length")
+        h = C.c_void_p()
+        check(load().b200_csr_from_coo(self._h, int(rows), int(cols), int(r32.size), r32.ctypes.data, c32.ctypes.data, vv.ctypes.data,
+                                       val_bits, int(bool(saturating)), C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def rmat(self, scale: int, edge_factor: int, a: float, b: float, c: float, seed: int = 42, val_bits: int = 64) -> "DeviceCsr":
+        """R-MAT graph generated and assembled on the device (host twin: hostgen.rmat)."""
+        h = C.c_void_p()
+        check(load().b200_rmat(self._h, int(scale), int(edge_factor), float(a), float(b), float(c), int(seed), val_bits, C.byref(h)))
         return DeviceCsr(self, h)
 
     def thin(self, a: "DeviceCsr", density: float, seed: bytes = bytes([42] * 32), skip: int = 0):

@@ -318,7 +318,7 @@ static int grid_for(u64 n, int threads, int cap) { u64 g = (n + threads - 1) / t
 
 // value max + format check (explicit zeros, column range); synchronises when `check`.  `device_rowptr`: the
 // row_ptr never passed through the host, so its sanity and the longest row are established on the device too.
-static int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr = false) {
+int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr) {
     CUDA_TRY(cudaMemsetAsync(m->d_maxval, 0, 16, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, 32, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_flag + 16, 0, 48, ctx->stream));
@@ -1392,7 +1392,7 @@ extern "C" int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b20
 
 // ---------------------------------------------------------------------------- fixture generators on the device (gen.cuh)
 // exclusive u64 prefix of ctx->d_nnz_row[0..rows) into `out` (rows + 1 words); returns total and the longest row
-static int scan_row_counts(b200_ctx *ctx, u64 rows, u64 *out, u64 *total, u64 *max_len) {
+int scan_row_counts(b200_ctx *ctx, u64 rows, u64 *out, u64 *total, u64 *max_len) {
     CUDA_TRY(reset_scan(ctx, 0));
     launch_scan_rowptr(ctx, rows, out, ctx->stream, nullptr, 0);
     LAUNCH_CHECK(ctx);

@@ -145,6 +145,9 @@ int pick_mode_bits(const b200_ctx *ctx, int val_bits, u64 max_row_products, u64 
 int host_maxval(b200_ctx *ctx, const b200_csr *m);
 int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool alloc_arrays, b200_csr **out);
 int alloc_entries(b200_ctx *ctx, b200_csr *m);
+// value max + format check of a new handle (synchronises when `check`); row counts in ctx->d_nnz_row -> row_ptr (synchronises)
+int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr = false);
+int scan_row_counts(b200_ctx *ctx, u64 rows, u64 *out, u64 *total, u64 *max_len);
 // count / numeric kernels of the binned pipeline over the hash ("wide") and heavy lists only, writing C at its final offsets
 int legacy_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, u64 p_bound, int lg, Fan &fan);
 int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, b200_csr *C, u64 p_bound, u64 heavy_cap, int mode,

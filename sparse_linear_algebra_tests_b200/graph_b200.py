@@ -101,9 +101,18 @@ class B200Matrix:
         return cls.from_host(hostgen.identity(n, val_bits), ctx)
 
     @classmethod
-    def from_coo(cls, n: int, triplets: Iterable, val_bits: int = 64, ctx=None) -> "B200Matrix":
+    def from_coo(cls, n: int, triplets: Iterable, val_bits: int = 64, ctx=None, device: bool = True) -> "B200Matrix":
+        """src/graph_csr.rs:83-129 / src/graph_magnus.rs:34-76: sort by (row, column), sum duplicates, drop zeros -- on the
+        device (b200_csr_from_coo: radix sort + run sums); `device=False` assembles on the host and uploads."""
         t = np.asarray(list(triplets), dtype=np.uint64).reshape(-1, 3)
+        if device:
+            return cls((ctx or default_context()).from_coo(n, n, t[:, 0], t[:, 1], t[:, 2], val_bits))
         return cls.from_host(hostgen.from_coo(n, n, t[:, 0], t[:, 1], t[:, 2], val_bits), ctx)
+
+    @classmethod
+    def rmat(cls, scale: int, edge_factor: int = 16, abc=(0.45, 0.15, 0.15), seed: int = 42, val_bits: int = 64, ctx=None) -> "B200Matrix":
+        """R-MAT input of BASELINE configs[3], generated on the device (b200_rmat)."""
+        return cls((ctx or default_context()).rmat(scale, edge_factor, abc[0], abc[1], abc[2], seed, val_bits))
 
     @classmethod
     def from_edges(cls, n: int, edges: Iterable, val_bits: int = 64, ctx=None) -> "B200Matrix":

@@ -90,3 +90,51 @@ def test_rectangular_right_operand_and_empty_chunks(gpu_ctx, oracle, cfg):
     c = a.matmul(b, want_stats=True)
     assert c.last_stats.sym_bin_rows[9] > 0
     assert_same(c.to_host(), oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, b_h)), "rectangular")
+
+
+# ------------------------------------------------------------------ COO -> CSR and the R-MAT generator on the device
+@pytest.mark.parametrize("saturating", [False, True])
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("rows,cols,n", [(1, 1, 5), (7, 3, 40), (300, 70000, 20000), (100000, 100000, 700000), (5, 5, 0)])
+def test_from_coo_on_device(gpu_ctx, bits, saturating, rows, cols, n):
+    """b200_csr_from_coo against the host restatement of CsrMatrix::from_coo (src/graph_csr.rs:83-129; saturating flavour
+    linalg/src/csr.rs:158-195): duplicates (a third of the triplets repeat), sums that wrap to zero and explicit zeros are
+    dropped, trailing empty rows closed."""
+    rng = np.random.default_rng(rows * 31 + n)
+    r = rng.integers(0, rows, n); c = rng.integers(0, cols, n)
+    if n >= 9:
+        r[n // 3: 2 * (n // 3)] = r[: n // 3]; c[n // 3: 2 * (n // 3)] = c[: n // 3]       # duplicates
+    top = (1 << bits) - 1
+    v = rng.integers(0, 4, n).astype(np.uint64)
+    big = rng.random(n) < 0.2
+    v[big] = np.uint64(top) - rng.integers(0, 3, int(big.sum())).astype(np.uint64)          # near the top: wraps / saturates
+    if n >= 9:
+        half = np.uint64(1 << (bits - 1))
+        v[0] = half; v[n // 3] = half                                                        # wraps to exactly zero (plain +=)
+    want = hostgen.from_coo(rows, cols, r, c, v.astype(hostgen.vdtype(bits)), bits, saturating=saturating)
+    got = gpu_ctx.from_coo(rows, cols, r, c, v, bits, saturating)
+    rp, ci, vv = got.download()
+    assert got.rows == rows and got.cols == cols
+    assert np.array_equal(rp, want.row_ptr) and np.array_equal(ci, want.col_idx) and np.array_equal(vv, want.values)
+
+
+def test_from_coo_rejects_out_of_range(gpu_ctx):
+    from sparse_linear_algebra_tests_b200 import B200Error
+    with pytest.raises(B200Error):
+        gpu_ctx.from_coo(4, 4, [0, 4], [1, 1], [1, 1], 64)
+    with pytest.raises(B200Error):
+        gpu_ctx.from_coo(4, 4, [0, 1], [1, 9], [1, 1], 64)
+
+
+@pytest.mark.parametrize("scale,abc,bits", [(10, (0.45, 0.15, 0.15), 64), (16, (0.57, 0.19, 0.19), 32), (18, (0.45, 0.15, 0.15), 64)])
+def test_device_rmat_equals_host_generator(gpu_ctx, scale, abc, bits):
+    want = hostgen.rmat(scale, 16, abc[0], abc[1], abc[2], 42, bits)
+    got = gpu_ctx.rmat(scale, 16, abc[0], abc[1], abc[2], 42, bits)
+    rp, ci, vv = got.download()
+    assert np.array_equal(rp, want.row_ptr) and np.array_equal(ci, want.col_idx) and np.array_equal(vv, want.values)
+
+
+def test_graph_type_from_coo_uses_the_device(gpu_ctx, oracle):
+    """B200Matrix.from_coo (the MagnusMatrix::from_coo surface): duplicate-edge sum = 2 + 3 = 5 (linalg/src/csr.rs:839-849)."""
+    m = B200Matrix.from_coo(3, [(0, 1, 2), (0, 1, 3), (2, 0, 7)], 64, gpu_ctx)
+    assert m.get(0, 1) == 5 and m.get(2, 0) == 7 and m.nnz() == 2
