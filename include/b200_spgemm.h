@@ -205,6 +205,16 @@ int b200_csr_from_coo_device(b200_ctx *ctx, uint64_t rows, uint64_t cols, uint64
  * edge_factor * 2^scale edges; level l of edge e takes draw e * scale + l of a counter-based splitmix64(seed): u < a -> quadrant
  * (0,0), < a+b -> (0,1), < a+b+c -> (1,0), else (1,1); duplicate edges are summed by from_coo (plain +=). */
 int b200_rmat(b200_ctx *ctx, int scale, uint64_t edge_factor, double a, double b, double c, uint64_t seed, int val_bits, b200_csr **out);
+/* ---- locality pre-pass: CsrMatrix::rcm / permute / unpermute / bandwidth_stats, src/graph_csr.rs:663-818 -------
+ * (max |r - c|, mean |r - c|) over the stored entries: bandwidth_stats (:802-818); a device reduction. */
+int b200_csr_bandwidth_stats(b200_ctx *ctx, const b200_csr *m, uint64_t *max_bw, double *avg_bw);
+/* Rows and columns reordered by perm[new] = old (host array of n = rows entries): permute (:727-785); the entries are relabelled
+ * and re-assembled on the device (radix sort), every row sorted by its new columns.  unpermute (:787-799) is a permute by the
+ * inverse.  B200_ERR_BADARG unless perm is a permutation of 0..n-1, B200_ERR_SHAPE unless the matrix is square. */
+int b200_csr_permute(b200_ctx *ctx, const b200_csr *A, const uint32_t *perm, b200_csr **out);
+/* Reverse Cuthill-McKee order of the pattern, perm_out[new] = old (host array of n entries): the ordering loop of rcm (:663-723).
+ * The queue is sequential by definition, so it runs on the host inside the library; apply it with b200_csr_permute. */
+int b200_csr_rcm_order(b200_ctx *ctx, const b200_csr *A, uint32_t *perm_out);
 /* Host twin of the generator the device kernels use (runs without a GPU): StdRng::from_seed(seed32).next_u64() outputs
  * number first .. first+n-1. */
 int b200_stdrng_u64(const uint8_t *seed32, uint64_t first, uint64_t n, uint64_t *out);

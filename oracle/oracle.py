@@ -73,6 +73,12 @@ def lib():
         L.oracle_rmat.argtypes = [C.c_int, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int]
         L.oracle_time_matmul.restype = C.c_double
         L.oracle_time_matmul.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int]
+        L.oracle_rcm_order.argtypes = [_P, C.c_void_p]
+        L.oracle_rcm_order.restype = None
+        L.oracle_permute.argtypes = [_P, C.c_void_p]
+        L.oracle_permute.restype = _P
+        L.oracle_bandwidth_stats.argtypes = [_P, C.c_void_p, C.c_void_p]
+        L.oracle_bandwidth_stats.restype = None
         L.oracle_max_threads.restype = C.c_int
         for f, t in (("oracle_sadd_u32", C.c_uint32), ("oracle_smul_u32", C.c_uint32),
                      ("oracle_sadd_u64", C.c_uint64), ("oracle_smul_u64", C.c_uint64)):
@@ -252,6 +258,29 @@ def reference_bench_instance(side: int = 30, target_epn: float = 3.0, val_bits: 
     full = lattice([side, side, side], True, val_bits)
     density = target_epn / (full.nnz() / full.rows)
     return thin_stdrng(full, bytes([42] * 32), density)
+
+
+def rcm_order(a: Csr) -> np.ndarray:
+    """CsrMatrix::rcm's ordering (graph_csr.rs:663-723): perm[new] = old."""
+    perm = np.zeros(a.rows, dtype=np.uint32)
+    with _Wrapped(a) as pa:
+        lib().oracle_rcm_order(pa, perm.ctypes.data)
+    return perm
+
+
+def permute(a: Csr, perm) -> Csr:
+    """CsrMatrix::permute (graph_csr.rs:727-785)."""
+    perm = np.ascontiguousarray(perm, dtype=np.uint32)
+    with _Wrapped(a) as pa:
+        return _take(lib().oracle_permute(pa, perm.ctypes.data))
+
+
+def bandwidth_stats(a: Csr):
+    """CsrMatrix::bandwidth_stats (graph_csr.rs:802-818): (max |r-c|, mean |r-c|)."""
+    mx, avg = C.c_uint64(), C.c_double()
+    with _Wrapped(a) as pa:
+        lib().oracle_bandwidth_stats(pa, C.byref(mx), C.byref(avg))
+    return int(mx.value), float(avg.value)
 
 
 def time_matmul(a: Csr, b: Csr, par: bool, nthreads: int, iters: int) -> float:

@@ -522,6 +522,85 @@ ocsr_t *oracle_rmat(int scale, uint64_t edge_factor, double a, double b, double 
 }
 
 /* ------------------------------------------------------- timing helpers */
+/* ---------------------------------------------------------------------------------------------
+ * Locality pre-pass: CsrMatrix::rcm / permute / bandwidth_stats, graph_csr.rs:663-818.
+ * --------------------------------------------------------------------------------------------- */
+/* CsrMatrix::rcm's ordering -- graph_csr.rs:663-723: for every unvisited seed in index order, a plain BFS (own
+ * visited set) whose LAST dequeued node is the start (:674-694); then a BFS from the start where each node's unvisited
+ * neighbours are appended by ascending degree (:697-717); the whole order reversed (:721).  perm[new] = old.
+ * `sort_unstable_by_key` (:711) leaves the order of equal degrees to the implementation; Rust's is an insertion sort
+ * for slices of <= 20 elements, i.e. equal degrees keep their adjacency order -- restated here for every length. */
+void oracle_rcm_order(const ocsr_t *A, uint32_t *perm) {
+    const uint64_t n = A->rows;
+    uint8_t *visited = (uint8_t *)calloc(n ? n : 1, 1), *vis2 = (uint8_t *)malloc(n ? n : 1);
+    uint32_t *queue = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t)), *order = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    uint32_t *nbrs = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    uint64_t no = 0;
+    for (uint64_t seed = 0; seed < n; seed++) {
+        if (visited[seed]) continue;
+        memset(vis2, 0, n);
+        uint64_t qh = 0, qt = 0; uint32_t last = (uint32_t)seed;
+        queue[qt++] = (uint32_t)seed; vis2[seed] = 1;
+        while (qh < qt) {
+            const uint32_t u = queue[qh++]; last = u;
+            for (uint64_t i = A->row_ptr[u]; i < A->row_ptr[u + 1]; i++) { const uint32_t v = A->col_idx[i]; if (!vis2[v]) { vis2[v] = 1; queue[qt++] = v; } }
+        }
+        qh = qt = 0; queue[qt++] = last; visited[last] = 1;
+        while (qh < qt) {
+            const uint32_t u = queue[qh++]; order[no++] = u;
+            uint64_t k = 0;
+            for (uint64_t i = A->row_ptr[u]; i < A->row_ptr[u + 1]; i++) { const uint32_t v = A->col_idx[i]; if (!visited[v]) nbrs[k++] = v; }
+            for (uint64_t a = 1; a < k; a++) {                      /* insertion sort by degree: stable */
+                const uint32_t v = nbrs[a]; const uint64_t dv = A->row_ptr[v + 1] - A->row_ptr[v];
+                uint64_t b = a;
+                while (b > 0 && A->row_ptr[nbrs[b - 1] + 1] - A->row_ptr[nbrs[b - 1]] > dv) { nbrs[b] = nbrs[b - 1]; b--; }
+                nbrs[b] = v;
+            }
+            for (uint64_t a = 0; a < k; a++) { const uint32_t v = nbrs[a]; if (!visited[v]) { visited[v] = 1; queue[qt++] = v; } }
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) perm[i] = order[n - 1 - i];
+    free(visited); free(vis2); free(queue); free(order); free(nbrs);
+}
+
+/* CsrMatrix::permute -- graph_csr.rs:727-785: perm[new] = old; rows moved, columns relabelled through the inverse,
+ * every row re-sorted by column. */
+static int cmp_pair_u64(const void *a, const void *b) { const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+ocsr_t *oracle_permute(const ocsr_t *A, const uint32_t *perm) {
+    const uint64_t n = A->rows;
+    uint32_t *inv = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    for (uint64_t i = 0; i < n; i++) inv[perm[i]] = (uint32_t)i;
+    ocsr_t *C = ocsr_alloc(n, A->cols, A->nnz, A->val_bits);
+    for (uint64_t nr = 0; nr < n; nr++) C->row_ptr[nr + 1] = C->row_ptr[nr] + (A->row_ptr[perm[nr] + 1] - A->row_ptr[perm[nr]]);
+    const size_t vb = (size_t)A->val_bits / 8;
+    uint64_t maxlen = 1;
+    for (uint64_t r = 0; r < n; r++) if (A->row_ptr[r + 1] - A->row_ptr[r] > maxlen) maxlen = A->row_ptr[r + 1] - A->row_ptr[r];
+    uint64_t *pairs = (uint64_t *)malloc(maxlen * sizeof(uint64_t));      /* (new column << 32 | position in the old row) */
+    for (uint64_t nr = 0; nr < n; nr++) {
+        const uint64_t os = A->row_ptr[perm[nr]], len = A->row_ptr[perm[nr] + 1] - os, ns = C->row_ptr[nr];
+        for (uint64_t j = 0; j < len; j++) pairs[j] = ((uint64_t)inv[A->col_idx[os + j]] << 32) | j;
+        qsort(pairs, len, sizeof(uint64_t), cmp_pair_u64);
+        for (uint64_t j = 0; j < len; j++) {
+            C->col_idx[ns + j] = (uint32_t)(pairs[j] >> 32);
+            memcpy((char *)C->values + (ns + j) * vb, (const char *)A->values + (os + (pairs[j] & 0xFFFFFFFFu)) * vb, vb);
+        }
+    }
+    free(pairs); free(inv);
+    return C;
+}
+
+/* CsrMatrix::bandwidth_stats -- graph_csr.rs:802-818: (max |r-c|, sum |r-c| / max(count, 1)). */
+void oracle_bandwidth_stats(const ocsr_t *A, uint64_t *max_bw, double *avg_bw) {
+    uint64_t mx = 0, sum = 0, cnt = 0;
+    for (uint64_t r = 0; r < A->rows; r++)
+        for (uint64_t i = A->row_ptr[r]; i < A->row_ptr[r + 1]; i++) {
+            const uint64_t c = A->col_idx[i], d = r > c ? r - c : c - r;
+            if (d > mx) mx = d;
+            sum += d; cnt++;
+        }
+    *max_bw = mx; *avg_bw = (double)sum / (double)(cnt ? cnt : 1);
+}
+
 /* The reference's protocol (graph_magnus.rs:758-772): wall clock around ITERS multiplies,
  * results dropped (allocation + free inside the timed region). Returns seconds per iter. */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }

@@ -58,6 +58,7 @@ EXPORTS = [
     "b200_csr_download", "b200_csr_download_idx64", "b200_csr_download_async", "b200_spgemm", "b200_row_products",
     "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
     "b200_lattice", "b200_thin", "b200_stdrng_u64", "b200_csr_from_coo", "b200_csr_from_coo_device", "b200_rmat",
+    "b200_csr_bandwidth_stats", "b200_csr_permute", "b200_csr_rcm_order",
 ]
 
 _lib = None
@@ -107,6 +108,9 @@ def load():
         "b200_csr_from_coo": [vp, u64, u64, u64, vp, vp, vp, i32, i32, C.POINTER(vp)],
         "b200_csr_from_coo_device": [vp, u64, u64, u64, vp, vp, vp, i32, i32, C.POINTER(vp)],
         "b200_rmat": [vp, i32, u64, C.c_double, C.c_double, C.c_double, u64, i32, C.POINTER(vp)],
+        "b200_csr_bandwidth_stats": [vp, vp, C.POINTER(u64), C.POINTER(C.c_double)],
+        "b200_csr_permute": [vp, vp, vp, C.POINTER(vp)],
+        "b200_csr_rcm_order": [vp, vp, vp],
     }
     for name, args in sigs.items():
         f = getattr(L, name)
@@ -256,6 +260,27 @@ class Context:
         check(load().b200_csr_from_coo(self._h, int(rows), int(cols), int(r32.size), r32.ctypes.data, c32.ctypes.data, vv.ctypes.data,
                                        val_bits, int(bool(saturating)), C.byref(h)))
         return DeviceCsr(self, h)
+
+    def bandwidth_stats(self, a: "DeviceCsr"):
+        """(max |r-c|, mean |r-c|) over the stored entries (src/graph_csr.rs:802-818)."""
+        mx, avg = C.c_uint64(), C.c_double()
+        check(load().b200_csr_bandwidth_stats(self._h, a._h, C.byref(mx), C.byref(avg)))
+        return int(mx.value), float(avg.value)
+
+    def permute(self, a: "DeviceCsr", perm) -> "DeviceCsr":
+        """Rows and columns reordered by perm[new] = old (src/graph_csr.rs:727-785)."""
+        p = np.ascontiguousarray(perm, dtype=np.uint32)
+        if p.size != a.rows:
+            raise B200Error(B200_ERR_BADARG, f"perm has {p.size} entries, the matrix {a.rows} rows")
+        h = C.c_void_p()
+        check(load().b200_csr_permute(self._h, a._h, p.ctypes.data, C.byref(h)))
+        return DeviceCsr(self, h)
+
+    def rcm_order(self, a: "DeviceCsr") -> np.ndarray:
+        """Reverse Cuthill-McKee order of the pattern, perm[new] = old (src/graph_csr.rs:663-723)."""
+        p = np.zeros(max(a.rows, 1), dtype=np.uint32)
+        check(load().b200_csr_rcm_order(self._h, a._h, p.ctypes.data))
+        return p[:a.rows]
 
     def rmat(self, scale: int, edge_factor: int, a: float, b: float, c: float, seed: int = 42, val_bits: int = 64) -> "DeviceCsr":
         """R-MAT graph generated and assembled on the device (host twin: hostgen.rmat)."""

@@ -373,3 +373,155 @@ extern "C" int b200_rmat(b200_ctx *ctx, int scale, uint64_t edge_factor, double 
     if (val_bits == 32) return rmat_t<u32>(ctx, scale, (u64)m128, a, b, c, seed, out);
     return rmat_t<u64>(ctx, scale, (u64)m128, a, b, c, seed, out);
 }
+
+// =======================================================================================
+// Locality pre-pass: CsrMatrix::rcm / permute / bandwidth_stats, /root/reference/src/graph_csr.rs:663-818.
+//   permute          on the device: every entry is relabelled (inv[row], inv[col]) and the triplets go through the same
+//                    radix-sort assembly as from_coo (a permutation creates no duplicates), so rows come out sorted;
+//   bandwidth_stats  one reduction kernel (max and sum of |r - c|);
+//   rcm_order        the Cuthill-McKee queue is sequential by definition (a node's place depends on every node queued
+//                    before it); the ordering runs on the host inside the library, on a downloaded pattern, exactly as
+//                    the reference's loop does -- applying it (permute) and measuring it (bandwidth) are device work.
+// =======================================================================================
+template <typename VT>
+__global__ void __launch_bounds__(256) k_perm_keys(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col, const u32 *__restrict__ inv_r,
+                                                   const u32 *__restrict__ inv_c, int cbits, u64 *__restrict__ keys) {
+    // a warp per row: entries of a row are contiguous
+    const u32 lane = threadIdx.x & 31;
+    const u64 wpb = blockDim.x >> 5;
+    for (u64 r = (u64)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (u64)gridDim.x * wpb) {
+        const u64 s = rp[r], e = rp[r + 1];
+        const u64 hi = (u64)inv_r[r] << cbits;
+        for (u64 i = s + lane; i < e; i += 32) keys[i] = hi | inv_c[col[i]];
+    }
+}
+__global__ void __launch_bounds__(256) k_invert_perm(u64 n, const u32 *__restrict__ perm, u32 *__restrict__ inv, u32 *bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u32 o = perm[i];
+        if (o >= n) { atomicOr(bad, 1u); continue; }
+        if (atomicExch(&inv[o], (u32)i) != 0xFFFFFFFFu) atomicOr(bad, 2u);     // an old index named twice: not a permutation
+    }
+}
+__global__ void __launch_bounds__(256) k_bandwidth(u64 rows, const u64 *__restrict__ rp, const u32 *__restrict__ col, ull *out /* max, sum */) {
+    const u32 lane = threadIdx.x & 31;
+    const u64 wpb = blockDim.x >> 5;
+    u64 mx = 0, sum = 0;
+    for (u64 r = (u64)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (u64)gridDim.x * wpb) {
+        const u64 s = rp[r], e = rp[r + 1];
+        for (u64 i = s + lane; i < e; i += 32) { const u64 c = col[i], d = r > c ? r - c : c - r; mx = mx > d ? mx : d; sum += d; }
+    }
+    mx = warp_max_u64(mx); sum = warp_sum_u64(sum);
+    if (lane == 0) { if (mx) atomicMax(&out[0], (ull)mx); if (sum) atomicAdd(&out[1], (ull)sum); }
+}
+
+extern "C" int b200_csr_bandwidth_stats(b200_ctx *ctx, const b200_csr *m, uint64_t *max_bw, double *avg_bw) {
+    if (!ctx || !m || !max_bw || !avg_bw) return set_err(B200_ERR_BADARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, m);
+    cudaStream_t s = ctx->stream;
+    ull *d = reinterpret_cast<ull *>(ctx->d_flag + 16);                    // 16 bytes of the context's flag words (8-byte aligned)
+    CUDA_TRY(cudaMemsetAsync(d, 0, 16, s));
+    if (m->rows && m->nnz) {
+        const int g = (int)std::max<u64>(1, std::min<u64>((m->rows + 7) / 8, (u64)ctx->num_sms * 16));
+        k_bandwidth<<<g, 256, 0, s>>>(m->rows, m->d_rp, m->d_col, d);
+        LAUNCH_CHECK(ctx);
+    }
+    ull h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *max_bw = h[0];
+    *avg_bw = (double)h[1] / (double)(m->nnz ? m->nnz : 1);
+    return B200_OK;
+}
+
+template <typename VT>
+static int permute_t(b200_ctx *ctx, const b200_csr *A, const u32 *d_inv, b200_csr **out) {
+    cudaStream_t s = ctx->stream;
+    const u64 n = A->nnz, cap = std::max<u64>(n, 1);
+    const int bits = bits_for(A->rows);
+    u64 *keys = nullptr, *keys2 = nullptr; VT *vals = nullptr, *vals2 = nullptr;
+    auto cleanup = [&]() { dfree(ctx, keys); dfree(ctx, keys2); dfree(ctx, vals); dfree(ctx, vals2); };
+    int r = dmalloc(ctx, (void **)&keys, cap * 8);
+    if (r == B200_OK) r = dmalloc(ctx, (void **)&keys2, cap * 8);
+    if (r == B200_OK) r = dmalloc(ctx, (void **)&vals, cap * sizeof(VT));
+    if (r == B200_OK) r = dmalloc(ctx, (void **)&vals2, cap * sizeof(VT));
+    if (r == B200_OK && n) {
+        const int g = (int)std::max<u64>(1, std::min<u64>((A->rows + 7) / 8, (u64)ctx->num_sms * 16));
+        k_perm_keys<VT><<<g, 256, 0, s>>>(A->rows, A->d_rp, A->d_col, d_inv, d_inv, bits, keys);
+        ctx->launches++;
+        if (cudaMemcpyAsync(vals, A->d_val, n * sizeof(VT), cudaMemcpyDeviceToDevice, s) != cudaSuccess) r = set_err(B200_ERR_CUDA, "permute: copying the values failed");
+    }
+    if (r == B200_OK) r = coo_build<VT>(ctx, A->rows, A->cols, n, keys, vals, keys2, vals2, bits, bits, 0, out);
+    cleanup();
+    return r;
+}
+
+// perm[new] = old (host array of A.rows entries); A must be square.
+extern "C" int b200_csr_permute(b200_ctx *ctx, const b200_csr *A, const uint32_t *perm, b200_csr **out) {
+    if (!ctx || !A || !out || (A->rows && !perm)) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->rows != A->cols) return set_err(B200_ERR_SHAPE, "permute: the matrix must be square (%llux%llu)", (ull)A->rows, (ull)A->cols);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A);
+    cudaStream_t s = ctx->stream;
+    const u64 n = A->rows;
+    u32 *d_perm = nullptr, *d_inv = nullptr;
+    TRY(dmalloc(ctx, (void **)&d_perm, std::max<u64>(n, 1) * 4));
+    int r = dmalloc(ctx, (void **)&d_inv, std::max<u64>(n, 1) * 4);
+    if (r == B200_OK && n) {
+        cudaMemcpyAsync(d_perm, perm, n * 4, cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(d_inv, 0xFF, n * 4, s);
+        cudaMemsetAsync(ctx->d_flag, 0, 4, s);
+        k_invert_perm<<<(int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ctx->num_sms * 16)), 256, 0, s>>>(n, d_perm, d_inv, ctx->d_flag);
+        ctx->launches++;
+        if (cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+            r = set_err(B200_ERR_CUDA, "permute: %s", cudaGetErrorString(cudaGetLastError()));
+        else if (ctx->h_flag[0]) r = set_err(B200_ERR_BADARG, "permute: perm is not a permutation of 0..n-1");
+    }
+    if (r == B200_OK) r = A->val_bits == 32 ? permute_t<u32>(ctx, A, d_inv, out) : permute_t<u64>(ctx, A, d_inv, out);
+    dfree(ctx, d_perm); dfree(ctx, d_inv);
+    return r;
+}
+
+// Reverse Cuthill-McKee order of A's pattern, perm[new] = old (host array of A.rows entries).  CsrMatrix::rcm,
+// /root/reference/src/graph_csr.rs:663-723, step for step: per unvisited seed in index order a plain BFS whose last
+// dequeued node becomes the start, then a BFS from the start appending each node's unvisited neighbours by ascending
+// degree (equal degrees keep adjacency order: Rust's sort_unstable is an insertion sort on the short slices this sees),
+// the whole order reversed.
+extern "C" int b200_csr_rcm_order(b200_ctx *ctx, const b200_csr *A, uint32_t *perm_out) {
+    if (!ctx || !A || (A->rows && !perm_out)) return set_err(B200_ERR_BADARG, "NULL argument");
+    if (A->rows != A->cols) return set_err(B200_ERR_SHAPE, "rcm: the matrix must be square (%llux%llu)", (ull)A->rows, (ull)A->cols);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A);
+    const u64 n = A->rows;
+    std::vector<u64> rp(n + 1);
+    std::vector<u32> col(std::max<u64>(A->nnz, 1));
+    CUDA_TRY(cudaMemcpyAsync(rp.data(), A->d_rp, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (A->nnz) CUDA_TRY(cudaMemcpyAsync(col.data(), A->d_col, A->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned char> visited(n, 0);
+    std::vector<u32> stamp(n, 0), queue(std::max<u64>(n, 1)), order, nbrs;
+    order.reserve(n);
+    u32 epoch = 0;
+    auto deg = [&](u32 v) { return rp[v + 1] - rp[v]; };
+    for (u64 seed = 0; seed < n; seed++) {
+        if (visited[seed]) continue;
+        // (the first BFS's own visited set is an epoch stamp: the reference allocates a fresh vector per seed)
+        if (++epoch == 0) { std::fill(stamp.begin(), stamp.end(), 0u); epoch = 1; }
+        u64 qh = 0, qt = 0; u32 last = (u32)seed;
+        queue[qt++] = (u32)seed; stamp[seed] = epoch;
+        while (qh < qt) {
+            const u32 u = queue[qh++]; last = u;
+            for (u64 i = rp[u]; i < rp[u + 1]; i++) { const u32 v = col[i]; if (stamp[v] != epoch) { stamp[v] = epoch; queue[qt++] = v; } }
+        }
+        qh = qt = 0; queue[qt++] = last; visited[last] = 1;
+        while (qh < qt) {
+            const u32 u = queue[qh++]; order.push_back(u);
+            nbrs.clear();
+            for (u64 i = rp[u]; i < rp[u + 1]; i++) { const u32 v = col[i]; if (!visited[v]) nbrs.push_back(v); }
+            std::stable_sort(nbrs.begin(), nbrs.end(), [&](u32 a, u32 b) { return deg(a) < deg(b); });
+            for (u32 v : nbrs) if (!visited[v]) { visited[v] = 1; queue[qt++] = v; }
+        }
+    }
+    for (u64 i = 0; i < n; i++) perm_out[i] = order[n - 1 - i];
+    return B200_OK;
+}

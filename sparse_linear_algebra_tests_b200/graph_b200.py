@@ -44,6 +44,7 @@ class B200Matrix:
         self._dev = dev
         self._host = host          # lazily downloaded copy for get()/print()/NDIndex
         self.last_stats: Stats | None = None
+        self.perm: np.ndarray | None = None   # perm[new] = old, set by rcm() / permute() (src/graph_csr.rs:51)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -228,6 +229,30 @@ class B200Matrix:
 
     def same_pattern(self, other: "B200Matrix") -> bool:
         return self._dev.ctx.same_pattern(self._dev, other._dev)
+
+    # ------------------------------------------------------------------ locality pre-pass (src/graph_csr.rs:663-818), in place like the reference
+    def permute(self, perm) -> None:
+        """Reorder rows and columns by perm[new] = old and remember it (src/graph_csr.rs:727-785); applied on the device."""
+        perm = np.ascontiguousarray(perm, dtype=np.uint32)
+        self._dev, self._host = self._dev.ctx.permute(self._dev, perm), None
+        self.perm = perm.copy()
+
+    def rcm(self) -> None:
+        """Reverse Cuthill-McKee reordering (src/graph_csr.rs:663-723); the permutation stays in `perm`."""
+        self.permute(self._dev.ctx.rcm_order(self._dev))
+
+    def unpermute(self) -> None:
+        """Undo the stored permutation (src/graph_csr.rs:787-799); no-op without one."""
+        if self.perm is None:
+            return
+        inv = np.empty_like(self.perm)
+        inv[self.perm] = np.arange(self.perm.size, dtype=np.uint32)
+        self.permute(inv)
+        self.perm = None
+
+    def bandwidth_stats(self):
+        """(max |r-c|, mean |r-c|) over the stored entries (src/graph_csr.rs:802-818)."""
+        return self._dev.ctx.bandwidth_stats(self._dev)
 
     # ------------------------------------------------------------------ drivers built on matmul/add
     def reachability_sum(self):

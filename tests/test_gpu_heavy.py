@@ -138,3 +138,54 @@ def test_graph_type_from_coo_uses_the_device(gpu_ctx, oracle):
     """B200Matrix.from_coo (the MagnusMatrix::from_coo surface): duplicate-edge sum = 2 + 3 = 5 (linalg/src/csr.rs:839-849)."""
     m = B200Matrix.from_coo(3, [(0, 1, 2), (0, 1, 3), (2, 0, 7)], 64, gpu_ctx)
     assert m.get(0, 1) == 5 and m.get(2, 0) == 7 and m.nnz() == 2
+
+
+# ------------------------------------------------------------------ locality pre-pass: rcm / permute / unpermute / bandwidth_stats
+@pytest.mark.parametrize("bits", [32, 64])
+def test_permute_and_bandwidth_match_the_oracle(gpu_ctx, oracle, bits):
+    """b200_csr_permute / _bandwidth_stats / _rcm_order against the restatement of src/graph_csr.rs:663-818 on the thinned
+    10^3 torus (isolated nodes, many components), a random permutation, and the RCM order itself."""
+    a_h = hostgen.reference_bench_instance(10, 3.0, bits)
+    a_o = to_o(oracle, a_h)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    assert a.bandwidth_stats() == oracle.bandwidth_stats(a_o)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(a_h.rows).astype(np.uint32)
+    got = gpu_ctx.permute(a.device, perm)
+    want = oracle.permute(a_o, perm)
+    rp, ci, vv = got.download()
+    assert np.array_equal(rp, want.row_ptr) and np.array_equal(ci, want.col_idx) and np.array_equal(vv, want.values)
+    order = gpu_ctx.rcm_order(a.device)
+    assert np.array_equal(order, oracle.rcm_order(a_o))
+    a.rcm()
+    assert a.perm is not None and np.array_equal(a.perm, order)
+    assert_same(a.to_host(), oracle.permute(a_o, order), "rcm")
+    assert a.bandwidth_stats() == oracle.bandwidth_stats(oracle.permute(a_o, order))
+    a.unpermute()
+    assert a.perm is None
+    assert_same(a.to_host(), a_h, "unpermute")
+
+
+def test_rcm_roundtrips_of_the_reference(gpu_ctx, oracle):
+    """test_rcm_unpermute_roundtrip / _lattice / _directed (src/graph_csr.rs:1107-1146) on the device handles; the product
+    of a permuted matrix has the nnz of the original's (analyze_graph_structure, :1549)."""
+    cases = [B200Matrix.from_edges_undirected(6, [(0, 3), (1, 4), (2, 5), (0, 1), (3, 4)], 64, gpu_ctx),
+             B200Matrix.lattice([4, 4], False, 64, gpu_ctx),
+             B200Matrix.from_edges(5, [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0), (0, 3)], 64, gpu_ctx)]
+    for m in cases:
+        orig = m.to_host()
+        nnz2 = m.matmul(m).nnz()
+        m.rcm()
+        assert m.perm is not None
+        assert m.matmul(m).nnz() == nnz2
+        m.unpermute()
+        assert m.perm is None
+        assert_same(m.to_host(), orig, "rcm + unpermute")
+
+
+def test_permute_rejects_a_non_permutation(gpu_ctx):
+    from sparse_linear_algebra_tests_b200 import B200Error
+    m = B200Matrix.identity(4, 64, gpu_ctx)
+    for bad in ([0, 1, 1, 2], [0, 1, 2, 7]):
+        with pytest.raises(B200Error):
+            gpu_ctx.permute(m.device, np.array(bad, np.uint32))

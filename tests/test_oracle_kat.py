@@ -162,3 +162,46 @@ def test_matmul_against_scipy_random(oracle):
             ref = (a.to_scipy() @ b.to_scipy()).tocsr(); ref.sort_indices()
             assert np.array_equal(ref.indptr.astype(np.uint64), c.row_ptr) and np.array_equal(ref.indices.astype(np.uint32), c.col_idx)
             assert np.array_equal(ref.data.astype(np.uint64), c.values.astype(np.uint64))
+
+
+# ------------------------------------------------------------------ locality pre-pass (src/graph_csr.rs:663-818)
+def _same(a, b):
+    return np.array_equal(a.row_ptr, b.row_ptr) and np.array_equal(a.col_idx, b.col_idx) and np.array_equal(a.values, b.values)
+
+
+def _inverse(perm):
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size, dtype=perm.dtype)
+    return inv
+
+
+@pytest.mark.parametrize("which", ["small", "lattice", "directed"])
+def test_rcm_unpermute_roundtrip(oracle, which):
+    O = oracle
+    """test_rcm_unpermute_roundtrip / _lattice / _directed (src/graph_csr.rs:1107-1146): rcm then unpermute restores the
+    three arrays; the order is a permutation."""
+    if which == "small":
+        a = O.from_edges_undirected(6, [(0, 3), (1, 4), (2, 5), (0, 1), (3, 4)])
+    elif which == "lattice":
+        a = O.lattice([4, 4], False)
+    else:
+        a = O.from_edges(5, [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0), (0, 3)])
+    perm = O.rcm_order(a)
+    assert sorted(perm.tolist()) == list(range(a.rows))
+    p = O.permute(a, perm)
+    assert p.nnz() == a.nnz()
+    assert _same(O.permute(p, _inverse(perm)), a)
+
+
+def test_bandwidth_stats_and_rcm_on_a_shuffled_band(oracle):
+    O = oracle
+    """A path graph relabelled at random has bandwidth ~n; Cuthill-McKee from a pseudo-peripheral end brings it back to 1."""
+    n = 200
+    rng = np.random.default_rng(5)
+    lab = rng.permutation(n)
+    a = O.from_edges_undirected(n, [(int(lab[i]), int(lab[i + 1])) for i in range(n - 1)])
+    mx, avg = O.bandwidth_stats(a)
+    assert mx > 50 and avg > 10
+    p = O.permute(a, O.rcm_order(a))
+    assert O.bandwidth_stats(p) == (1, 1.0)
+    assert O.bandwidth_stats(O.empty(4)) == (0, 0.0)
