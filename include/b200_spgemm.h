@@ -42,6 +42,7 @@ extern "C" {
 
 typedef struct b200_ctx b200_ctx;
 typedef struct b200_csr b200_csr;
+typedef struct b200_comm b200_comm;   /* one rank (one GPU) of a multi-GPU job: an NCCL communicator bound to a b200_ctx */
 
 /* Per-multiply measurements; device times are CUDA-event times on the ctx stream. */
 typedef struct b200_stats {
@@ -180,6 +181,29 @@ int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *
 /* 1 if A and B have identical row_ptr and col_idx (the stabilisation test of
  * power_until_stable, src/graph_csr.rs:567-570). */
 int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same);
+
+/* ---- multi-GPU: the path shards by rows of the left operand -- row i of C needs row i of A and all of B
+ * (src/graph_csr.rs:433-446); the reference itself is single-process (rayon), so these have no counterpart there. ----------------
+ * One b200_comm per (process, GPU).  NCCL is loaded at run time; without it these return B200_ERR_NCCL.
+ *   one process per GPU:  rank 0 calls b200_comm_unique_id, the launcher's own channel (torch.distributed store, MPI, a file)
+ *                         carries the 128 bytes to every rank, every rank calls b200_comm_init_rank with its own context;
+ *   one process, N GPUs:  b200_comm_init_all over N contexts (out[i] belongs to ctxs[i]); each communicator is then driven by
+ *                         its own host thread (tools/b200_bench.cpp).
+ * Typical job: rank `root` builds A; b200_comm_broadcast_csr replicates it; every rank calls b200_shard_rows_by_products
+ * (same cuts everywhere), keeps b200_csr_row_block(cuts[rank], cuts[rank+1]) and multiplies its block by the replicated
+ * operand -- repeated exponentiation A^k = A^(k-1) x A needs nothing else.  b200_comm_allgather_csr assembles the row blocks
+ * (rank order = row order) into the whole matrix on every rank: the optional gather of C, and the per-step exchange of a
+ * squaring chain (power_until_stable, src/graph_csr.rs:561-575, where the right operand grows too). */
+int b200_comm_unique_id(uint8_t id128[128]);
+int b200_comm_init_rank(b200_ctx *ctx, int nranks, int rank, const uint8_t id128[128], b200_comm **out);
+int b200_comm_init_all(b200_ctx **ctxs, int ngpus, b200_comm **out);
+int b200_comm_destroy(b200_comm *c);
+int b200_comm_rank(const b200_comm *c, int *rank, int *size);
+int b200_comm_broadcast_csr(b200_comm *c, const b200_csr *src /* NULL off the root */, int root, b200_csr **out);
+int b200_comm_allgather_csr(b200_comm *c, const b200_csr *block, b200_csr **out);
+/* In-place reduction of n <= 32 host scalars over the ranks: op 0 sum of u64, 1 max of u64, 2 sum of f64, 3 max of f64
+ * (max-over-ranks step time, total products). */
+int b200_comm_allreduce(b200_comm *c, void *host_scalars, int n, int op);
 
 /* ---- fixture generators on the device: large inputs without a host build ---------------------------
  * N-d Moore lattice / torus, CsrMatrix::lattice (src/graph_csr.rs:177-222; MagnusMatrix::lattice, src/graph_magnus.rs:146):

@@ -6,9 +6,9 @@ The CUDA kernels and the C ABI are in `csrc/` (libb200spgemm.so); importing this
 does not need a GPU, using it does.
 """
 from . import hostgen
-from ._native import B200Error, Context, DeviceCsr, ShapeMismatch, Stats, EXPORTS, LIB_PATH
+from ._native import B200Error, Comm, Context, DeviceCsr, ShapeMismatch, Stats, EXPORTS, LIB_PATH
 from .graph_b200 import B200Matrix, default_context, set_default_context
 from .einsum import InvalidSpec, einsum_sparse_driven, einsum_sparse_hash
 
-__all__ = ["B200Matrix", "Context", "DeviceCsr", "Stats", "B200Error", "ShapeMismatch", "hostgen",
+__all__ = ["B200Matrix", "Context", "Comm", "DeviceCsr", "Stats", "B200Error", "ShapeMismatch", "hostgen",
            "default_context", "set_default_context", "EXPORTS", "LIB_PATH", "einsum_sparse_driven", "einsum_sparse_hash", "InvalidSpec"]

@@ -59,6 +59,8 @@ EXPORTS = [
     "b200_shard_rows_by_products", "b200_csr_row_block", "b200_csr_add", "b200_csr_same_pattern",
     "b200_lattice", "b200_thin", "b200_stdrng_u64", "b200_csr_from_coo", "b200_csr_from_coo_device", "b200_rmat",
     "b200_csr_bandwidth_stats", "b200_csr_permute", "b200_csr_rcm_order",
+    "b200_comm_unique_id", "b200_comm_init_rank", "b200_comm_init_all", "b200_comm_destroy", "b200_comm_rank",
+    "b200_comm_broadcast_csr", "b200_comm_allgather_csr", "b200_comm_allreduce",
 ]
 
 _lib = None
@@ -111,6 +113,14 @@ def load():
         "b200_csr_bandwidth_stats": [vp, vp, C.POINTER(u64), C.POINTER(C.c_double)],
         "b200_csr_permute": [vp, vp, vp, C.POINTER(vp)],
         "b200_csr_rcm_order": [vp, vp, vp],
+        "b200_comm_unique_id": [vp],
+        "b200_comm_init_rank": [vp, i32, i32, vp, C.POINTER(vp)],
+        "b200_comm_init_all": [vp, i32, vp],
+        "b200_comm_destroy": [vp],
+        "b200_comm_rank": [vp, C.POINTER(i32), C.POINTER(i32)],
+        "b200_comm_broadcast_csr": [vp, vp, i32, C.POINTER(vp)],
+        "b200_comm_allgather_csr": [vp, vp, C.POINTER(vp)],
+        "b200_comm_allreduce": [vp, vp, i32, i32],
     }
     for name, args in sigs.items():
         f = getattr(L, name)
@@ -310,6 +320,53 @@ class Context:
         h = C.c_void_p()
         check(load().b200_csr_row_block(self._h, a._h, r0, r1, C.byref(h)))
         return DeviceCsr(self, h)
+
+
+class Comm:
+    """One rank of a multi-GPU job (b200_comm): an NCCL communicator bound to an engine context."""
+
+    def __init__(self, ctx: Context, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        check(load().b200_comm_init_rank(ctx._h, int(nranks), int(rank), buf, C.byref(h)))
+        self.ctx, self._h, self.rank, self.size = ctx, h, int(rank), int(nranks)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        check(load().b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def broadcast(self, src: "DeviceCsr | None", root: int = 0) -> "DeviceCsr":
+        """Replicate `src` (given on `root`) on every rank (four ncclBroadcast)."""
+        h = C.c_void_p()
+        check(load().b200_comm_broadcast_csr(self._h, src._h if src is not None else None, int(root), C.byref(h)))
+        return DeviceCsr(self.ctx, h)
+
+    def allgather(self, block: "DeviceCsr") -> "DeviceCsr":
+        """Row blocks in rank order -> the whole matrix on every rank (device buffers, grouped ncclBroadcast)."""
+        h = C.c_void_p()
+        check(load().b200_comm_allgather_csr(self._h, block._h, C.byref(h)))
+        return DeviceCsr(self.ctx, h)
+
+    def allreduce(self, values, op: str):
+        """op in {"sum_u64", "max_u64", "sum_f64", "max_f64"} over at most 32 scalars; returns the reduced numpy array."""
+        code = {"sum_u64": 0, "max_u64": 1, "sum_f64": 2, "max_f64": 3}[op]
+        a = np.ascontiguousarray(values, dtype=np.uint64 if code < 2 else np.float64).copy()
+        check(load().b200_comm_allreduce(self._h, a.ctypes.data, int(a.size), code))
+        return a
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().b200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DeviceCsr:

@@ -1293,24 +1293,62 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     return B200_OK;
 }
 
+// sum of (P_i + 1) over tiles of 4096 rows (the +1 spreads empty rows over the parts too)
+#define SHARD_TILE 4096
+__global__ void __launch_bounds__(256) k_shard_tile_sums(u64 rows, const u64 *__restrict__ prod, u64 *__restrict__ sums) {
+    __shared__ u64 s_w[8];
+    const u64 base = (u64)blockIdx.x * SHARD_TILE;
+    u64 v = 0;
+    for (u32 j = threadIdx.x; j < SHARD_TILE; j += 256) if (base + j < rows) v += prod[base + j] + 1;
+    v = warp_sum_u64(v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { u64 t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; sums[blockIdx.x] = t; }
+}
+// Cut k = first index i of the prefix pre[0..rows] (pre[0] = 0, pre[i] = sum_{j<i} (P_j + 1)) with pre[i] >= k * total / nparts.
+// The per-row counts stay on the device: the host reads one sum per 4096 rows, then the one tile each cut falls into.
 extern "C" int b200_shard_rows_by_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int nparts, uint64_t *cuts) {
-    if (!cuts || nparts < 1) return set_err(B200_ERR_BADARG, "bad nparts/cuts");
-    std::vector<uint64_t> p(A ? A->rows : 0);
-    TRY(b200_row_products(ctx, A, B, p.data()));
-    // cut k is the first row whose product prefix reaches k/nparts of the total (+1 per row so empty rows spread too)
-    std::vector<unsigned __int128> pre(p.size() + 1, 0);
-    for (size_t i = 0; i < p.size(); i++) pre[i + 1] = pre[i] + p[i] + 1;
-    const unsigned __int128 total = pre[p.size()];
-    cuts[0] = 0; cuts[nparts] = A->rows;
+    if (!ctx || !A || !B || !cuts || nparts < 1) return set_err(B200_ERR_BADARG, "bad nparts/cuts");
+    if (A->cols != B->rows) return set_err(B200_ERR_SHAPE, "shape mismatch");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    RESOLVE(ctx, A); RESOLVE(ctx, B);
+    const u64 rows = A->rows;
+    cuts[0] = 0; cuts[nparts] = rows;
+    if (rows == 0) { for (int k = 1; k < nparts; k++) cuts[k] = 0; return B200_OK; }
+    TRY(ensure_row_scratch(ctx, rows));
+    TRY(ensure_desc(ctx, B));
+    TRY(launch_row_products(ctx, A, B));
+    const u64 tiles = (rows + SHARD_TILE - 1) / SHARD_TILE;
+    u64 *d_sums = nullptr;
+    TRY(dmalloc(ctx, (void **)&d_sums, tiles * 8));
+    k_shard_tile_sums<<<(unsigned)tiles, 256, 0, ctx->stream>>>(rows, ctx->d_prod, d_sums);
+    ctx->launches++;
+    std::vector<u64> sums(tiles), tile(SHARD_TILE);
+    cudaError_t e = cudaMemcpyAsync(sums.data(), d_sums, tiles * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dfree(ctx, d_sums);
+    if (e != cudaSuccess) return set_err(B200_ERR_CUDA, "shard_rows_by_products: %s", cudaGetErrorString(e));
+    std::vector<unsigned __int128> pre(tiles + 1, 0);
+    for (u64 t = 0; t < tiles; t++) pre[t + 1] = pre[t] + sums[t];
+    const unsigned __int128 total = pre[tiles];
     for (int k = 1; k < nparts; k++) {
-        unsigned __int128 target = total * (unsigned)k / (unsigned)nparts;
-        size_t lo = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
-        if (lo > p.size()) lo = p.size();
-        cuts[k] = std::max<uint64_t>(lo, cuts[k - 1]);
+        const unsigned __int128 target = total * (unsigned)k / (unsigned)nparts;
+        u64 lo = 0;
+        if (target > 0) {
+            // tile t with pre[t] < target <= pre[t + 1]: the cut is inside it (or at its end)
+            const u64 t = (u64)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin()) - 1;
+            const u64 base = t * SHARD_TILE, cnt = std::min<u64>(SHARD_TILE, rows - base);
+            CUDA_TRY(cudaMemcpyAsync(tile.data(), ctx->d_prod + base, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            unsigned __int128 run = pre[t];
+            u64 i = 0;
+            while (i < cnt && run < target) { run += tile[i] + 1; i++; }
+            lo = base + i;
+        }
+        cuts[k] = std::max<uint64_t>(std::min<u64>(lo, rows), cuts[k - 1]);
     }
     return B200_OK;
 }
-
 extern "C" int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t r0, uint64_t r1, b200_csr **out) {
     if (!ctx || !A || !out) return set_err(B200_ERR_BADARG, "NULL argument");
     if (r0 > r1 || r1 > A->rows) return set_err(B200_ERR_BADARG, "row range [%llu,%llu) outside 0..%llu", (ull)r0, (ull)r1, (ull)A->rows);

@@ -155,3 +155,39 @@ def allgather_csr(block: hostgen.HostCsr, group=None, device="cpu") -> hostgen.H
     col = np.concatenate([parts[1][r][:nnz_l[r]].view(np.uint32) for r in range(world)])
     val = np.concatenate([parts[2][r][:nnz_l[r]].view(np.uint32 if bits == 32 else np.uint64) for r in range(world)])
     return hostgen.HostCsr(sum(rows_l), block.cols, np.concatenate(rp).astype(np.uint64), col, val)
+
+
+# ------------------------------------------------------------------------------------------ device collectives (NCCL below the C ABI)
+def make_comm(ctx, rank: int, world: int, group=None):
+    """A `Comm` (b200_comm) for this rank: rank 0 creates the NCCL id, torch.distributed's object broadcast (any backend)
+    carries its 128 bytes -- the only thing torch does for the data path."""
+    import torch.distributed as dist
+    from ._native import Comm
+    box = [Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return Comm(ctx, world, rank, box[0])
+
+
+class ShardedSquaring:
+    """power_until_stable (src/graph_csr.rs:561-575) over N GPUs: cur <- cur x cur until the pattern stops changing.
+
+    Both operands grow, so unlike the power chain every step ends with an exchange: rank r multiplies its
+    product-balanced row block of `cur` by the whole `cur` and `Comm.allgather` (device buffers, NCCL) assembles the next
+    `cur` on every rank.  The stabilisation test (equal nnz, row_ptr and col_idx, :567-570) runs on every rank's own copy."""
+
+    def __init__(self, ctx, comm, a_dev):
+        self.ctx, self.comm, self.cur = ctx, comm, a_dev
+
+    def step(self):
+        cuts = self.ctx.shard_rows_by_products(self.cur, self.cur, self.comm.size)
+        blk = self.ctx.row_block(self.cur, int(cuts[self.comm.rank]), int(cuts[self.comm.rank + 1]))
+        nxt = self.comm.allgather(self.ctx.spgemm(blk, self.cur))
+        stable = nxt.nnz == self.cur.nnz and self.ctx.same_pattern(nxt, self.cur)
+        self.cur = nxt
+        return stable
+
+    def run(self, max_steps: int = 64):
+        for k in range(1, max_steps + 1):
+            if self.step():
+                return self.cur, k
+        raise RuntimeError("power_until_stable did not stabilise")
