@@ -54,6 +54,12 @@ def parse_args():
     ap.add_argument("--strong", action="store_true", help="strong scaling: the torus stays side^3 whatever --gpus is (e.g. --side 200 --max-power 5)")
     ap.add_argument("--max-power", type=int, default=7)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (its pinned staging is 12 B per result entry)")
+    # BASELINE configs[3]: A^2 of an R-MAT graph built on the device (b200_rmat), rows sharded by product count; always strong
+    # scaling (the graph does not grow with --gpus), device-timed only
+    ap.add_argument("--workload", default="torus", choices=["torus", "rmat"])
+    ap.add_argument("--scale", type=int, default=20)
+    ap.add_argument("--ef", type=int, default=16)
+    ap.add_argument("--abc", type=float, nargs=3, default=[0.45, 0.15, 0.15])
     return ap.parse_args()
 
 
@@ -62,6 +68,12 @@ def dist_env():
 
 
 def workload_config(args, world):
+    if args.workload == "rmat":
+        return {"workload": f"A^2 of an R-MAT graph, scale {args.scale} ({1 << args.scale} nodes), {args.ef} edges/node, quadrants "
+                            f"{args.abc[0]:g}/{args.abc[1]:g}/{args.abc[2]:g}, splitmix64 seed 42 (BASELINE configs[3]; SURVEY.md App. C), built on the device",
+                "val_bits": args.bits, "left": "row block of A per GPU", "right": "A (replicated, one NCCL broadcast below the C ABI)",
+                "sharding": "contiguous row blocks balanced by intermediate-product count" if world > 1 else "single GPU",
+                "l2": "flushed between timed steps (256 MiB write)"}
     dims = [args.side * (1 if args.strong else world), args.side, args.side]
     return {"workload": f"repeated exponentiation A^2..A^{MAX_POWER} on the {dims[0]}x{dims[1]}x{dims[2]} Moore torus, "
                         f"~{args.epn:g} e/n, StdRng([42;32]) thinning (graph_magnus.rs:699-788)",
@@ -199,6 +211,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "rmat":
+        return run_rmat(args, torch, dist, dev, rank, local_rank, world)
     stream = torch.cuda.Stream(dev)                                 # the engine runs on this (non-default) torch stream,
     torch.cuda.set_stream(stream)                                   # so torch.cuda.Event on it brackets every engine kernel
     ctx = Context(local_rank, stream.cuda_stream)
@@ -329,8 +343,10 @@ def run_b200(args):
         tj = json.load(open(tpath))
         if tj.get("source_sha") == source_sha():
             traffic = float(tj["traffic"])
-    kernels = "k_fz_prepass + k_fz_numeric (pre-pass; fused numeric + placement, C written once)" if top.get("pipeline") == 1 else \
-              "binned pipeline (pre-pass, per-bin numeric, row_ptr scan, host report, compaction)"
+    kernels = {1: "k_fz_prepass + k_fz_numeric (pre-pass; fused numeric + placement, C written once)",
+               3: "pre-pass, row-per-warp count kernels, row_ptr scan, row-per-warp numeric kernels (C written once)",
+               4: "k_rw_fused, ONE cooperative launch: count phase, placement, numeric phase (C written once, no host wait)"}.get(
+                   top.get("pipeline"), "binned pipeline (pre-pass, per-bin numeric, row_ptr scan, compaction)")
     roofline = {"bound": "hbm", "kernel": f"all kernels of the largest multiply A^{MAX_POWER} = A^{MAX_POWER - 1} x A: " + kernels,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes": top["bytes_algorithmic"], "ms": top["ms_total"], "traffic": traffic,
@@ -421,6 +437,93 @@ def run_b200(args):
                                "sample": f"full A^2..A^{MAX_POWER} chain, reference protocol (1 warm-up + 3 timed multiplies per power)",
                                "ms_per_power": [s * 1e3 for s in secs], "ms_per_step": sum(secs) * 1e3}
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rmat(args, torch, dist, dev, rank, local_rank, world):
+    """BASELINE configs[3]: rank 0 builds the graph on its GPU (b200_rmat: generator + radix-sort assembly), b200_comm_broadcast_csr
+    replicates it, every rank multiplies its product-balanced row block by the replicated operand.  Strong scaling."""
+    from sparse_linear_algebra_tests_b200 import Context
+    from sparse_linear_algebra_tests_b200.distributed import make_comm
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = Context(local_rank, stream.cuda_stream)
+    t0 = time.perf_counter()
+    A = ctx.rmat(args.scale, args.ef, args.abc[0], args.abc[1], args.abc[2], 42, args.bits) if rank == 0 else None
+    build_s = time.perf_counter() - t0
+    comm = None
+    if world > 1:
+        comm = make_comm(ctx, rank, world)
+        A = comm.broadcast(A, 0)
+        cuts = ctx.shard_rows_by_products(A, A, world)
+        blk = ctx.row_block(A, int(cuts[rank]), int(cuts[rank + 1]))
+    else:
+        blk = A
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        c = ctx.spgemm(blk, A)
+        ctx.synchronize()
+        del c
+    c, st = ctx.spgemm(blk, A, True)
+    st = st.as_dict()
+    del c
+    ctx.set_timing(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = ctx.kernel_launches()
+    step_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        c = ctx.spgemm(blk, A)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        del c
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = float(np.mean(step_ms))
+    mine = torch.tensor([my_ms, float(np.min(step_ms)), float(np.max(step_ms)), float(st["products"]), float(st["nnz_c"]), float(launches)], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    if rank == 0:
+        per_rank = [{"rank": i, "ms_mean": float(t[0]), "ms_min": float(t[1]), "ms_max": float(t[2]), "products": int(t[3]), "nnz": int(t[4])} for i, t in enumerate(allr)]
+        ms_per_step = max(p["ms_mean"] for p in per_rank)
+        total_products = sum(p["products"] for p in per_rank)
+        total_nnz = sum(p["nnz"] for p in per_rank)
+        vb = args.bits // 8
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = (float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if os.path.exists(peaks_path) else (6650.0, "fallback (B200_PROFILING.md)")
+        alg = algorithmic_bytes(A.nnz, A.nnz, total_nnz, A.rows, A.rows, vb)                 # whole job: A read once, A (right) once, C written once
+        achieved = alg / (ms_per_step * 1e-3) / 1e9
+        cfg = workload_config(args, world)
+        cfg.update({"nodes": A.rows, "nnz_A": A.nnz, "products_per_step": int(total_products), "nnz_C": int(total_nnz), "max_row_products": st["max_row_products"],
+                    "operand_build_s_rank0": build_s, "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
+        out = {"metric": METRIC, "value": total_products / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": f"u{args.bits}", "data": "synthetic",
+               "config": cfg, "per_rank": per_rank, "gpu_launches": int(sum(float(t[5]) for t in allr)), "wall_s_timed_region": wall, "clocks": clocks, "e2e": None,
+               "roofline": {"bound": "hbm", "kernel": "all kernels of the multiply, all GPUs (aggregate algorithmic bytes over the max-over-ranks time)", "achieved": achieved,
+                            "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes": alg,
+                            "ms": ms_per_step, "traffic": None}}
+        print(json.dumps(out), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -738,7 +738,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     };
     // hash + in-row sort kernels (any column space): warp per row for the two smallest bins, CTA per row above
     auto launch_warp_hash = [&](int first_bin, int nb, u64 n, cudaStream_t bs) -> int {
-        const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4);
+        const size_t smem = 8 * (accb * B200_WARP_SLOTS + (size_t)B200_WARP_SLOTS * 4 + B200_WARP_ORDER_BYTES);
         const int g = (int)std::min<u64>((n + 7) / 8, (u64)ctx->num_sms * 16);
         const int wlg = std::min(lg, 5);
         if (mode == 0) k_num_warp<VT, 0><<<g, 256, smem, bs>>>(na, ctx->d_bin_rows, ctrl, first_bin, nb, wlg, o);
@@ -750,7 +750,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     auto launch_cta_hash = [&](int bin, int hb, u64 n, cudaStream_t bs) -> int {
         const u32 slots = b200_hash_slots(hb);
         const int threads = bin_threads(ctx, hb, lg);
-        const size_t smem = (size_t)slots * (4 + accb);
+        const size_t smem = (size_t)slots * (4 + accb) + ((size_t)b200_order_buckets(slots) + 1) * 4;   // table + the ordering step's bucket counters
         if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
         const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
         if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctrl, bin, slots, lg, o);

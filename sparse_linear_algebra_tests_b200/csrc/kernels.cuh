@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(256) k_num_tiny(NumArgs<VT> a, const u32 *__re
 // =======================================================================================
 // 4a. warp per row (8 rows in flight per CTA), 256-slot key table per warp: rows with P <= 128
 #define B200_WARP_SLOTS 256
+#define B200_WARP_ORDER_BYTES 528   // (B200_WARP_SLOTS / 2 + 1) bucket counters of the ordering step, rounded to 16 bytes
 __global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int first_bin,
                                                   int nbins, int lg, u32 *__restrict__ nnz_row, u32 bin_stride) {
     __shared__ u32 s_keys[8][B200_WARP_SLOTS];
@@ -521,6 +522,10 @@ __device__ __forceinline__ void cta_row_range(u32 count, u32 &begin, u32 &end) {
 // inside the word, so a compare-exchange is two 64-bit loads and at most two stores (the accumulators stay where the hash
 // put them).  Pair t of a stage always belongs to 64-element block t / 32 and the loop below gives warp w the pairs
 // 32w .. 32w+31 (+ multiples of blockDim), so all stages with k <= 64 are warp-local: __syncwarp instead of a CTA barrier.
+// ordering step of the hash kernels: buckets per row (a power of two, about the row's capacity) and the bucket population
+// beyond which the row falls back to the bitonic network
+#define B200_ORDER_MAXB 96u
+__host__ __device__ __forceinline__ u32 b200_order_buckets(u32 slots) { const u32 nb = slots / 2; return nb < 2048u ? nb : 2048u; }
 __device__ __forceinline__ void smem_bitonic_words(u64 *w, u32 n) {
     const u32 tid = threadIdx.x, nt = blockDim.x;
     for (u32 k = 2; k <= n; k <<= 1) {
@@ -545,10 +550,12 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
                                                   int nbins, int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t per_warp = Acc<MODE>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4;
+    const size_t per_warp = Acc<MODE>::bytes(B200_WARP_SLOTS) + (size_t)B200_WARP_SLOTS * 4 + B200_WARP_ORDER_BYTES;
     unsigned char *base = smem_raw + wid * per_warp;
     Acc<MODE> acc; acc.bind(base, B200_WARP_SLOTS);
     u32 *keys = reinterpret_cast<u32 *>(base + Acc<MODE>::bytes(B200_WARP_SLOTS));
+    u32 *bcnt = keys + B200_WARP_SLOTS;                                    // bucket counters / offsets of the ordering step
+    constexpr u32 NB = B200_WARP_SLOTS / 2;
     u32 count = 0;
     for (int b = 0; b < nbins; b++) count += o.bin_cnt[first_bin + b];
     const u32 G = 1u << lg, sub = lane & (G - 1), grp = lane >> lg, ngrp = 32u >> lg;
@@ -570,40 +577,84 @@ __global__ void __launch_bounds__(256) k_num_warp(NumArgs<VT> a, const u32 *__re
                               acc.add(h, av, a.valB[jb]);
                           });
         __syncwarp();
-        // order the row: packed (column << 32 | slot) words gathered through registers at the front of the key array
-        // (<= 128 of them fit its 1 KB exactly), sorted by the warp; the accumulators stay in their hash slots
-        u32 rk[PER]; u32 mine = 0;
+        // order the row (see k_num_cta): bucket ranking over NB = 128 buckets of the row's column range, by the warp alone;
+        // the bitonic network only for rows whose columns crowd into one bucket
+        u32 rk[PER]; u32 mine = 0, cmin = 0xFFFFFFFFu, cmax = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) { rk[i] = keys[i * 32 + lane]; mine += rk[i] != B200_EMPTY_KEY; }
+        for (int i = 0; i < PER; i++) {
+            rk[i] = keys[i * 32 + lane];
+            if (rk[i] != B200_EMPTY_KEY) { mine++; cmin = min(cmin, rk[i]); cmax = max(cmax, rk[i]); }
+        }
+        for (u32 t = lane; t <= NB; t += 32) bcnt[t] = 0;
         u32 incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
         const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u32 pos = incl - mine;
+        cmin = __reduce_min_sync(0xFFFFFFFFu, cmin); cmax = __reduce_max_sync(0xFFFFFFFFu, cmax);
         __syncwarp();
         u64 *words = reinterpret_cast<u64 *>(keys);
-#pragma unroll
-        for (int i = 0; i < PER; i++) if (rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * 32 + lane);
-        u32 n2 = 1; while (n2 < total) n2 <<= 1;
-        for (u32 t = total + lane; t < n2; t += 32) words[t] = ~0ull;
-        __syncwarp();
-        for (u32 k = 2; k <= n2; k <<= 1) {
-            for (u32 j = k >> 1; j > 0; j >>= 1) {
-                for (u32 t = lane; t < (n2 >> 1); t += 32) {
-                    const u32 i = 2 * t - (t & (j - 1));
-                    const u32 l = i + j;
-                    const u64 x = words[i], y = words[l];
-                    if ((x > y) == ((i & k) == 0)) { words[i] = y; words[l] = x; }
-                }
-                __syncwarp();
-            }
-        }
         const u64 obase = o.base[row];
-        for (u32 t = lane; t < total; t += 32) {
-            const u64 wd = words[t];
-            const VT v = emit_val<VT>(acc.get((u32)wd));
-            o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
-            vmax = vmax > (u64)v ? vmax : (u64)v;
+        int bshift = 0;
+        if (total) { const u32 span1 = cmax - cmin; const int bits = span1 ? 32 - __clz(span1) : 0; bshift = bits > 7 ? bits - 7 : 0; }
+        static_assert(NB == 128, "bshift assumes 128 buckets");
+        u32 bp[PER];
+        bool crowded = false;
+#pragma unroll
+        for (int i = 0; i < PER; i++)
+            if (rk[i] != B200_EMPTY_KEY) { bp[i] = atomicAdd(&bcnt[(rk[i] - cmin) >> bshift], 1u); crowded |= bp[i] >= 24u; }
+        __syncwarp();
+        if (__any_sync(0xFFFFFFFFu, crowded)) {
+#pragma unroll
+            for (int i = 0; i < PER; i++) if (rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * 32 + lane);
+            u32 n2 = 1; while (n2 < total) n2 <<= 1;
+            for (u32 t = total + lane; t < n2; t += 32) words[t] = ~0ull;
+            __syncwarp();
+            for (u32 k = 2; k <= n2; k <<= 1) {
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 t = lane; t < (n2 >> 1); t += 32) {
+                        const u32 i = 2 * t - (t & (j - 1));
+                        const u32 l = i + j;
+                        const u64 x = words[i], y = words[l];
+                        if ((x > y) == ((i & k) == 0)) { words[i] = y; words[l] = x; }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (u32 t = lane; t < total; t += 32) {
+                const u64 wd = words[t];
+                const VT v = emit_val<VT>(acc.get((u32)wd));
+                o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
+                vmax = vmax > (u64)v ? vmax : (u64)v;
+            }
+        } else {
+            {   // counters -> offsets: lane l owns counters 4l .. 4l + 3
+                u32 c[4], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { c[i] = bcnt[lane * 4 + i]; sum += c[i]; }
+                u32 inc2 = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc2, d); if (lane >= d) inc2 += t; }
+                u32 run = inc2 - sum;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { bcnt[lane * 4 + i] = run; run += c[i]; }
+                if (lane == 0) bcnt[NB] = total;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < PER; i++)
+                if (rk[i] != B200_EMPTY_KEY) words[bcnt[(rk[i] - cmin) >> bshift] + bp[i]] = ((u64)rk[i] << 32) | (u64)(i * 32 + lane);
+            __syncwarp();
+            for (u32 t = lane; t < total; t += 32) {
+                const u64 wd = words[t];
+                const u32 c = (u32)(wd >> 32), b = (c - cmin) >> bshift;
+                const u32 lo = bcnt[b], hi = bcnt[b + 1];
+                u32 rank = 0;
+                for (u32 j = lo; j < hi; j++) rank += (u32)(words[j] >> 32) < c ? 1u : 0u;
+                const VT v = emit_val<VT>(acc.get((u32)wd));
+                o.col[obase + lo + rank] = c; put_val(o, obase + lo + rank, v);
+                vmax = vmax > (u64)v ? vmax : (u64)v;
+            }
         }
         if (lane == 0 && o.nnz_out) o.nnz_out[row] = total;
         __syncwarp();
@@ -619,8 +670,11 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
     __shared__ EnumSmem s_enum;
+    __shared__ u32 s_mm[2];
     Acc<MODE> acc; acc.bind(smem_raw, slots);
     u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
+    u32 *bcnt = keys + slots;                                               // bucket counters / offsets of the ordering step: NB + 1 words
+    const u32 NB = b200_order_buckets(slots);
     const u32 count = o.bin_cnt[bin];
     const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
@@ -641,29 +695,84 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
                               acc.add(h, av, a.valB[jb]);
                           });
         __syncthreads();
-        // order the row: packed (column << 32 | slot) words are gathered at the front of the key array and sorted; the
-        // accumulators stay in their hash slots and are read through the word's low half on the way out
-        u32 rk[16]; u32 mine = 0;
+        // Order the row.  The stored columns go through registers; the accumulators stay in their hash slots and are read
+        // through the low half of a packed (column << 32 | slot) word on the way out.  Bucket ranking instead of a sort: the
+        // row's column range is cut into NB equal buckets (a shift, no division), a counter per bucket gives every column its
+        // bucket and a place in it, a scan of the counters the buckets' offsets, and a column's final place is its bucket's
+        // offset plus the number of smaller columns IN ITS BUCKET (a handful: NB is about the row's length).  ~40
+        // instructions per entry where the bitonic network spends log^2(n) / 2 compare-exchange stages.  Rows whose columns
+        // crowd into one bucket (> B200_ORDER_MAXB there) take the bitonic network instead.
+        u32 rk[16]; u32 mine = 0, cmin = 0xFFFFFFFFu, cmax = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            if (i < (int)per) { rk[i] = keys[i * nt + tid]; mine += rk[i] != B200_EMPTY_KEY; }
+            if (i < (int)per) {
+                rk[i] = keys[i * nt + tid];
+                if (rk[i] != B200_EMPTY_KEY) { mine++; cmin = min(cmin, rk[i]); cmax = max(cmax, rk[i]); }
+            }
         }
+        if (tid == 0) { s_mm[0] = 0xFFFFFFFFu; s_mm[1] = 0; }
+        for (u32 t = tid; t <= NB; t += nt) bcnt[t] = 0;
         u32 total;
         u32 pos = block_excl_scan(mine, s_warp, total);                  // its barriers order the key reads above before the words below
-        u64 *words = reinterpret_cast<u64 *>(keys);                      // n2 <= cap = slots / 2 words fit the key array exactly
+        cmin = __reduce_min_sync(0xFFFFFFFFu, cmin); cmax = __reduce_max_sync(0xFFFFFFFFu, cmax);
+        if ((tid & 31) == 0 && cmin <= cmax) { atomicMin(&s_mm[0], cmin); atomicMax(&s_mm[1], cmax); }
+        __syncthreads();
+        cmin = s_mm[0]; cmax = s_mm[1];
+        u64 *words = reinterpret_cast<u64 *>(keys);                      // total <= cap = slots / 2 words fit the key array exactly
+        const u64 obase = o.base[row];
+        // bucket of a column: (c - cmin) >> bshift, at most NB of them
+        int bshift = 0;
+        if (total) { const u32 span1 = cmax - cmin; const int bits = span1 ? 32 - __clz(span1) : 0; const int lb = 31 - __clz(NB); bshift = bits > lb ? bits - lb : 0; }
+        unsigned short bp[16];
+        bool crowded = false;
 #pragma unroll
         for (int i = 0; i < 16; i++)
-            if (i < (int)per && rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * nt + tid);
-        u32 n2 = 1; while (n2 < total) n2 <<= 1;
-        for (u32 t = total + tid; t < n2; t += nt) words[t] = ~0ull;
-        __syncthreads();
-        smem_bitonic_words(words, n2);
-        const u64 obase = o.base[row];
-        for (u32 t = tid; t < total; t += nt) {
-            const u64 wd = words[t];
-            const VT v = emit_val<VT>(acc.get((u32)wd));
-            o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
-            vmax = vmax > (u64)v ? vmax : (u64)v;
+            if (i < (int)per && rk[i] != B200_EMPTY_KEY) {
+                const u32 p = atomicAdd(&bcnt[(rk[i] - cmin) >> bshift], 1u);
+                bp[i] = (unsigned short)p;
+                crowded |= p >= B200_ORDER_MAXB;
+            }
+        if (__syncthreads_or(crowded)) {
+            // ---- fallback: gather the words at the front of the key array and sort them
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i < (int)per && rk[i] != B200_EMPTY_KEY) words[pos++] = ((u64)rk[i] << 32) | (u64)(i * nt + tid);
+            u32 n2 = 1; while (n2 < total) n2 <<= 1;
+            for (u32 t = total + tid; t < n2; t += nt) words[t] = ~0ull;
+            __syncthreads();
+            smem_bitonic_words(words, n2);
+            for (u32 t = tid; t < total; t += nt) {
+                const u64 wd = words[t];
+                const VT v = emit_val<VT>(acc.get((u32)wd));
+                o.col[obase + t] = (u32)(wd >> 32); put_val(o, obase + t, v);
+                vmax = vmax > (u64)v ? vmax : (u64)v;
+            }
+        } else {
+            // ---- counters -> offsets (thread t scans NB / nt consecutive counters, a block scan joins them); bcnt[NB] = total
+            {
+                const u32 cpt = (NB + nt - 1) / nt, c0 = tid * cpt;
+                u32 sum = 0;
+                for (u32 i = 0; i < cpt && c0 + i < NB; i++) sum += bcnt[c0 + i];
+                u32 tt;
+                u32 run = block_excl_scan(sum, s_warp, tt);
+                for (u32 i = 0; i < cpt && c0 + i < NB; i++) { const u32 c = bcnt[c0 + i]; bcnt[c0 + i] = run; run += c; }
+                if (tid == 0) bcnt[NB] = total;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i < (int)per && rk[i] != B200_EMPTY_KEY) words[bcnt[(rk[i] - cmin) >> bshift] + bp[i]] = ((u64)rk[i] << 32) | (u64)(i * nt + tid);
+            __syncthreads();
+            for (u32 t = tid; t < total; t += nt) {
+                const u64 wd = words[t];
+                const u32 c = (u32)(wd >> 32), b = (c - cmin) >> bshift;
+                const u32 lo = bcnt[b], hi = bcnt[b + 1];
+                u32 rank = 0;
+                for (u32 j = lo; j < hi; j++) rank += (u32)(words[j] >> 32) < c ? 1u : 0u;
+                const VT v = emit_val<VT>(acc.get((u32)wd));
+                o.col[obase + lo + rank] = c; put_val(o, obase + lo + rank, v);
+                vmax = vmax > (u64)v ? vmax : (u64)v;
+            }
         }
         if (tid == 0 && o.nnz_out) o.nnz_out[row] = total;
         __syncthreads();
