@@ -14,18 +14,24 @@ fn main() {
     let csrc = root.join("sparse_linear_algebra_tests_b200").join("csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".to_string());
-    let obj = out.join("api.o");
     let lib = out.join("libb200spgemm.a");
 
-    let status = Command::new(&nvcc)
-        .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-c"])
-        .arg(csrc.join("api.cu"))
-        .arg("-o")
-        .arg(&obj)
-        .status()
-        .expect("nvcc not found: set NVCC or install CUDA 12.8+ (sm_100a)");
-    assert!(status.success(), "nvcc failed on api.cu");
-    let status = Command::new("ar").arg("rcs").arg(&lib).arg(&obj).status().expect("ar not found");
+    // one object per translation unit, as in csrc/Makefile
+    let units = ["api", "fused", "rowwarp", "heavy", "coo", "comm"];
+    let mut objs = Vec::new();
+    for u in units {
+        let obj = out.join(format!("{u}.o"));
+        let status = Command::new(&nvcc)
+            .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-c"])
+            .arg(csrc.join(format!("{u}.cu")))
+            .arg("-o")
+            .arg(&obj)
+            .status()
+            .expect("nvcc not found: set NVCC or install CUDA 12.8+ (sm_100a)");
+        assert!(status.success(), "nvcc failed on {u}.cu");
+        objs.push(obj);
+    }
+    let status = Command::new("ar").arg("rcs").arg(&lib).args(&objs).status().expect("ar not found");
     assert!(status.success(), "ar failed");
 
     let cuda_lib = env::var("CUDA_LIB_DIR").unwrap_or_else(|_| "/usr/local/cuda/lib64".to_string());
@@ -34,7 +40,8 @@ fn main() {
     println!("cargo:rustc-link-lib=static=b200spgemm");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in ["api.cu", "kernels.cuh", "common.cuh"] {
+    println!("cargo:rustc-link-lib=dylib=dl");       // comm.cu binds NCCL at run time (dlopen of libnccl.so.2)
+    for f in ["api.cu", "fused.cu", "rowwarp.cu", "heavy.cu", "coo.cu", "comm.cu", "kernels.cuh", "devutil.cuh", "engine.cuh", "gen.cuh", "common.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include").join("b200_spgemm.h").display());

@@ -30,6 +30,10 @@ pub struct B200Ctx {
 pub struct B200Csr {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct B200CommRaw {
+    _private: [u8; 0],
+}
 
 /// Mirror of `b200_stats` (include/b200_spgemm.h).
 #[repr(C)]
@@ -50,7 +54,8 @@ pub struct B200Stats {
     pub acc_mode: i32,
     pub kernel_launches: i32,
     pub sym_bin_rows: [u32; 16],
-    pub num_bin_rows: [u32; 16],
+    pub pipeline: u32,
+    pub reserved: [u32; 15],
 }
 
 pub const B200_OK: c_int = 0;
@@ -84,6 +89,23 @@ extern "C" {
     fn b200_thin(
         ctx: *mut B200Ctx, a: *const B200Csr, density: f64, seed32: *const u8, skip_draws: u64, out: *mut *mut B200Csr, draws_consumed: *mut u64,
     ) -> c_int;
+    fn b200_csr_from_coo(
+        ctx: *mut B200Ctx, rows: u64, cols: u64, n: u64, row_idx: *const u32, col_idx: *const u32, values: *const c_void, val_bits: c_int,
+        saturating: c_int, out: *mut *mut B200Csr,
+    ) -> c_int;
+    fn b200_rmat(ctx: *mut B200Ctx, scale: c_int, edge_factor: u64, a: f64, b: f64, c: f64, seed: u64, val_bits: c_int, out: *mut *mut B200Csr) -> c_int;
+    fn b200_csr_bandwidth_stats(ctx: *mut B200Ctx, m: *const B200Csr, max_bw: *mut u64, avg_bw: *mut f64) -> c_int;
+    fn b200_csr_permute(ctx: *mut B200Ctx, a: *const B200Csr, perm: *const u32, out: *mut *mut B200Csr) -> c_int;
+    fn b200_csr_rcm_order(ctx: *mut B200Ctx, a: *const B200Csr, perm_out: *mut u32) -> c_int;
+    fn b200_shard_rows_by_products(ctx: *mut B200Ctx, a: *const B200Csr, b: *const B200Csr, nparts: c_int, cuts: *mut u64) -> c_int;
+    // multi-GPU: one communicator per (process, GPU); see include/b200_spgemm.h
+    fn b200_comm_unique_id(id128: *mut u8) -> c_int;
+    fn b200_comm_init_rank(ctx: *mut B200Ctx, nranks: c_int, rank: c_int, id128: *const u8, out: *mut *mut B200CommRaw) -> c_int;
+    fn b200_comm_init_all(ctxs: *mut *mut B200Ctx, ngpus: c_int, out: *mut *mut B200CommRaw) -> c_int;
+    fn b200_comm_destroy(c: *mut B200CommRaw) -> c_int;
+    fn b200_comm_broadcast_csr(c: *mut B200CommRaw, src: *const B200Csr, root: c_int, out: *mut *mut B200Csr) -> c_int;
+    fn b200_comm_allgather_csr(c: *mut B200CommRaw, block: *const B200Csr, out: *mut *mut B200Csr) -> c_int;
+    fn b200_comm_allreduce(c: *mut B200CommRaw, host_scalars: *mut c_void, n: c_int, op: c_int) -> c_int;
 }
 
 struct Ctx(*mut B200Ctx);
@@ -349,6 +371,58 @@ impl B200Matrix {
         (Self::wrap(self.n, h), taken)
     }
 
+    /// `from_coo` on the device (src/graph_magnus.rs:34-76: sort by (row, column), sum duplicates, drop zeros): the triplets
+    /// are uploaded once and ordered by the engine's radix sort.  Plain `+=` duplicate sum, like the reference.
+    pub fn from_coo_device(n: usize, triplets: &[(usize, usize, u64)]) -> Self {
+        let r: Vec<u32> = triplets.iter().map(|t| t.0 as u32).collect();
+        let c: Vec<u32> = triplets.iter().map(|t| t.1 as u32).collect();
+        let v: Vec<u64> = triplets.iter().map(|t| t.2).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe {
+            b200_csr_from_coo(ctx(), n as u64, n as u64, r.len() as u64, r.as_ptr(), c.as_ptr(), v.as_ptr() as *const c_void, 64, 0, &mut h)
+        });
+        Self::wrap(n, h)
+    }
+
+    /// R-MAT graph of 2^scale nodes generated on the device (BASELINE configs[3]; the reference has no such generator).
+    pub fn rmat_device(scale: u32, edge_factor: u64, abc: (f64, f64, f64), seed: u64) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { b200_rmat(ctx(), scale as c_int, edge_factor, abc.0, abc.1, abc.2, seed, 64, &mut h) });
+        Self::wrap(1usize << scale, h)
+    }
+
+    // ------------------------------------------------------------------ locality pre-pass (src/graph_csr.rs:663-818)
+    /// Reorder rows and columns by `perm[new] = old`; returns the reordered matrix (the caller keeps `perm`, as `CsrMatrix.perm`).
+    pub fn permute(&self, perm: &[u32]) -> Self {
+        assert_eq!(perm.len(), self.n);
+        let mut h = std::ptr::null_mut();
+        check(unsafe { b200_csr_permute(ctx(), self.handle, perm.as_ptr(), &mut h) });
+        Self::wrap(self.n, h)
+    }
+
+    /// Reverse Cuthill-McKee: (reordered matrix, perm) with `perm[new] = old`.
+    pub fn rcm(&self) -> (Self, Vec<u32>) {
+        let mut perm = vec![0u32; self.n];
+        check(unsafe { b200_csr_rcm_order(ctx(), self.handle, perm.as_mut_ptr()) });
+        (self.permute(&perm), perm)
+    }
+
+    /// Undo `perm` (a permute by its inverse).
+    pub fn unpermute(&self, perm: &[u32]) -> Self {
+        let mut inv = vec![0u32; perm.len()];
+        for (new_idx, &old) in perm.iter().enumerate() {
+            inv[old as usize] = new_idx as u32;
+        }
+        self.permute(&inv)
+    }
+
+    /// (max |r-c|, mean |r-c|) over the stored entries.
+    pub fn bandwidth_stats(&self) -> (usize, f64) {
+        let (mut mx, mut avg) = (0u64, 0f64);
+        check(unsafe { b200_csr_bandwidth_stats(ctx(), self.handle, &mut mx, &mut avg) });
+        (mx as usize, avg)
+    }
+
     // ------------------------------------------------------------------ queries
     pub fn get(&self, r: usize, c: usize) -> u64 {
         let (rp, ci, vv) = self.host();
@@ -514,5 +588,80 @@ impl NDIndex<u64> for B200Matrix {
     fn sparse_row_entry(&self, row: usize, idx: usize) -> (usize, u64) {
         let (rp, ci, vv) = self.host();
         (ci[rp[row] + idx], vv[rp[row] + idx])
+    }
+}
+
+
+/// One rank (one GPU) of a multi-GPU job: `b200_comm` bound to this process's engine context.
+/// One process per GPU: rank 0 calls `B200Comm::unique_id()`, the launcher carries the 128 bytes to the other ranks
+/// (MPI, a file, a socket), every rank calls `B200Comm::init_rank`.  The path shards by rows of the left operand:
+/// `broadcast` replicates the right operand once, `shard` gives every rank its product-balanced row block, and the
+/// power chain `A^k = A^(k-1) x A` then runs on the blocks without communication; `allgather` assembles the blocks
+/// (the optional gather of C, or the per-step exchange of a squaring chain, src/graph_csr.rs:561-575).
+pub struct B200Comm {
+    raw: *mut B200CommRaw,
+    pub rank: usize,
+    pub size: usize,
+}
+
+impl Drop for B200Comm {
+    fn drop(&mut self) {
+        unsafe { b200_comm_destroy(self.raw) };
+    }
+}
+
+impl B200Comm {
+    pub fn unique_id() -> [u8; 128] {
+        let mut id = [0u8; 128];
+        check(unsafe { b200_comm_unique_id(id.as_mut_ptr()) });
+        id
+    }
+
+    pub fn init_rank(nranks: usize, rank: usize, id: &[u8; 128]) -> Self {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { b200_comm_init_rank(ctx(), nranks as c_int, rank as c_int, id.as_ptr(), &mut raw) });
+        Self { raw, rank, size: nranks }
+    }
+
+    /// Replicate `src` (given on `root`, `None` elsewhere) on every rank.
+    pub fn broadcast(&self, src: Option<&B200Matrix>, root: usize) -> B200Matrix {
+        let mut h = std::ptr::null_mut();
+        let p = src.map_or(std::ptr::null(), |m| m.handle as *const B200Csr);
+        check(unsafe { b200_comm_broadcast_csr(self.raw, p, root as c_int, &mut h) });
+        let (mut rows, mut cols, mut nnz, mut bits) = (0u64, 0u64, 0u64, 0);
+        check(unsafe { b200_csr_info(h, &mut rows, &mut cols, &mut nnz, &mut bits) });
+        B200Matrix::wrap(rows as usize, h)
+    }
+
+    /// This rank's rows of `a` for `a x b`, cut so that every rank holds the same share of the intermediate products.
+    pub fn shard(&self, a: &B200Matrix, b: &B200Matrix) -> B200Matrix {
+        let mut cuts = vec![0u64; self.size + 1];
+        check(unsafe { b200_shard_rows_by_products(ctx(), a.handle, b.handle, self.size as c_int, cuts.as_mut_ptr()) });
+        let mut h = std::ptr::null_mut();
+        check(unsafe { b200_csr_row_block(ctx(), a.handle, cuts[self.rank], cuts[self.rank + 1], &mut h) });
+        B200Matrix::wrap((cuts[self.rank + 1] - cuts[self.rank]) as usize, h)
+    }
+
+    /// Row blocks in rank order -> the whole matrix on every rank.
+    pub fn allgather(&self, block: &B200Matrix) -> B200Matrix {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { b200_comm_allgather_csr(self.raw, block.handle, &mut h) });
+        let (mut rows, mut cols, mut nnz, mut bits) = (0u64, 0u64, 0u64, 0);
+        check(unsafe { b200_csr_info(h, &mut rows, &mut cols, &mut nnz, &mut bits) });
+        B200Matrix::wrap(rows as usize, h)
+    }
+
+    /// Max over the ranks (e.g. of a step time in ms).
+    pub fn max_f64(&self, v: f64) -> f64 {
+        let mut x = v;
+        check(unsafe { b200_comm_allreduce(self.raw, &mut x as *mut f64 as *mut c_void, 1, 3) });
+        x
+    }
+
+    /// Sum over the ranks (e.g. of intermediate products).
+    pub fn sum_u64(&self, v: u64) -> u64 {
+        let mut x = v;
+        check(unsafe { b200_comm_allreduce(self.raw, &mut x as *mut u64 as *mut c_void, 1, 0) });
+        x
     }
 }

@@ -1293,19 +1293,23 @@ extern "C" int b200_row_products(b200_ctx *ctx, const b200_csr *A, const b200_cs
     return B200_OK;
 }
 
-// sum of (P_i + 1) over tiles of 4096 rows (the +1 spreads empty rows over the parts too)
+// Cost of a row in the balance: its intermediate products, +1 so that empty rows spread over the parts too, and rows of the
+// heavy list (more products than the largest shared-memory table takes) count 2.5 x -- measured on R-MAT row blocks, where
+// the global-memory heavy-row kernels run at ~0.4 of the hash kernels' products/s and equal product counts left the rank
+// holding the hub rows 1.4 x behind the others.
+__host__ __device__ __forceinline__ u64 shard_cost(u64 p) { return p + 1 + (p > (u64)b200_hash_cap(B200_NUM_HASH_BINS - 1) ? p + p / 2 : 0); }
 #define SHARD_TILE 4096
 __global__ void __launch_bounds__(256) k_shard_tile_sums(u64 rows, const u64 *__restrict__ prod, u64 *__restrict__ sums) {
     __shared__ u64 s_w[8];
     const u64 base = (u64)blockIdx.x * SHARD_TILE;
     u64 v = 0;
-    for (u32 j = threadIdx.x; j < SHARD_TILE; j += 256) if (base + j < rows) v += prod[base + j] + 1;
+    for (u32 j = threadIdx.x; j < SHARD_TILE; j += 256) if (base + j < rows) v += shard_cost(prod[base + j]);
     v = warp_sum_u64(v);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) { u64 t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; sums[blockIdx.x] = t; }
 }
-// Cut k = first index i of the prefix pre[0..rows] (pre[0] = 0, pre[i] = sum_{j<i} (P_j + 1)) with pre[i] >= k * total / nparts.
+// Cut k = first index i of the prefix pre[0..rows] (pre[0] = 0, pre[i] = sum_{j<i} cost(P_j)) with pre[i] >= k * total / nparts.
 // The per-row counts stay on the device: the host reads one sum per 4096 rows, then the one tile each cut falls into.
 extern "C" int b200_shard_rows_by_products(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int nparts, uint64_t *cuts) {
     if (!ctx || !A || !B || !cuts || nparts < 1) return set_err(B200_ERR_BADARG, "bad nparts/cuts");
@@ -1342,7 +1346,7 @@ extern "C" int b200_shard_rows_by_products(b200_ctx *ctx, const b200_csr *A, con
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             unsigned __int128 run = pre[t];
             u64 i = 0;
-            while (i < cnt && run < target) { run += tile[i] + 1; i++; }
+            while (i < cnt && run < target) { run += shard_cost(tile[i]); i++; }
             lo = base + i;
         }
         cuts[k] = std::max<uint64_t>(std::min<u64>(lo, rows), cuts[k - 1]);

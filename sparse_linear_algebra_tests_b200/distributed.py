@@ -23,20 +23,29 @@ import numpy as np
 from . import hostgen
 
 
-def product_balanced_cuts(row_products: np.ndarray, nparts: int) -> np.ndarray:
-    """cuts[0..nparts]: part k = rows [cuts[k], cuts[k+1]) holds ~1/nparts of sum(P_i + 1).
+HEAVY_FROM = 8192   # rows with more intermediate products take the heavy-row kernels (b200_hash_cap(7), csrc/common.cuh)
 
-    Same rule as b200_shard_rows_by_products (csrc/api.cu): prefix of (P_i + 1) -- the +1 spreads
-    empty rows too -- and cut k at the first prefix >= k * total / nparts."""
+
+def row_cost(row_products: np.ndarray) -> np.ndarray:
+    """shard_cost of csrc/api.cu: products + 1 (empty rows spread too), heavy rows 2.5 x (their kernels' products/s)."""
     p = np.asarray(row_products, dtype=np.uint64)
-    pre = np.zeros(p.shape[0] + 1, dtype=np.uint64)
-    np.cumsum(p + np.uint64(1), out=pre[1:])
+    return p + np.uint64(1) + np.where(p > np.uint64(HEAVY_FROM), p + p // np.uint64(2), np.uint64(0)).astype(np.uint64)
+
+
+def product_balanced_cuts(row_products: np.ndarray, nparts: int) -> np.ndarray:
+    """cuts[0..nparts]: part k = rows [cuts[k], cuts[k+1]) holds ~1/nparts of sum(cost(P_i)).
+
+    Same rule as b200_shard_rows_by_products (csrc/api.cu): prefix of the row costs, cut k at the first prefix
+    >= k * total / nparts."""
+    c = row_cost(row_products)
+    pre = np.zeros(c.shape[0] + 1, dtype=np.uint64)
+    np.cumsum(c, out=pre[1:])
     total = int(pre[-1])
     cuts = np.zeros(nparts + 1, dtype=np.uint64)
-    cuts[nparts] = p.shape[0]
+    cuts[nparts] = c.shape[0]
     for k in range(1, nparts):
         lo = int(np.searchsorted(pre, np.uint64(total * k // nparts), side="left"))
-        cuts[k] = max(min(lo, p.shape[0]), int(cuts[k - 1]))
+        cuts[k] = max(min(lo, c.shape[0]), int(cuts[k - 1]))
     return cuts
 
 

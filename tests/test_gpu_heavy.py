@@ -189,3 +189,14 @@ def test_permute_rejects_a_non_permutation(gpu_ctx):
     for bad in ([0, 1, 1, 2], [0, 1, 2, 7]):
         with pytest.raises(B200Error):
             gpu_ctx.permute(m.device, np.array(bad, np.uint32))
+
+
+def test_device_cut_points_follow_the_host_rule(gpu_ctx):
+    """b200_shard_rows_by_products (tile sums on the device, one tile per cut read back) gives the cuts of
+    distributed.product_balanced_cuts on the same per-row counts -- with heavy rows (weighted 2.5 x) in the operand."""
+    from sparse_linear_algebra_tests_b200.distributed import product_balanced_cuts
+    a = gpu_ctx.rmat(14, 16, 0.57, 0.19, 0.19, 42, 64)
+    prods = gpu_ctx.row_products(a, a)
+    assert int(prods.max()) > 8192
+    for parts in (1, 2, 3, 8):
+        assert np.array_equal(gpu_ctx.shard_rows_by_products(a, a, parts), product_balanced_cuts(prods, parts))
