@@ -175,6 +175,18 @@ extern "C" int b200_ctx_get_config(b200_ctx *ctx, b200_config *c) {
 }
 
 static int env_int_early(const char *name) { const char *v = getenv(name); return v && *v ? atoi(v) : 0; }
+extern "C" int b200_ctx_destroy(b200_ctx *ctx);
+// (inside b200_ctx_create, once the context exists: a failing call releases what has been set up so far)
+#define CUDA_TRY_X(expr)                                                                           \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            const int _c = set_err(_e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA, \
+                                   "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            b200_ctx_destroy(ctx); cudaGetLastError();                                             \
+            return _c;                                                                             \
+        }                                                                                          \
+    } while (0)
 extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     if (!out) return set_err(B200_ERR_BADARG, "b200_ctx_create: out is NULL");
     int n = 0;
@@ -194,37 +206,37 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device; ctx->num_sms = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin; ctx->total_mem = prop.totalGlobalMem;
     if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
-    else { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    else { CUDA_TRY_X(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    CUDA_TRY_X(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CUDA_TRY_X(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     static_assert(sizeof(B200Ctrl) <= B200_CTRL_BYTES, "control block outgrew its slot");
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));
+    CUDA_TRY_X(cudaMallocHost((void **)&ctx->h_ctrl, sizeof(B200Ctrl) + 64));
     memset(ctx->h_ctrl, 0, sizeof(B200Ctrl) + 64);
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_report, sizeof(B200Ctrl) * 2));
+    CUDA_TRY_X(cudaMallocHost((void **)&ctx->h_report, sizeof(B200Ctrl) * 2));
     memset(ctx->h_report, 0, sizeof(B200Ctrl) * 2);
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_flag, 128));
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_flag, 128));
-    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
-    for (int i = 0; i < B200_NAUX; i++) { CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    CUDA_TRY_X(cudaMalloc((void **)&ctx->d_flag, 128));
+    CUDA_TRY_X(cudaMallocHost((void **)&ctx->h_flag, 128));
+    for (int i = 0; i < 4; i++) CUDA_TRY_X(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < B200_NAUX; i++) { CUDA_TRY_X(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking)); CUDA_TRY_X(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)); }
+    CUDA_TRY_X(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY_X(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    CUDA_TRY_X(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     // one auxiliary stream measured as good as three, with half the event calls
     b200_config_default(&ctx->cfg);
     config_from_env(&ctx->cfg);
     ctx->naux_enabled = std::max(0, std::min(B200_NAUX, (int)ctx->cfg.aux_streams));
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_freport, (size_t)B200_REPORT_SLOTS * sizeof(B200Ctrl) * 2));
+    CUDA_TRY_X(cudaMallocHost((void **)&ctx->h_freport, (size_t)B200_REPORT_SLOTS * sizeof(B200Ctrl) * 2));
     memset(ctx->h_freport, 0, (size_t)B200_REPORT_SLOTS * sizeof(B200Ctrl) * 2);
-    for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) CUDA_TRY(cudaEventCreate(&ctx->f_ev[i][j]));
+    for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) CUDA_TRY_X(cudaEventCreate(&ctx->f_ev[i][j]));
     ctx->f_dirty = true;
     fz_setup(ctx);
     rw_setup(ctx);
     rwf_setup(ctx);
     hv_setup(ctx);
     ctx->cap_cta_tot = 8192;
-    CUDA_TRY(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
+    CUDA_TRY_X(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
@@ -792,18 +804,20 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
             else k_num_rank<u64, 2><<<g, 1024, heavy_rank_smem, bs>>>(na64, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, cap, nwords, 5, o64);
             LAUNCH_CHECK(ctx);
         } else {
-            u64 max_slots = 1; while (max_slots < 2 * heavy_cap) max_slots <<= 1;
-            const size_t per_cta = (size_t)nwords * 8 + (size_t)max_slots * 12 + 256;
+            u64 max_slots = 2; while (max_slots < 2 * heavy_cap) max_slots <<= 1;
+            // per CTA: table (keys u32, sums u64), a place and an order word per entry, the ordering step's bucket counters
+            const size_t per_cta = (size_t)max_slots * 12 + (size_t)max_slots * 4 + ((size_t)max_slots / 2 + 1) * 4 + ((size_t)B200_HEAVY_NB_MAX + 1) * 4 + 256;
             const size_t budget = (size_t)8 << 30;
             const int g = (int)std::min<u64>(std::min<u64>(n, (u64)ctx->num_sms), std::max<u64>(1, budget / per_cta));
             TRY(ensure_heavy_scratch(ctx, per_cta * g));
             unsigned char *base = (unsigned char *)ctx->d_heavy;
             u64 *s_vals = (u64 *)base;                                            // g * max_slots u64
             u32 *s_keys = (u32 *)(base + (size_t)g * max_slots * 8);              // g * max_slots u32
-            u32 *s_bm = s_keys + (size_t)g * max_slots;                           // g * nwords
-            u32 *s_pre = s_bm + (size_t)g * nwords;                               // g * nwords
-            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o64, skip);
-            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, nwords, max_slots, s_bm, s_pre, s_keys, s_vals, o, skip);
+            u32 *s_place = s_keys + (size_t)g * max_slots;                        // g * max_slots u32
+            u32 *s_order = s_place + (size_t)g * max_slots;                       // g * (max_slots / 2 + 1) u32
+            u32 *s_cnt = s_order + (size_t)g * (max_slots / 2 + 1);               // g * (B200_HEAVY_NB_MAX + 1) u32
+            if (mode == 2) k_num_heavy<u64, 2><<<g, 1024, 0, ctx->stream>>>(na64, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, max_slots, s_place, s_order, s_cnt, s_keys, s_vals, o64, skip);
+            else k_num_heavy<VT, 1><<<g, 1024, 0, ctx->stream>>>(na, ctx->d_bin_rows, ctrl, ctx->d_nnz_row, max_slots, s_place, s_order, s_cnt, s_keys, s_vals, o, skip);
             LAUNCH_CHECK(ctx);
             // the rows with enough products per column chunk: dense accumulation chunk by chunk (heavy.cu)
             if (hv_on) TRY(hv_numeric(ctx, A, B, ctrl, *hv, mode, bpat, o.base, o.col, (void *)o.val, o.narrow, ctx->stream));
@@ -919,6 +933,16 @@ int legacy_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl
 }
 
 template <typename VT>
+// (inside spgemm_typed: a failing CUDA call must not leak the half-built product)
+#define CUDA_TRY_C(expr)                                                                           \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            b200_csr_free(ctx, C);                                                                 \
+            return set_err(_e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA,       \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
 static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st) {
     const u64 rows = A->rows, ncols = B->cols;
     cudaStream_t s = ctx->stream;
@@ -928,7 +952,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     TRY(csr_alloc(ctx, rows, ncols, 0, A->val_bits, false, &C));
     if (st) { memset(st, 0, sizeof(*st)); st->rows = rows; st->cols = ncols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; }
     if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
-        CUDA_TRY(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8 + 16, s));   // row_ptr and the max-value scalar behind it
+        CUDA_TRY_C(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8 + 16, s));   // row_ptr and the max-value scalar behind it
         TRY(alloc_entries(ctx, C));
         C->h_maxval = 0; C->h_maxval_known = true;
         if (st) st->bytes_algorithmic = (A->nnz + B->nnz) * (4 + sizeof(VT)) + (A->rows + B->rows + rows + 3) * 8;
@@ -1043,9 +1067,12 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
         // auto: only while a warp's share of shared memory leaves >= 16 warps per SM (wide arcs of an N-GPU row block do not:
         // the binned kernels, whose bitmap is per bin, are faster there -- measured on rank 0's block of the 8-GPU torus)
+        // ... and while rows average >= 48 intermediate products: below that (the first two powers of the torus chain) a row is a
+        // handful of products, the warp-per-row phases are all latency, and the binned kernels' tiny-row path is 20-30 % faster
+        // (30^3: A^2 51 vs 72 us, A^3 68 vs 82 us; from A^4 on the one-launch multiply is level or ahead)
         const size_t per_warp = rw_smem_per_warp(false, mode1, nw, (u32)cap);
-        if (per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 4 || per_warp <= 14 * 1024)) {
-            if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
+        if (per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 4 || (per_warp <= 14 * 1024 && meanP >= 48.0))) {
+            if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY_C(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
             if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
             C->cap_entries = std::max<u64>((u64)hb128, 1);
             r = alloc_entries(ctx, C);
@@ -1082,7 +1109,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         const u64 tile_rows = std::max(256 / G, B200_PREPASS_MIN_ROWS);   // B200_PREPASS_ROWS(G)
         const u64 tiles_pre = (rows + tile_rows - 1) / tile_rows;
         scan_bytes = B200_CTRL_BYTES + (ctx->cap_tiles + tiles_pre) * 8;
-        CUDA_TRY(reset_scan(ctx, tiles_pre));
+        CUDA_TRY_C(reset_scan(ctx, tiles_pre));
         // column windows only matter when some bin's bitmap is narrower than B; square operands get circular windows
         bool windows = false;
         for (int hb = 0; hb < B200_NUM_HASH_BINS; hb++) windows |= caps.cap[hb] < all_groups;
@@ -1118,13 +1145,13 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             // the host-side bound is too loose to decide: read the pre-pass's exact scratch size sum(min(P_i, cols)) (one
             // small synchronous copy; multiplies of this size run for milliseconds) and keep the faster scratch path while
             // it fits a third of the free memory
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+            CUDA_TRY_C(cudaMemcpyAsync(ctx->h_ctrl, ctx->d_ctrl, sizeof(B200Ctrl), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY_C(cudaStreamSynchronize(s));
             tmp_entries = ctx->h_ctrl->total_bound;
             // scratch the context already owns decides first (steady state of a loop: no driver query at all)
             if ((size_t)tmp_entries * 4 > ctx->cap_tmp_col || (size_t)tmp_entries * sizeof(VT) > ctx->cap_tmp_val) {
                 size_t free_b = 0, tot_b = 0;
-                CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+                CUDA_TRY_C(cudaMemGetInfo(&free_b, &tot_b));
                 const size_t reusable = ctx->cap_tmp_col + ctx->cap_tmp_val;
                 exact = (unsigned __int128)tmp_entries * esz > (unsigned __int128)((free_b + reusable) / 3);
             }
@@ -1175,7 +1202,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             r = launch_numeric<VT>(ctx, A, B, rows, p_bound, std::max<u64>(1, hc.max_row_nnz), mode1, packed, bpat, lg, o, fan, caps, nullptr, false, rw, C, &hv);
             fan.join();
             if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
-            CUDA_TRY(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
+            CUDA_TRY_C(cudaMemcpyAsync(C->d_maxval, &ctx->d_ctrl->max_val_out, 8, cudaMemcpyDeviceToDevice, s));   // read back lazily (host_maxval)
             if (timing) cudaEventRecord(ctx->ev[3], s);
             {
                 // the exact placement has waited for the device anyway: its statistics are complete here
@@ -1188,7 +1215,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 for (int i = 0; i < B200_STAT_BINS; i++) xs->sym_bin_rows[i] = hc.sym_bin_count[i];
                 xs->pipeline = rw.hb_max >= 0 ? 3 : 2;
                 if (timing && st) {
-                    CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+                    CUDA_TRY_C(cudaEventSynchronize(ctx->ev[3]));
                     cudaEventElapsedTime(&xs->ms_symbolic, ctx->ev[0], ctx->ev[1]);   // pre-pass + counts + row_ptr scan
                     cudaEventElapsedTime(&xs->ms_numeric, ctx->ev[2], ctx->ev[3]);    // numeric kernels into the final arrays
                     cudaEventElapsedTime(&xs->ms_total, ctx->ev[0], ctx->ev[3]);
@@ -1367,10 +1394,12 @@ extern "C" int b200_csr_row_block(b200_ctx *ctx, const b200_csr *A, uint64_t r0,
     TRY(csr_alloc(ctx, rows, A->cols, nnz, A->val_bits, true, &m));
     k_rebase_rowptr<<<grid_for(rows + 1, 256, ctx->num_sms * 8), 256, 0, ctx->stream>>>(rows + 1, A->d_rp + r0, ends[0], m->d_rp);
     ctx->launches++;
-    if (nnz) {
-        cudaMemcpyAsync(m->d_col, A->d_col + ends[0], nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream);
-        cudaMemcpyAsync(m->d_val, (const char *)A->d_val + ends[0] * (A->val_bits / 8), nnz * (size_t)(A->val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess && nnz) {
+        ce = cudaMemcpyAsync(m->d_col, A->d_col + ends[0], nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(m->d_val, (const char *)A->d_val + ends[0] * (A->val_bits / 8), nnz * (size_t)(A->val_bits / 8), cudaMemcpyDeviceToDevice, ctx->stream);
     }
+    if (ce != cudaSuccess) { b200_csr_free(ctx, m); return set_err(B200_ERR_CUDA, "row_block: %s", cudaGetErrorString(ce)); }
     m->max_row_len = A->max_row_len;
     int r = finish_new_csr(ctx, m, true, true);
     if (r != B200_OK) { b200_csr_free(ctx, m); return r; }
@@ -1418,6 +1447,7 @@ extern "C" int b200_csr_add(b200_ctx *ctx, const b200_csr *A, const b200_csr *B,
 }
 
 extern "C" int b200_csr_same_pattern(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int *same) {
+    if (ctx && A && B && (A->ctx != ctx || B->ctx != ctx)) return set_err(B200_ERR_BADARG, "operand handles belong to another context");
     if (!ctx || !A || !B || !same) return set_err(B200_ERR_BADARG, "NULL argument");
     RESOLVE(ctx, A); RESOLVE(ctx, B);
     if (A->rows != B->rows || A->cols != B->cols || A->nnz != B->nnz) { *same = 0; return B200_OK; }

@@ -1240,17 +1240,25 @@ __global__ void __launch_bounds__(1024) k_sym_heavy(SymArgs a, const u32 *__rest
     }
 }
 
-template <typename VT, int MODE>   // MODE 1: plain 64-bit global atomics (u32 products clamped); MODE 2: saturating CAS
+#define B200_HEAVY_NB_MAX 16384u   // bucket counters of the ordering step, at most
+template <typename VT, int MODE>
 __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl,
-                                                    const u32 *__restrict__ nnz_row, u32 nwords, u64 max_slots,
-                                                    u32 *__restrict__ scratch_bm, u32 *__restrict__ scratch_pre,
+                                                    const u32 *__restrict__ nnz_row, u64 max_slots,
+                                                    u32 *__restrict__ scratch_place, u32 *__restrict__ scratch_order, u32 *__restrict__ scratch_cnt,
                                                     u32 *__restrict__ scratch_keys, u64 *__restrict__ scratch_vals, OutArgs<VT> o, HvSkip skip) {
-    __shared__ u32 s_warp[33];
+    // Heavy rows that the chunked kernels leave alone (wide column space, too few products per chunk): one CTA per row, an
+    // open-addressing table in global memory sized from the row's exact length (count pass), then the bucket ranking of the
+    // hash kernels in global memory -- the row's column range cut into ~nnz / 8 buckets, a counter per bucket, a scan of
+    // the counters, and each column's place = its bucket's offset + the smaller columns in its bucket.  (Round 1 ranked
+    // through a bitmap of the whole column space: clearing and prefix-scanning ncols / 32 words per row cost more than the
+    // row's products on a 4 M-column R-MAT.)
+    __shared__ u32 s_warp[33], s_mm[2];
     __shared__ EnumSmem s_enum;
     const u32 count = o.bin_cnt[B200_BIN_HEAVY];
     const u64 off = (u64)B200_BIN_HEAVY * o.bin_stride;
-    u32 *bm = scratch_bm + (u64)blockIdx.x * nwords;
-    u32 *wpre = scratch_pre + (u64)blockIdx.x * nwords;
+    u32 *place = scratch_place + (u64)blockIdx.x * max_slots;
+    u32 *order = scratch_order + (u64)blockIdx.x * (max_slots / 2 + 1);
+    u32 *bcnt = scratch_cnt + (u64)blockIdx.x * (B200_HEAVY_NB_MAX + 1);
     u32 *keys = scratch_keys + (u64)blockIdx.x * max_slots;
     ull *vals = (ull *)(scratch_vals + (u64)blockIdx.x * max_slots);
     const u32 nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -1261,15 +1269,19 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
         const u32 nnz = nnz_row[row];
         u64 slots = 1; while (slots < 2ull * nnz) slots <<= 1;            // <= max_slots by host sizing
         const int shift = 64 - (63 - __clzll(slots));
+        u32 NB = 256; while (NB < B200_HEAVY_NB_MAX && (u64)NB * 8 < nnz) NB <<= 1;
         for (u64 t = tid; t < slots; t += nt) { keys[t] = B200_EMPTY_KEY; vals[t] = 0; }
-        for (u32 t = tid; t < nwords; t += nt) bm[t] = 0;
+        for (u32 t = tid; t <= NB; t += nt) bcnt[t] = 0;
+        if (tid == 0) { s_mm[0] = 0xFFFFFFFFu; s_mm[1] = 0; }
         __syncthreads();
         const u64 s = a.rpA[row];
         const u32 lenA = (u32)(a.rpA[row + 1] - s);
         const VT *Av = a.valA + s;
+        u32 cmin = 0xFFFFFFFFu, cmax = 0;
         enumerate_products<VT, true>(a.colA + s, Av, lenA, a.bdesc, s_enum, s_warp,
                           [&](u32, u32 jb, VT av) {
                               const u32 c = a.colB[jb];
+                              cmin = min(cmin, c); cmax = max(cmax, c);
                               ull x;
                               if (MODE == 2) x = sat_mul((u64)av, (u64)a.valB[jb]);
                               else if (sizeof(VT) == 4) { u64 p = (u64)av * (u64)a.valB[jb]; x = p > 0xFFFFFFFFull ? 0xFFFFFFFFull : p; }
@@ -1279,7 +1291,7 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                                   u32 cur = ld_volatile_u32(&keys[h]);
                                   if (cur == B200_EMPTY_KEY) {
                                       cur = atomicCAS(&keys[h], B200_EMPTY_KEY, c);
-                                      if (cur == B200_EMPTY_KEY) { atomicOr(&bm[c >> 5], 1u << (c & 31)); cur = c; }
+                                      if (cur == B200_EMPTY_KEY) cur = c;
                                   }
                                   if (cur == c) {
                                       if (MODE == 2) {
@@ -1296,28 +1308,50 @@ __global__ void __launch_bounds__(1024) k_num_heavy(NumArgs<VT> a, const u32 *__
                                   h = (h + 1) & (slots - 1);
                               }
                           });
+        cmin = __reduce_min_sync(0xFFFFFFFFu, cmin); cmax = __reduce_max_sync(0xFFFFFFFFu, cmax);
+        if (lane == 0 && cmin <= cmax) { atomicMin(&s_mm[0], cmin); atomicMax(&s_mm[1], cmax); }
         __threadfence_block();
         __syncthreads();
-        u32 carry = 0;
-        for (u32 base = 0; base < nwords; base += nt) {
-            const u32 wd = base + tid < nwords ? __ldcg(&bm[base + tid]) : 0u;
-            u32 total;
-            const u32 ex = block_excl_scan(__popc(wd), s_warp, total);
-            if (base + tid < nwords) wpre[base + tid] = carry + ex;
-            carry += total;
-        }
-        __syncthreads();
-        const u64 obase = o.base[row];
+        cmin = s_mm[0]; cmax = s_mm[1];
+        int bshift = 0;
+        if (nnz) { const u32 span1 = cmax - cmin; const int bits = span1 ? 32 - __clz(span1) : 0; const int lb = 31 - __clz(NB); bshift = bits > lb ? bits - lb : 0; }
+        // ---- a place in its bucket for every stored column
         for (u64 t = tid; t < slots; t += nt) {
             const u32 c = __ldcg(&keys[t]);
-            if (c != B200_EMPTY_KEY) {
-                const u32 wd = __ldcg(&bm[c >> 5]);
-                const u64 pos = obase + __ldcg(&wpre[c >> 5]) + __popc(wd & ((1u << (c & 31)) - 1u));
-                ull v = __ldcg(&vals[t]);
-                if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
-                o.col[pos] = c; put_val(o, pos, (VT)v);
-                vmax = vmax > v ? vmax : v;
-            }
+            if (c != B200_EMPTY_KEY) place[t] = atomicAdd(&bcnt[(c - cmin) >> bshift], 1u);
+        }
+        __syncthreads();
+        // ---- counters -> offsets
+        {
+            const u32 cpt = (NB + nt - 1) / nt, c0 = tid * cpt;
+            u32 sum = 0;
+            for (u32 i = 0; i < cpt && c0 + i < NB; i++) sum += __ldcg(&bcnt[c0 + i]);
+            u32 tt;
+            u32 run = block_excl_scan(sum, s_warp, tt);
+            for (u32 i = 0; i < cpt && c0 + i < NB; i++) { const u32 c = __ldcg(&bcnt[c0 + i]); bcnt[c0 + i] = run; run += c; }
+            if (tid == 0) bcnt[NB] = nnz;
+        }
+        __threadfence_block();
+        __syncthreads();
+        // ---- slots in bucket order
+        for (u64 t = tid; t < slots; t += nt) {
+            const u32 c = __ldcg(&keys[t]);
+            if (c != B200_EMPTY_KEY) order[__ldcg(&bcnt[(c - cmin) >> bshift]) + place[t]] = (u32)t;
+        }
+        __threadfence_block();
+        __syncthreads();
+        // ---- rank inside the bucket, emit
+        const u64 obase = o.base[row];
+        for (u32 t = tid; t < nnz; t += nt) {
+            const u32 sl = __ldcg(&order[t]);
+            const u32 c = __ldcg(&keys[sl]), b = (c - cmin) >> bshift;
+            const u32 lo = __ldcg(&bcnt[b]), hi = __ldcg(&bcnt[b + 1]);
+            u32 rank = 0;
+            for (u32 j = lo; j < hi; j++) rank += __ldcg(&keys[__ldcg(&order[j])]) < c ? 1u : 0u;
+            ull v = __ldcg(&vals[sl]);
+            if (sizeof(VT) == 4 && v > 0xFFFFFFFFull) v = 0xFFFFFFFFull;
+            o.col[obase + lo + rank] = c; put_val(o, obase + lo + rank, (VT)v);
+            vmax = vmax > v ? vmax : v;
         }
         __syncthreads();
     }
