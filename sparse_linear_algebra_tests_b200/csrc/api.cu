@@ -47,9 +47,15 @@ static CsrView<VT> view(const b200_csr *m) {
 }
 
 
+static void entry_cache_flush(b200_ctx *ctx);
 int dmalloc(b200_ctx *ctx, void **p, size_t bytes) {
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess && ctx->entry_cache && !ctx->entry_cache->empty()) {   // out of memory with blocks parked in the entry cache: release them, retry
+        cudaGetLastError();
+        entry_cache_flush(ctx);
+        e = cudaMallocAsync(p, bytes, ctx->stream);
+    }
     if (e != cudaSuccess) { cudaGetLastError(); return set_err(B200_ERR_ALLOC, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
     return B200_OK;
 }
@@ -240,6 +246,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
+    ctx->entry_cache = new std::vector<std::pair<void *, size_t>>(); ctx->entry_cache_bytes = 0;
     setup_kernels_vt<u32>(ctx->smem_optin);
     setup_kernels_vt<u64>(ctx->smem_optin);
     allow_big_smem(k_sym_cta<false>, ctx->smem_optin); allow_big_smem(k_sym_cta<true>, ctx->smem_optin);
@@ -258,6 +265,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->entry_cache) { for (auto &b : *ctx->entry_cache) dfree(ctx, b.first); delete ctx->entry_cache; ctx->entry_cache = nullptr; }
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val); dfree(ctx, ctx->d_hv);
     dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_rowwin); dfree(ctx, ctx->d_rowclass); dfree(ctx, ctx->d_spill_acc); dfree(ctx, ctx->d_spill_col);
     cudaStreamSynchronize(ctx->stream);
@@ -290,12 +298,36 @@ extern "C" int b200_ctx_set_timing(b200_ctx *ctx, int enabled) {
 
 // ---------------------------------------------------------------------------- CSR handles
 // col_idx and values of m->nnz entries in ONE allocation (values behind the columns, 256-byte aligned)
+static void entry_cache_flush(b200_ctx *ctx) {
+    if (!ctx->entry_cache) return;
+    for (auto &b : *ctx->entry_cache) dfree(ctx, b.first);
+    ctx->entry_cache->clear(); ctx->entry_cache_bytes = 0;
+    cudaStreamSynchronize(ctx->stream);                                   // the pool can hand the memory out again
+}
 int alloc_entries(b200_ctx *ctx, b200_csr *m) {
     const u64 cap = std::max(m->nnz, m->cap_entries);                     // products of the fused path are allocated from a bound
     m->cap_entries = cap;
     const size_t col_bytes = ((size_t)cap * 4 + 255) & ~(size_t)255;
     // (+32: the chunked heavy-row kernel fetches B-row segments as 16-byte aligned bulk copies, which may run a few entries past nnz)
-    TRY(dmalloc(ctx, (void **)&m->d_col, col_bytes + (size_t)cap * (size_t)(m->val_bits / 8) + 32));
+    const size_t need = col_bytes + (size_t)cap * (size_t)(m->val_bits / 8) + 32;
+    m->d_col = nullptr;
+    if (ctx->entry_cache && need >= ((size_t)1 << 20)) {
+        // smallest cached block that holds the request without wasting more than a quarter of it
+        int best = -1;
+        for (size_t i = 0; i < ctx->entry_cache->size(); i++) {
+            const size_t b = (*ctx->entry_cache)[i].second;
+            if (b >= need && b <= need + need / 4 && (best < 0 || b < (*ctx->entry_cache)[best].second)) best = (int)i;
+        }
+        if (best >= 0) {
+            m->d_col = (u32 *)(*ctx->entry_cache)[best].first; m->entry_bytes = (*ctx->entry_cache)[best].second;
+            ctx->entry_cache_bytes -= m->entry_bytes;
+            ctx->entry_cache->erase(ctx->entry_cache->begin() + best);
+        }
+    }
+    if (!m->d_col) {
+        TRY(dmalloc(ctx, (void **)&m->d_col, need));
+        m->entry_bytes = need;
+    }
     m->d_val = (unsigned char *)m->d_col + col_bytes;
     m->val_shares_col = true;
     return B200_OK;
@@ -320,7 +352,14 @@ extern "C" int b200_csr_free(b200_ctx *ctx, b200_csr *m) {
     if (m->pending_slot >= 0 && ctx->slot_owner[m->pending_slot] == m) ctx->slot_owner[m->pending_slot] = nullptr;   // its report is simply never read
     delete m->stats;
     if (m->ev_copy) { cudaStreamWaitEvent(ctx->stream, m->ev_copy, 0); cudaEventDestroy(m->ev_copy); }   // frees are ordered after a pending download
-    dfree(ctx, m->d_rp); dfree(ctx, m->d_col); if (!m->val_shares_col) dfree(ctx, m->d_val);
+    dfree(ctx, m->d_rp);
+    // large entry arrays go to the context's cache (ordered on ctx->stream like a free); small ones back to the pool
+    if (m->d_col && m->val_shares_col && m->entry_bytes >= ((size_t)1 << 20) && ctx->entry_cache &&
+        ctx->entry_cache->size() < 16 && ctx->entry_cache_bytes + m->entry_bytes <= ctx->total_mem / 3) {
+        ctx->entry_cache->push_back({(void *)m->d_col, m->entry_bytes});
+        ctx->entry_cache_bytes += m->entry_bytes;
+    } else dfree(ctx, m->d_col);
+    if (!m->val_shares_col) dfree(ctx, m->d_val);
     dfree(ctx, m->d_desc); dfree(ctx, m->d_span); dfree(ctx, m->d_cspan); dfree(ctx, m->d_pack);
     delete m;
     return B200_OK;

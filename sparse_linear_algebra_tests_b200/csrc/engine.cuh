@@ -45,6 +45,7 @@ struct b200_csr {
     cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
     b200_ctx *ctx;
     // ---- fused path (fused.cu): a product is returned before the host knows its size
+    size_t entry_bytes;     // bytes of the col/val allocation (entry cache)
     u64 cap_entries;        // entries the col/val allocation holds (>= nnz; products are allocated from a bound)
     u64 max_row_span;       // every row's columns lie on an arc of the index circle of at most this many + 1 columns (cols: unknown)
     int pending_slot;       // >= 0: nnz / max_row_len / h_maxval arrive with report slot `pending_slot` (see resolve_pending)
@@ -92,6 +93,9 @@ struct b200_ctx {
     cudaEvent_t f_ev[B200_REPORT_SLOTS][3];
     u32 fepoch;
     u64 *d_cta_tot; u64 cap_cta_tot;   // per-CTA totals of the one-launch multiply (rowwarp.cu)
+    // entry arrays (col_idx | values, one allocation) of freed handles, kept for the next product of about that size: a loop
+    // of large multiplies (12-GB results on the 200^3 chain) otherwise stalls in the stream-ordered allocator every few steps
+    std::vector<std::pair<void *, size_t>> *entry_cache; size_t entry_cache_bytes;
     void *d_hv; size_t cap_hv;         // chunked heavy-row kernels (heavy.cu): control words | per-(row, chunk) counters | unit lists
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
 };
