@@ -241,6 +241,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     rw_setup(ctx);
     rwf_setup(ctx);
     hv_setup(ctx);
+    dn_setup(ctx);
     ctx->cap_cta_tot = 8192;
     CUDA_TRY_X(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
@@ -271,6 +272,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFreeHost(ctx->h_freport);
     for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->f_ev[i][j]);
+    if (ctx->d_rowstat) cudaFree(ctx->d_rowstat);
     cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag); cudaFree(ctx->d_cta_tot);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
@@ -1092,6 +1094,26 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         cap = std::min<u64>(cap, std::min<u64>(std::min<u64>(p_bound, 8192), groups * 128));
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
         rw.hb_max = B200_RW_MAX_HB; rw.nw = ((u32)groups * 4u + 31u) & ~31u; rw.cap = (u32)cap; rw.all_fit = all_fit;   // (a lane owns nw / 32 consecutive words)
+    }
+    // One pass over the products (pipeline 5, dense.cu): 32-bit sums proven, a square low-degree right operand with a known offset
+    // range, C allocated from the host-known bound.
+    if (ctx->cfg.pipeline == 5 && mode1 == 0 && packed && B->rows == B->cols && cheap_bound && B->nnz < 0xFFFFFFFFull && ncols < 0x7FFFFFFFull) {
+        r = ensure_cs_bounds(ctx, B);
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+        if (B->cs_state == 1) {
+            if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY_C(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
+            if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
+            C->cap_entries = std::max<u64>((u64)hb128, 1);
+            r = alloc_entries(ctx, C);
+            if (r == B200_OK) r = dn_launch(ctx, A, B, C, ctx->d_ctrl, bpat, ctx->cfg.fused_threads > 0 && ctx->cfg.fused_threads <= 8 ? ctx->cfg.fused_threads : 3, mirror, epoch, s);
+            if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+            if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
+            trace_dump(ctx, "one-pass multiply (dense windows)");
+            mark_pending(ctx, C, slot, epoch, A, B, mode1, 5, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
+            *out = C;
+            if (st) { TRY(resolve_pending(ctx, C)); *st = *C->stats; }
+            return B200_OK;
+        }
     }
     // One cooperative launch for the whole multiply (pipeline 4, the default where it applies): every row shares one window
     // (the whole column space or the operand-level arc) that fits a warp's bitmap, rows are short enough for a single warp,

@@ -96,6 +96,7 @@ struct b200_ctx {
     // entry arrays (col_idx | values, one allocation) of freed handles, kept for the next product of about that size: a loop
     // of large multiplies (12-GB results on the 200^3 chain) otherwise stalls in the stream-ordered allocator every few steps
     std::vector<std::pair<void *, size_t>> *entry_cache; size_t entry_cache_bytes;
+    u64 *d_rowstat; u64 cap_rowstat;   // per-row look-back status of the one-pass multiply (dense.cu)
     void *d_hv; size_t cap_hv;         // chunked heavy-row kernels (heavy.cu): control words | per-(row, chunk) counters | unit lists
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
 };
@@ -179,6 +180,10 @@ int hv_plan(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, int mode, u64 p
 int hv_count(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, const HvPlan &p, cudaStream_t s);
 int hv_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ctrl, const HvPlan &p, int mode, bool bpat,
                const u64 *base, u32 *col, void *val, u32 narrow, cudaStream_t s);
+// ---- dense.cu: the multiply as one pass over the products (dense window accumulators, look-back placement over rows)
+void dn_setup(b200_ctx *ctx);
+int dn_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, bool bpat, int ctas_per_sm, u64 *mirror, u32 epoch,
+              cudaStream_t s);
 // ---- fused.cu
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);

@@ -8,6 +8,7 @@ import pytest
 from sparse_linear_algebra_tests_b200 import B200Error, B200Matrix, hostgen
 
 pytestmark = pytest.mark.gpu
+DEFAULT_PIPELINE = 4     # what `pipeline = 0` picks for A^7 of the headline chain
 
 
 def to_o(O, h):
@@ -40,7 +41,7 @@ def chain_check(O, ctx, a_h, powers, left_h=None, what=""):
 
 
 # ------------------------------------------------------------------ the headline instance, every power, both value widths
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3, 4], ids=["default", "fused", "binned", "rowwarp", "onelaunch"])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3, 4, 5], ids=["default", "fused", "binned", "rowwarp", "onelaunch", "onepass"])
 @pytest.mark.parametrize("bits", [64, 32])
 def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, cfg, bits, pipeline):
     """BASELINE configs[1]: the reference's exact operand (StdRng([42;32]) thinning of the 30^3 Moore torus, 81 434 nnz),
@@ -52,7 +53,7 @@ def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, cfg, bits,
     gpu = chain_check(oracle, gpu_ctx, a_h, 7, what=f"u{bits} pipeline {pipeline}")
     assert [g.nnz() for g in gpu] == [251590, 655391, 1574848, 3383207, 6590100, 11736555]
     st = gpu[-1].device.product_stats()
-    assert st.nnz_c == 11736555 and st.pipeline == {0: 4, 1: 1, 2: 2, 3: 3, 4: 4}[pipeline]
+    assert st.nnz_c == 11736555 and st.pipeline == {0: DEFAULT_PIPELINE, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5}[pipeline]
     if pipeline == 1:
         assert st.sym_bin_rows[2] == 0, "a row of the headline multiply left the fused kernel for the counted lists"
 
@@ -229,3 +230,35 @@ def test_upload_rejects_unsorted_or_repeated_columns(gpu_ctx):
         gpu_ctx.upload(2, 8, rp, np.array([1, 4, 7], np.uint32), np.ones(3, np.uint64))        # lengths do not match row_ptr
     with pytest.raises(B200Error):
         gpu_ctx.upload(3, 8, rp, np.array([1, 4, 7, 0, 2], np.uint32), np.ones(5, np.uint64))  # row_ptr too short
+
+
+# ------------------------------------------------------------------ the one-pass multiply (dense.cu, pipeline 5)
+@pytest.mark.parametrize("ctas", [3, 8], ids=["window-18k", "window-6k-pieces"])
+@pytest.mark.parametrize("bits", [64, 32])
+def test_one_pass_dense_windows(gpu_ctx, oracle, cfg, bits, ctas):
+    """Pipeline 5 on tori whose rows wrap around the index space (arc origin > 0, rows written rotated), with the window
+    shrunk (8 CTAs per SM: ~6 K columns) so that the later powers of the 30^3 chain are produced in column pieces."""
+    cfg(pipeline=5, fused_threads=ctas)
+    a_h = hostgen.reference_bench_instance(30, 3.0, bits)
+    gpu = chain_check(oracle, gpu_ctx, a_h, 6 if ctas == 8 else 7, what=f"one-pass u{bits} ctas {ctas}")
+    assert gpu[-1].device.product_stats().pipeline == 5
+    long_h = hostgen.thinned_torus([64, 6, 6], 4.0 / 26.0, bytes([7] * 32), bits)
+    chain_check(oracle, gpu_ctx, long_h, 5, what="one-pass long torus")
+
+
+def test_one_pass_row_blocks_empty_rows_and_values(gpu_ctx, oracle, cfg):
+    """Row blocks at both ends of the index space (rectangular left operand), rows without products, values > 1 on both sides."""
+    cfg(pipeline=5)
+    rng = np.random.default_rng(11)
+    a_h = hostgen.thinned_torus([40, 10, 10], 5.0 / 26.0, bytes([3] * 32), 64)
+    a_h.values[:] = rng.integers(1, 30, a_h.values.size)
+    a_o = to_o(oracle, a_h)
+    full = oracle.matmul_par(oracle.matmul_par(a_o, a_o), a_o)
+    a = B200Matrix.from_host(a_h, gpu_ctx)
+    for r0, r1 in ((0, 700), (1500, 2600), (3300, 4000)):
+        blk = B200Matrix.from_host(a_h.row_block(r0, r1), gpu_ctx)
+        first = blk.matmul(a)
+        assert first.device.product_stats().pipeline == 5
+        got = first.matmul(a)                                                # (64-bit sums from here on: the engine picks another pipeline by itself)
+        want = hostgen.HostCsr(full.rows, full.cols, full.row_ptr, full.col_idx, full.values).row_block(r0, r1)
+        assert_same(got.to_host(), want, f"rows {r0}..{r1}")
