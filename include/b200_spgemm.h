@@ -62,7 +62,7 @@ typedef struct b200_stats {
                                    and 2 share list 2), [9] heavy, [10..15] hash lists of bins 0..5 (window too wide).
                                    fused pipeline: [0] tiny, [1] dense, [2] other (counted beforehand), [3] empty rows,
                                    [9] heavy and [10..15] hash lists of the "other" rows                          */
-    uint32_t pipeline;          /* 1 fused, 2 binned                                                             */
+    uint32_t pipeline;          /* pipeline that produced the result: 1 fused, 2 binned, 3 row-per-warp, 4 one launch, 5 one pass */
     uint32_t reserved[15];
 } b200_stats;
 
@@ -75,7 +75,9 @@ typedef struct b200_config {
                                     selectable); 2 binned (a kernel per row bin, scratch or exact placement); 3 exact
                                     placement with the row-per-warp count / numeric kernels over the bin lists; 4 the whole
                                     multiply as ONE cooperative launch (count, placement, numeric; C written once, no
-                                    host wait) -- needs one window for all rows that fits a warp's bitmap                  */
+                                    host wait) -- needs one window for all rows that fits a warp's bitmap; 5 one pass over
+                                    the products (dense window accumulators per row, look-back placement over rows; needs
+                                    32-bit sums, a square low-degree right operand; measured slower, kept selectable)      */
     int32_t placement;           /* binned pipeline: -1 auto, 0 scratch CSR + compaction, 1 exact (count pass first)       */
     int32_t exact_limit_mb;      /* binned, auto placement: scratch bound above which the exact placement runs; -1 auto    */
     int32_t force_acc_mode;      /* -1 auto (proved from the operands); 1 / 2 force the 64-bit / saturating accumulators   */
@@ -90,7 +92,8 @@ typedef struct b200_config {
     int32_t lanes_per_entry_lg;  /* lanes cooperating on one A entry, log2; -1 auto                                        */
     int32_t expand_div, hash_div, grid_div, grid_mul;   /* binned: thread / grid sizing divisors (8, 32, 8, 4)            */
     int32_t aux_streams;         /* auxiliary streams the per-bin kernels fan out over (default 1, at most 3)              */
-    int32_t fused_threads;       /* fused: threads per CTA of the numeric kernel (0 auto = 256; multiple of 32, <= 256)    */
+    int32_t fused_threads;       /* fused: threads per CTA of the numeric kernel (0 auto = 256; multiple of 32, <= 256);
+                                    pipeline 5: CTAs per SM the window is cut for (1..8, default 3)                        */
     int32_t fused_window_cols;   /* fused: preferred cap of the dense accumulator window in columns (0 auto)               */
     int32_t fused_dense_pmax;    /* fused: rows with more intermediate products go to the heavy kernel (0 auto = 65536)    */
     int32_t heavy_chunk_cols;    /* heavy rows: columns per chunk of the chunked kernel (0 auto, from shared memory)       */
