@@ -106,7 +106,11 @@ typedef struct b200_config {
                                     (0 auto: 1024 per column chunk, at least 8193)                                         */
     int32_t heavy_unit_products; /* heavy rows: intermediate products per work unit of the chunked kernel -- rows with more are
                                     cut into several units of consecutive chunks, one CTA each (0 auto = 2^20)              */
-    int32_t reserved[3];
+    int32_t narrow_download;     /* b200_csr_download_async: u64 values whose maximum is known to be < 2^32 cross PCIe as u32 (a
+                                    third fewer bytes) and host threads widen them into the caller's array.  Default 0: on a
+                                    16-core host the widening (8 threads, streaming stores) costs what the bus saves (5.42 vs
+                                    5.53 ms per A^2..A^7 step); worth switching on where host cores are plentiful           */
+    int32_t reserved[2];
 } b200_config;
 int b200_config_default(b200_config *cfg);
 
@@ -153,7 +157,8 @@ int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint3
 int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values);
 /* Asynchronous variant into pinned host memory: ordered after the work queued on the ctx stream so far, run on
  * the context's own copy stream so that it overlaps the next multiply; b200_ctx_synchronize waits for it, and
- * freeing the handle is ordered after it. */
+ * freeing the handle is ordered after it.  The host arrays must not be read before b200_ctx_synchronize returns (u64
+ * values proven to fit 32 bits travel narrow and are widened into `values` by the library's host threads). */
 int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values);
 
 /* C = A x B.  Replaces CsrMatrix::matmul / matmul_par (src/graph_csr.rs:306-346, 350-484),

@@ -152,7 +152,7 @@ extern "C" int b200_config_default(b200_config *c) {
     c->pipeline = 0; c->placement = -1; c->exact_limit_mb = -1; c->force_acc_mode = -1; c->window_cap_groups = -1; c->window_mul = 3;
     c->circular_windows = 1; c->arc_window = 1; c->touched_span = 1; c->narrow_scratch = 1; c->expand_kernel = 1; c->pack_b = -1;
     c->lanes_per_entry_lg = -1; c->expand_div = 8; c->hash_div = 32; c->grid_div = 8; c->grid_mul = 4; c->aux_streams = 1;
-    c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1; c->heavy_min_products = 0; c->heavy_unit_products = 0;
+    c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1; c->heavy_min_products = 0; c->heavy_unit_products = 0; c->narrow_download = 0;
     return B200_OK;
 }
 static void config_from_env(b200_config *c) {
@@ -162,7 +162,7 @@ static void config_from_env(b200_config *c) {
         {"B200_SPAN", &c->touched_span}, {"B200_NARROW", &c->narrow_scratch}, {"B200_EXPAND", &c->expand_kernel}, {"B200_PACK", &c->pack_b},
         {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
         {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
-        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel}, {"B200_HEAVY_PMIN", &c->heavy_min_products}, {"B200_HEAVY_UNIT", &c->heavy_unit_products},
+        {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel}, {"B200_HEAVY_PMIN", &c->heavy_min_products}, {"B200_HEAVY_UNIT", &c->heavy_unit_products}, {"B200_NARROW_DL", &c->narrow_download},
         {"B200_RW_CAP", &c->rw_cap_percent},
     };
     for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
@@ -182,6 +182,8 @@ extern "C" int b200_ctx_get_config(b200_ctx *ctx, b200_config *c) {
 
 static int env_int_early(const char *name) { const char *v = getenv(name); return v && *v ? atoi(v) : 0; }
 extern "C" int b200_ctx_destroy(b200_ctx *ctx);
+static void narrow_destroy(b200_ctx *ctx);
+static void narrow_reap(b200_ctx *ctx);
 // (inside b200_ctx_create, once the context exists: a failing call releases what has been set up so far)
 #define CUDA_TRY_X(expr)                                                                           \
     do {                                                                                           \
@@ -266,6 +268,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->stream);
+    narrow_destroy(ctx);
     if (ctx->entry_cache) { for (auto &b : *ctx->entry_cache) dfree(ctx, b.first); delete ctx->entry_cache; ctx->entry_cache = nullptr; }
     dfree(ctx, ctx->d_prod); dfree(ctx, ctx->d_tmp_ptr); dfree(ctx, ctx->d_nnz_row); dfree(ctx, ctx->d_bin_rows); dfree(ctx, ctx->d_win); dfree(ctx, ctx->d_scan); dfree(ctx, ctx->d_heavy); dfree(ctx, ctx->d_tmp_col); dfree(ctx, ctx->d_tmp_val); dfree(ctx, ctx->d_hv);
     dfree(ctx, ctx->d_fz); dfree(ctx, ctx->d_units); dfree(ctx, ctx->d_rowwin); dfree(ctx, ctx->d_rowclass); dfree(ctx, ctx->d_spill_acc); dfree(ctx, ctx->d_spill_col);
@@ -287,6 +290,7 @@ extern "C" int b200_ctx_synchronize(b200_ctx *ctx) {
     if (!ctx) return set_err(B200_ERR_BADARG, "ctx is NULL");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->copy));
+    if (ctx->post) { CUDA_TRY(cudaStreamSynchronize(ctx->post)); narrow_reap(ctx); }
     return B200_OK;
 }
 extern "C" int b200_ctx_kernel_launches(b200_ctx *ctx, uint64_t *out) {
@@ -511,6 +515,114 @@ extern "C" int b200_csr_max_value(b200_ctx *ctx, const b200_csr *m, uint64_t *ou
     return B200_OK;
 }
 
+// ---- narrow downloads.  The end-to-end chain is PCIe-bound (291.6 MB of results at 57 GB/s); u64 path counts that are proven
+// to fit 32 bits (the report of the multiply that produced them carries their maximum) are narrowed by a kernel on the copy
+// stream, cross the bus as u32 in chunks, and a small pool of host threads widens every chunk into the caller's u64 array
+// while the next chunk is in flight.
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <immintrin.h>
+#define NARROW_CHUNK ((size_t)4 << 20)        // elements per chunk (16 MiB on the bus)
+// u32 -> u64 with streaming stores: the destination is written once and not read here, so no read-for-ownership traffic
+__attribute__((target("avx2"))) static void widen_avx2(const u32 *src, u64 *dst, size_t n) {
+    size_t j = 0;
+    while (j < n && ((uintptr_t)(dst + j) & 31)) { dst[j] = (u64)src[j]; j++; }
+    for (; j + 8 <= n; j += 8) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(src + j));
+        _mm256_stream_si256((__m256i *)(dst + j), _mm256_cvtepu32_epi64(_mm256_castsi256_si128(v)));
+        _mm256_stream_si256((__m256i *)(dst + j + 4), _mm256_cvtepu32_epi64(_mm256_extracti128_si256(v, 1)));
+    }
+    for (; j < n; j++) dst[j] = (u64)src[j];
+    _mm_sfence();
+}
+static void widen_plain(const u32 *src, u64 *dst, size_t n) { for (size_t j = 0; j < n; j++) dst[j] = (u64)src[j]; }
+#define NARROW_MIN ((u64)1 << 18)             // smaller arrays are copied as they are
+struct NarrowStage { u32 *h; size_t cap; cudaEvent_t done; bool used; };
+struct NarrowJob { struct NarrowState *ns; const u32 *src; u64 *dst; size_t n; };
+struct NarrowState {
+    std::vector<std::thread> th; std::mutex m; std::condition_variable cv, cv_done;
+    const u32 *src = nullptr; u64 *dst = nullptr; size_t n = 0; long gen = 0; int remaining = 0; bool stop = false; int T = 1;
+    bool avx2 = __builtin_cpu_supports("avx2");
+    std::vector<NarrowStage> stages; std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
+    std::vector<NarrowJob *> jobs;           // callback arguments, freed at synchronize / destroy
+    void worker(int i) {
+        long seen = 0;
+        while (true) {
+            std::unique_lock<std::mutex> l(m);
+            cv.wait(l, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            const u32 *s_ = src; u64 *d_ = dst; const size_t n_ = n;
+            l.unlock();
+            const size_t lo = n_ * (size_t)i / (size_t)T, hi = n_ * (size_t)(i + 1) / (size_t)T;
+            if (avx2) widen_avx2(s_ + lo, d_ + lo, hi - lo); else widen_plain(s_ + lo, d_ + lo, hi - lo);
+            l.lock();
+            if (--remaining == 0) cv_done.notify_all();
+        }
+    }
+    void run(const u32 *s_, u64 *d_, size_t n_) {          // called from one CUDA callback thread at a time (one post stream)
+        std::unique_lock<std::mutex> l(m);
+        src = s_; dst = d_; n = n_; remaining = T; gen++;
+        cv.notify_all();
+        cv_done.wait(l, [&] { return remaining == 0; });
+    }
+};
+static void CUDART_CB narrow_cb(void *arg) { NarrowJob *j = (NarrowJob *)arg; j->ns->run(j->src, j->dst, j->n); }
+__global__ void __launch_bounds__(256) k_narrow_vals(u64 n, const u64 *__restrict__ in, u32 *__restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (u32)in[i];
+}
+static NarrowState *narrow_state(b200_ctx *ctx) {
+    if (ctx->narrow) return ctx->narrow;
+    NarrowState *ns = new NarrowState();
+    int cores = (int)std::thread::hardware_concurrency();
+    cpu_set_t set; CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+    ns->T = std::max(2, std::min(16, cores / 2));
+    for (int i = 0; i < ns->T; i++) ns->th.emplace_back([ns, i] { ns->worker(i); });
+    if (cudaStreamCreateWithFlags(&ctx->post, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->post = nullptr; }
+    ctx->narrow = ns;
+    return ns;
+}
+static void narrow_reap(b200_ctx *ctx) {                    // after the post stream has drained
+    if (!ctx->narrow) return;
+    for (NarrowJob *j : ctx->narrow->jobs) delete j;
+    ctx->narrow->jobs.clear();
+    for (auto &st : ctx->narrow->stages) st.used = false;
+    ctx->narrow->ev_next = 0;
+}
+static void narrow_destroy(b200_ctx *ctx) {
+    NarrowState *ns = ctx->narrow;
+    if (!ns) return;
+    if (ctx->post) cudaStreamSynchronize(ctx->post);
+    narrow_reap(ctx);
+    { std::lock_guard<std::mutex> l(ns->m); ns->stop = true; }
+    ns->cv.notify_all();
+    for (auto &t : ns->th) t.join();
+    for (auto &st : ns->stages) { cudaFreeHost(st.h); cudaEventDestroy(st.done); }
+    for (auto e : ns->ev_pool) cudaEventDestroy(e);
+    if (ctx->post) cudaStreamDestroy(ctx->post);
+    delete ns; ctx->narrow = nullptr; ctx->post = nullptr;
+}
+// pinned staging of at least `elems` u32: a stage not in use since the last synchronize, else a new one
+static NarrowStage *narrow_stage(NarrowState *ns, size_t elems) {
+    NarrowStage *best = nullptr;
+    for (auto &st : ns->stages) if (!st.used && st.cap >= elems && (!best || st.cap < best->cap)) best = &st;
+    if (!best) {
+        NarrowStage st; st.cap = elems + elems / 8; st.used = false; st.h = nullptr;
+        if (cudaMallocHost((void **)&st.h, st.cap * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(st.h); return nullptr; }
+        ns->stages.push_back(st);
+        best = &ns->stages.back();
+    }
+    best->used = true;
+    return best;
+}
+static cudaEvent_t narrow_event(NarrowState *ns) {
+    if (ns->ev_next == ns->ev_pool.size()) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; } ns->ev_pool.push_back(e); }
+    return ns->ev_pool[ns->ev_next++];
+}
+
 extern "C" int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
     if (!ctx || !m) return set_err(B200_ERR_BADARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -518,17 +630,40 @@ extern "C" int b200_csr_download_async(b200_ctx *ctx, const b200_csr *m, uint64_
     // the copies run on the context's copy stream, after everything queued on the compute stream so far
     b200_csr *mm = const_cast<b200_csr *>(m);
     if (!mm->ev_copy) CUDA_TRY(cudaEventCreateWithFlags(&mm->ev_copy, cudaEventDisableTiming));
+    // values that fit 32 bits: narrow on the device, widen on the host (the staging is allocated before anything is queued)
+    NarrowState *ns = nullptr; NarrowStage *stage = nullptr; u32 *d_narrow = nullptr;
+    if (values && m->val_bits == 64 && ctx->cfg.narrow_download && m->nnz >= NARROW_MIN && m->h_maxval_known && m->h_maxval <= 0xFFFFFFFFull) {
+        ns = narrow_state(ctx);
+        if (ctx->post) stage = narrow_stage(ns, m->nnz);
+        if (stage && dmalloc(ctx, (void **)&d_narrow, m->nnz * 4) != B200_OK) { stage->used = false; stage = nullptr; }
+    }
     CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ctx->ev_ready, 0));
     if (row_ptr) CUDA_TRY(cudaMemcpyAsync(row_ptr, m->d_rp, (m->rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->copy));
     if (col_idx && m->nnz) CUDA_TRY(cudaMemcpyAsync(col_idx, m->d_col, m->nnz * 4, cudaMemcpyDeviceToHost, ctx->copy));
-    if (values && m->nnz) CUDA_TRY(cudaMemcpyAsync(values, m->d_val, m->nnz * (size_t)(m->val_bits / 8), cudaMemcpyDeviceToHost, ctx->copy));
+    if (stage) {
+        k_narrow_vals<<<grid_for(m->nnz, 256, ctx->num_sms * 4), 256, 0, ctx->copy>>>(m->nnz, (const u64 *)m->d_val, d_narrow);
+        ctx->launches++;
+        for (size_t off = 0; off < m->nnz; off += NARROW_CHUNK) {
+            const size_t n = std::min<size_t>(NARROW_CHUNK, m->nnz - off);
+            CUDA_TRY(cudaMemcpyAsync(stage->h + off, d_narrow + off, n * 4, cudaMemcpyDeviceToHost, ctx->copy));
+            cudaEvent_t e = narrow_event(ns);
+            if (!e) return set_err(B200_ERR_CUDA, "download: event creation failed");
+            CUDA_TRY(cudaEventRecord(e, ctx->copy));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->post, e, 0));
+            NarrowJob *job = new NarrowJob{ns, stage->h + off, (u64 *)values + off, n};
+            ns->jobs.push_back(job);
+            CUDA_TRY(cudaLaunchHostFunc(ctx->post, narrow_cb, job));
+        }
+        CUDA_TRY(cudaFreeAsync(d_narrow, ctx->copy));
+    } else if (values && m->nnz) CUDA_TRY(cudaMemcpyAsync(values, m->d_val, m->nnz * (size_t)(m->val_bits / 8), cudaMemcpyDeviceToHost, ctx->copy));
     CUDA_TRY(cudaEventRecord(mm->ev_copy, ctx->copy));
     return B200_OK;
 }
 extern "C" int b200_csr_download(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint32_t *col_idx, void *values) {
     TRY(b200_csr_download_async(ctx, m, row_ptr, col_idx, values));
     CUDA_TRY(cudaStreamSynchronize(ctx->copy));
+    if (ctx->post) CUDA_TRY(cudaStreamSynchronize(ctx->post));             // (narrow downloads: the host threads' widening runs behind the copies)
     return B200_OK;
 }
 extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_t *row_ptr, uint64_t *col_idx, void *values) {

@@ -96,6 +96,9 @@ struct b200_ctx {
     // entry arrays (col_idx | values, one allocation) of freed handles, kept for the next product of about that size: a loop
     // of large multiplies (12-GB results on the 200^3 chain) otherwise stalls in the stream-ordered allocator every few steps
     std::vector<std::pair<void *, size_t>> *entry_cache; size_t entry_cache_bytes;
+    // narrow downloads: u64 values proven < 2^32 cross PCIe as u32 and are widened by host threads into the caller's array
+    cudaStream_t post;                  // host callbacks (the widening) run behind the copy stream's chunks
+    struct NarrowState *narrow;
     u64 *d_rowstat; u64 cap_rowstat;   // per-row look-back status of the one-pass multiply (dense.cu)
     void *d_hv; size_t cap_hv;         // chunked heavy-row kernels (heavy.cu): control words | per-(row, chunk) counters | unit lists
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)

@@ -250,7 +250,7 @@ def test_one_pass_row_blocks_empty_rows_and_values(gpu_ctx, oracle, cfg):
     """Row blocks at both ends of the index space (rectangular left operand), rows without products, values > 1 on both sides."""
     cfg(pipeline=5)
     rng = np.random.default_rng(11)
-    a_h = hostgen.thinned_torus([40, 10, 10], 5.0 / 26.0, bytes([3] * 32), 64)
+    a_h = hostgen.thinned_torus([40, 10, 10], 3.5 / 26.0, bytes([3] * 32), 64)      # (mean row <= 4: sector-packed right operand)
     a_h.values[:] = rng.integers(1, 30, a_h.values.size)
     a_o = to_o(oracle, a_h)
     full = oracle.matmul_par(oracle.matmul_par(a_o, a_o), a_o)
@@ -262,3 +262,28 @@ def test_one_pass_row_blocks_empty_rows_and_values(gpu_ctx, oracle, cfg):
         got = first.matmul(a)                                                # (64-bit sums from here on: the engine picks another pipeline by itself)
         want = hostgen.HostCsr(full.rows, full.cols, full.row_ptr, full.col_idx, full.values).row_block(r0, r1)
         assert_same(got.to_host(), want, f"rows {r0}..{r1}")
+
+
+def test_narrow_download_widens_to_the_same_bytes(gpu_ctx, oracle, cfg):
+    """b200_config.narrow_download: u64 values proven < 2^32 cross PCIe as u32 and host threads widen them -- the arrays the
+    caller gets are the same (asynchronous variant into pinned memory, several products in flight, then one synchronize)."""
+    import torch
+    a_h = hostgen.reference_bench_instance(30, 3.0, 64)
+    a = gpu_ctx.upload(a_h.rows, a_h.cols, a_h.row_ptr, a_h.col_idx, a_h.values)
+    a_o = to_o(oracle, a_h)
+    want, p_o = [], a_o
+    for _ in range(4):
+        p_o = oracle.matmul_par(p_o, a_o); want.append(p_o)
+    for on in (1, 0):
+        cfg(narrow_download=on)
+        p, got, bufs = a, [], []
+        for w in want:
+            p = gpu_ctx.spgemm(p, a)
+            b = (torch.empty((a_h.rows + 1) * 8, dtype=torch.uint8).pin_memory(), torch.empty(w.nnz() * 4, dtype=torch.uint8).pin_memory(),
+                 torch.empty(w.nnz() * 8, dtype=torch.uint8).pin_memory())
+            p.download_async_into(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr())
+            got.append(p); bufs.append(b)
+        gpu_ctx.synchronize()
+        for w, b in zip(want, bufs):
+            assert np.array_equal(b[0].numpy().view(np.uint64), w.row_ptr) and np.array_equal(b[1].numpy().view(np.uint32), w.col_idx)
+            assert np.array_equal(b[2].numpy().view(np.uint64), w.values), f"narrow_download={on}"
