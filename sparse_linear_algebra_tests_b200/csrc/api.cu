@@ -938,7 +938,8 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     auto launch_cta_hash = [&](int bin, int hb, u64 n, cudaStream_t bs) -> int {
         const u32 slots = b200_hash_slots(hb);
         const int threads = bin_threads(ctx, hb, lg);
-        const size_t smem = (size_t)slots * (4 + accb) + ((size_t)b200_order_buckets(slots) + 1) * 4;   // table + the ordering step's bucket counters
+        // table + the ordering step's bucket counters + the enumeration's per-thread arrays
+        const size_t smem = (size_t)slots * (4 + accb) + (((size_t)b200_order_buckets(slots) + 1 + 3) & ~(size_t)3) * 4 + EnumPtrs::bytes((u32)threads);
         if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
         const int g = (int)std::min<u64>(n, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 4);
         if (mode == 0) k_num_cta<VT, 0><<<g, threads, smem, bs>>>(na, ctx->d_bin_rows, ctrl, bin, slots, lg, o);
@@ -1022,9 +1023,10 @@ static int launch_sym_heavy(b200_ctx *ctx, const SymArgs &sa, u64 rows, u32 nwor
     const size_t smem_max = ctx->smem_optin - 1024;
     const bool hv_on = hv && hv->on && A && B;
     const HvSkip skip{ctx->d_prod, hv_on ? hv->pmin : ~0ull, hv_on ? hv->cap_li : 0u};
-    if ((size_t)nwords * 4 <= smem_max) {
+    const size_t bm_smem = (((size_t)nwords + 3) & ~(size_t)3) * 4 + EnumPtrs::bytes(1024);
+    if (bm_smem <= smem_max) {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * 2);
-        k_sym_cta<true><<<g, 1024, (size_t)nwords * 4, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows, skip);
+        k_sym_cta<true><<<g, 1024, bm_smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_HEAVY, 2, nwords, 5, ctx->d_nnz_row, (u32)ctx->cap_rows, skip);
     } else {
         const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms);
         TRY(ensure_heavy_scratch(ctx, (size_t)g * nwords * 4));
@@ -1065,7 +1067,7 @@ static int launch_counts(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, co
         if (caps.cap[hb] < nw4_full && !(hb <= rw.hb_max && rw.all_fit)) {
             const u32 slots = b200_hash_slots(hb);
             const int threads = bin_threads(ctx, hb, lg);
-            const size_t smem = (size_t)slots * 4;
+            const size_t smem = (size_t)slots * 4 + EnumPtrs::bytes((u32)threads);   // key table + the enumeration's per-thread arrays
             if (smem > smem_max) return set_err(B200_ERR_CUDA, "hash bin %d needs %zu B of shared memory", hb, smem);
             const int g = (int)std::min<u64>(rows, (u64)ctx->num_sms * ctas_per_sm(ctx, threads, smem) * 2);
             k_sym_cta<false><<<g, threads, smem, fan.pick()>>>(sa, ctx->d_bin_rows, ctrl, B200_BIN_WIDE0 + hb, slots, nwords, lg, ctx->d_nnz_row, bstride, HvSkip{nullptr, ~0ull, 0u});

@@ -288,11 +288,18 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s_warp /*>=33*/, u32 
 // long B row no longer pins one lane group while the rest of the CTA waits at the barrier), and consecutive threads
 // read consecutive B entries.  f(p, jb, a_ik): p = running product index in the row, jb = index into B's arrays.
 struct EnumSmem { u32 pre[1025]; u32 start[1024]; u64 av[1024]; };
+// the same three arrays sized by the CTA's own thread count, carved out of dynamic shared memory: the hash kernels run with
+// 32..1024 threads, and 16 KB of static arrays per 32-thread CTA held their occupancy at 15 % (R-MAT scale 20, ncu)
+struct EnumPtrs {
+    u64 *av; u32 *pre; u32 *start;
+    __device__ __forceinline__ void bind(unsigned char *base, u32 nt) { av = reinterpret_cast<u64 *>(base); pre = reinterpret_cast<u32 *>(av + nt); start = pre + nt + 1; }
+    static __host__ __device__ size_t bytes(u32 nt) { return (size_t)nt * 16 + 8; }
+};
 template <bool NEEDED> struct EnumStore { EnumSmem s; };                   // kernels that enumerate only in some variants
 template <> struct EnumStore<false> { u32 s; };
-template <typename VT, bool NUMERIC, typename F>
+template <typename VT, bool NUMERIC, typename ES, typename F>
 __device__ __forceinline__ u32 enumerate_products(const u32 *__restrict__ Ac, const VT *__restrict__ Av, u32 lenA,
-                                                  const uint2 *__restrict__ bdesc, EnumSmem &es, u32 *s_warp, F f) {
+                                                  const uint2 *__restrict__ bdesc, ES &es, u32 *s_warp, F f) {
     const u32 nt = blockDim.x, tid = threadIdx.x;
     u32 done = 0;
     for (u32 base = 0; base < lenA; base += nt) {
@@ -469,13 +476,13 @@ __global__ void __launch_bounds__(256) k_sym_warp(SymArgs a, const u32 *__restri
 template <bool BITMAP>
 __global__ void __launch_bounds__(1024) k_sym_cta(SymArgs a, const u32 *__restrict__ bin_rows, B200Ctrl *ctrl, int bin, u32 slots,
                                                   u32 nwords, int lg, u32 *__restrict__ nnz_row, u32 bin_stride, HvSkip skip) {
-    extern __shared__ u32 smem[];
+    extern __shared__ __align__(16) u32 smem[];
     __shared__ u32 s_count, s_warp[33];
-    __shared__ EnumSmem s_enum;
     const u32 count = ctrl->sym_bin_count[bin];
     const u64 off = (u64)bin * bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;
     const u32 tabn = BITMAP ? nwords : slots;
+    EnumPtrs s_enum; s_enum.bind(reinterpret_cast<unsigned char *>(smem + ((tabn + 3u) & ~3u)), nt);   // behind the table, 16-byte aligned
     const int shift = 32 - (31 - __clz(slots));
     for (u32 r = blockIdx.x; r < count; r += gridDim.x) {
         const u32 row = bin_rows[off + r];
@@ -669,12 +676,12 @@ __global__ void __launch_bounds__(1024) k_num_cta(NumArgs<VT> a, const u32 *__re
                                                   int lg, OutArgs<VT> o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 s_warp[33];
-    __shared__ EnumSmem s_enum;
     __shared__ u32 s_mm[2];
     Acc<MODE> acc; acc.bind(smem_raw, slots);
     u32 *keys = reinterpret_cast<u32 *>(smem_raw + Acc<MODE>::bytes(slots));
     u32 *bcnt = keys + slots;                                               // bucket counters / offsets of the ordering step: NB + 1 words
     const u32 NB = b200_order_buckets(slots);
+    EnumPtrs s_enum; s_enum.bind(reinterpret_cast<unsigned char *>(bcnt + ((NB + 1 + 3u) & ~3u)), blockDim.x);   // behind the counters, 16-byte aligned
     const u32 count = o.bin_cnt[bin];
     const u64 off = (u64)bin * o.bin_stride;
     const u32 nt = blockDim.x, tid = threadIdx.x;

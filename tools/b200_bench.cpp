@@ -125,6 +125,7 @@ static int run_chain(const Args &args) {
     for (int g = 0; g < S.n; g++) th.emplace_back(rank_main, &S, g);
     for (auto &t : th) t.join();
     const int steps = (int)S.ms[0].size();
+    // the reference's chain table starts `step,nnz,...` (src/graph_magnus.rs:734); `multiply` is its step, times are the max over GPUs
     printf("config,gpus,multiply,nnz,products,ms_max_over_gpus,products_per_s\n");
     double tot_ms = 0; uint64_t tot_prod = 0;
     std::vector<uint64_t> nnz_k(steps, 0);
@@ -157,7 +158,9 @@ static int run_sweep(const Args &args) {
     const double epns[5] = {2, 3, 4, 8, 26};
     uint8_t seed[32]; memset(seed, 42, 32);
     uint64_t skip = 0;
-    printf("side,nodes,e_per_n,nnz_a,nnz_c,products,b200_ms\n");
+    // the reference's columns (src/graph_magnus.rs:805) up to `components`, then this engine's: mean and best of the 10 timed
+    // multiplies in microseconds (the reference prints elapsed / ITERS), the product's nnz and the intermediate products
+    printf("side,nodes,e_per_n,nnz,components,b200_us,b200_best_us,nnz_c,products\n");
     for (int si = 0; si < 4; si++) {
         const uint64_t dims[3] = {(uint64_t)sides[si], (uint64_t)sides[si], (uint64_t)sides[si]};
         b200_csr *full = nullptr;
@@ -167,19 +170,29 @@ static int run_sweep(const Args &args) {
             CHECK(b200_thin(ctx, full, std::min(1.0, epns[ei] / 26.0), seed, skip, &a, &draws));
             skip += draws;
             uint64_t rows, nnz_a; CHECK(b200_csr_info(a, &rows, nullptr, &nnz_a, nullptr));
-            double best = 1e30; b200_stats st; memset(&st, 0, sizeof(st));
+            double best = 1e30, sum = 0; b200_stats st; memset(&st, 0, sizeof(st));
             for (int it = 0; it < 11; it++) {                        // 1 warm-up + 10 timed (:856)
                 b200_csr *c = nullptr;
                 CHECK(b200_ctx_synchronize(ctx));
                 const double t0 = now_ms();
                 CHECK(b200_spgemm(ctx, a, a, &c, nullptr));
                 CHECK(b200_ctx_synchronize(ctx));
-                if (it) best = std::min(best, now_ms() - t0);
+                const double dt = now_ms() - t0;
+                if (it) { best = std::min(best, dt); sum += dt; }
                 if (it == 10) CHECK(b200_csr_product_stats(ctx, c, &st));
                 CHECK(b200_csr_free(ctx, c));
             }
-            printf("%d,%llu,%g,%llu,%llu,%llu,%.4f\n", sides[si], (unsigned long long)rows, epns[ei], (unsigned long long)nnz_a, (unsigned long long)st.nnz_c,
-                   (unsigned long long)st.products, best);
+            // num_components (src/graph_csr.rs:654-657) of the instance: union-find over the downloaded pattern
+            std::vector<uint64_t> rp(rows + 1); std::vector<uint32_t> ci(std::max<uint64_t>(nnz_a, 1)); std::vector<uint64_t> vv(std::max<uint64_t>(nnz_a, 1));
+            CHECK(b200_csr_download(ctx, a, rp.data(), ci.data(), args.bits == 64 ? (void *)vv.data() : (void *)vv.data()));
+            std::vector<uint32_t> parent(rows);
+            for (uint64_t i = 0; i < rows; i++) parent[i] = (uint32_t)i;
+            auto find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+            for (uint64_t r = 0; r < rows; r++) for (uint64_t i = rp[r]; i < rp[r + 1]; i++) { const uint32_t x = find((uint32_t)r), y = find(ci[i]); if (x != y) parent[x] = y; }
+            uint64_t components = 0;
+            for (uint64_t i = 0; i < rows; i++) components += find((uint32_t)i) == i;
+            printf("%d,%llu,%.0f,%llu,%llu,%.1f,%.1f,%llu,%llu\n", sides[si], (unsigned long long)rows, epns[ei], (unsigned long long)nnz_a, (unsigned long long)components,
+                   sum / 10 * 1e3, best * 1e3, (unsigned long long)st.nnz_c, (unsigned long long)st.products);
             CHECK(b200_csr_free(ctx, a));
         }
         CHECK(b200_csr_free(ctx, full));
