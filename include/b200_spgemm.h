@@ -62,7 +62,7 @@ typedef struct b200_stats {
                                    and 2 share list 2), [9] heavy, [10..15] hash lists of bins 0..5 (window too wide).
                                    fused pipeline: [0] tiny, [1] dense, [2] other (counted beforehand), [3] empty rows,
                                    [9] heavy and [10..15] hash lists of the "other" rows                          */
-    uint32_t pipeline;          /* pipeline that produced the result: 1 fused, 2 binned, 3 row-per-warp, 4 one launch, 5 one pass */
+    uint32_t pipeline;          /* pipeline that produced the result: 1 fused, 2 binned, 3 row-per-warp, 4 one launch, 5 one pass, 6 left multiply */
     uint32_t reserved[15];
 } b200_stats;
 
@@ -77,7 +77,10 @@ typedef struct b200_config {
                                     multiply as ONE cooperative launch (count, placement, numeric; C written once, no
                                     host wait) -- needs one window for all rows that fits a warp's bitmap; 5 one pass over
                                     the products (dense window accumulators per row, look-back placement over rows; needs
-                                    32-bit sums, a square low-degree right operand; measured slower, kept selectable)      */
+                                    32-bit sums, a square low-degree right operand; measured slower, kept selectable);
+                                    6 left multiply: short rows in A, long rows in B -- a row of C is the union of a few long
+                                    sorted rows of B streamed with coalesced loads, one cooperative launch (auto where it
+                                    applies)                                                                               */
     int32_t placement;           /* binned pipeline: -1 auto, 0 scratch CSR + compaction, 1 exact (count pass first)       */
     int32_t exact_limit_mb;      /* binned, auto placement: scratch bound above which the exact placement runs; -1 auto    */
     int32_t force_acc_mode;      /* -1 auto (proved from the operands); 1 / 2 force the 64-bit / saturating accumulators   */
@@ -110,7 +113,12 @@ typedef struct b200_config {
                                     third fewer bytes) and host threads widen them into the caller's array.  Default 0: on a
                                     16-core host the widening (8 threads, streaming stores) costs what the bus saves (5.42 vs
                                     5.53 ms per A^2..A^7 step); worth switching on where host cores are plentiful           */
-    int32_t reserved[2];
+    int32_t commute_swap;        /* operands known to commute (both are powers of one base handle, e.g. the steps of a power
+                                    chain): evaluate B x A instead of A x B when A's rows are long and B's short -- the result is
+                                    the same matrix bit for bit (the saturating path-count semiring is associative), but a row
+                                    of it is then the union of a few long sorted rows (pipeline 6).  Default 0: on the 30^3 chain (B200) the swapped
+                                    steps measured level with pipeline 4 on A^7 (0.31 ms) and 10-20 % behind on A^5 / A^6      */
+    int32_t reserved[1];
 } b200_config;
 int b200_config_default(b200_config *cfg);
 

@@ -17,7 +17,7 @@ fn main() {
     let lib = out.join("libb200spgemm.a");
 
     // one object per translation unit, as in csrc/Makefile
-    let units = ["api", "fused", "rowwarp", "heavy", "coo", "comm"];
+    let units = ["api", "fused", "rowwarp", "heavy", "coo", "comm", "dense", "leftmul"];
     let mut objs = Vec::new();
     for u in units {
         let obj = out.join(format!("{u}.o"));
@@ -41,7 +41,7 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
     println!("cargo:rustc-link-lib=dylib=dl");       // comm.cu binds NCCL at run time (dlopen of libnccl.so.2)
-    for f in ["api.cu", "fused.cu", "rowwarp.cu", "heavy.cu", "coo.cu", "comm.cu", "kernels.cuh", "devutil.cuh", "engine.cuh", "gen.cuh", "common.cuh"] {
+    for f in ["api.cu", "fused.cu", "rowwarp.cu", "heavy.cu", "coo.cu", "comm.cu", "dense.cu", "leftmul.cu", "kernels.cuh", "devutil.cuh", "engine.cuh", "gen.cuh", "common.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include").join("b200_spgemm.h").display());

@@ -47,7 +47,7 @@ class Config(C.Structure):
         "pipeline", "placement", "exact_limit_mb", "force_acc_mode", "window_cap_groups", "window_mul", "circular_windows",
         "arc_window", "touched_span", "narrow_scratch", "expand_kernel", "pack_b", "lanes_per_entry_lg", "expand_div", "hash_div",
         "grid_div", "grid_mul", "aux_streams", "fused_threads", "fused_window_cols", "fused_dense_pmax", "heavy_chunk_cols",
-        "heavy_kernel", "fused_ring_slots", "fused_product_slots", "rw_cap_percent", "heavy_min_products", "heavy_unit_products", "narrow_download")] + [("reserved", C.c_int32 * 2)]
+        "heavy_kernel", "fused_ring_slots", "fused_product_slots", "rw_cap_percent", "heavy_min_products", "heavy_unit_products", "narrow_download", "commute_swap")] + [("reserved", C.c_int32 * 1)]
 
 
 EXPORTS = [

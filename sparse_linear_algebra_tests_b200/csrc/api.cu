@@ -153,6 +153,7 @@ extern "C" int b200_config_default(b200_config *c) {
     c->circular_windows = 1; c->arc_window = 1; c->touched_span = 1; c->narrow_scratch = 1; c->expand_kernel = 1; c->pack_b = -1;
     c->lanes_per_entry_lg = -1; c->expand_div = 8; c->hash_div = 32; c->grid_div = 8; c->grid_mul = 4; c->aux_streams = 1;
     c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1; c->heavy_min_products = 0; c->heavy_unit_products = 0; c->narrow_download = 0;
+    c->commute_swap = 0;
     return B200_OK;
 }
 static void config_from_env(b200_config *c) {
@@ -163,7 +164,7 @@ static void config_from_env(b200_config *c) {
         {"B200_LG", &c->lanes_per_entry_lg}, {"B200_EDIV", &c->expand_div}, {"B200_TDIV", &c->hash_div}, {"B200_GDIV", &c->grid_div},
         {"B200_GMUL", &c->grid_mul}, {"B200_NAUX", &c->aux_streams}, {"B200_FUSED_THREADS", &c->fused_threads}, {"B200_FUSED_WINDOW", &c->fused_window_cols},
         {"B200_FUSED_PMAX", &c->fused_dense_pmax}, {"B200_FUSED_RING", &c->fused_ring_slots}, {"B200_FUSED_PBUF", &c->fused_product_slots}, {"B200_HEAVY_CHUNK", &c->heavy_chunk_cols}, {"B200_HEAVY_KERNEL", &c->heavy_kernel}, {"B200_HEAVY_PMIN", &c->heavy_min_products}, {"B200_HEAVY_UNIT", &c->heavy_unit_products}, {"B200_NARROW_DL", &c->narrow_download},
-        {"B200_RW_CAP", &c->rw_cap_percent},
+        {"B200_RW_CAP", &c->rw_cap_percent}, {"B200_COMMUTE", &c->commute_swap},
     };
     for (auto &t : tab) { const char *v = getenv(t.name); if (v && *v) *t.field = atoi(v); }
 }
@@ -244,6 +245,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     rwf_setup(ctx);
     hv_setup(ctx);
     dn_setup(ctx);
+    lm_setup(ctx);
     ctx->cap_cta_tot = 8192;
     CUDA_TRY_X(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
@@ -344,6 +346,8 @@ int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool all
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
     m->cr_start = 0; m->cr_len = cols;
     m->pending_slot = -1; m->max_row_span = cols;
+    static u64 next_uid = 0;
+    m->uid = __sync_add_and_fetch(&next_uid, 1); m->lin_base = m->uid; m->lin_pow = 1;
     int r = dmalloc(ctx, (void **)&m->d_rp, (rows + 1) * 8 + 16);           // row_ptr + the max-value scalar
     if (r == B200_OK) m->d_maxval = (ull *)(m->d_rp + rows + 1);
     if (r == B200_OK && alloc_arrays) r = alloc_entries(ctx, m);
@@ -1232,6 +1236,51 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         cap = std::max<u64>(64, std::min<u64>(2048, (cap + 31) / 32 * 32));
         rw.hb_max = B200_RW_MAX_HB; rw.nw = ((u32)groups * 4u + 31u) & ~31u; rw.cap = (u32)cap; rw.all_fit = all_fit;   // (a lane owns nw / 32 consecutive words)
     }
+    // Left multiply (pipeline 6, leftmul.cu): A's rows are short, B's long -- a row of C is the union of a few long sorted rows of
+    // B, streamed as contiguous lists.  Window: for square operands whose entry offsets (c - row) are bounded on the index
+    // circle the window travels with the row (the bound of a product is the sum of its operands' bounds, carried on the
+    // handles); else the operand-level arc or the whole column space, as pipeline 4.
+    if (B->rows == B->cols && A->rows == A->cols) {
+        if (A->cs_state == 0 && A->max_row_len <= 64) { r = ensure_cs_bounds(ctx, A); if (r != B200_OK) { b200_csr_free(ctx, C); return r; } }
+        if (B->cs_state == 0 && B->max_row_len <= 64) { r = ensure_cs_bounds(ctx, B); if (r != B200_OK) { b200_csr_free(ctx, C); return r; } }
+        if (A->cs_state == 1 && B->cs_state == 1) {
+            const long long lo = A->cs_lo + B->cs_lo, hi = A->cs_hi + B->cs_hi, half = (long long)(ncols / 2);
+            if (lo > -half && hi < half - 1) { C->cs_lo = lo; C->cs_hi = hi; C->cs_state = 1; }
+        }
+    }
+    {
+        const double meanA = (double)A->nnz / (double)rows, meanB = (double)B->nnz / (double)B->rows;
+        const bool shape_ok = A->max_row_len <= 32 && meanB >= 48.0 && meanB >= 4.0 * meanA;
+        if ((ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && shape_ok)) && cheap_bound && ncols < 0xFFFF0000ull && rows < 0xFFFF0000ull &&
+            ctx->cfg.window_cap_groups < 0 && ctx->cfg.placement < 0) {
+            u64 words = (u64)all_groups * 4; u32 org = all_rot; bool per_row = false;
+            if (C->cs_state == 1 && ctx->cfg.circular_windows) {
+                const u64 w = ((u64)(C->cs_hi - C->cs_lo + 1) + 31) / 32;
+                if (w < words) { words = w; per_row = true; org = (u32)(C->cs_lo < 0 ? (long long)ncols + C->cs_lo : C->cs_lo); }
+            }
+            const u32 nw = (u32)((words + 31) & ~31ull);
+            const double meanP = meanA * meanB;
+            const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.0;
+            u64 cap = (u64)(factor * meanP) + 32;
+            cap = std::min<u64>(cap, std::min<u64>(p_bound, words * 32));
+            cap = std::max<u64>(64, std::min<u64>(4096, (cap + 31) / 32 * 32));
+            const size_t per_warp = lm_smem_per_warp(mode1, nw, (u32)cap);
+            if (words <= 2048 && per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 6 || per_warp <= 24 * 1024)) {
+                if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY_C(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
+                if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
+                C->cap_entries = std::max<u64>((u64)hb128, 1);
+                r = alloc_entries(ctx, C);
+                if (r == B200_OK) r = lm_launch(ctx, A, B, C, ctx->d_ctrl, mode1, org, per_row, nw, (u32)cap, ctx->cfg.fused_threads == 4 ? 0 : ctx->cfg.fused_threads == 6 ? 1 : -1, mirror, epoch, s);
+                if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
+                if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
+                trace_dump(ctx, "left multiply");
+                mark_pending(ctx, C, slot, epoch, A, B, mode1, 6, (int32_t)(ctx->launches - launches0), timing, std::min<u64>(p_bound, ncols));
+                *out = C;
+                if (st) { TRY(resolve_pending(ctx, C)); *st = *C->stats; }
+                return B200_OK;
+            }
+        }
+    }
     // One pass over the products (pipeline 5, dense.cu): 32-bit sums proven, a square low-degree right operand with a known offset
     // range, C allocated from the host-known bound.
     if (ctx->cfg.pipeline == 5 && mode1 == 0 && packed && B->rows == B->cols && cheap_bound && B->nnz < 0xFFFFFFFFull && ncols < 0x7FFFFFFFull) {
@@ -1489,10 +1538,20 @@ extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, 
     if (A->ctx != ctx || B->ctx != ctx) return set_err(B200_ERR_BADARG, "operand handles belong to another context");
     CUDA_TRY(cudaSetDevice(ctx->device));
     RESOLVE(ctx, A); RESOLVE(ctx, B);
+    // Operands that are powers of one base handle commute, and the saturating path-count semiring is associative (every
+    // entry of any product of such powers is min(cap, its exact integer value), whatever the order of evaluation): when A's
+    // rows are long and B's short -- a power chain step A^(k-1) x A -- the engine evaluates B x A, whose rows are unions of
+    // a few long sorted rows (pipeline 6).  Same matrix, bit for bit.
+    const u64 lin_base = A->lin_base == B->lin_base ? A->lin_base : 0, lin_pow = A->lin_pow + B->lin_pow;
+    if (lin_base && ctx->cfg.commute_swap && (ctx->cfg.pipeline == 0 || ctx->cfg.pipeline == 6) && A != B && A->rows && A->nnz && B->nnz) {
+        const double meanA = (double)A->nnz / (double)A->rows, meanB = (double)B->nnz / (double)B->rows;
+        if (B->max_row_len <= 32 && meanA >= 48.0 && meanA >= 4.0 * meanB) std::swap(A, B);
+    }
     bool handled = false;
     TRY(A->val_bits == 32 ? spgemm_fused<u32>(ctx, A, B, C, stats, &handled) : spgemm_fused<u64>(ctx, A, B, C, stats, &handled));
-    if (handled) return B200_OK;
-    return A->val_bits == 32 ? spgemm_typed<u32>(ctx, A, B, C, stats) : spgemm_typed<u64>(ctx, A, B, C, stats);
+    if (!handled) TRY(A->val_bits == 32 ? spgemm_typed<u32>(ctx, A, B, C, stats) : spgemm_typed<u64>(ctx, A, B, C, stats));
+    if (lin_base) { (*C)->lin_base = lin_base; (*C)->lin_pow = lin_pow; }
+    return B200_OK;
 }
 
 extern "C" int b200_csr_product_stats(b200_ctx *ctx, const b200_csr *C, b200_stats *stats) {

@@ -53,6 +53,9 @@ struct b200_csr {
     u64 est_nnz;            // while pending: host-side estimate of nnz (heuristics of a multiply queued behind this one)
     b200_stats *stats;      // measurements of the multiply that produced this handle (filled when the report is read)
     bool stats_timed;       // the report slot's events were recorded for it
+    // lineage: this handle holds (base handle `lin_base`) ^ lin_pow.  Every handle is its own base to the power 1; a product
+    // of two powers of one base is a power of that base.  Powers of one matrix commute (b200_spgemm may swap them).
+    u64 uid, lin_base, lin_pow;
 };
 
 struct b200_ctx {
@@ -187,6 +190,11 @@ int hv_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, B200Ctrl *ct
 void dn_setup(b200_ctx *ctx);
 int dn_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, bool bpat, int ctas_per_sm, u64 *mirror, u32 epoch,
               cudaStream_t s);
+// ---- leftmul.cu: short rows in A, long rows in B -- one cooperative launch, B's rows streamed as contiguous lists
+void lm_setup(b200_ctx *ctx);
+size_t lm_smem_per_warp(int mode, u32 nw, u32 cap);
+int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, B200Ctrl *ctrl, int mode, u32 org, bool per_row, u32 nw, u32 cap,
+              int tune, u64 *mirror, u32 epoch, cudaStream_t s);
 // ---- fused.cu
 template <typename VT>
 int spgemm_fused(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr **out, b200_stats *st_out, bool *handled);

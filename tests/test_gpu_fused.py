@@ -41,7 +41,7 @@ def chain_check(O, ctx, a_h, powers, left_h=None, what=""):
 
 
 # ------------------------------------------------------------------ the headline instance, every power, both value widths
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3, 4, 5], ids=["default", "fused", "binned", "rowwarp", "onelaunch", "onepass"])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3, 4, 5, 6], ids=["default", "fused", "binned", "rowwarp", "onelaunch", "onepass", "leftmul"])
 @pytest.mark.parametrize("bits", [64, 32])
 def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, cfg, bits, pipeline):
     """BASELINE configs[1]: the reference's exact operand (StdRng([42;32]) thinning of the 30^3 Moore torus, 81 434 nnz),
@@ -53,7 +53,7 @@ def test_reference_instance_30_every_power_bit_exact(gpu_ctx, oracle, cfg, bits,
     gpu = chain_check(oracle, gpu_ctx, a_h, 7, what=f"u{bits} pipeline {pipeline}")
     assert [g.nnz() for g in gpu] == [251590, 655391, 1574848, 3383207, 6590100, 11736555]
     st = gpu[-1].device.product_stats()
-    assert st.nnz_c == 11736555 and st.pipeline == {0: DEFAULT_PIPELINE, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5}[pipeline]
+    assert st.nnz_c == 11736555 and st.pipeline == {0: DEFAULT_PIPELINE, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6}[pipeline]
     if pipeline == 1:
         assert st.sym_bin_rows[2] == 0, "a row of the headline multiply left the fused kernel for the counted lists"
 
