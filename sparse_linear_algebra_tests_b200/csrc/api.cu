@@ -1258,7 +1258,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 const u64 w = ((u64)(C->cs_hi - C->cs_lo + 1) + 31) / 32;
                 if (w < words) { words = w; per_row = true; org = (u32)(C->cs_lo < 0 ? (long long)ncols + C->cs_lo : C->cs_lo); }
             }
-            const u32 nw = (u32)((words + 31) & ~31ull);
+            u32 nw = (u32)((words + 31) & ~31ull);
+            if (per_row) { nw = (u32)((words + 127) / 128); nw = (nw | 1u) * 128u; }   // 128 x odd words: conflict-free 128-bit sweeps (leftmul.cu)
             const double meanP = meanA * meanB;
             const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.0;
             u64 cap = (u64)(factor * meanP) + 32;

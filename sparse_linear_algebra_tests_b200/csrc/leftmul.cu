@@ -48,6 +48,13 @@ struct LmArgs {
 __device__ __forceinline__ void lm_red_or(u32 addr, u32 v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void lm_red_add(u32 addr, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void lm_st_u16(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
+// the same, predicated in the instruction (no branch around a slot of a batch)
+__device__ __forceinline__ void lm_red_or_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }" :: "r"(addr), "r"(v), "r"((u32)on) : "memory"); }
+__device__ __forceinline__ void lm_red_add_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.add.u32 [%0], %1; }" :: "r"(addr), "r"(v), "r"((u32)on) : "memory"); }
+__device__ __forceinline__ void lm_st_u16_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; }" :: "r"(addr), "h"((unsigned short)v), "r"((u32)on) : "memory"); }
+__device__ __forceinline__ uint4 lm_ld_v4(u32 addr) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory"); return r; }
+__device__ __forceinline__ void lm_st_v4(u32 addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ void lm_st_v2(u32 addr, u32 a, u32 b) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(addr), "r"(a), "r"(b) : "memory"); }
 __device__ __forceinline__ u32 lm_ld_u32(u32 addr) { u32 r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory"); return r; }
 __device__ __forceinline__ u32 lm_ld_u16(u32 addr) { unsigned short r; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr) : "memory"); return r; }
 __device__ __forceinline__ u32 lm_ldg_u32(const u32 *p) { return __ldg(p); }
@@ -100,9 +107,12 @@ template <int U> struct LmCols { u32 c[U]; };
 template <int U, typename XV> struct LmEntries { u32 c[U]; XV v[U]; };
 
 // One warp's share of shared memory: bits u32[nw] | prefix u16[nw] | acc[cap] | window offsets u16[cap]   (nw % 32 == 0).
-// Every phase leaves the words it touched zeroed.  The sweeps over the touched words give every lane an ODD number of
-// consecutive words, so the lanes' accesses fall on different banks.
-template <typename VT, int MODE, int TUNE>
+// Every phase leaves the words it touched zeroed.  The sweeps over the bitmap come in two builds:
+//   FULL = false  a window much wider than a row (whole column space): the marks track the lowest / highest word touched, a lane
+//                 sweeps an ODD number of consecutive words of that span (the lanes' accesses fall on different banks);
+//   FULL = true   a window cut to the rows (travelling with the row): no tracking, a lane owns nw / 32 = 4 x odd consecutive
+//                 words and sweeps them with 128-bit accesses (a quarter warp covers all banks).
+template <typename VT, int MODE, int TUNE, bool FULL>
 struct LmWarp {
     static constexpr int LM_U = LmTune<TUNE>::U, LM_UA = LmTune<TUNE>::UA;
     typedef typename std::conditional<MODE == 0, u32, VT>::type XT;          // what the accumulate phase keeps of a value
@@ -140,14 +150,16 @@ struct LmWarp {
                 },
                 [&](const LmCols<LM_U> &q, u32, u32 base, u32 len) {
 #pragma unroll
-                    for (int u = 0; u < LM_U; u++) if (base + 32u * u + lane < len) {
+                    for (int u = 0; u < LM_U; u++) {
+                        const bool on = base + 32u * u + lane < len;
                         const u32 d = lm_dcol(q.c[u], org, ncols);
-                        lm_red_or(sm_bits + (d >> 5) * 4u, __funnelshift_l(0u, 1u, d));
-                        lo = min(lo, d); hi = max(hi, d);
+                        lm_red_or_if(on, sm_bits + (d >> 5) * 4u, __funnelshift_l(0u, 1u, d));
+                        if (!FULL && on) { lo = min(lo, d); hi = max(hi, d); }
                     }
                 });
         }
-        wlo = __reduce_min_sync(FULLMASK, lo) >> 5; whi = __reduce_max_sync(FULLMASK, hi) >> 5;
+        if (FULL) { wlo = 0; whi = nw - 1; }
+        else { wlo = __reduce_min_sync(FULLMASK, lo) >> 5; whi = __reduce_max_sync(FULLMASK, hi) >> 5; }
         return psum;
     }
 
@@ -158,7 +170,14 @@ struct LmWarp {
         mid();
         __syncwarp();
         u32 mine = 0;
-        if (wlo <= whi) {
+        if (FULL) {
+            const u32 wpl = nw >> 5, a0 = sm_bits + (u32)lane * wpl * 4u;
+            for (u32 i = 0; i < wpl; i += 4) {
+                const uint4 b = lm_ld_v4(a0 + i * 4u);
+                mine += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+                lm_st_v4(a0 + i * 4u, make_uint4(0u, 0u, 0u, 0u));
+            }
+        } else if (wlo <= whi) {
             const u32 wpl = ((whi - wlo + 32u) >> 5) | 1u, w0 = wlo + (u32)lane * wpl;
             for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { mine += __popc(bits[w0 + i]); bits[w0 + i] = 0; }
         }
@@ -176,15 +195,30 @@ struct LmWarp {
         __syncwarp();
         if (wlo > whi) return 0u;
         // ---- rank: consecutive words per lane over the touched span, warp scan of the lanes' popcounts
-        const u32 wpl = ((whi - wlo + 32u) >> 5) | 1u, w0 = wlo + (u32)lane * wpl;
+        const u32 wpl = FULL ? nw >> 5 : ((whi - wlo + 32u) >> 5) | 1u, w0 = wlo + (u32)lane * wpl;
+        const u32 a0 = sm_bits + w0 * 4u, q0 = sm_pref + w0 * 2u;
         u32 mine = 0;
-        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) mine += __popc(bits[w0 + i]);
+        if (FULL) {
+            for (u32 i = 0; i < wpl; i += 4) { const uint4 b = lm_ld_v4(a0 + i * 4u); mine += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w); }
+        } else {
+            for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) mine += __popc(bits[w0 + i]);
+        }
         u32 incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
         const u32 nnz = __shfl_sync(FULLMASK, incl, 31);
+        if (FULL && nnz == 0) return 0u;
         u32 run = incl - mine;
-        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { pref[w0 + i] = (unsigned short)run; run += __popc(bits[w0 + i]); }
+        if (FULL) {
+            for (u32 i = 0; i < wpl; i += 4) {
+                const uint4 b = lm_ld_v4(a0 + i * 4u);
+                const u32 r1 = run + __popc(b.x), r2 = r1 + __popc(b.y), r3 = r2 + __popc(b.z);
+                lm_st_v2(q0 + i * 2u, run | (r1 << 16), r2 | (r3 << 16));
+                run = r3 + __popc(b.w);
+            }
+        } else {
+            for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { pref[w0 + i] = (unsigned short)run; run += __popc(bits[w0 + i]); }
+        }
         __syncwarp();
         // ranks are in d order; with an origin > 0 the entries whose column lies below it (d >= ncols - org) belong in FRONT
         // of the others: the row is written rotated by r0 = entries with d < ncols - org
@@ -214,17 +248,20 @@ struct LmWarp {
                         const XT x = shfl_any(xa, (int)j);
                         u32 d[LM_UA], sb[LM_UA], sp[LM_UA];
 #pragma unroll
-                        for (int u = 0; u < LM_UA; u++) if (base + 32u * u + lane < len) {
-                            d[u] = lm_dcol(q.c[u], org, ncols);
+                        for (int u = 0; u < LM_UA; u++) {
+                            d[u] = base + 32u * u + lane < len ? lm_dcol(q.c[u], org, ncols) : 0u;     // (an idle slot reads word 0 and stores nothing)
                             sb[u] = lm_ld_u32(sm_bits + (d[u] >> 5) * 4u); sp[u] = lm_ld_u16(sm_pref + (d[u] >> 5) * 2u);
                         }
 #pragma unroll
-                        for (int u = 0; u < LM_UA; u++) if (base + 32u * u + lane < len) {
+                        for (int u = 0; u < LM_UA; u++) {
                             const u32 pos = sp[u] + __popc(sb[u] & (__funnelshift_l(0u, 1u, d[u]) - 1u)) - pass;
-                            if (!MULTI || pos < cap) {
+                            const bool on = base + 32u * u + lane < len && (!MULTI || pos < cap);
+                            if (MODE == 0) {
+                                lm_st_u16_if(on, sm_offs + pos * 2u, d[u]);
+                                lm_red_add_if(on, sm_acc + pos * 4u, (u32)x * (u32)q.v[u]);
+                            } else if (on) {
                                 lm_st_u16(sm_offs + pos * 2u, d[u]);
-                                if (MODE == 0) lm_red_add(sm_acc + pos * 4u, (u32)x * (u32)q.v[u]);
-                                else acc.addv(pos, lm_product<MODE, VT>((VT)x, (VT)q.v[u]));
+                                acc.addv(pos, lm_product<MODE, VT>((VT)x, (VT)q.v[u]));
                             }
                         }
                     });
@@ -255,13 +292,14 @@ struct LmWarp {
                 __syncwarp();
             }
         }
-        for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) bits[w0 + i] = 0;
+        if (FULL) { for (u32 i = 0; i < wpl; i += 4) lm_st_v4(a0 + i * 4u, make_uint4(0u, 0u, 0u, 0u)); }
+        else { for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) bits[w0 + i] = 0; }
         __syncwarp();
         return nnz;
     }
 };
 
-template <typename VT, int MODE, int TUNE>
+template <typename VT, int MODE, int TUNE, bool FULL>
 __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u64 s_base; __shared__ ull s_P, s_maxP; __shared__ u32 s_maxN, s_last, s_scan[LM_WARPS + 1];
@@ -271,7 +309,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
     const u32 nslices = gridDim.x, slice = blockIdx.x;
     const u64 S = (p.rows + nslices - 1) / nslices;                        // rows per slice of the row_ptr phase
     const u64 r_lo = min(p.rows, (u64)slice * S), r_hi = min(p.rows, r_lo + S);
-    typedef LmWarp<VT, MODE, TUNE> W;
+    typedef LmWarp<VT, MODE, TUNE, FULL> W;
     W w(p, smem_raw + (size_t)wid * W::bytes(p.nw, p.cap), lane);
     w.zero();
     if (tid == 0) { s_P = 0; s_maxP = 0; s_maxN = 0; }
@@ -381,16 +419,16 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
 
 // ---------------------------------------------------------------------------- host side
 struct LmKernel { const void *fn; int regs; size_t static_smem; };
-static LmKernel g_lm[2][3][2];                                            // [value width][accumulator mode][tune]
-template <typename VT, int MODE, int TUNE>
+static LmKernel g_lm[2][3][2][2];                                         // [value width][accumulator mode][tune][full sweeps]
+template <typename VT, int MODE, int TUNE, bool FULL>
 static void lm_register(size_t optin) {
-    LmKernel &k = g_lm[sizeof(VT) == 8][MODE][TUNE];
-    k.fn = (const void *)k_lm<VT, MODE, TUNE>;
+    LmKernel &k = g_lm[sizeof(VT) == 8][MODE][TUNE][FULL];
+    k.fn = (const void *)k_lm<VT, MODE, TUNE, FULL>;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k.fn) == cudaSuccess) { k.regs = fa.numRegs; k.static_smem = fa.sharedSizeBytes; } else { cudaGetLastError(); k.regs = 64; k.static_smem = 0; }
     if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - k.static_smem)) != cudaSuccess) cudaGetLastError();
 }
-template <typename VT, int MODE> static void lm_register2(size_t o) { lm_register<VT, MODE, 0>(o); lm_register<VT, MODE, 1>(o); }
+template <typename VT, int MODE> static void lm_register2(size_t o) { lm_register<VT, MODE, 0, false>(o); lm_register<VT, MODE, 1, false>(o); lm_register<VT, MODE, 0, true>(o); lm_register<VT, MODE, 1, true>(o); }
 void lm_setup(b200_ctx *ctx) {
     const size_t o = ctx->smem_optin;
     lm_register2<u32, 0>(o); lm_register2<u32, 1>(o);
@@ -419,7 +457,8 @@ int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, 
     const bool v64 = A->val_bits == 64;
     const size_t smem = lm_smem_per_warp(mode, nw, cap) * LM_WARPS;
     if (tune < 0) tune = (smem + 1024) * 6 <= (size_t)228 * 1024 ? 1 : 0;   // the residency of tune 1 needs six CTAs' worth of shared memory
-    const LmKernel &k = g_lm[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][tune ? 1 : 0];
+    const bool full = per_row && nw % 128 == 0 && (nw / 128) % 2 == 1;     // a travelling window is cut to the rows: sweep all of it, 128 bits at a time
+    const LmKernel &k = g_lm[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][tune ? 1 : 0][full ? 1 : 0];
     if (!k.fn) return set_err(B200_ERR_CUDA, "left-multiply kernel variant is not registered");
     if (smem + k.static_smem > ctx->smem_optin) return set_err(B200_ERR_CUDA, "left-multiply kernel needs %zu B of shared memory", smem);
     int per_sm = 0;
@@ -432,7 +471,7 @@ int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, 
     const cudaError_t le = v64 ? lm_go<u64>(ctx, A, B, C, ctrl, org, per_row, nw, cap, mirror, epoch, k.fn, grid, smem, s)
                                : lm_go<u32>(ctx, A, B, C, ctrl, org, per_row, nw, cap, mirror, epoch, k.fn, grid, smem, s);
     ctx->launches++;
-    if (ctx->trace) { fprintf(stderr, "[b200 trace] left multiply: tune %d grid %d (%d/SM) regs %d smem %zu nw %u cap %u org %u per_row %d\n", tune, grid, per_sm, k.regs, smem, nw, cap, org, (int)per_row); trace_mark(ctx, __LINE__); }
+    if (ctx->trace) { fprintf(stderr, "[b200 trace] left multiply: full %d tune %d grid %d (%d/SM) regs %d smem %zu nw %u cap %u org %u per_row %d\n", (int)full, tune, grid, per_sm, k.regs, smem, nw, cap, org, (int)per_row); trace_mark(ctx, __LINE__); }
     if (le != cudaSuccess) return set_err(B200_ERR_CUDA, "left-multiply kernel launch failed: %s", cudaGetErrorString(le));
     return B200_OK;
 }
