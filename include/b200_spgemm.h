@@ -116,8 +116,7 @@ typedef struct b200_config {
     int32_t commute_swap;        /* operands known to commute (both are powers of one base handle, e.g. the steps of a power
                                     chain): evaluate B x A instead of A x B when A's rows are long and B's short -- the result is
                                     the same matrix bit for bit (the saturating path-count semiring is associative), but a row
-                                    of it is then the union of a few long sorted rows (pipeline 6).  Default 0: on the 30^3 chain (B200) the swapped
-                                    steps measured level with pipeline 4 on A^7 (0.31 ms) and 10-20 % behind on A^5 / A^6      */
+                                    of it is then the union of a few long sorted rows (pipeline 6).  Default 1 (30^3 chain on B200: A^7 0.316 -> 0.25 ms)            */
     int32_t reserved[1];
 } b200_config;
 int b200_config_default(b200_config *cfg);

@@ -153,7 +153,7 @@ extern "C" int b200_config_default(b200_config *c) {
     c->circular_windows = 1; c->arc_window = 1; c->touched_span = 1; c->narrow_scratch = 1; c->expand_kernel = 1; c->pack_b = -1;
     c->lanes_per_entry_lg = -1; c->expand_div = 8; c->hash_div = 32; c->grid_div = 8; c->grid_mul = 4; c->aux_streams = 1;
     c->fused_threads = 0; c->fused_window_cols = 0; c->fused_dense_pmax = 0; c->heavy_chunk_cols = 0; c->heavy_kernel = 1; c->heavy_min_products = 0; c->heavy_unit_products = 0; c->narrow_download = 0;
-    c->commute_swap = 0;
+    c->commute_swap = 1;
     return B200_OK;
 }
 static void config_from_env(b200_config *c) {
@@ -1263,6 +1263,12 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
             const double meanP = meanA * meanB;
             const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.0;
             u64 cap = (u64)(factor * meanP) + 32;
+            // a row of C is a union of rows of B: when B is itself a product, its own compression (entries per intermediate
+            // product) and the skew of its rows (longest / mean) predict the longest row of C better than the product count
+            if (ctx->cfg.rw_cap_percent <= 0 && B->stats && B->stats->products && B->stats->nnz_c && meanB > 0.0) {
+                const double cr = (double)B->stats->nnz_c / (double)B->stats->products, skew = (double)B->max_row_len / meanB;
+                cap = std::min<u64>(cap, (u64)(1.1 * meanP * cr * skew) + 32);
+            }
             cap = std::min<u64>(cap, std::min<u64>(p_bound, words * 32));
             cap = std::max<u64>(64, std::min<u64>(4096, (cap + 31) / 32 * 32));
             const size_t per_warp = lm_smem_per_warp(mode1, nw, (u32)cap);
@@ -1271,7 +1277,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
                 C->cap_entries = std::max<u64>((u64)hb128, 1);
                 r = alloc_entries(ctx, C);
-                if (r == B200_OK) r = lm_launch(ctx, A, B, C, ctx->d_ctrl, mode1, org, per_row, nw, (u32)cap, ctx->cfg.fused_threads == 4 ? 0 : ctx->cfg.fused_threads == 6 ? 1 : -1, mirror, epoch, s);
+                if (r == B200_OK) r = lm_launch(ctx, A, B, C, ctx->d_ctrl, mode1, org, per_row, nw, (u32)cap, ctx->cfg.fused_threads == 4 ? 0 : ctx->cfg.fused_threads == 6 ? 1 : ctx->cfg.fused_threads == 5 ? 2 : -1, mirror, epoch, s);
                 if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
                 if (timing) cudaEventRecord(ctx->f_ev[slot][2], s);
                 trace_dump(ctx, "left multiply");

@@ -30,6 +30,7 @@
 template <int TUNE> struct LmTune;
 template <> struct LmTune<0> { static constexpr int U = 8, UA = 4, CTAS = 4; };
 template <> struct LmTune<1> { static constexpr int U = 4, UA = 2, CTAS = 6; };
+template <> struct LmTune<2> { static constexpr int U = 8, UA = 4, CTAS = 5; };
 #define FULLMASK 0xFFFFFFFFu
 
 template <typename VT>
@@ -75,29 +76,38 @@ __device__ __forceinline__ u32 lm_dcol(u32 c, u32 org, u32 ncols) {
 }
 
 // The batches of one block of <= 32 lists (lane l < nl: list l starts at entry b0 of B's arrays and has bl entries), in
-// order; `load(payload, list, start, base, len)` fetches entries base + 32 u + lane (u < LM_U) of a list, `proc` consumes
-// them.  The next batch is loaded before the current one is consumed.
-template <int U, typename PAY, typename LOAD, typename PROC>
-__device__ __forceinline__ void lm_batches(u32 nl, u64 b0, u32 bl, LOAD load, PROC proc) {
-    u32 j = 0, len = 0;
-    for (;; j++) { if (j >= nl) return; len = __shfl_sync(FULLMASK, bl, j); if (len) break; }
-    u64 st = shfl_u64(b0, j);
-    u32 base = 0;
-    PAY cur;
-    load(cur, j, st, base, len);
+// order.  `sel(list)` yields what a batch needs of its list besides the entries (a_ik), `load(payload, start, base, len)`
+// fetches entries base + 32 u + lane (u < U) of a list, `proc(payload, sel's value, base, len)` consumes them.  Two payloads
+// alternate: while one batch is consumed the next one's loads are in flight, and no register is copied between them (a copy
+// would wait for the loads it copies) -- the loop body exists twice, once per payload.  Everything warp-wide (the
+// shuffles that pick the next list) happens before a batch's loads are issued.
+struct LmCur { u32 j, base, len; u64 st; };
+template <int U, typename PAY, typename SEL, typename LOAD, typename PROC>
+__device__ __forceinline__ void lm_batches(u32 nl, u64 b0, u32 bl, SEL sel, LOAD load, PROC proc) {
+    auto next_list = [&](LmCur &c) {                                      // c.j: first list to try
+        c.base = 0; c.len = 0;
+        for (; c.j < nl; c.j++) { c.len = __shfl_sync(FULLMASK, bl, c.j); if (c.len) break; }
+        if (c.j < nl) c.st = shfl_u64(b0, c.j);
+    };
+    auto advance = [&](LmCur c) -> LmCur { c.base += 32u * U; if (c.base >= c.len) { c.j++; next_list(c); } return c; };
+    LmCur a; a.j = 0; a.st = 0;
+    next_list(a);
+    if (a.j >= nl) return;
+    PAY A, B;
+    auto xa = sel(a.j);
+    load(A, a.st, a.base, a.len);
     while (true) {
-        u32 nj = j, nbase = base + 32u * U, nlen = len; u64 nst = st;
-        if (nbase >= len) {
-            nbase = 0; nlen = 0;
-            for (nj = j + 1; nj < nl; nj++) { nlen = __shfl_sync(FULLMASK, bl, nj); if (nlen) break; }
-            if (nj < nl) nst = shfl_u64(b0, nj);
-        }
-        const bool more = nj < nl;
-        PAY nxt;
-        if (more) load(nxt, nj, nst, nbase, nlen);
-        proc(cur, j, base, len);
-        if (!more) break;
-        cur = nxt; j = nj; st = nst; base = nbase; len = nlen;
+        LmCur b = advance(a);
+        const bool mb = b.j < nl;
+        auto xb = xa;
+        if (mb) { xb = sel(b.j); load(B, b.st, b.base, b.len); }
+        proc(A, xa, a.base, a.len);
+        if (!mb) break;
+        a = advance(b);
+        const bool ma = a.j < nl;
+        if (ma) { xa = sel(a.j); load(A, a.st, a.base, a.len); }
+        proc(B, xb, b.base, b.len);
+        if (!ma) break;
     }
 }
 
@@ -143,12 +153,13 @@ struct LmWarp {
             if (ab) { b0 = 0; bl = 0; if (t < lenA) { const u32 k = p.colA[rs + t]; b0 = p.rpB[k]; bl = (u32)(p.rpB[k + 1] - b0); } }
             psum += bl;
             lm_batches<LM_U, LmCols<LM_U>>(min(32u, lenA - ab), b0, bl,
-                [&](LmCols<LM_U> &q, u32, u64 st, u32 base, u32 len) {
+                [&](u32) { return 0; },
+                [&](LmCols<LM_U> &q, u64 st, u32 base, u32 len) {
                     const u32 *src = p.colB + st + base + lane;
 #pragma unroll
                     for (int u = 0; u < LM_U; u++) if (base + 32u * u + lane < len) q.c[u] = lm_ldg_u32(src + 32 * u);
                 },
-                [&](const LmCols<LM_U> &q, u32, u32 base, u32 len) {
+                [&](const LmCols<LM_U> &q, int, u32 base, u32 len) {
 #pragma unroll
                     for (int u = 0; u < LM_U; u++) {
                         const bool on = base + 32u * u + lane < len;
@@ -237,15 +248,15 @@ struct LmWarp {
                 u64 b0 = dsc.b0; u32 bl = dsc.bl; XT xa = dsc.xa;
                 if (ab) { b0 = 0; bl = 0; xa = 0; if (t < lenA) { const u32 k = p.colA[rs + t]; b0 = p.rpB[k]; bl = (u32)(p.rpB[k + 1] - b0); xa = (XT)p.valA[rs + t]; } }
                 lm_batches<LM_UA, LmEntries<LM_UA, XV>>(min(32u, lenA - ab), b0, bl,
-                    [&](LmEntries<LM_UA, XV> &q, u32, u64 st, u32 base, u32 len) {
+                    [&](u32 j) { return shfl_any(xa, (int)j); },
+                    [&](LmEntries<LM_UA, XV> &q, u64 st, u32 base, u32 len) {
                         const u32 *src = p.colB + st + base + lane;
                         const XV *vsrc = reinterpret_cast<const XV *>(p.valB + st + base + lane);
                         constexpr int VS = sizeof(VT) / sizeof(XV);          // (little endian: the low word comes first)
 #pragma unroll
                         for (int u = 0; u < LM_UA; u++) if (base + 32u * u + lane < len) { q.c[u] = lm_ldg_u32(src + 32 * u); q.v[u] = __ldg(vsrc + 32 * u * VS); }
                     },
-                    [&](const LmEntries<LM_UA, XV> &q, u32 j, u32 base, u32 len) {
-                        const XT x = shfl_any(xa, (int)j);
+                    [&](const LmEntries<LM_UA, XV> &q, XT x, u32 base, u32 len) {
                         u32 d[LM_UA], sb[LM_UA], sp[LM_UA];
 #pragma unroll
                         for (int u = 0; u < LM_UA; u++) {
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
 
 // ---------------------------------------------------------------------------- host side
 struct LmKernel { const void *fn; int regs; size_t static_smem; };
-static LmKernel g_lm[2][3][2][2];                                         // [value width][accumulator mode][tune][full sweeps]
+static LmKernel g_lm[2][3][3][2];                                         // [value width][accumulator mode][tune][full sweeps]
 template <typename VT, int MODE, int TUNE, bool FULL>
 static void lm_register(size_t optin) {
     LmKernel &k = g_lm[sizeof(VT) == 8][MODE][TUNE][FULL];
@@ -428,7 +439,7 @@ static void lm_register(size_t optin) {
     if (cudaFuncGetAttributes(&fa, k.fn) == cudaSuccess) { k.regs = fa.numRegs; k.static_smem = fa.sharedSizeBytes; } else { cudaGetLastError(); k.regs = 64; k.static_smem = 0; }
     if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - k.static_smem)) != cudaSuccess) cudaGetLastError();
 }
-template <typename VT, int MODE> static void lm_register2(size_t o) { lm_register<VT, MODE, 0, false>(o); lm_register<VT, MODE, 1, false>(o); lm_register<VT, MODE, 0, true>(o); lm_register<VT, MODE, 1, true>(o); }
+template <typename VT, int MODE> static void lm_register2(size_t o) { lm_register<VT, MODE, 0, false>(o); lm_register<VT, MODE, 1, false>(o); lm_register<VT, MODE, 0, true>(o); lm_register<VT, MODE, 1, true>(o); lm_register<VT, MODE, 2, false>(o); lm_register<VT, MODE, 2, true>(o); }
 void lm_setup(b200_ctx *ctx) {
     const size_t o = ctx->smem_optin;
     lm_register2<u32, 0>(o); lm_register2<u32, 1>(o);
@@ -456,9 +467,12 @@ int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, 
               int tune, u64 *mirror, u32 epoch, cudaStream_t s) {
     const bool v64 = A->val_bits == 64;
     const size_t smem = lm_smem_per_warp(mode, nw, cap) * LM_WARPS;
-    if (tune < 0) tune = (smem + 1024) * 6 <= (size_t)228 * 1024 ? 1 : 0;   // the residency of tune 1 needs six CTAs' worth of shared memory
+    // measured on the 30^3 chain (A x A^4 .. A x A^6): six lighter CTAs per SM win while a CTA needs <= 24 KB of shared memory
+    // (0.132 vs 0.145 ms); above that the deep batches of tune 0 do (A x A^6: 0.248 vs 0.258 with five CTAs, 0.303 with six)
+    if (tune < 0) tune = smem <= 24 * 1024 ? 1 : 0;
+    if (tune > 2) tune = 0;
     const bool full = per_row && nw % 128 == 0 && (nw / 128) % 2 == 1;     // a travelling window is cut to the rows: sweep all of it, 128 bits at a time
-    const LmKernel &k = g_lm[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][tune ? 1 : 0][full ? 1 : 0];
+    const LmKernel &k = g_lm[v64 ? 1 : 0][v64 ? mode : std::min(mode, 1)][tune][full ? 1 : 0];
     if (!k.fn) return set_err(B200_ERR_CUDA, "left-multiply kernel variant is not registered");
     if (smem + k.static_smem > ctx->smem_optin) return set_err(B200_ERR_CUDA, "left-multiply kernel needs %zu B of shared memory", smem);
     int per_sm = 0;
