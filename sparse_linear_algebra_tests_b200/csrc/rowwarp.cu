@@ -224,7 +224,7 @@ struct RwWarp {
         __syncwarp();
         u32 mine = 0;
         if (wlo <= whi) {                                                    // (a row without products touches nothing)
-            const u32 wpl = (whi - wlo + 32u) >> 5, w0 = wlo + (u32)lane * wpl;
+            const u32 wpl = ((whi - wlo + 32u) >> 5) | 1u, w0 = wlo + (u32)lane * wpl;   // (odd: the lanes fall on different banks)
             for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) { mine += __popc(bm[w0 + i]); bm[w0 + i] = 0; }
         }
         if (SUMP) P = warp_sum_u32(psum);
@@ -242,7 +242,7 @@ struct RwWarp {
         __syncwarp();
         if (wlo > whi) return 0u;                                            // no products (uniform over the warp)
         // ---- rank: consecutive words per lane over the touched span, warp scan of the lanes' popcounts
-        const u32 wpl = (whi - wlo + 32u) >> 5, w0 = wlo + (u32)lane * wpl;
+        const u32 wpl = ((whi - wlo + 32u) >> 5) | 1u, w0 = wlo + (u32)lane * wpl;   // (odd: the lanes fall on different banks)
         u32 mine = 0;
         for (u32 i = 0; i < wpl; i++) if (w0 + i <= whi) mine += __popc(bw[w0 + i].x);
         u32 incl = mine;
