@@ -96,7 +96,8 @@ typedef struct b200_config {
     int32_t expand_div, hash_div, grid_div, grid_mul;   /* binned: thread / grid sizing divisors (8, 32, 8, 4)            */
     int32_t aux_streams;         /* auxiliary streams the per-bin kernels fan out over (default 1, at most 3)              */
     int32_t fused_threads;       /* fused: threads per CTA of the numeric kernel (0 auto = 256; multiple of 32, <= 256);
-                                    pipeline 5: CTAs per SM the window is cut for (1..8, default 3)                        */
+                                    pipeline 5: CTAs per SM the window is cut for (1..8, default 3); pipeline 6: 4 / 5 / 6
+                                    pick the kernel build for that many CTAs per SM (0 auto)                                 */
     int32_t fused_window_cols;   /* fused: preferred cap of the dense accumulator window in columns (0 auto)               */
     int32_t fused_dense_pmax;    /* fused: rows with more intermediate products go to the heavy kernel (0 auto = 65536)    */
     int32_t heavy_chunk_cols;    /* heavy rows: columns per chunk of the chunked kernel (0 auto, from shared memory)       */

@@ -246,6 +246,7 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     hv_setup(ctx);
     dn_setup(ctx);
     lm_setup(ctx);
+    ctx->lm_min_list = env_int_early("B200_LM_MINLIST") > 0 ? (double)env_int_early("B200_LM_MINLIST") : 48.0;
     ctx->cap_cta_tot = 8192;
     CUDA_TRY_X(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
     ctx->timing = true;
@@ -1250,7 +1251,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
     {
         const double meanA = (double)A->nnz / (double)rows, meanB = (double)B->nnz / (double)B->rows;
-        const bool shape_ok = A->max_row_len <= 32 && meanB >= 48.0 && meanB >= 4.0 * meanA;
+        const bool shape_ok = A->max_row_len <= 32 && meanB >= ctx->lm_min_list && meanB >= 4.0 * meanA;
         if ((ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && shape_ok)) && cheap_bound && ncols < 0xFFFF0000ull && rows < 0xFFFF0000ull &&
             ctx->cfg.window_cap_groups < 0 && ctx->cfg.placement < 0) {
             u64 words = (u64)all_groups * 4; u32 org = all_rot; bool per_row = false;
@@ -1552,7 +1553,7 @@ extern "C" int b200_spgemm(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, 
     const u64 lin_base = A->lin_base == B->lin_base ? A->lin_base : 0, lin_pow = A->lin_pow + B->lin_pow;
     if (lin_base && ctx->cfg.commute_swap && (ctx->cfg.pipeline == 0 || ctx->cfg.pipeline == 6) && A != B && A->rows && A->nnz && B->nnz) {
         const double meanA = (double)A->nnz / (double)A->rows, meanB = (double)B->nnz / (double)B->rows;
-        if (B->max_row_len <= 32 && meanA >= 48.0 && meanA >= 4.0 * meanB) std::swap(A, B);
+        if (B->max_row_len <= 32 && meanA >= ctx->lm_min_list && meanA >= 4.0 * meanB) std::swap(A, B);
     }
     bool handled = false;
     TRY(A->val_bits == 32 ? spgemm_fused<u32>(ctx, A, B, C, stats, &handled) : spgemm_fused<u64>(ctx, A, B, C, stats, &handled));

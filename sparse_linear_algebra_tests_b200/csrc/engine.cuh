@@ -104,6 +104,7 @@ struct b200_ctx {
     struct NarrowState *narrow;
     u64 *d_rowstat; u64 cap_rowstat;   // per-row look-back status of the one-pass multiply (dense.cu)
     void *d_hv; size_t cap_hv;         // chunked heavy-row kernels (heavy.cu): control words | per-(row, chunk) counters | unit lists
+    double lm_min_list;     // left multiply (leftmul.cu): shortest mean list (row of B) it is chosen for (48; developer override B200_LM_MINLIST)
     b200_config cfg;        // tuning switches (b200_ctx_configure; the MagnusConfig analogue)
 };
 

@@ -5,14 +5,14 @@
 // and of any short-row selector / stencil operator applied to a denser matrix.  The row-wise kernels of rowwarp.cu walk
 // such a multiply one gathered 32-byte record per A entry; here a product is one element of a contiguous list:
 //   * a warp owns an output row; lane l < len(A[i,:]) holds list l's extent (row_ptr_B[k], row_ptr_B[k+1]) and a_ik;
-//   * the lists are streamed in batches of LM_U x 32 consecutive entries: the batch's loads are issued together and the
-//     NEXT batch's loads are issued before the current one is consumed, so a lane keeps 2 x LM_U independent, fully
-//     coalesced loads in flight (no dependent gather per product at all);
+//   * the lists are streamed in batches of U x 32 consecutive entries: a batch's loads are issued together, and two register
+//     sets alternate so that the NEXT batch's loads are in flight while the current one is consumed -- fully coalesced, no
+//     dependent gather per product at all; the slots of a batch are predicated instructions, not branches;
 //   * count   : every column sets its bit in the warp's window bitmap (red.shared.or); length = popcount of the touched words;
 //   * numeric : mark again, exclusive prefix popcount kept beside each word, then every product goes to acc[rank(column)]
 //               (accumulators dense in rank space, as rowwarp.cu), emitted with coalesced stores in column order -- no sort.
 // The whole multiply is ONE cooperative launch with the phases of k_rw_fused: lengths -> grid sync -> row_ptr -> values;
-// C is written once.  The window is either one arc for every row ({org, words}; the whole column space when nothing
+// C is written once.  Rows are handed out from a device counter (one moving front of neighbouring rows over the whole grid).  The window is either one arc for every row ({org, words}; the whole column space when nothing
 // better is known) or, for square operands whose entry offsets (c - row) are bounded on both sides, a window that
 // travels with the row: bit d of row i is column (i + org + d) mod n.
 //
@@ -52,6 +52,11 @@ __device__ __forceinline__ void lm_st_u16(u32 addr, u32 v) { asm volatile("st.sh
 // the same, predicated in the instruction (no branch around a slot of a batch)
 __device__ __forceinline__ void lm_red_or_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }" :: "r"(addr), "r"(v), "r"((u32)on) : "memory"); }
 __device__ __forceinline__ void lm_red_add_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.add.u32 [%0], %1; }" :: "r"(addr), "r"(v), "r"((u32)on) : "memory"); }
+// offs[pos] = d and acc[pos] += v under one predicate (32-bit sums)
+__device__ __forceinline__ void lm_put_if(bool on, u32 offs_addr, u32 d, u32 acc_addr, u32 v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %4, 0; @q st.shared.u16 [%0], %1; @q red.shared.add.u32 [%2], %3; }"
+                 :: "r"(offs_addr), "h"((unsigned short)d), "r"(acc_addr), "r"(v), "r"((u32)on) : "memory");
+}
 __device__ __forceinline__ void lm_st_u16_if(bool on, u32 addr, u32 v) { asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; }" :: "r"(addr), "h"((unsigned short)v), "r"((u32)on) : "memory"); }
 __device__ __forceinline__ uint4 lm_ld_v4(u32 addr) { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory"); return r; }
 __device__ __forceinline__ void lm_st_v4(u32 addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
@@ -268,8 +273,7 @@ struct LmWarp {
                             const u32 pos = sp[u] + __popc(sb[u] & (__funnelshift_l(0u, 1u, d[u]) - 1u)) - pass;
                             const bool on = base + 32u * u + lane < len && (!MULTI || pos < cap);
                             if (MODE == 0) {
-                                lm_st_u16_if(on, sm_offs + pos * 2u, d[u]);
-                                lm_red_add_if(on, sm_acc + pos * 4u, (u32)x * (u32)q.v[u]);
+                                lm_put_if(on, sm_offs + pos * 2u, d[u], sm_acc + pos * 4u, (u32)x * (u32)q.v[u]);
                             } else if (on) {
                                 lm_st_u16(sm_offs + pos * 2u, d[u]);
                                 acc.addv(pos, lm_product<MODE, VT>((VT)x, (VT)q.v[u]));
