@@ -358,7 +358,10 @@ def run_b200(args):
             traffic = float(tj["traffic"])
     kernels = {1: "k_fz_prepass + k_fz_numeric (pre-pass; fused numeric + placement, C written once)",
                3: "pre-pass, row-per-warp count kernels, row_ptr scan, row-per-warp numeric kernels (C written once)",
-               4: "k_rw_fused, ONE cooperative launch: count phase, placement, numeric phase (C written once, no host wait)"}.get(
+               4: "k_rw_fused, ONE cooperative launch: count phase, placement, numeric phase (C written once, no host wait)",
+               5: "k_dn, ONE launch: dense window accumulators per row, look-back placement over rows",
+               6: "k_lm, ONE cooperative launch (operands commute: evaluated as A x A^(k-1), rows of A^(k-1) streamed as sorted lists): "
+                  "count phase, placement, numeric phase (C written once, no host wait)"}.get(
                    top.get("pipeline"), "binned pipeline (pre-pass, per-bin numeric, row_ptr scan, compaction)")
     roofline = {"bound": "hbm", "kernel": f"all kernels of the largest multiply A^{MAX_POWER} = A^{MAX_POWER - 1} x A: " + kernels,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,

@@ -249,6 +249,8 @@ extern "C" int b200_ctx_create(int device, void *cuda_stream, b200_ctx **out) {
     ctx->lm_min_list = env_int_early("B200_LM_MINLIST") > 0 ? (double)env_int_early("B200_LM_MINLIST") : 48.0;
     ctx->cap_cta_tot = 8192;
     CUDA_TRY_X(cudaMalloc((void **)&ctx->d_cta_tot, ctx->cap_cta_tot * 8));
+    CUDA_TRY_X(cudaMalloc((void **)&ctx->d_lm_tot, ctx->cap_cta_tot * 8));   // slice totals of the left multiply: zero between multiplies
+    CUDA_TRY_X(cudaMemset(ctx->d_lm_tot, 0, ctx->cap_cta_tot * 8)); ctx->lm_tot_dirty = false;
     ctx->timing = true;
     ctx->hosttime = env_int_early("B200_HOSTTIME") != 0;
     ctx->trace = env_int_early("B200_TRACE") != 0; ctx->marks = new std::vector<std::pair<int, cudaEvent_t>>();
@@ -279,7 +281,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *ctx) {
     cudaFreeHost(ctx->h_freport);
     for (int i = 0; i < B200_REPORT_SLOTS; i++) for (int j = 0; j < 3; j++) cudaEventDestroy(ctx->f_ev[i][j]);
     if (ctx->d_rowstat) cudaFree(ctx->d_rowstat);
-    cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag); cudaFree(ctx->d_cta_tot);
+    cudaFreeHost(ctx->h_ctrl); cudaFreeHost(ctx->h_report); cudaFree(ctx->d_flag); cudaFreeHost(ctx->h_flag); cudaFree(ctx->d_cta_tot); cudaFree(ctx->d_lm_tot);
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B200_NAUX; i++) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
@@ -1142,10 +1144,14 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         *out = C;
         return B200_OK;
     }
+    // (the left multiply reads B's row_ptr directly: where it is the likely choice, B's per-row descriptors are built only if
+    //  the multiply falls through to the other pipelines -- in a swapped power chain B is a fresh product every step)
+    const bool lm_try = ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && A->max_row_len <= 32 && (double)B->nnz / (double)B->rows >= ctx->lm_min_list &&
+                                                   (double)B->nnz / (double)B->rows >= 4.0 * ((double)A->nnz / (double)rows));
     int r = ensure_row_scratch(ctx, rows);
-    if (r == B200_OK) r = ensure_desc(ctx, B);
+    if (r == B200_OK && !lm_try) r = ensure_desc(ctx, B);
     const bool packed = want_pack(ctx, B);
-    if (r == B200_OK && packed) r = ensure_pack(ctx, B);
+    if (r == B200_OK && packed && !lm_try) r = ensure_pack(ctx, B);
     if (r == B200_OK) r = host_maxval(ctx, A);
     if (r == B200_OK) r = host_maxval(ctx, B);
     if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
@@ -1288,6 +1294,11 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
                 return B200_OK;
             }
         }
+    }
+    if (lm_try) {                                                         // not taken after all: the other pipelines need B's descriptors
+        r = ensure_desc(ctx, B);
+        if (r == B200_OK && packed) r = ensure_pack(ctx, B);
+        if (r != B200_OK) { b200_csr_free(ctx, C); return r; }
     }
     // One pass over the products (pipeline 5, dense.cu): 32-bit sums proven, a square low-degree right operand with a known offset
     // range, C allocated from the host-known bound.

@@ -95,6 +95,7 @@ struct b200_ctx {
     b200_csr *slot_owner[B200_REPORT_SLOTS];
     cudaEvent_t f_ev[B200_REPORT_SLOTS][3];
     u32 fepoch;
+    u64 *d_lm_tot; bool lm_tot_dirty;  // per-slice totals of the left multiply (leftmul.cu), left zeroed by its last CTA
     u64 *d_cta_tot; u64 cap_cta_tot;   // per-CTA totals of the one-launch multiply (rowwarp.cu)
     // entry arrays (col_idx | values, one allocation) of freed handles, kept for the next product of about that size: a loop
     // of large multiplies (12-GB results on the 200^3 chain) otherwise stalls in the stream-ordered allocator every few steps

@@ -961,8 +961,8 @@ static int fz_wait_report(b200_ctx *ctx, int slot, u32 epoch, B200Ctrl *out) {
             if ((++spins & 0xFFF) == 0) {
                 const cudaError_t q = cudaStreamQuery(ctx->stream);
                 if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
-                if (q != cudaSuccess) { ctx->f_dirty = true; return set_err(B200_ERR_CUDA, "multiply failed on the device: %s", cudaGetErrorString(q)); }
-                if ((u32)(chunk[i] >> 32) != epoch) { ctx->f_dirty = true; return set_err(B200_ERR_CUDA, "the multiply finished without reporting (slot %d, epoch %u)", slot, epoch); }
+                if (q != cudaSuccess) { ctx->f_dirty = true; ctx->lm_tot_dirty = true; return set_err(B200_ERR_CUDA, "multiply failed on the device: %s", cudaGetErrorString(q)); }
+                if ((u32)(chunk[i] >> 32) != epoch) { ctx->f_dirty = true; ctx->lm_tot_dirty = true; return set_err(B200_ERR_CUDA, "the multiply finished without reporting (slot %d, epoch %u)", slot, epoch); }
             }
 #if defined(__x86_64__)
             __builtin_ia32_pause();
@@ -1005,7 +1005,7 @@ int resolve_pending(b200_ctx *ctx, const b200_csr *cm) {
     m->pending_slot = -1;
     if (ctx->slot_owner[slot] == m) ctx->slot_owner[slot] = nullptr;
     if (r != B200_OK) return r;
-    if (hc.error_flag) { ctx->f_dirty = true; return set_err(B200_ERR_CUDA, "a kernel of the multiply reported an impossible state (flag %u)", hc.error_flag); }
+    if (hc.error_flag) { ctx->f_dirty = true; ctx->lm_tot_dirty = true; return set_err(B200_ERR_CUDA, "a kernel of the multiply reported an impossible state (flag %u)", hc.error_flag); }
     m->nnz = hc.total_nnz; m->max_row_len = hc.max_row_nnz; m->h_maxval = hc.max_val_out; m->h_maxval_known = true;
     if (m->stats) {
         b200_stats *st = m->stats;

@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
         __syncthreads();
         u32 *cw = reinterpret_cast<u32 *>(p.ctrl);
         for (u32 i = tid; i < sizeof(B200Ctrl) / 4; i += blockDim.x) cw[i] = 0;
+        for (u32 i = tid; i < nslices; i += blockDim.x) p.cta_tot[i] = 0;     // every CTA is past its last read of the totals
     }
 }
 
@@ -459,7 +460,7 @@ static cudaError_t lm_go(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b2
     p.rpA = A->d_rp; p.colA = A->d_col; p.valA = (const VT *)A->d_val;
     p.rpB = B->d_rp; p.colB = B->d_col; p.valB = (const VT *)B->d_val;
     p.rows = A->rows; p.ncols = (u32)B->cols; p.org = org; p.per_row = per_row ? 1u : 0u; p.nw = nw; p.cap = cap; p.nsm = (u32)ctx->num_sms;
-    p.nnz_row = ctx->d_nnz_row; p.cta_tot = ctx->d_cta_tot; p.rpC = C->d_rp; p.colC = C->d_col; p.valC = (VT *)C->d_val;
+    p.nnz_row = ctx->d_nnz_row; p.cta_tot = ctx->d_lm_tot; p.rpC = C->d_rp; p.colC = C->d_col; p.valC = (VT *)C->d_val;
     p.ctrl = ctrl; p.host_mirror = mirror; p.epoch = epoch; p.maxval_dst = C->d_maxval;
     void *kargs[] = {(void *)&p};
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LM_THREADS), kargs, smem, s);
@@ -485,11 +486,12 @@ int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, 
     int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
     if (grid > ctx->num_sms) grid = grid / ctx->num_sms * ctx->num_sms;
     if ((u64)grid > ctx->cap_cta_tot) return set_err(B200_ERR_CUDA, "internal: %d CTAs exceed the per-CTA scratch", grid);
-    if (cudaMemsetAsync(ctx->d_cta_tot, 0, (size_t)grid * 8, s) != cudaSuccess) return set_err(B200_ERR_CUDA, "clearing the slice totals failed");
+    // (the slice totals are zero: the last CTA of the previous left multiply left them so; after a failed multiply they are cleared here)
+    if (ctx->lm_tot_dirty) { if (cudaMemsetAsync(ctx->d_lm_tot, 0, ctx->cap_cta_tot * 8, s) != cudaSuccess) return set_err(B200_ERR_CUDA, "clearing the slice totals failed"); ctx->lm_tot_dirty = false; }
     const cudaError_t le = v64 ? lm_go<u64>(ctx, A, B, C, ctrl, org, per_row, nw, cap, mirror, epoch, k.fn, grid, smem, s)
                                : lm_go<u32>(ctx, A, B, C, ctrl, org, per_row, nw, cap, mirror, epoch, k.fn, grid, smem, s);
     ctx->launches++;
     if (ctx->trace) { fprintf(stderr, "[b200 trace] left multiply: full %d tune %d grid %d (%d/SM) regs %d smem %zu nw %u cap %u org %u per_row %d\n", (int)full, tune, grid, per_sm, k.regs, smem, nw, cap, org, (int)per_row); trace_mark(ctx, __LINE__); }
-    if (le != cudaSuccess) return set_err(B200_ERR_CUDA, "left-multiply kernel launch failed: %s", cudaGetErrorString(le));
+    if (le != cudaSuccess) { ctx->lm_tot_dirty = true; return set_err(B200_ERR_CUDA, "left-multiply kernel launch failed: %s", cudaGetErrorString(le)); }
     return B200_OK;
 }

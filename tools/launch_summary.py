@@ -24,29 +24,28 @@ for r in rows[hi + 1:]:
     d[r[idx["Metric Name"]]] = v
 ids = list(L)
 is_flush = lambda d: "elementwise" in d["name"] or "fill" in d["name"].lower()
-# chains = runs of engine kernels that start right after a flush kernel and hold 6 pre-passes
+# a chain = the engine kernels between two flush kernels; a multiply ends with its placement kernel (k_compact_rows: binned
+# pipeline) or IS one launch (k_rw_fused, k_lm, k_dn); helper kernels (descriptors, packs, bounds) belong to the multiply they precede
+ENDS = ("k_compact_rows", "k_rw_fused", "k_lm", "k_dn")
 flushes = [i for i, k in enumerate(ids) if is_flush(L[k])]
 best = None
 for f in flushes:
-    j = f + 1; pre = 0; run = []
+    j = f + 1; run = []; done = 0
     while j < len(ids) and not is_flush(L[ids[j]]):
-        n = L[ids[j]]["name"]
-        if n.startswith("k_prepass"):
-            pre += 1
-            if pre > 6: break
-        if pre >= 1: run.append(ids[j])
+        run.append(ids[j])
+        if L[ids[j]]["name"].startswith(ENDS): done += 1
         j += 1
-    if pre >= 6: best = run
+    if done == 6: best = run
 if best is None:
-    raise SystemExit("no complete chain after an L2 flush found")
+    raise SystemExit("no complete chain (6 multiplies) after an L2 flush found")
 step_us = sum(L[k]["gpu__time_duration.sum"] for k in best)
 print(f"last timed step: {len(best)} kernels, {step_us:.1f} us serialised by the profiler (compare shares, not absolutes)")
 mult, cur = [], []
 for k in best:
-    if L[k]["name"].startswith("k_prepass") and cur:
-        mult.append(cur); cur = []
     cur.append(k)
-mult.append(cur)
+    if L[k]["name"].startswith(ENDS):
+        mult.append(cur); cur = []
+if cur: mult[-1].extend(cur)
 for p, m in enumerate(mult, start=2):
     t = sum(L[k]["gpu__time_duration.sum"] for k in m)
     rd = sum(L[k].get("dram__bytes_read.sum", 0) for k in m); wr = sum(L[k].get("dram__bytes_write.sum", 0) for k in m)
