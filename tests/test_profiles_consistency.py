@@ -60,7 +60,7 @@ def test_round2_launch_list_traffic_and_bench_agree():
     step = L[last_flush + 1:]
     assert len(step) == 17 and all(d["name"].startswith("void k_") for d in step)
     a7 = step[-1]
-    assert "k_rw_fused" in a7["name"]
+    assert "k_lm" in a7["name"]                                             # the operands commute: evaluated as A x A^6 (leftmul.cu)
     tj = json.load(open(os.path.join(PROF, "r2_traffic.json")))
     listed = a7["dram__bytes_read.sum"] + a7["dram__bytes_write.sum"]
     assert abs(listed - tj["traffic"]) / tj["traffic"] < 0.05

