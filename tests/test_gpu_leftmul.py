@@ -136,3 +136,26 @@ def test_swap_needs_a_common_base(gpu_ctx, oracle, cfg):
     xp = x.matmul(p, want_stats=True)                         # short rows on the left, long on the right: pipeline 6 by shape
     assert xp.last_stats.pipeline == 6
     assert_same(xp.to_host(), oracle.matmul_par(to_o(oracle, x_h), to_o(oracle, p.to_host())), "X x A^5")
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_left_multiply_edge_shapes(gpu_ctx, oracle, cfg, bits):
+    """Forced pipeline 6 on the shapes the reference's own tests use (src/graph_csr.rs:1000-1100: identity, empty, single
+    entries) plus ragged ones: 1 x 1, identity, an empty left operand row block, a single full row, 33 columns (one bit past
+    a bitmap word), a left row of 70 entries (three blocks of lists) against lists of one entry."""
+    rng = np.random.default_rng(5)
+    cfg(pipeline=6)
+    ident = lambda n: hostgen.identity(n, bits)
+    cases = [
+        (ident(1), ident(1)),
+        (ident(5), ident(5)),
+        (random_csr(rng, 7, 33, 5, 9, bits), random_csr(rng, 33, 33, 33, 9, bits)),
+        (random_csr(rng, 4, 90, 70, 3, bits), ident(90)),
+        (hostgen.from_coo(3, 40, np.array([1] * 40, np.uint32), np.arange(40, dtype=np.uint32), np.full(40, 2, np.uint64), bits),
+         random_csr(rng, 40, 64, 64, 1000, bits)),
+        (random_csr(rng, 50, 50, 2, 1, bits, empty_every=2), random_csr(rng, 50, 300, 120, 7, bits, empty_every=3)),
+    ]
+    for i, (a_h, b_h) in enumerate(cases):
+        a, b = B200Matrix.from_host(a_h, gpu_ctx), B200Matrix.from_host(b_h, gpu_ctx)
+        c = a.matmul(b, want_stats=True)
+        assert_same(c.to_host(), oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, b_h)), f"case {i} u{bits} (pipeline {c.last_stats.pipeline})")
