@@ -56,6 +56,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (its pinned staging is 12 B per result entry)")
     # BASELINE configs[3]: A^2 of an R-MAT graph built on the device (b200_rmat), rows sharded by product count; always strong
     # scaling (the graph does not grow with --gpus), device-timed only
+    ap.add_argument("--chain", default="right", choices=["right", "halo", "auto"],
+                    help="N > 1: a rank's steps as block(A^(k-1)) x A ('right', the default), as left multiplies over its block plus a halo "
+                         "of neighbouring rows computed redundantly ('halo', no communication either), or whichever is faster in warm-up "
+                         "('auto').  Measured on the 30^3-per-GPU chain the halo chain loses (DESIGN.md section 6): kept as an option")
+    ap.add_argument("--as-rank", type=int, default=None, help="developer: run rank R of a --gpus N job alone on one GPU (no process group)")
     ap.add_argument("--workload", default="torus", choices=["torus", "rmat"])
     ap.add_argument("--scale", type=int, default=20)
     ap.add_argument("--ef", type=int, default=16)
@@ -216,11 +221,18 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    sim = args.as_rank is not None and world == 1                   # one rank of an N-rank job, alone (its steps need nobody else)
+    if sim:
+        rank, world = args.as_rank, max(1, args.gpus)
+    multi = world > 1 and not sim                                   # a process group exists
+    lead = rank == 0 or sim                                         # builds the operand, prints the line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if multi:
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "rmat":
+        if sim:
+            raise SystemExit("bench.py: --as-rank covers the torus chain only")
         return run_rmat(args, torch, dist, dev, rank, local_rank, world)
     stream = torch.cuda.Stream(dev)                                 # the engine runs on this (non-default) torch stream,
     torch.cuda.set_stream(stream)                                   # so torch.cuda.Event on it brackets every engine kernel
@@ -229,15 +241,15 @@ def run_b200(args):
     vdt = torch.int32 if args.bits == 32 else torch.int64          # bit containers for NCCL
 
     # ---- operand: rank 0 builds A, one NCCL broadcast replicates it (the only collective of the job)
-    if rank == 0:
+    if lead:
         a_h = build_operand(args, world, ctx)
         meta = torch.tensor([a_h.rows, a_h.cols, a_h.nnz()], dtype=torch.int64, device=dev)
     else:
         a_h, meta = None, torch.zeros(3, dtype=torch.int64, device=dev)
-    if world > 1:
+    if multi:
         dist.broadcast(meta, 0)
     n_rows, n_cols, n_nnz = (int(x) for x in meta.tolist())
-    if rank == 0:
+    if lead:
         d_rp = torch.from_numpy(a_h.row_ptr.view(np.int64)).to(dev)
         d_ci = torch.from_numpy(a_h.col_idx.view(np.int32)).to(dev)
         d_vv = torch.from_numpy(a_h.values.view(np.int32 if args.bits == 32 else np.int64)).to(dev)
@@ -245,7 +257,7 @@ def run_b200(args):
         d_rp = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
         d_ci = torch.empty(n_nnz, dtype=torch.int32, device=dev)
         d_vv = torch.empty(n_nnz, dtype=vdt, device=dev)
-    if world > 1:
+    if multi:
         for t in (d_rp, d_ci, d_vv):
             dist.broadcast(t, 0)
     torch.cuda.synchronize(dev)
@@ -260,20 +272,38 @@ def run_b200(args):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def chain(collect_stats=False):
-        p, stats, keep = A_blk, [], []
-        for _k in range(2, MAX_POWER + 1):
+    # ---- N > 1: the same rows through left multiplies (distributed.HaloPowerChain).  A rank's block of A^(k-1) is no power of
+    # A, so `block x A` cannot use the engine's left-multiply kernel; A_k x A^(k-1) over the block plus a halo of neighbouring
+    # rows (computed redundantly, nothing exchanged) can.  Rows [r0, r1) of its products are the rank's blocks, bit for bit
+    # (checked below against the right multiplies); only the block's products count as work.
+    halo = None
+    if world > 1 and args.chain != "right":
+        from sparse_linear_algebra_tests_b200.distributed import CudaEngine, HaloPowerChain
+        a_all = a_h if a_h is not None else hostgen.HostCsr(
+            n_rows, n_cols, d_rp.cpu().numpy().view(np.uint64), d_ci.cpu().numpy().view(np.uint32),
+            d_vv.cpu().numpy().view(np.uint32 if args.bits == 32 else np.uint64))
+        hc = HaloPowerChain(CudaEngine(ctx), a_all, r0, r1, MAX_POWER, a_dev=A)
+        if args.chain == "halo" or hc.overhead <= 0.25:                  # (a graph without locality: the halo is everything)
+            halo = hc
+    use_halo = halo is not None and args.chain == "halo"
+
+    def chain(collect_stats=False, left=None):
+        """One step: every power of this rank.  `left`: through the halo chain (default: the mode chosen below)."""
+        left = use_halo if left is None else left
+        p, stats, keep = (A if left else A_blk), [], []
+        for i in range(MAX_POWER - 1):
+            x, y = (halo.left[i], p) if left else (p, A)
             if collect_stats:
-                c, st = ctx.spgemm(p, A, True)
+                c, st = ctx.spgemm(x, y, True)
                 stats.append(st.as_dict())
             else:
-                c = ctx.spgemm(p, A)
+                c = ctx.spgemm(x, y)
             keep.append(c)
             p = c
         return keep, stats
 
     def barrier():
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
@@ -284,15 +314,58 @@ def run_b200(args):
         powers, _ = chain()
         ctx.synchronize()
         del powers
-    # one instrumented pass for per-multiply numbers (events inside the engine; not part of the timed steps)
-    powers, st = chain(True)
+    # one instrumented pass for per-multiply numbers (events inside the engine; not part of the timed steps); the products and
+    # entries of the rank's own rows come from the right multiplies in every mode
+    powers, st = chain(True, left=False)
     prods = [s["products"] for s in st]
     nnzs = [s["nnz_c"] for s in st]
+    halo_note = None
+    if halo is not None:
+        def dev_bytes(ptr, nbytes):
+            class _V:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            return torch.as_tensor(_V(), device=dev)
+        hp, hst = chain(True, left=True)
+        for k, (g, c) in zip(range(2, MAX_POWER + 1), zip(powers, hp)):   # bit for bit: row_ptr, col_idx, values of the block
+            b = halo.block(c)
+            ctx.synchronize()
+            if b.nnz != g.nnz:
+                raise SystemExit(f"bench.py: rank {rank}: A^{k} block through the halo chain has {b.nnz} entries, right multiply {g.nnz}")
+            for pa, pb, nb in zip(g.device_ptrs(), b.device_ptrs(), ((g.rows + 1) * 8, g.nnz * 4, g.nnz * vbytes)):
+                if nb and not torch.equal(dev_bytes(pa, nb), dev_bytes(pb, nb)):
+                    raise SystemExit(f"bench.py: rank {rank}: A^{k} block through the halo chain differs from the right multiply")
+            del b
+        del hp
+        if args.chain == "auto":                                          # whichever is faster on this rank, measured
+            t_mode = []
+            for left in (False, True):
+                best_ms = 1e30
+                for _ in range(4):
+                    flush.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    pw, _ = chain(left=left)
+                    e1.record(stream)
+                    e1.synchronize()
+                    best_ms = min(best_ms, e0.elapsed_time(e1))
+                    del pw
+                t_mode.append(best_ms)
+            use_halo = t_mode[1] < t_mode[0]
+            halo_note = {"right_ms": t_mode[0], "halo_ms": t_mode[1]}
+        if use_halo:
+            for _ in range(2):
+                powers2, _ = chain()
+                ctx.synchronize()
+                del powers2
+            _, st = chain(True)
+            for s_, p_, n_ in zip(st, prods, nnzs):                        # the halo rows are redundant work: not counted
+                s_["products_with_halo"], s_["products"] = s_["products"], p_
+                s_["nnz_with_halo"], s_["nnz_c"] = s_["nnz_c"], n_
     del powers
 
     ctx.set_timing(False)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if lead:
         sampler.start()
     barrier()
     launches0 = ctx.kernel_launches()
@@ -310,14 +383,14 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if lead else None
     ctx.set_timing(True)
 
     my_ms = float(np.mean(step_ms))
     # per-rank step time and product count, so that jitter (spread of one rank's steps) and imbalance (spread over ranks)
     # can be told apart in the line
     mine = torch.tensor([my_ms, float(np.min(step_ms)), float(np.max(step_ms)), float(sum(prods))], dtype=torch.float64, device=dev)
-    if world > 1:
+    if multi:
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
     else:
@@ -325,12 +398,28 @@ def run_b200(args):
     per_rank = [{"rank": i, "ms_mean": float(t[0]), "ms_min": float(t[1]), "ms_max": float(t[2]), "products": int(t[3])} for i, t in enumerate(allr)]
     t_ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(sum(prods)), float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
+    if multi:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_per_step = float(t_ms.item())
     total_products, total_launches = float(tot[0].item()), int(tot[1].item())
     value = total_products / (ms_per_step * 1e-3)
+    chain_cfg = {}
+    if world > 1:
+        n_halo = torch.tensor([1.0 if use_halo else 0.0], dtype=torch.float64, device=dev)
+        if multi:
+            dist.all_reduce(n_halo, op=dist.ReduceOp.SUM)
+        chain_cfg["chain"] = {
+            "mode": args.chain, "ranks_on_halo_chain": int(n_halo.item()),
+            "halo": "A_k x A^(k-1) over the rank's rows plus a halo of neighbouring rows computed redundantly (no communication); "
+                    "rows [r0, r1) of every power compared bit for bit with the right multiplies before timing; only the block's products count",
+            "right": "block(A^(k-1)) x A",
+            "rank0_redundant_work_estimate": halo.overhead if halo is not None else None, "rank0_warmup_ms": halo_note}
+        if use_halo:
+            chain_cfg["left"] = "A restricted to the rows a rank needs at power k (block + halo), whole-size handle"
+            chain_cfg["right"] = "A^(k-1), the rank's rows (block + halo) resident"
+        if sim:
+            chain_cfg["simulated"] = f"rank {rank} of {world} alone on one GPU: value is this rank's share only"
 
     # ---- per-multiply detail (rank-local, instrumented pass repeated for a best-of-5)
     best = [dict(s) for s in st]
@@ -341,6 +430,9 @@ def run_b200(args):
             if s["ms_total"] < b["ms_total"]:
                 b.update(s)
         del powers
+    if use_halo:
+        for b, p_, n_ in zip(best, prods, nnzs):
+            b["products"], b["nnz_c"] = p_, n_
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
@@ -374,15 +466,16 @@ def run_b200(args):
     # ---- end to end through the public API with host buffers (pinned H2D of A, pinned D2H of every power)
     e2e = None
     if args.no_e2e:
-        if rank == 0:
+        if lead:
             cfg = workload_config(args, world)
             cfg.update({"nodes": n_rows, "nnz_A": n_nnz, "products_per_step": int(total_products), "nnz_per_power_rank0": nnzs,
                         "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
+            cfg.update(chain_cfg)
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                               "dtype": f"u{args.bits}", "data": "synthetic", "config": cfg, "per_power": per_power, "per_rank": per_rank, "gpu_launches": total_launches,
                               "wall_s_timed_region": wall, "clocks": clocks, "e2e": None, "roofline": roofline}), flush=True)
-        if world > 1:
+        if multi:
             dist.destroy_process_group()
         return
     a_loc = hostgen.HostCsr(n_rows, n_cols, d_rp.cpu().numpy().view(np.uint64), d_ci.cpu().numpy().view(np.uint32),
@@ -420,7 +513,7 @@ def run_b200(args):
         e_t.append(time.perf_counter() - t0)
         del keep
     e_ms = torch.tensor([float(np.mean(e_t)) * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
+    if multi:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     # the last power read back must equal the resident result (cheap end-to-end sanity: nnz via row_ptr)
     last_rp = h_out[-1][0].numpy().view(np.uint64)
@@ -428,13 +521,14 @@ def run_b200(args):
     e2e = {"value": total_products / (float(e_ms.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(e_ms.item()),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timing": "wall clock, synchronize on both sides, max over ranks"}
 
-    if rank != 0:
-        if world > 1:
+    if not lead:
+        if multi:
             dist.destroy_process_group()
         return
     cfg = workload_config(args, world)
     cfg.update({"nodes": n_rows, "nnz_A": n_nnz, "products_per_step": int(total_products), "nnz_per_power_rank0": nnzs,
                 "parallelism": f"row-sharded x{world}" if world > 1 else "1 GPU"})
+    cfg.update(chain_cfg)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": f"u{args.bits}",
            "data": "synthetic", "config": cfg, "per_power": per_power, "per_rank": per_rank, "gpu_launches": total_launches, "wall_s_timed_region": wall,
@@ -453,7 +547,7 @@ def run_b200(args):
                                "sample": f"full A^2..A^{MAX_POWER} chain, reference protocol (1 warm-up + 3 timed multiplies per power)",
                                "ms_per_power": [s * 1e3 for s in secs], "ms_per_step": sum(secs) * 1e3}
     print(json.dumps(out), flush=True)
-    if world > 1:
+    if multi:
         dist.destroy_process_group()
 
 

@@ -348,6 +348,7 @@ int csr_alloc(b200_ctx *ctx, u64 rows, u64 cols, u64 nnz, int val_bits, bool all
     memset(m, 0, sizeof(*m));
     m->rows = rows; m->cols = cols; m->nnz = nnz; m->val_bits = val_bits; m->ctx = ctx;
     m->cr_start = 0; m->cr_len = cols;
+    m->ar_start = 0; m->ar_len = rows;
     m->pending_slot = -1; m->max_row_span = cols;
     static u64 next_uid = 0;
     m->uid = __sync_add_and_fetch(&next_uid, 1); m->lin_base = m->uid; m->lin_pow = 1;
@@ -426,14 +427,28 @@ int finish_new_csr(b200_ctx *ctx, b200_csr *m, bool check, bool device_rowptr) {
     return B200_OK;
 }
 
-static int check_host_rowptr(u64 rows, const uint64_t *row_ptr, u64 *nnz, u64 *max_len) {
+// (also finds the active row arc of the handle: the complement of the longest run of empty rows on the row circle)
+static int check_host_rowptr(u64 rows, const uint64_t *row_ptr, u64 *nnz, u64 *max_len, u64 *ar_start, u64 *ar_len) {
     if (row_ptr[0] != 0) return set_err(B200_ERR_FORMAT, "row_ptr[0] must be 0");
     u64 ml = 0;
+    const u64 none = ~0ull;
+    u64 first = none, last = none, gap_len = 0, gap_end = 0;              // longest run of empty rows between two non-empty ones
     for (u64 i = 0; i < rows; i++) {
         if (row_ptr[i + 1] < row_ptr[i]) return set_err(B200_ERR_FORMAT, "row_ptr is not monotone at row %llu", (ull)i);
         u64 l = row_ptr[i + 1] - row_ptr[i]; if (l > ml) ml = l;
+        if (l) {
+            if (first == none) first = i;
+            else if (i - last - 1 > gap_len) { gap_len = i - last - 1; gap_end = i; }
+            last = i;
+        }
     }
     *nnz = row_ptr[rows]; *max_len = ml;
+    *ar_start = 0; *ar_len = rows;
+    if (first != none) {
+        const u64 wrap = (rows - 1 - last) + first;                         // the run of empty rows through the end of the matrix
+        if (wrap >= gap_len) { *ar_start = first; *ar_len = last - first + 1; }
+        else { *ar_start = gap_end; *ar_len = rows - gap_len; }
+    }
     return B200_OK;
 }
 
@@ -443,12 +458,12 @@ static int upload_common(b200_ctx *ctx, uint64_t rows, uint64_t cols, const uint
     if (val_bits != 32 && val_bits != 64) return set_err(B200_ERR_BADARG, "val_bits must be 32 or 64, got %d", val_bits);
     if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return set_err(B200_ERR_BADARG, "rows/cols must fit in u32 (NodeId)");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    u64 nnz = 0, max_len = 0;
-    TRY(check_host_rowptr(rows, row_ptr, &nnz, &max_len));
+    u64 nnz = 0, max_len = 0, ar_start = 0, ar_len = rows;
+    TRY(check_host_rowptr(rows, row_ptr, &nnz, &max_len, &ar_start, &ar_len));
     if (nnz && (!col_idx || !values)) return set_err(B200_ERR_BADARG, "NULL col_idx/values with nnz > 0");
     b200_csr *m = nullptr;
     TRY(csr_alloc(ctx, rows, cols, nnz, val_bits, true, &m));
-    m->max_row_len = max_len;
+    m->max_row_len = max_len; m->ar_start = ar_start; m->ar_len = ar_len;
     cudaError_t e = cudaMemcpyAsync(m->d_rp, row_ptr, (rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->d_val, values, nnz * (size_t)(val_bits / 8), cudaMemcpyHostToDevice, ctx->stream);
     u64 *tmp = nullptr;
@@ -693,11 +708,13 @@ extern "C" int b200_csr_download_idx64(b200_ctx *ctx, const b200_csr *m, uint64_
 
 // ---------------------------------------------------------------------------- SpGEMM
 
+// rows of the handle's active arc (mean row lengths in the heuristics: see b200_csr::ar_len)
+static inline u64 act_rows(const b200_csr *m) { return std::max<u64>(1, std::min<u64>(m->ar_len, m->rows)); }
 // lanes cooperating on one A entry while walking its B row: largest power of two <= mean B row length / 2
 int pick_lg(const b200_ctx *ctx, const b200_csr *B, int max_lg) {
     const int forced = ctx->cfg.lanes_per_entry_lg;
     if (forced >= 0) return std::min(forced, max_lg);
-    const double avg = B->rows ? (double)B->nnz / (double)B->rows : 1.0;
+    const double avg = B->rows ? (double)B->nnz / (double)act_rows(B) : 1.0;
     int lg = 0;
     while (lg < max_lg && (double)(2 << lg) <= avg / 2.0) lg++;
     return lg;
@@ -753,7 +770,7 @@ int ensure_cs_bounds(b200_ctx *ctx, const b200_csr *B) {
 bool want_pack(const b200_ctx *ctx, const b200_csr *B) {
     const int forced = ctx->cfg.pack_b;
     if (forced >= 0) return forced != 0;
-    return B->rows && (double)B->nnz / (double)B->rows <= 4.0;
+    return B->rows && (double)B->nnz / (double)act_rows(B) <= 4.0;
 }
 int ensure_pack(b200_ctx *ctx, const b200_csr *B) {
     if (B->d_pack) return B200_OK;
@@ -1009,7 +1026,7 @@ static int launch_numeric(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, u
     }
     // launch order: the bin that holds the row of mean size first (it carries most of the work), then outwards from
     // it, larger bins before smaller; the host-side estimate of the mean is nnz(A)/rows * nnz(B)/rows(B)
-    const double meanP = (A->rows ? (double)A->nnz / (double)A->rows : 0.0) * (B->rows ? (double)B->nnz / (double)B->rows : 0.0);
+    const double meanP = (A->rows ? (double)A->nnz / (double)act_rows(A) : 0.0) * (B->rows ? (double)B->nnz / (double)act_rows(B) : 0.0);
     int center = -1;                                                       // -1: tiny, 1: small (hash bins 0-1), 2..: hash bin
     if (meanP > 32.0) { center = 1; while (center < B200_NUM_HASH_BINS - 1 && meanP > (double)b200_hash_cap(center)) center++; }
     auto run = [&](int id) -> int { return id < 0 ? do_tiny() : id <= 1 ? do_small() : do_bin(id); };
@@ -1135,6 +1152,10 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     const bool timing = ctx->timing && st;
     b200_csr *C = nullptr;
     TRY(csr_alloc(ctx, rows, ncols, 0, A->val_bits, false, &C));
+    C->ar_start = A->ar_start; C->ar_len = A->ar_len;                       // rows of C outside A's active arc are empty
+    // mean row lengths for the heuristics below count the rows of the active arcs only (whole-size handles that hold a row
+    // block plus a halo: the empty rows outside say nothing about the lists a kernel will see)
+    const u64 actA = std::max<u64>(1, std::min<u64>(A->ar_len, rows)), actB = std::max<u64>(1, std::min<u64>(B->ar_len, B->rows));
     if (st) { memset(st, 0, sizeof(*st)); st->rows = rows; st->cols = ncols; st->nnz_a = A->nnz; st->nnz_b = B->nnz; }
     if (rows == 0 || A->nnz == 0 || B->nnz == 0) {
         CUDA_TRY_C(cudaMemsetAsync(C->d_rp, 0, (rows + 1) * 8 + 16, s));   // row_ptr and the max-value scalar behind it
@@ -1146,8 +1167,8 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     }
     // (the left multiply reads B's row_ptr directly: where it is the likely choice, B's per-row descriptors are built only if
     //  the multiply falls through to the other pipelines -- in a swapped power chain B is a fresh product every step)
-    const bool lm_try = ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && A->max_row_len <= 32 && (double)B->nnz / (double)B->rows >= ctx->lm_min_list &&
-                                                   (double)B->nnz / (double)B->rows >= 4.0 * ((double)A->nnz / (double)rows));
+    const bool lm_try = ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && A->max_row_len <= 32 && (double)B->nnz / (double)actB >= ctx->lm_min_list &&
+                                                   (double)B->nnz / (double)actB >= 4.0 * ((double)A->nnz / (double)actA));
     int r = ensure_row_scratch(ctx, rows);
     if (r == B200_OK && !lm_try) r = ensure_desc(ctx, B);
     const bool packed = want_pack(ctx, B);
@@ -1236,7 +1257,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         }
         if (groups > B200_RW_MAX_GROUPS) { groups = B200_RW_MAX_GROUPS; all_fit = false; }
         if (ctx->cfg.window_cap_groups >= 0 && (u64)ctx->cfg.window_cap_groups < groups) { groups = std::max<u64>(1, (u64)ctx->cfg.window_cap_groups); all_fit = false; }
-        const double meanP = ((double)A->nnz / (double)rows) * ((double)B->nnz / (double)B->rows);
+        const double meanP = ((double)A->nnz / (double)actA) * ((double)B->nnz / (double)actB);
         const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.4;
         u64 cap = (u64)(factor * meanP) + 32;
         cap = std::min<u64>(cap, std::min<u64>(std::min<u64>(p_bound, 8192), groups * 128));
@@ -1256,7 +1277,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         }
     }
     {
-        const double meanA = (double)A->nnz / (double)rows, meanB = (double)B->nnz / (double)B->rows;
+        const double meanA = (double)A->nnz / (double)actA, meanB = (double)B->nnz / (double)actB;
         const bool shape_ok = A->max_row_len <= 32 && meanB >= ctx->lm_min_list && meanB >= 4.0 * meanA;
         if ((ctx->cfg.pipeline == 6 || (ctx->cfg.pipeline == 0 && shape_ok)) && cheap_bound && ncols < 0xFFFF0000ull && rows < 0xFFFF0000ull &&
             ctx->cfg.window_cap_groups < 0 && ctx->cfg.placement < 0) {
@@ -1326,7 +1347,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
     if ((ctx->cfg.pipeline == 4 || ctx->cfg.pipeline == 0) && all_groups <= B200_RW_MAX_GROUPS && p_bound <= 16384 && cheap_bound &&
         B->nnz < 0xFFFFFFFFull && ctx->cfg.window_cap_groups < 0 && ctx->cfg.placement < 0) {
         const u32 nw = (all_groups * 4u + 31u) & ~31u;
-        const double meanP = ((double)A->nnz / (double)rows) * ((double)B->nnz / (double)B->rows);
+        const double meanP = ((double)A->nnz / (double)actA) * ((double)B->nnz / (double)actB);
         const double factor = ctx->cfg.rw_cap_percent > 0 ? 0.01 * ctx->cfg.rw_cap_percent : 1.4;
         u64 cap = (u64)(factor * meanP) + 32;
         cap = std::min<u64>(cap, std::min<u64>(p_bound, (u64)all_groups * 128));
@@ -1337,7 +1358,9 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         // handful of products, the warp-per-row phases are all latency, and the binned kernels' tiny-row path is 20-30 % faster
         // (30^3: A^2 51 vs 72 us, A^3 68 vs 82 us; from A^4 on the one-launch multiply is level or ahead)
         const size_t per_warp = rw_smem_per_warp(false, mode1, nw, (u32)cap);
-        if (per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 4 || (per_warp <= 14 * 1024 && meanP >= 48.0))) {
+        // ... and while most rows are inside A's active arc: the kernel cuts the rows into static per-CTA ranges, so a whole-size
+        // left operand that holds one GPU's rows keeps a fraction of the grid busy (measured: 0.71 ms against 0.10 for a rank of 8)
+        if (per_warp * 4 + 1024 <= ctx->smem_optin && (ctx->cfg.pipeline == 4 || (per_warp <= 14 * 1024 && meanP >= 48.0 && actA * 2 > rows))) {
             if (ctx->scan_clean_bytes < B200_CTRL_BYTES) { CUDA_TRY_C(cudaMemsetAsync(ctx->d_ctrl, 0, B200_CTRL_BYTES, s)); ctx->scan_clean_bytes = B200_CTRL_BYTES; }
             if (timing) cudaEventRecord(ctx->f_ev[slot][1], s);
             C->cap_entries = std::max<u64>((u64)hb128, 1);
@@ -1527,7 +1550,7 @@ static int spgemm_typed(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b20
         if (ctx->trace) trace_mark(ctx, __LINE__);
         {
             // lanes per row of the compaction from an estimate of the mean row (products / ~1.5); any value is correct
-            const double meanP = ((double)A->nnz / (double)rows) * (B->rows ? (double)B->nnz / (double)B->rows : 0.0);
+            const double meanP = ((double)A->nnz / (double)actA) * (B->rows ? (double)B->nnz / (double)actB : 0.0);
             const double avg = std::min((double)ncols, meanP / 1.5);
             const int llg = avg <= 2 ? 0 : avg <= 6 ? 2 : avg <= 24 ? 3 : 5;
             const u64 want = (rows << llg) / 256 + 1;

@@ -42,6 +42,10 @@ struct b200_csr {
     u32 cr_start; u64 cr_len;
     // square operands used on the right: signed offsets (c - k) of all entries lie in [cs_lo, cs_hi]; cs_state 0 unknown, 1 known, 2 none
     long long cs_lo, cs_hi; int cs_state;
+    // active row arc: every non-empty row is (ar_start + o) mod rows for some o < ar_len (ar_len = rows: unknown / everything).
+    // Known for host uploads (row_ptr passes through the host) and inherited by products from their left operand: a rank of a
+    // sharded power chain holds its block of rows plus a halo inside whole-size matrices, the other rows are empty.
+    u64 ar_start, ar_len;
     cudaEvent_t ev_copy;    // last asynchronous download of this handle on the copy stream (created on first use)
     b200_ctx *ctx;
     // ---- fused path (fused.cu): a product is returned before the host knows its size

@@ -38,6 +38,7 @@ struct LmArgs {
     const u64 *rpA; const u32 *colA; const VT *valA;
     const u64 *rpB; const u32 *colB; const VT *valB;
     u64 rows; u32 ncols;
+    u32 row_off, nact;              // active row arc of A: tickets 0 .. nact-1 are rows (row_off + t) mod rows, the others are empty
     u32 org;                        // window origin (per_row: added to the row index)
     u32 per_row;                    // 1: the window travels with the row
     u32 nw, cap, nsm;               // bitmap words per warp (multiple of 32), accumulator slots per warp, SMs
@@ -338,6 +339,9 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
     // row): the warps of the whole grid work on one moving front of neighbouring rows -- their lists are neighbours too and
     // come from L2 -- and nobody waits at the end of a phase for a slice that happened to hold the long rows.
     auto grab = [&](u32 *ticket) -> u32 { return lane == 0 ? atomicAdd(ticket, 1u) : 0u; };
+    // (tickets run over A's active row arc only: a whole-size left operand that holds a row block plus a halo hands out no empty rows)
+    auto torow = [&](u32 t) -> u64 { if (t >= p.nact) return p.rows; const u64 r = (u64)t + p.row_off; return r >= p.rows ? r - p.rows : r; };
+    auto active = [&](u64 r) -> bool { return (r >= p.row_off ? r - p.row_off : r + p.rows - p.row_off) < (u64)p.nact; };
     typedef typename W::XT XT;
     // lists of the row's first 32 A entries (loaded once per row and phase; mark and accumulate share them)
     auto lists = [&](u64 rs, u32 lenA, bool needv) -> LmDesc<XT> {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
     {
         u64 Psum = 0; u32 maxP = 0, maxN = 0;
         u32 *ticket = &p.ctrl->scan_ticket[0];
-        u64 row = __shfl_sync(FULLMASK, grab(ticket), 0), nxt = __shfl_sync(FULLMASK, grab(ticket), 0);
+        u64 row = torow(__shfl_sync(FULLMASK, grab(ticket), 0)), nxt = torow(__shfl_sync(FULLMASK, grab(ticket), 0));
         u64 rs = 0; u32 lenA = 0;
         if (row < p.rows) { rs = p.rpA[row]; lenA = (u32)(p.rpA[row + 1] - rs); }
         while (row < p.rows) {
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
             if (lenA) nnz = w.count_row(lists(rs, lenA, false), rs, lenA, origin(row), P, mid); else mid();
             if (lane == 0) { p.nnz_row[row] = nnz; if (nnz) atomicAdd((ull *)&p.cta_tot[row / S], (ull)nnz); }
             Psum += P; maxP = max(maxP, P); maxN = max(maxN, nnz);
-            row = nxt; nxt = __shfl_sync(FULLMASK, nn_l0, 0); rs = rs_n; lenA = lenA_n;
+            row = nxt; nxt = torow(__shfl_sync(FULLMASK, nn_l0, 0)); rs = rs_n; lenA = lenA_n;
         }
         if (lane == 0) { atomicAdd(&s_P, (ull)Psum); atomicMax(&s_maxP, (ull)maxP); atomicMax(&s_maxN, maxN); }
     }
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
         u64 run = s_base;
         for (u64 r0 = r_lo; r0 < r_hi; r0 += LM_THREADS) {
             const u64 r = r0 + tid;
-            const u32 v = r < r_hi ? __ldcg(&p.nnz_row[r]) : 0u;
+            const u32 v = r < r_hi && active(r) ? __ldcg(&p.nnz_row[r]) : 0u;      // (rows outside the arc were never counted)
             u32 incl = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(FULLMASK, incl, d); if (lane >= d) incl += t; }
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
     {
         u64 vmax = 0;
         u32 *ticket = &p.ctrl->scan_ticket[1];
-        u64 row = __shfl_sync(FULLMASK, grab(ticket), 0), nxt = __shfl_sync(FULLMASK, grab(ticket), 0);
+        u64 row = torow(__shfl_sync(FULLMASK, grab(ticket), 0)), nxt = torow(__shfl_sync(FULLMASK, grab(ticket), 0));
         u64 rs = 0, obase = 0; u32 lenA = 0;
         if (row < p.rows) { rs = p.rpA[row]; lenA = (u32)(p.rpA[row + 1] - rs); obase = __ldcg(&p.rpC[row]); }
         while (row < p.rows) {
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(LM_THREADS, LmTune<TUNE>::CTAS) k_lm(LmArgs<VT
             u64 rs_n = 0, obase_n = 0; u32 lenA_n = 0;
             auto mid = [&]() { if (nxt < p.rows) { rs_n = p.rpA[nxt]; lenA_n = (u32)(p.rpA[nxt + 1] - rs_n); obase_n = __ldcg(&p.rpC[nxt]); } };
             if (lenA) w.numeric_row(lists(rs, lenA, true), rs, lenA, origin(row), p.colC + obase, p.valC + obase, vmax, mid); else mid();
-            row = nxt; nxt = __shfl_sync(FULLMASK, nn_l0, 0); rs = rs_n; lenA = lenA_n; obase = obase_n;
+            row = nxt; nxt = torow(__shfl_sync(FULLMASK, nn_l0, 0)); rs = rs_n; lenA = lenA_n; obase = obase_n;
         }
         vmax = warp_max_u64(vmax);
         if (lane == 0 && vmax) atomicMax(&p.ctrl->max_val_out, (ull)vmax);
@@ -459,6 +463,7 @@ static cudaError_t lm_go(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b2
     LmArgs<VT> p;
     p.rpA = A->d_rp; p.colA = A->d_col; p.valA = (const VT *)A->d_val;
     p.rpB = B->d_rp; p.colB = B->d_col; p.valB = (const VT *)B->d_val;
+    p.row_off = A->ar_len && A->ar_len < A->rows ? (u32)A->ar_start : 0u; p.nact = (u32)(A->ar_len && A->ar_len < A->rows ? A->ar_len : A->rows);
     p.rows = A->rows; p.ncols = (u32)B->cols; p.org = org; p.per_row = per_row ? 1u : 0u; p.nw = nw; p.cap = cap; p.nsm = (u32)ctx->num_sms;
     p.nnz_row = ctx->d_nnz_row; p.cta_tot = ctx->d_lm_tot; p.rpC = C->d_rp; p.colC = C->d_col; p.valC = (VT *)C->d_val;
     p.ctrl = ctrl; p.host_mirror = mirror; p.epoch = epoch; p.maxval_dst = C->d_maxval;
@@ -482,7 +487,7 @@ int lm_launch(b200_ctx *ctx, const b200_csr *A, const b200_csr *B, b200_csr *C, 
     if (smem + k.static_smem > ctx->smem_optin) return set_err(B200_ERR_CUDA, "left-multiply kernel needs %zu B of shared memory", smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, LM_THREADS, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return set_err(B200_ERR_CUDA, "left-multiply kernel does not fit an SM"); }
-    const u64 want = (A->rows + LM_WARPS - 1) / LM_WARPS;
+    const u64 want = ((A->ar_len && A->ar_len < A->rows ? A->ar_len : A->rows) + LM_WARPS - 1) / LM_WARPS;
     int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->num_sms * per_sm));
     if (grid > ctx->num_sms) grid = grid / ctx->num_sms * ctx->num_sms;
     if ((u64)grid > ctx->cap_cta_tot) return set_err(B200_ERR_CUDA, "internal: %d CTAs exceed the per-CTA scratch", grid);

@@ -9,6 +9,8 @@ because row i of C depends only on row i of A and on B (src/graph_csr.rs:433-446
     not row count (`product_balanced_cuts`);
   * in repeated exponentiation every rank keeps its row block of A^(k-1) resident and multiplies it
     by the replicated A: no communication per step (`ShardedPowerChain`);
+  * `HaloPowerChain` is the same chain through left multiplies (the engine's fastest kernel on a power chain): the rank
+    computes its block plus a shrinking halo of neighbouring rows redundantly instead of exchanging them;
   * `allgather_csr` optionally assembles the full C from the row blocks (variable sizes).
 
 Everything here is engine-agnostic plumbing: the multiply itself is `engine.spgemm`, which in the
@@ -126,6 +128,75 @@ class ShardedPowerChain:
 
     def local_products(self) -> int:
         return int(np.asarray(self.engine.row_products(self.block, self.a), dtype=np.uint64).sum())
+
+
+def halo_row_sets(a: hostgen.HostCsr, r0: int, r1: int, max_power: int) -> list:
+    """need[k] (k = 1 .. max_power, need[0] unused): boolean masks of the rows of A^k a rank must hold so that rows [r0, r1)
+    of A^max_power follow from LEFT multiplies alone.  Row i of A^k = A x A^(k-1) reads the rows of A^(k-1) that A[i, :] points
+    at (src/graph_csr.rs:433-446 with the operands swapped; powers of one matrix commute), so need[max_power] = [r0, r1) and
+    need[k-1] = need[k] | columns(A[need[k], :]).  On a banded or lattice operand the sets grow by one halo per power; on a
+    graph without locality they reach every row after a step or two (`halo_overhead` tells the two apart)."""
+    lens = np.diff(a.row_ptr.astype(np.int64))
+    need = [None] * (max_power + 1)
+    m = np.zeros(a.rows, dtype=bool)
+    m[r0:r1] = True
+    need[max_power] = m
+    for k in range(max_power, 1, -1):
+        nxt = need[k].copy()
+        nxt[a.col_idx[np.repeat(need[k], lens)]] = True
+        need[k - 1] = nxt
+    return need
+
+
+def restrict_rows(a: hostgen.HostCsr, mask: np.ndarray) -> hostgen.HostCsr:
+    """A with the rows outside `mask` emptied (same shape: the column space and the row numbering stay global)."""
+    lens = np.diff(a.row_ptr.astype(np.int64))
+    keep = np.repeat(mask, lens)
+    rp = np.zeros(a.rows + 1, dtype=np.uint64)
+    np.cumsum(np.where(mask, lens, 0), out=rp[1:])
+    return hostgen.HostCsr(a.rows, a.cols, rp, a.col_idx[keep].copy(), a.values[keep].copy())
+
+
+def halo_overhead(need: list, r0: int, r1: int, growth: float = 2.0) -> float:
+    """Share of redundant work of a halo chain: rows of need[k] beyond the block, weighted by growth^k (the products of a
+    power chain roughly double per power).  0 = none, 1 = as much again as the useful work."""
+    own = max(r1 - r0, 1)
+    num = den = 0.0
+    for k in range(2, len(need)):
+        w = growth ** k
+        num += w * (int(need[k].sum()) - own) / own
+        den += w
+    return num / den if den else 0.0
+
+
+class HaloPowerChain:
+    """Rows [r0, r1) of A^2 .. A^max_power on one rank, without communication, through LEFT multiplies.
+
+    `ShardedPowerChain` multiplies the rank's row block of A^(k-1) by the replicated A: the long rows are on the left and the
+    engine cannot use its left-multiply kernel (a row block is no power of A, so the operands do not commute).  Here the
+    rank evaluates A_k x A^(k-1) instead, where A_k is A with the rows outside need[k] emptied (`halo_row_sets`): whole-size
+    handles whose rows outside need[k] are empty, so rows and columns keep their global numbers and rows [r0, r1) of every
+    product are bit for bit the rank's block of A^k.  The halo rows are computed redundantly by the neighbours instead of
+    being exchanged: communication-avoiding, and worth it while `overhead` stays small (lattices, banded matrices)."""
+
+    def __init__(self, engine: Engine, a_host: hostgen.HostCsr, r0: int, r1: int, max_power: int, a_dev=None):
+        self.engine, self.r0, self.r1, self.max_power = engine, r0, r1, max_power
+        self.need = halo_row_sets(a_host, r0, r1, max_power)
+        self.overhead = halo_overhead(self.need, r0, r1)
+        self.a = a_dev if a_dev is not None else engine.upload(a_host)
+        self.left = [engine.upload(restrict_rows(a_host, self.need[k])) for k in range(2, max_power + 1)]
+
+    def run(self) -> list:
+        """[A^2, .., A^max_power] as whole-size handles; rows outside need[k] are empty."""
+        p, out = self.a, []
+        for ak in self.left:
+            p = self.engine.spgemm(ak, p)
+            out.append(p)
+        return out
+
+    def block(self, c):
+        """The rank's row block of a product of `run`, as its own handle (local row numbers, global columns)."""
+        return self.engine.row_block(c, self.r0, self.r1)
 
 
 def allgather_csr(block: hostgen.HostCsr, group=None, device="cpu") -> hostgen.HostCsr:

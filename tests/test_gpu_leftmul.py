@@ -159,3 +159,47 @@ def test_left_multiply_edge_shapes(gpu_ctx, oracle, cfg, bits):
         a, b = B200Matrix.from_host(a_h, gpu_ctx), B200Matrix.from_host(b_h, gpu_ctx)
         c = a.matmul(b, want_stats=True)
         assert_same(c.to_host(), oracle.matmul_par(to_o(oracle, a_h), to_o(oracle, b_h)), f"case {i} u{bits} (pipeline {c.last_stats.pipeline})")
+
+
+@pytest.mark.parametrize("arc", [(300, 400), (3600, 800), (0, 4000), (1234, 1), (3999, 2)])
+def test_left_multiply_over_an_active_row_arc(gpu_ctx, oracle, cfg, arc):
+    """A whole-size left operand whose rows outside an arc of the row circle are empty (a rank's rows of a sharded chain,
+    possibly wrapping past the last row): the kernel hands out the rows of the arc only, the others come out empty."""
+    from sparse_linear_algebra_tests_b200.distributed import restrict_rows
+    O = oracle
+    a_h = hostgen.thin(hostgen.lattice([40, 10, 10], True, 64), 3.0 / 26.0, bytes([42] * 32))
+    ao = to_o(O, a_h)
+    p4 = O.matmul_par(O.matmul_par(O.matmul_par(ao, ao), ao), ao)
+    p4_h = hostgen.HostCsr(p4.rows, p4.cols, p4.row_ptr, p4.col_idx, p4.values)
+    mask = np.zeros(a_h.rows, dtype=bool)
+    start, length = arc                                        # rows (start + o) mod rows, o < length: the second and last wrap
+    mask[np.arange(start, start + length) % a_h.rows] = True
+    cfg(pipeline=6)
+    c = left_check(O, gpu_ctx, restrict_rows(a_h, mask), p4_h, f"arc {arc}")
+    lens = np.diff(c.to_host().row_ptr.astype(np.int64))
+    assert not lens[~mask].any() and lens[mask].any()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_power_chain_blocks_match_the_reference_chain(gpu_ctx, oracle, world):
+    """distributed.HaloPowerChain on the CUDA engine, every rank of a `world`-rank job in turn on this GPU: rows [r0, r1) of
+    A^2..A^6 through left multiplies over block + halo equal the blocks of the reference chain (graph_magnus.rs:758-772),
+    and the late powers do take the left-multiply kernel (whole-size handles with empty rows outside the arc)."""
+    from sparse_linear_algebra_tests_b200.distributed import CudaEngine, HaloPowerChain, product_balanced_cuts
+    O = oracle
+    a_h = hostgen.thin(hostgen.lattice([48, 10, 10], True, 64), 3.0 / 26.0, bytes([42] * 32))
+    ao = to_o(O, a_h)
+    ref, p = [], ao
+    for _ in range(2, 7):
+        p = O.matmul_par(p, ao)
+        ref.append(p)
+    cuts = product_balanced_cuts(O.row_products(ao, ao), world)
+    eng = CudaEngine(gpu_ctx)
+    for rank in range(world):
+        r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+        ch = HaloPowerChain(eng, a_h, r0, r1, 6)
+        outs = ch.run()
+        for k, (c, want) in zip(range(2, 7), zip(outs, ref)):
+            got = eng.download(ch.block(c))
+            assert_same(got, want.row_block(r0, r1), f"rank {rank}/{world} A^{k}")
+        assert outs[-1].product_stats().pipeline == 6, f"rank {rank}/{world}: A^6 did not take the left multiply"

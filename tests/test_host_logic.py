@@ -140,3 +140,35 @@ def test_engine_chacha12_host_twin_matches_the_pinned_generator():
     # counters beyond 2^32 blocks use the high counter word
     far = (1 << 35) + 5
     assert np.array_equal(_native.stdrng_u64(bytes([42] * 32), far, 16)[8:], _native.stdrng_u64(bytes([42] * 32), far + 8, 8))
+
+
+def test_halo_chain_gives_the_ranks_row_blocks(oracle):
+    """distributed.HaloPowerChain (left multiplies over a rank's rows plus a halo, nothing exchanged): rows [r0, r1) of every
+    power equal the rank's block of the reference chain A^k = A^(k-1) x A (graph_magnus.rs:758-772), also for a block whose
+    halo wraps round the torus; the row sets shrink to the block at the last power; without locality the halo is everything."""
+    from sparse_linear_algebra_tests_b200.distributed import HaloPowerChain, halo_row_sets, restrict_rows
+
+    class Eng:
+        def upload(self, h): return oracle.Csr(h.rows, h.cols, h.row_ptr, h.col_idx, h.values)
+        def spgemm(self, a, b): return oracle.matmul(a, b)
+        def row_block(self, a, r0, r1): return a.row_block(r0, r1)
+
+    a = hostgen.thin(hostgen.lattice([24, 4, 4], True, 64), 3.0 / 26.0, bytes([42] * 32))
+    full = Eng().upload(a)
+    ref, p = [], full
+    for _ in range(2, 6):
+        p = oracle.matmul(p, full)
+        ref.append(p)
+    for r0, r1 in ((0, 96), (96, 200), (288, 384)):
+        ch = HaloPowerChain(Eng(), a, r0, r1, 5)
+        assert int(ch.need[5].sum()) == r1 - r0 and all(ch.need[k][r0:r1].all() for k in range(1, 6))
+        assert all((ch.need[k] <= ch.need[k - 1]).all() for k in range(2, 6))
+        assert 0.0 < ch.overhead < 1.5
+        for c, want in zip(ch.run(), ref):
+            b, w = ch.block(c), want.row_block(r0, r1)
+            assert np.array_equal(b.row_ptr, w.row_ptr) and np.array_equal(b.col_idx, w.col_idx) and np.array_equal(b.values, w.values)
+    r = restrict_rows(a, halo_row_sets(a, 10, 20, 3)[3])
+    assert r.rows == a.rows and r.nnz() == int(a.row_ptr[20] - a.row_ptr[10]) and int(r.row_ptr[10]) == 0
+    g = hostgen.rmat(8, 8, 0.45, 0.15, 0.15, 42, 64) if hasattr(hostgen, "rmat") else None
+    if g is not None:
+        assert halo_row_sets(g, 0, 32, 4)[1].sum() > 0.5 * g.rows
