@@ -1,6 +1,7 @@
 """N > 1 host logic on CPU: world_size 2 over gloo.  The multiply is injected (CPU oracle) -- the product's
 CudaEngine needs a B200 -- everything else (broadcast of A, product-balanced row blocks, resident-block power
-chain without communication, variable-size all-gather of C) is the code the GPU ranks run."""
+chain without communication -- as right multiplies and as the halo chain of left multiplies --, variable-size all-gather
+of C) is the code the GPU ranks run."""
 import os
 import sys
 
@@ -51,6 +52,15 @@ def _worker(rank, world, port, q):
             blk = chain.step()
             full = eng.spgemm(full, eng.upload(a_h))
             gathered = allgather_csr(eng.download(blk))
+            ok &= (np.array_equal(gathered.row_ptr, full.row_ptr) and np.array_equal(gathered.col_idx, full.col_idx)
+                   and np.array_equal(gathered.values, full.values))
+        # the same blocks through left multiplies over block + halo (HaloPowerChain): nothing exchanged between the ranks
+        from sparse_linear_algebra_tests_b200.distributed import HaloPowerChain
+        halo = HaloPowerChain(eng, a_h, chain.r0, chain.r1, 4)
+        full = eng.upload(a_h)
+        for c in halo.run():
+            full = eng.spgemm(full, eng.upload(a_h))
+            gathered = allgather_csr(eng.download(halo.block(c)))
             ok &= (np.array_equal(gathered.row_ptr, full.row_ptr) and np.array_equal(gathered.col_idx, full.col_idx)
                    and np.array_equal(gathered.values, full.values))
         loads = [None] * world
